@@ -1,0 +1,141 @@
+/*
+ * mosh2.h -- C-ABI of libmosh2.so, the B200 (sm_100a) MoSh++ Stage-II pose solver.
+ *
+ * The reference has no FFI: its Stage-II plug-in point is a Python callable,
+ *     MoSh.mosh_stageii(self, mosh_stageii_func)          src/moshpp/mosh_head.py:268-301
+ * invoked as mosh_stageii_func(mocap_fname, cfg, markers_latent, latent_labels, betas,
+ * marker_meta, v_template_fname) (mosh_head.py:280-286; reference implementation
+ * src/moshpp/chmosh.py:458-741).  moshpp_b200/chmosh.py keeps that signature and drives this
+ * library through ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every host buffer is caller-owned, C-contiguous,
+ * float64 / int32 / uint8; the library owns all device memory behind the opaque handles; every
+ * entry point returns 0 or a negative MOSH2_E_* code and never throws across the ABI;
+ * mosh2_last_error() returns a thread-local message.  One model handle per GPU; calls on one
+ * handle / job must be serialised by the caller, different handles are independent.
+ */
+#ifndef MOSH2_H_
+#define MOSH2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOSH2_VERSION 100
+
+enum {
+    MOSH2_OK = 0,
+    MOSH2_E_INVALID = -1,   /* bad argument / inconsistent sizes            */
+    MOSH2_E_CUDA = -2,      /* CUDA runtime error (message in last_error)   */
+    MOSH2_E_NO_DEVICE = -3, /* no usable sm_100 device                      */
+    MOSH2_E_TOO_LARGE = -4  /* model does not fit the kernel's shared memory */
+};
+
+enum { MOSH2_F32 = 0, MOSH2_F64 = 1 };
+
+/* per-frame status bits written to mosh2_result.status */
+enum {
+    MOSH2_ST_SOLVED = 1,       /* both dog-legs of the frame terminated by the reference's stop rules */
+    MOSH2_ST_SKIPPED = 2,      /* no visible marker: frame skipped (chmosh.py:586-588)                  */
+    MOSH2_ST_HAS_VELO = 4,     /* the velocity term was active (third processed frame on, chmosh.py:624) */
+    MOSH2_ST_HAS_EXTRAP = 8,   /* the DMPL extrapolation term was active (chmosh.py:694-697)            */
+    MOSH2_ST_GN_FALLBACK = 16, /* a Gauss-Newton system was not positive definite; Cauchy step used     */
+    MOSH2_ST_MAXITER = 32      /* a dog-leg hit maxiter                                                 */
+};
+
+/* Constants of one (body model, betas, latent markers) triple, as laid out by
+ * moshpp_b200/pack.py:build_pack (what chmosh.py:488-514,548-579 sets up before the frame loop;
+ * models/smpl_fast_derivatives.py:52-241; transformed_lm.py:59-113; prior/gmm_prior_ch.py:107-134).
+ * "slot" = 3*marker + t, t = 0..2 the three attachment vertices of a marker. */
+typedef struct mosh2_model_desc {
+    int32_t n_joints, n_markers, body_dof, p_red, n_hand_red, n_hand_full, n_dmpl;
+    int32_t kw, na, n_levels;
+    const int32_t *parents;   /* [n_joints], -1 for the root                                 */
+    const int32_t *fk_order;  /* [n_joints] joints sorted by depth                           */
+    const int32_t *level_ofs; /* [n_levels+1] offsets into fk_order                          */
+    const int32_t *w_joint;   /* [3M*kw] skinning joint ids, -1 padded                       */
+    const int32_t *anc_joint; /* [3M*na] union of ancestors of the slot's joints, -1 padded  */
+    const int32_t *anc_mask;  /* [3M*na] bit i: w_joint[slot][i] lies in the ancestor's subtree */
+    const int8_t *anc_pos;    /* [3M*n_joints] index of a joint in anc_joint[slot], or -1    */
+    const double *hand_comps; /* [n_hand_red * n_hand_full]  selected_components             */
+    const double *hands_mean; /* [n_hand_full]                                               */
+    const double *v0;         /* [3M*3]  shaped template rows                                */
+    const double *sd;         /* [3M*3*n_dmpl] DMPL directions of the slots                  */
+    const double *pd;         /* [(n_joints-1) * 9M * 9] pose-blend slabs                    */
+    const double *w_val;      /* [3M*kw]                                                     */
+    const double *j0;         /* [n_joints*3]                                                */
+    const double *jd;         /* [n_joints*3*n_dmpl]                                         */
+    const double *coefs;      /* [M*3] marker attachment coefficients                        */
+    int32_t prior_k, prior_d, prior_off; /* max-mixture prior on pose[prior_off : prior_off+prior_d] */
+    const double *prior_means;   /* [K*D]                                                    */
+    const double *prior_Q;       /* [K*D*D]  0.5 * inv(cov_k)                                */
+    const double *prior_neglogw; /* [K]                                                      */
+    int32_t n_free1, n_free2;    /* free variables of Step 1 / Step 2 (chmosh.py:645-649,676-699) */
+    const int32_t *free1, *free2; /* indices into x = [trans(3) | pose(p_red) | dmpl(n_dmpl)] */
+    int32_t finger_lo, finger_hi; /* reduced-pose ids penalised by poseH in Step 2            */
+} mosh2_model_desc;
+
+/* Stage-II weights and dog-leg options (support_data/conf/moshpp_conf.yaml:95-125,
+ * chmosh.py:460,596-609,651-653,669-671,697,703-705). */
+typedef struct mosh2_options {
+    double wt_data, wt_poseB, wt_poseH, wt_velo, wt_dmpl, wt_annealing, wt_extrap_dmpl;
+    double num_train_markers;
+    double delta_0, e3_first, e3;
+    int32_t maxiter;
+    int32_t optimize_fingers, optimize_dynamics;
+} mosh2_options;
+
+/* Outputs, one row per input frame (rows of skipped frames are zero). */
+typedef struct mosh2_result {
+    double *fullpose;    /* [F * 3*n_joints]            chmosh.py:719   */
+    double *pose;        /* [F * p_red]   reduced pose (debug)          */
+    double *trans;       /* [F * 3]                      chmosh.py:720   */
+    double *dmpls;       /* [F * n_dmpl] or NULL         chmosh.py:722   */
+    double *markers_sim; /* [F * M * 3]                  chmosh.py:716   */
+    double *errs;        /* [F * 6] SSE of data,poseB,velo,poseH,dmpl,extrap_dmpl  chmosh.py:712-714 */
+    int32_t *status;     /* [F] MOSH2_ST_* bits                           */
+    int32_t *counters;   /* [F * 4] dog-leg iterations, residual evals, Jacobian builds, minimisations */
+} mosh2_result;
+
+typedef struct mosh2_model mosh2_model;
+typedef struct mosh2_job mosh2_job;
+
+int mosh2_version(void);
+const char *mosh2_last_error(void);
+int mosh2_device_count(void);
+
+void mosh2_default_options(mosh2_options *opt);
+
+/* Uploads the constants to `device` (both f32 and f64 copies). */
+int mosh2_model_create(const mosh2_model_desc *desc, int device, mosh2_model **out);
+void mosh2_model_destroy(mosh2_model *m);
+
+/* A job = device buffers for one sequence of n_frames frames.
+ * chunk_len <= 0 solves the sequence exactly like the reference (one sequential pass);
+ * chunk_len > 0 cuts it into chunks solved concurrently, each started chunk_warmup frames early. */
+int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, int32_t chunk_len,
+                     int32_t chunk_warmup, int32_t precision, mosh2_job **out);
+/* obs [F*M*3] metres in latent-label order, vis [F*M] 0/1.  Async on the job's stream. */
+int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis);
+int mosh2_job_launch(mosh2_job *j);                 /* async */
+int mosh2_job_download(mosh2_job *j, const mosh2_result *res); /* async D2H + stream sync */
+int mosh2_job_sync(mosh2_job *j);
+/* device time of the last launch (CUDA events on the job's stream), ms; valid after a sync */
+int mosh2_job_kernel_ms(mosh2_job *j, float *ms);
+int mosh2_job_num_chunks(mosh2_job *j);
+/* work done by the last launch over ALL processed frames (warm-up included):
+ * out4 = {dog-leg iterations, residual evaluations, Jacobian/normal-equation builds, minimisations} */
+int mosh2_job_totals(mosh2_job *j, int32_t *out4);
+void mosh2_job_destroy(mosh2_job *j);
+
+/* upload + launch + download in one call (the call the Python wrapper makes). */
+int mosh2_solve(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const double *obs,
+                const uint8_t *vis, int32_t chunk_len, int32_t chunk_warmup, int32_t precision,
+                const mosh2_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSH2_H_ */

@@ -1,0 +1,228 @@
+"""``mosh_stageii`` -- drop-in for the reference's Stage-II callable, running on libmosh2.so (B200).
+
+Reference: src/moshpp/chmosh.py:458-741.  Same positional signature, same return dictionary
+(chmosh.py:726-741), same frame-skip rule (586-588); it plugs into the reference's own call site
+``MoSh.mosh_stageii(mosh_stageii_func)`` (mosh_head.py:268-301) unchanged:
+
+    from moshpp_b200.chmosh import mosh_stageii
+    mp.mosh_stageii(mosh_stageii)
+
+What runs where
+  host (this file, pack.py, mocap_interface.py): file IO, label matching, once-per-subject packing;
+  device (csrc/): every per-frame evaluation -- SMPL forward, Jacobians, priors, normal equations,
+  Cholesky, dog-leg, the frame loop itself.  There is no CPU solver: without libmosh2.so or a GPU the
+  call raises.
+
+Parallel-in-time schedule: the frames are cut into chunks solved concurrently,
+each started ``chunk_warmup`` frames early.  The reference's recursion is contractive, so the chunked
+result converges geometrically in the warm-up length to the sequential one (1e-6 rad at 64 frames);
+``chunk_len=0`` runs the reference's single sequential pass exactly.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import pickle
+import time
+from typing import Optional
+
+import numpy as np
+
+from . import lib as _lib
+from . import pack as _pack
+from .mocap_interface import MocapSession
+
+logger = logging.getLogger('moshpp_b200')
+
+NUM_SMS_B200 = 148
+DEFAULT_WARMUP = 64
+
+
+def _get(node, key, default=None):
+    try:
+        return node[key]
+    except (KeyError, TypeError, IndexError):
+        return getattr(node, key, default)
+
+
+def _read_vertices(fname: str) -> np.ndarray:
+    """v_template file (the reference uses psbody.mesh.Mesh, smpl_fast_derivatives.py:73-78)."""
+    if fname.endswith('.npy'):
+        return np.load(fname)
+    if fname.endswith('.obj'):
+        return np.array([[float(x) for x in l.split()[1:4]] for l in open(fname) if l.startswith('v ')])
+    if fname.endswith('.ply'):
+        with open(fname, 'rb') as f:
+            header = []
+            while True:
+                line = f.readline().decode('latin-1').strip()
+                header.append(line)
+                if line == 'end_header':
+                    break
+            n = int([h for h in header if h.startswith('element vertex')][0].split()[-1])
+            nprops = 0
+            in_vertex = False
+            for h in header:
+                if h.startswith('element'):
+                    in_vertex = h.startswith('element vertex')
+                elif h.startswith('property') and in_vertex:
+                    nprops += 1
+            if any('ascii' in h for h in header):
+                return np.array([[float(x) for x in f.readline().split()[:3]] for _ in range(n)])
+            if any('binary_little_endian' in h for h in header) and all(
+                    h.split()[1] == 'float' for h in header if h.startswith('property') and 'list' not in h):
+                return np.frombuffer(f.read(4 * nprops * n), dtype='<f4').reshape(n, nprops)[:, :3].astype(np.float64)
+    raise NotImplementedError(f'cannot read v_template from {fname}')
+
+
+def auto_chunk_len(n_frames: int, sm_budget: int = NUM_SMS_B200) -> int:
+    """Shortest chunks that still give about one chunk per available SM (latency = chunk_len + warm-up)."""
+    return max(4, int(math.ceil(n_frames / max(1, sm_budget))))
+
+
+def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname=None):
+    """Everything chmosh.py:475-514,548-579 does before the frame loop -> (StageIIPack, options, flags)."""
+    sm, mp = cfg.surface_model, cfg.moshpp
+    latent_labels = list(latent_labels)
+    flags = {}
+    for body_part, key in {'finger': 'optimize_fingers', 'face': 'optimize_face'}.items():       # chmosh.py:475-486
+        on = bool(_get(mp, key, False))
+        if on:
+            if not np.any([body_part in m for m in marker_meta['marker_type_mask'].keys()]):
+                logger.warning(f'{key} was activated but no {body_part} marker type detected in the marker layout')
+                on = False
+            elif not np.any([(body_part in t) and l in latent_labels for l, t in marker_meta['marker_type'].items()]):
+                logger.warning(f'{key} was activated but no {body_part} marker type detected in the mocaps')
+                on = False
+            if not on:
+                try:
+                    mp[key] = False
+                except Exception:
+                    pass
+        flags[key] = on
+    if flags['optimize_face']:
+        raise NotImplementedError('optimize_face (expressions / jaw) is not built yet (SURVEY.md 8(f-4))')
+
+    v_template = _read_vertices(v_template_fname) if v_template_fname else None
+    model = _pack.load_surface_model(sm.fname, pose_hand_prior_fname=_get(mp, 'pose_hand_prior_fname'),
+                                     use_hands_mean=bool(sm.use_hands_mean), dof_per_hand=int(sm.dof_per_hand),
+                                     v_template=v_template, surface_model_type=sm.type)
+    if model.model_type != sm.type:
+        raise ValueError(f'{model.model_type} != {sm.type}')                                       # bodymodel_loader.py:108
+    prior = None
+    prior_fname = _get(mp, 'pose_body_prior_fname')
+    if prior_fname and model.model_type != 'mano':
+        prior = _pack.create_gmm_body_prior(prior_fname, exclude_hands=model.model_type in ('smplh', 'smplx'))
+    dyn = bool(_get(mp, 'optimize_dynamics', False))
+    dmpl_dirs = None
+    if dyn:                                                                                        # chmosh.py:507-514
+        if sm.type not in ('smpl', 'smplh'):
+            logger.warning('DMPL with %s is rejected by the reference (chmosh.py:508-509); running the '
+                           'extension defined in DESIGN.md', sm.type)
+        with open(sm.dmpl_fname, 'rb') as f:
+            dmpl_dirs = pickle.load(f, encoding='latin-1')['eigvec']
+    pk = _pack.build_pack(model, np.asarray(betas, dtype=np.float64), np.asarray(markers_latent, dtype=np.float64),
+                          num_betas=int(sm.num_betas), prior=prior, dmpl_dirs=dmpl_dirs,
+                          num_dmpls=int(sm.num_dmpls) if dyn else 0,
+                          optimize_fingers=flags['optimize_fingers'],
+                          optimize_toes=bool(_get(mp, 'optimize_toes', False)))
+    opts = _lib.make_options(cfg.opt_settings.weights, maxiter=int(cfg.opt_settings.maxiter),
+                             optimize_fingers=flags['optimize_fingers'] and pk.finger_hi > pk.finger_lo,
+                             optimize_dynamics=dyn)
+    return pk, opts, flags
+
+
+def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.ndarray, latent_labels, pk,
+                          flags, dyn: bool) -> dict:
+    """chmosh.py:712-741: per-frame lists over the frames that had at least one visible marker."""
+    solved = (res.status & _lib.ST_SOLVED) != 0
+    fid = np.nonzero(solved)[0]
+    st = res.status[fid]
+    errs = {'data': res.errs[fid, 0]}
+    if pk.prior_k:
+        errs['poseB'] = res.errs[fid, 1]
+    if flags['optimize_fingers'] and pk.finger_hi > pk.finger_lo:
+        errs['poseH'] = res.errs[fid, 3]
+    if dyn:
+        errs['dmpl'] = res.errs[fid, 4]
+        errs['extrap_dmpl'] = res.errs[fid, 5][(st & _lib.ST_HAS_EXTRAP) != 0]
+    errs['velo'] = res.errs[fid, 2][(st & _lib.ST_HAS_VELO) != 0]
+    errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseH', 'dmpl') or len(v)}
+    labels = np.asarray(latent_labels, dtype=object)
+    data = {
+        'fullpose': res.fullpose[fid].copy(),
+        'trans': res.trans[fid].copy(),
+    }
+    if dyn:
+        data['dmpls'] = res.dmpls[fid, :pk.n_dmpl].copy()
+    data['stageii_debug_details'] = {
+        'stageii_errs': errs,
+        'markers_sim': [res.markers_sim[f][vis[f]] for f in fid],
+        'markers_obs': [obs[f][vis[f]] for f in fid],
+        'labels_obs': [labels[vis[f]].tolist() for f in fid],
+    }
+    return data
+
+
+def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_labels: list, betas: np.ndarray,
+                 marker_meta: dict, v_template_fname=None, *, device: int = 0, chunk_len: Optional[int] = None,
+                 chunk_warmup: int = DEFAULT_WARMUP, precision: str = 'f32', sm_budget: int = NUM_SMS_B200,
+                 labels_map: Optional[dict] = None) -> dict:
+    """Stage II of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:458-459).
+
+    Keyword-only extras: ``device``; ``chunk_len`` (None = automatic, 0 = the reference's single
+    sequential pass), ``chunk_warmup``; ``precision`` 'f32' | 'f64'; ``labels_map`` (the reference
+    passes its static synonym table general_labels_map, which is metadata outside this build).
+    """
+    t0 = time.time()
+    mocap = MocapSession(mocap_fname, mocap_unit=cfg.mocap.unit, mocap_rotate=cfg.mocap.rotate,
+                         labels_map=labels_map,
+                         only_subjects=[cfg.mocap.subject_name] if cfg.mocap.multi_subject else None)
+    pk, opts, flags = prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname)
+    dyn = bool(opts.optimize_dynamics)
+
+    end = len(mocap) if cfg.mocap.end_fidx == -1 else cfg.mocap.end_fidx
+    selected_frames = range(cfg.mocap.start_fidx, end, cfg.mocap.ds_rate)                         # chmosh.py:539-540
+    obs, vis = mocap.frames_for_labels(list(latent_labels), selected_frames)
+    F = obs.shape[0]
+    if F == 0:
+        raise ValueError('no frames selected')
+    if chunk_len is None:
+        chunk_len = auto_chunk_len(F, sm_budget)
+    if chunk_len >= F:
+        chunk_len = 0
+    prec = {'f32': _lib.MOSH2_F32, 'f64': _lib.MOSH2_F64}[precision]
+
+    model = _lib.Model(pk, device=device)
+    try:
+        job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, precision=prec)
+        try:
+            job.upload(obs, vis)
+            job.launch()
+            res = job.download()
+            kernel_ms = job.kernel_ms()
+            n_chunks = job.num_chunks
+        finally:
+            job.close()
+    finally:
+        model.close()
+
+    data = assemble_stageii_data(res, obs, vis, latent_labels, pk, flags, dyn)
+    dbg = data['stageii_debug_details']
+    dbg.update({
+        'markers_orig': mocap.markers[selected_frames],
+        'labels_orig': mocap.labels,
+        'mocap_fname': mocap_fname,
+        'mocap_frame_rate': mocap.frame_rate,
+        'mocap_time_length': mocap.time_length(),
+        'b200': {
+            'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
+            'chunk_warmup': chunk_warmup, 'precision': precision, 'status': res.status.copy(),
+            'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
+            'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
+        },
+    })
+    n_fb = int(((res.status & _lib.ST_GN_FALLBACK) != 0).sum())
+    if n_fb:
+        logger.warning('%d frames hit a non-positive-definite Gauss-Newton system (Cauchy step used)', n_fb)
+    return data

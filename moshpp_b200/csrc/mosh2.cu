@@ -1,0 +1,416 @@
+// mosh2.cu -- libmosh2.so: kernels and the C-ABI declared in include/mosh2.h.
+//
+// One CUDA thread block per chunk of frames runs the whole Stage-II schedule of
+// src/moshpp/chmosh.py:584-724 on device (mosh2_device.cuh).  Built for sm_100a only.
+#include "../../include/mosh2.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mosh2_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(MOSH2_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kThreads = 256;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+template <class real>
+__global__ void __launch_bounds__(kThreads, 1)
+mosh2_stageii_kernel(const mosh2::Model<real> m, const mosh2::Job<real> job, int big_in_global) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    mosh2::Work<real> w;
+    const mosh2::Dims d = mosh2::make_dims(m);
+    mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
+    mosh2::Arena G{job.gws ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
+    mosh2::carve(w, d, S, G, big_in_global != 0);
+    mosh2::Cta c{int(threadIdx.x), int(blockDim.x)};
+    mosh2::Solver<real> s(m, job, w, c);
+    s.run_chunk(blockIdx.x);
+}
+
+// device copy of every model array in one precision
+template <class real>
+struct DevModel {
+    mosh2::Model<real> m{};
+    std::vector<void *> owned;
+    ~DevModel() {
+        for (void *p : owned) cudaFree(p);
+    }
+    template <class T, class U>
+    int up(const U *src, size_t n, const T **dst) {
+        *dst = nullptr;
+        if (n == 0) {       // keep a valid pointer so kernels can form addresses
+            void *p = nullptr;
+            CU(cudaMalloc(&p, 16));
+            owned.push_back(p);
+            *dst = static_cast<const T *>(p);
+            return 0;
+        }
+        std::vector<T> tmp(n);
+        for (size_t i = 0; i < n; ++i) tmp[i] = static_cast<T>(src[i]);
+        void *p = nullptr;
+        CU(cudaMalloc(&p, n * sizeof(T)));
+        owned.push_back(p);
+        CU(cudaMemcpy(p, tmp.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+        *dst = static_cast<const T *>(p);
+        return 0;
+    }
+    int build(const mosh2_model_desc &d) {
+        const size_t nJ = d.n_joints, S = size_t(3) * d.n_markers, nd = d.n_dmpl;
+        m.nJ = d.n_joints; m.M = d.n_markers; m.body_dof = d.body_dof; m.p_red = d.p_red;
+        m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw; m.na = d.na;
+        m.n_levels = d.n_levels; m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
+        m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
+        int rc;
+        if ((rc = up<int>(d.parents, nJ, &m.parents))) return rc;
+        if ((rc = up<int>(d.fk_order, nJ, &m.fk_order))) return rc;
+        if ((rc = up<int>(d.level_ofs, size_t(d.n_levels) + 1, &m.level_ofs))) return rc;
+        if ((rc = up<int>(d.w_joint, S * d.kw, &m.w_joint))) return rc;
+        if ((rc = up<int>(d.anc_joint, S * d.na, &m.anc_joint))) return rc;
+        if ((rc = up<int>(d.anc_mask, S * d.na, &m.anc_mask))) return rc;
+        if ((rc = up<int8_t>(d.anc_pos, S * nJ, &m.anc_pos))) return rc;
+        std::vector<int> lo(d.n_hand_red, 0), hi(d.n_hand_red, 0);
+        for (int r = 0; r < d.n_hand_red; ++r) {
+            int a = d.n_hand_full, b = 0;
+            for (int c = 0; c < d.n_hand_full; ++c)
+                if (d.hand_comps[size_t(r) * d.n_hand_full + c] != 0.0) { if (c < a) a = c; b = c + 1; }
+            if (b <= a) a = b = 0;
+            lo[r] = a; hi[r] = b;
+        }
+        if ((rc = up<int>(lo.data(), lo.size(), &m.hand_lo))) return rc;
+        if ((rc = up<int>(hi.data(), hi.size(), &m.hand_hi))) return rc;
+        if ((rc = up<real>(d.hand_comps, size_t(d.n_hand_red) * d.n_hand_full, &m.hand_comps))) return rc;
+        if ((rc = up<real>(d.hands_mean, d.n_hand_full, &m.hands_mean))) return rc;
+        if ((rc = up<real>(d.v0, S * 3, &m.v0))) return rc;
+        if ((rc = up<real>(d.sd, S * 3 * nd, &m.sd))) return rc;
+        if ((rc = up<real>(d.pd, (nJ - 1) * S * 3 * 9, &m.pd))) return rc;
+        if ((rc = up<real>(d.w_val, S * d.kw, &m.w_val))) return rc;
+        if ((rc = up<real>(d.j0, nJ * 3, &m.j0))) return rc;
+        if ((rc = up<real>(d.jd, nJ * 3 * nd, &m.jd))) return rc;
+        if ((rc = up<real>(d.coefs, size_t(d.n_markers) * 3, &m.coefs))) return rc;
+        if ((rc = up<real>(d.prior_means, size_t(d.prior_k) * d.prior_d, &m.prior_means))) return rc;
+        if ((rc = up<real>(d.prior_Q, size_t(d.prior_k) * d.prior_d * d.prior_d, &m.prior_Q))) return rc;
+        if ((rc = up<real>(d.prior_neglogw, d.prior_k, &m.prior_nlw))) return rc;
+        if ((rc = up<int>(d.free1, d.n_free1, &m.free1))) return rc;
+        if ((rc = up<int>(d.free2, d.n_free2, &m.free2))) return rc;
+        return 0;
+    }
+};
+
+}  // namespace
+
+struct mosh2_model {
+    int device = 0;
+    DevModel<float> f32;
+    DevModel<double> f64;
+    int n_joints = 0, n_markers = 0, p_red = 0, n_dmpl = 0;
+};
+
+struct mosh2_job {
+    mosh2_model *model = nullptr;
+    int precision = MOSH2_F32;
+    int n_frames = 0, chunk_len = 0, warmup = 0, n_chunks = 1;
+    mosh2::Options opt{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t esz = 4;                 // element size of the compute type
+    size_t smem = 0, gws_stride = 0;
+    int big_in_global = 0;
+    // device buffers
+    void *d_obs = nullptr, *d_out = nullptr, *d_gws = nullptr;
+    uint8_t *d_vis = nullptr;
+    int *d_status = nullptr, *d_counters = nullptr, *d_totals = nullptr;
+    // pinned staging
+    void *h_obs = nullptr, *h_out = nullptr;
+    uint8_t *h_vis = nullptr;
+    int *h_status = nullptr, *h_counters = nullptr;
+    size_t n_obs = 0, n_out = 0;
+    size_t o_fullpose = 0, o_pose = 0, o_trans = 0, o_dmpls = 0, o_mk = 0, o_errs = 0;   // element offsets in d_out
+};
+
+namespace {
+
+template <class real>
+int launch(mosh2_job *j, const mosh2::Model<real> &m) {
+    mosh2::Job<real> job{};
+    job.n_frames = j->n_frames; job.chunk_len = j->chunk_len; job.warmup = j->warmup; job.n_chunks = j->n_chunks;
+    job.obs = static_cast<const real *>(j->d_obs);
+    job.vis = j->d_vis;
+    real *out = static_cast<real *>(j->d_out);
+    job.fullpose = out + j->o_fullpose; job.pose = out + j->o_pose; job.trans = out + j->o_trans;
+    job.dmpls = j->model->n_dmpl ? out + j->o_dmpls : nullptr;
+    job.markers_sim = out + j->o_mk; job.errs = out + j->o_errs;
+    job.status = j->d_status; job.counters = j->d_counters; job.totals = j->d_totals;
+    job.gws = static_cast<char *>(j->d_gws); job.gws_stride = j->gws_stride;
+    job.opt = j->opt;
+    CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
+    CU(cudaEventRecord(j->ev0, j->stream));
+    mosh2_stageii_kernel<real><<<j->n_chunks, kThreads, j->smem, j->stream>>>(m, job, j->big_in_global);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(j->ev1, j->stream));
+    return 0;
+}
+
+template <class real>
+void plan_workspace(const mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) {
+    mosh2::Work<real> w;
+    const mosh2::Dims d = mosh2::make_dims(m);
+    mosh2::Arena S{nullptr, 0}, G{nullptr, 0};
+    mosh2::carve(w, d, S, G, false);
+    *big = 0;
+    if (S.off > kMaxSmem) {
+        S.off = 0; G.off = 0;
+        mosh2::carve(w, d, S, G, true);
+        *big = 1;
+    }
+    *smem = (S.off + 15) & ~size_t(15);
+    *gws = (G.off + 255) & ~size_t(255);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mosh2_version(void) { return MOSH2_VERSION; }
+const char *mosh2_last_error(void) { return g_err.c_str(); }
+
+int mosh2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void mosh2_default_options(mosh2_options *o) {
+    if (!o) return;
+    // support_data/conf/moshpp_conf.yaml:99,118-125; chmosh.py:460,653,671,697
+    o->wt_data = 400; o->wt_poseB = 1.6; o->wt_poseH = 1.0; o->wt_velo = 2.5; o->wt_dmpl = 1.0;
+    o->wt_annealing = 2.5; o->wt_extrap_dmpl = 6.0; o->num_train_markers = 46;
+    o->delta_0 = 0.5; o->e3_first = 1e-3; o->e3 = 1e-2; o->maxiter = 100;
+    o->optimize_fingers = 0; o->optimize_dynamics = 0;
+}
+
+int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out) {
+    if (!d || !out) return fail(MOSH2_E_INVALID, "null argument");
+    *out = nullptr;
+    if (d->n_joints < 1 || d->n_markers < 1 || d->kw < 1 || d->kw > 30 || d->n_free1 < 1 || d->n_free2 < d->n_free1)
+        return fail(MOSH2_E_INVALID, "inconsistent model sizes");
+    if (d->body_dof + d->n_hand_full != 3 * d->n_joints || d->body_dof + d->n_hand_red != d->p_red)
+        return fail(MOSH2_E_INVALID, "pose layout mismatch: body_dof=%d hand_full=%d hand_red=%d p_red=%d joints=%d",
+                    d->body_dof, d->n_hand_full, d->n_hand_red, d->p_red, d->n_joints);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MOSH2_E_NO_DEVICE, "no CUDA device: libmosh2 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(MOSH2_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MOSH2_E_NO_DEVICE, "device %d is sm_%d%d; libmosh2 is built for sm_100a only", device, prop.major, prop.minor);
+    mosh2_model *m = new (std::nothrow) mosh2_model;
+    if (!m) return fail(MOSH2_E_INVALID, "out of host memory");
+    m->device = device; m->n_joints = d->n_joints; m->n_markers = d->n_markers; m->p_red = d->p_red; m->n_dmpl = d->n_dmpl;
+    int rc = m->f32.build(*d);
+    if (!rc) rc = m->f64.build(*d);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return 0;
+}
+
+void mosh2_model_destroy(mosh2_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    delete m;
+}
+
+int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, int32_t chunk_len,
+                     int32_t chunk_warmup, int32_t precision, mosh2_job **out) {
+    if (!m || !opt || !out || n_frames < 1) return fail(MOSH2_E_INVALID, "bad argument");
+    if (precision != MOSH2_F32 && precision != MOSH2_F64) return fail(MOSH2_E_INVALID, "precision must be MOSH2_F32 or MOSH2_F64");
+    *out = nullptr;
+    CU(cudaSetDevice(m->device));
+    mosh2_job *j = new (std::nothrow) mosh2_job;
+    if (!j) return fail(MOSH2_E_INVALID, "out of host memory");
+    j->model = m; j->precision = precision; j->n_frames = n_frames;
+    j->chunk_len = chunk_len > 0 ? chunk_len : 0;
+    j->warmup = chunk_warmup > 0 ? chunk_warmup : 0;
+    j->n_chunks = j->chunk_len ? (n_frames + j->chunk_len - 1) / j->chunk_len : 1;
+    j->esz = precision == MOSH2_F64 ? 8 : 4;
+    mosh2::Options &o = j->opt;
+    o.wt_data = opt->wt_data; o.wt_poseB = opt->wt_poseB; o.wt_poseH = opt->wt_poseH; o.wt_velo = opt->wt_velo;
+    o.wt_dmpl = opt->wt_dmpl; o.wt_annealing = opt->wt_annealing; o.wt_extrap = opt->wt_extrap_dmpl;
+    o.num_train_markers = opt->num_train_markers; o.delta_0 = opt->delta_0; o.e3_first = opt->e3_first; o.e3 = opt->e3;
+    o.maxiter = opt->maxiter; o.optimize_fingers = opt->optimize_fingers; o.optimize_dynamics = opt->optimize_dynamics;
+
+    size_t gws = 0;
+    if (precision == MOSH2_F64) plan_workspace(m->f64.m, &j->smem, &gws, &j->big_in_global);
+    else plan_workspace(m->f32.m, &j->smem, &gws, &j->big_in_global);
+    if (j->smem > kMaxSmem) {
+        const size_t need = j->smem;
+        delete j;
+        return fail(MOSH2_E_TOO_LARGE, "model needs %zu bytes of shared memory per block (max %zu)", need, kMaxSmem);
+    }
+    j->gws_stride = j->big_in_global ? gws : 0;
+
+    const size_t F = n_frames, M = m->n_markers, PF = size_t(3) * m->n_joints, PR = m->p_red, nd = m->n_dmpl;
+    j->n_obs = F * M * 3;
+    size_t off = 0;
+    j->o_fullpose = off; off += F * PF;
+    j->o_pose = off; off += F * PR;
+    j->o_trans = off; off += F * 3;
+    j->o_dmpls = off; off += F * nd;
+    j->o_mk = off; off += F * M * 3;
+    j->o_errs = off; off += F * mosh2::N_ERR;
+    j->n_out = off;
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    chk(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
+    chk(cudaEventCreate(&j->ev0));
+    chk(cudaEventCreate(&j->ev1));
+    chk(cudaMalloc(&j->d_obs, j->n_obs * j->esz));
+    chk(cudaMalloc(&j->d_out, j->n_out * j->esz));
+    chk(cudaMalloc(&j->d_vis, F * M));
+    chk(cudaMalloc(&j->d_status, F * sizeof(int)));
+    chk(cudaMalloc(&j->d_counters, F * 4 * sizeof(int)));
+    chk(cudaMalloc(&j->d_totals, 4 * sizeof(int)));
+    if (j->gws_stride) chk(cudaMalloc(&j->d_gws, j->gws_stride * j->n_chunks));
+    chk(cudaMallocHost(&j->h_obs, j->n_obs * j->esz));
+    chk(cudaMallocHost(&j->h_out, j->n_out * j->esz));
+    chk(cudaMallocHost(&j->h_vis, F * M));
+    chk(cudaMallocHost(&j->h_status, F * sizeof(int)));
+    chk(cudaMallocHost(&j->h_counters, F * 4 * sizeof(int)));
+    if (e != cudaSuccess) {
+        mosh2_job_destroy(j);
+        return fail(MOSH2_E_CUDA, "job allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = j;
+    return 0;
+}
+
+int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis) {
+    if (!j || !obs || !vis) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    if (j->precision == MOSH2_F64) memcpy(j->h_obs, obs, j->n_obs * sizeof(double));
+    else {
+        float *h = static_cast<float *>(j->h_obs);
+        for (size_t i = 0; i < j->n_obs; ++i) h[i] = float(obs[i]);
+    }
+    const size_t nv = size_t(j->n_frames) * j->model->n_markers;
+    memcpy(j->h_vis, vis, nv);
+    CU(cudaMemcpyAsync(j->d_obs, j->h_obs, j->n_obs * j->esz, cudaMemcpyHostToDevice, j->stream));
+    CU(cudaMemcpyAsync(j->d_vis, j->h_vis, nv, cudaMemcpyHostToDevice, j->stream));
+    return 0;
+}
+
+int mosh2_job_launch(mosh2_job *j) {
+    if (!j) return fail(MOSH2_E_INVALID, "null job");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaMemsetAsync(j->d_out, 0, j->n_out * j->esz, j->stream));
+    CU(cudaMemsetAsync(j->d_status, 0, size_t(j->n_frames) * sizeof(int), j->stream));
+    CU(cudaMemsetAsync(j->d_counters, 0, size_t(j->n_frames) * 4 * sizeof(int), j->stream));
+    CU(cudaMemsetAsync(j->d_totals, 0, 4 * sizeof(int), j->stream));
+    if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
+    return launch<float>(j, j->model->f32.m);
+}
+
+int mosh2_job_sync(mosh2_job *j) {
+    if (!j) return fail(MOSH2_E_INVALID, "null job");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaStreamSynchronize(j->stream));
+    return 0;
+}
+
+int mosh2_job_kernel_ms(mosh2_job *j, float *ms) {
+    if (!j || !ms) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaEventElapsedTime(ms, j->ev0, j->ev1));
+    return 0;
+}
+
+int mosh2_job_num_chunks(mosh2_job *j) { return j ? j->n_chunks : 0; }
+
+int mosh2_job_totals(mosh2_job *j, int32_t *out4) {
+    if (!j || !out4) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaStreamSynchronize(j->stream));
+    CU(cudaMemcpy(out4, j->d_totals, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mosh2_job_download(mosh2_job *j, const mosh2_result *r) {
+    if (!j || !r) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    const size_t F = j->n_frames;
+    CU(cudaMemcpyAsync(j->h_out, j->d_out, j->n_out * j->esz, cudaMemcpyDeviceToHost, j->stream));
+    CU(cudaMemcpyAsync(j->h_status, j->d_status, F * sizeof(int), cudaMemcpyDeviceToHost, j->stream));
+    CU(cudaMemcpyAsync(j->h_counters, j->d_counters, F * 4 * sizeof(int), cudaMemcpyDeviceToHost, j->stream));
+    CU(cudaStreamSynchronize(j->stream));
+    const size_t M = j->model->n_markers, PF = size_t(3) * j->model->n_joints, PR = j->model->p_red, nd = j->model->n_dmpl;
+    auto conv = [&](double *dst, size_t off, size_t n) {
+        if (!dst) return;
+        if (j->precision == MOSH2_F64) memcpy(dst, static_cast<double *>(j->h_out) + off, n * sizeof(double));
+        else {
+            const float *s = static_cast<float *>(j->h_out) + off;
+            for (size_t i = 0; i < n; ++i) dst[i] = double(s[i]);
+        }
+    };
+    conv(r->fullpose, j->o_fullpose, F * PF);
+    conv(r->pose, j->o_pose, F * PR);
+    conv(r->trans, j->o_trans, F * 3);
+    if (nd) conv(r->dmpls, j->o_dmpls, F * nd);
+    conv(r->markers_sim, j->o_mk, F * M * 3);
+    conv(r->errs, j->o_errs, F * mosh2::N_ERR);
+    if (r->status) memcpy(r->status, j->h_status, F * sizeof(int));
+    if (r->counters) memcpy(r->counters, j->h_counters, F * 4 * sizeof(int));
+    return 0;
+}
+
+void mosh2_job_destroy(mosh2_job *j) {
+    if (!j) return;
+    cudaSetDevice(j->model->device);
+    if (j->stream) cudaStreamSynchronize(j->stream);
+    cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_gws);
+    cudaFreeHost(j->h_obs); cudaFreeHost(j->h_out); cudaFreeHost(j->h_vis); cudaFreeHost(j->h_status); cudaFreeHost(j->h_counters);
+    if (j->ev0) cudaEventDestroy(j->ev0);
+    if (j->ev1) cudaEventDestroy(j->ev1);
+    if (j->stream) cudaStreamDestroy(j->stream);
+    delete j;
+}
+
+int mosh2_solve(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const double *obs, const uint8_t *vis,
+                int32_t chunk_len, int32_t chunk_warmup, int32_t precision, const mosh2_result *res) {
+    mosh2_job *j = nullptr;
+    int rc = mosh2_job_create(m, opt, n_frames, chunk_len, chunk_warmup, precision, &j);
+    if (rc) return rc;
+    rc = mosh2_job_upload(j, obs, vis);
+    if (!rc) rc = mosh2_job_launch(j);
+    if (!rc) rc = mosh2_job_download(j, res);
+    mosh2_job_destroy(j);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,1034 @@
+// mosh2_device.cuh -- the Stage-II "CTA program": one thread block solves one chunk of consecutive
+// frames of one sequence, frame after frame, with the reference's per-frame schedule
+// (src/moshpp/chmosh.py:584-724) and the chumpy dog-leg entirely on device.
+//
+// The program is written against a tiny CTA abstraction (tid, nthr, M2_SYNC, cta_reduce) so that the
+// very same source also compiles as a single-"thread" host build (MOSH2_EMU, tests/emu/) which the
+// CPU test-suite uses to check index math against the oracle.  The product library never contains
+// that build; libmosh2.so has no CPU path.
+//
+// Maths (DESIGN.md section 3 for the derivations):
+//   forward   fullpose = [theta_body, hands_mean + theta_hand C]; R_j = exp([w_j]x);
+//             v_posed = v0 + Sd delta + Pd vec(R_j - I); FK; p_i = Rg_j (v_posed - J_j) + tg_j;
+//             v = sum_i w_i p_i + trans; marker = v_c0 + k1 f1 + k2 f2 + k3 f3.
+//   Jacobian  d v / d w_{a,k} = u_{a,k} x sum_{j in subtree(a)} w_j (p_j - tg_a)            (rigid part)
+//                              + Rskin Pd_j dvec(R_j)/dw_k                                    (pose blend)
+//             with u_{a,k} = Rg_par(a) vee(dR_{a,k} R_a^T); hand columns chained through C^T.
+//   normal eq A = J^T J and g = -J^T r are accumulated marker tile by marker tile; the prior, velocity,
+//             finger and DMPL terms have closed-form contributions (Q_k = .5 inv(cov_k), diagonals).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(MOSH2_EMU)
+#define M2_HD __host__ __device__ __forceinline__
+#define M2_D __device__ __forceinline__
+#define M2_SYNC() __syncthreads()
+#define M2_GPU 1
+#else
+#define M2_HD inline
+#define M2_D inline
+#define M2_SYNC() ((void)0)
+#define M2_GPU 0
+#endif
+
+namespace mosh2 {
+
+enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32 };
+enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
+
+constexpr int kTileMarkers = 8;   // markers per Jacobian tile (24 rows)
+constexpr int kBS = 4;            // register tile of the J^T J accumulation
+
+struct Cta {
+    int tid, nthr;
+};
+
+template <class real>
+struct Model {
+    int nJ, M, body_dof, p_red, n_hand_red, n_hand_full, nd, kw, na, n_levels;
+    const int *parents, *fk_order, *level_ofs, *w_joint, *anc_joint, *anc_mask;
+    const int8_t *anc_pos;
+    const int *hand_lo, *hand_hi;   // non-zero column range of each row of hand_comps
+    const real *hand_comps, *hands_mean, *v0, *sd, *pd, *w_val, *j0, *jd, *coefs;
+    int prior_k, prior_d, prior_off;
+    const real *prior_means, *prior_Q, *prior_nlw;
+    int n1, n2;
+    const int *free1, *free2;
+    int finger_lo, finger_hi;
+};
+
+struct Options {
+    double wt_data, wt_poseB, wt_poseH, wt_velo, wt_dmpl, wt_annealing, wt_extrap;
+    double num_train_markers, delta_0, e3_first, e3;
+    int maxiter, optimize_fingers, optimize_dynamics;
+};
+
+template <class real>
+struct Job {
+    int n_frames, chunk_len, warmup, n_chunks;
+    const real *obs;        // F*M*3
+    const uint8_t *vis;     // F*M
+    real *fullpose, *pose, *trans, *dmpls, *markers_sim, *errs;
+    int *status, *counters;
+    int *totals;            // [4] iterations, evaluations, builds, minimisations over ALL processed frames (incl. warm-up)
+    char *gws;              // optional per-CTA global workspace (f64 / large models)
+    size_t gws_stride;
+    Options opt;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small math
+// ---------------------------------------------------------------------------------------------
+M2_HD float r_sqrt(float x) { return sqrtf(x); }
+M2_HD double r_sqrt(double x) { return sqrt(x); }
+M2_HD float r_abs(float x) { return fabsf(x); }
+M2_HD double r_abs(double x) { return fabs(x); }
+M2_HD void r_sincos(float x, float *s, float *c) {
+#if M2_GPU
+    sincosf(x, s, c);
+#else
+    *s = sinf(x);
+    *c = cosf(x);
+#endif
+}
+M2_HD void r_sincos(double x, double *s, double *c) {
+#if M2_GPU
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+template <class real> M2_HD real series_thresh();
+template <> M2_HD float series_thresh<float>() { return 0.25f; }
+template <> M2_HD double series_thresh<double>() { return 1e-2; }
+template <class real> M2_HD real pivot_eps();          // smallest accepted pivot of the unit-diagonal-scaled A
+template <> M2_HD float pivot_eps<float>() { return 1e-6f; }
+template <> M2_HD double pivot_eps<double>() { return 1e-13; }
+
+template <class real>
+M2_HD void mat3_mul(const real *A, const real *B, real *C) {   // C = A B (row-major 3x3)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+template <class real>
+M2_HD void mat3_vec(const real *A, const real *v, real *o) {
+    o[0] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+    o[1] = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+    o[2] = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+}
+template <class real>
+M2_HD void cross3(const real *a, const real *b, real *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// R = exp([w]x) and dR[k] = dR/dw_k (cv2.Rodrigues convention), cancellation-free near 0.
+template <class real>
+M2_HD void rodrigues(const real *w, real *R, real *dR) {
+    const real x = w[0], y = w[1], z = w[2];
+    const real t2 = x * x + y * y + z * z;
+    real a, b, c1, c2;
+    if (t2 < series_thresh<real>()) {
+        a = real(1) + t2 * (real(-1. / 6) + t2 * (real(1. / 120) + t2 * (real(-1. / 5040) + t2 * real(1. / 362880))));
+        b = real(.5) + t2 * (real(-1. / 24) + t2 * (real(1. / 720) + t2 * (real(-1. / 40320) + t2 * real(1. / 3628800))));
+        c1 = real(-1. / 3) + t2 * (real(1. / 30) + t2 * (real(-1. / 840) + t2 * (real(1. / 45360) + t2 * real(-1. / 3991680))));
+        c2 = real(-1. / 12) + t2 * (real(1. / 180) + t2 * (real(-1. / 6720) + t2 * (real(1. / 453600) + t2 * real(-1. / 47900160))));
+    } else {
+        const real t = r_sqrt(t2);
+        real s, c;
+        r_sincos(t, &s, &c);
+        a = s / t;
+        b = (real(1) - c) / t2;
+        c1 = (t * c - s) / (t2 * t);
+        c2 = (t * s - real(2) * (real(1) - c)) / (t2 * t2);
+    }
+    // K = [w]x, K2 = K K = w w^T - t2 I
+    const real K[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+    const real K2[9] = {x * x - t2, x * y, x * z, x * y, y * y - t2, y * z, x * z, y * z, z * z - t2};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = a * K[i] + b * K2[i];
+    R[0] += real(1);
+    R[4] += real(1);
+    R[8] += real(1);
+    if (!dR) return;
+    // dR/dw_k = c1 w_k K + a E_k + c2 w_k K2 + b (E_k K + K E_k),   E_k K + K E_k = e_k w^T + w e_k^T - 2 w_k I
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const real wk = w[k];
+        real *D = dR + 9 * k;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) D[i] = c1 * wk * K[i] + c2 * wk * K2[i];
+        // a E_k
+        if (k == 0) { D[5] -= a; D[7] += a; }
+        if (k == 1) { D[2] += a; D[6] -= a; }
+        if (k == 2) { D[1] -= a; D[3] += a; }
+        // b (e_k w^T + w e_k^T - 2 w_k I)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            D[3 * k + c] += b * w[c];
+            D[3 * c + k] += b * w[c];
+        }
+        D[0] -= real(2) * b * wk;
+        D[4] -= real(2) * b * wk;
+        D[8] -= real(2) * b * wk;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-wide reduction of nv (<= 8) per-thread values; result broadcast to every thread.
+// ---------------------------------------------------------------------------------------------
+template <class real, int NV>
+M2_D void cta_reduce(const Cta &c, real *vals, real *scratch /* >= 8*33 reals */) {
+#if M2_GPU
+    const int lane = c.tid & 31, warp = c.tid >> 5, nwarp = (c.nthr + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        real v = vals[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) scratch[i * 33 + warp] = v;
+    }
+    __syncthreads();
+    if (c.tid < NV) {
+        real s = 0;
+        for (int w = 0; w < nwarp; ++w) s += scratch[c.tid * 33 + w];
+        scratch[c.tid * 33 + 32] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = scratch[i * 33 + 32];
+    __syncthreads();
+#else
+    (void)c; (void)vals; (void)scratch;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+template <class real>
+struct Work {
+    // state
+    real *x, *xt, *pose_prev, *velo_tgt, *dm_tgt;
+    // forward scratch of the latest evaluation
+    real *fullpose, *Rl, *dRl, *Jp, *Rg, *tg, *vp, *pj, *Rsk, *mk, *rm, *Loc, *MtR, *obs, *py, *pq;
+    // Jacobian / normal equations
+    real *u, *dtg, *Jt, *Jf, *A, *Ld, *g, *Ag, *dsd, *dgn, *d, *tmp, *ds;
+    real *red, *sc;
+    int *colmap, *isc;
+    uint8_t *vis;
+};
+
+struct Dims {
+    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, npad, K, D, kw;
+};
+
+template <class real>
+M2_HD Dims make_dims(const Model<real> &m) {
+    Dims d;
+    d.nJ = m.nJ; d.M = m.M; d.S = 3 * m.M; d.PF = 3 * m.nJ; d.PR = m.p_red; d.nd = m.nd;
+    d.NX = 3 + m.p_red + m.nd; d.NCt = d.PF + m.nd; d.n1 = m.n1; d.n2 = m.n2;
+    d.npad = (m.n2 + 3) & ~3;
+    d.ld = d.npad | 1;          // odd leading dimension: conflict-free column walks of A / L
+    d.K = m.prior_k; d.D = m.prior_d; d.kw = m.kw;
+    return d;
+}
+
+struct Arena {
+    char *base;
+    size_t off;
+    template <class T> M2_HD T *take(size_t n) {
+        off = (off + 15) & ~size_t(15);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+// Lays the workspace out.  Arrays flagged "big" go to arena G when big_in_global is set (f64 runs of
+// large models), everything else to arena S (shared memory).  Returns the byte counts via the arenas.
+template <class real>
+M2_HD void carve(Work<real> &w, const Dims &d, Arena &S, Arena &G, bool big_in_global) {
+    Arena &B = big_in_global ? G : S;
+    w.x = S.take<real>(d.NX); w.xt = S.take<real>(d.NX);
+    w.pose_prev = S.take<real>(d.PR); w.velo_tgt = S.take<real>(d.PR); w.dm_tgt = S.take<real>(d.nd + 1);
+    w.fullpose = S.take<real>(d.PF); w.Rl = S.take<real>(9 * d.nJ); w.dRl = S.take<real>(27 * d.nJ);
+    w.Jp = S.take<real>(3 * d.nJ); w.Rg = S.take<real>(9 * d.nJ); w.tg = S.take<real>(3 * d.nJ);
+    w.vp = S.take<real>(3 * d.S); w.pj = S.take<real>(3 * d.S * d.kw); w.Rsk = S.take<real>(9 * d.S);
+    w.mk = S.take<real>(3 * d.M); w.rm = S.take<real>(3 * d.M); w.Loc = S.take<real>(27 * d.M);
+    w.MtR = S.take<real>(9 * d.S); w.obs = S.take<real>(3 * d.M);
+    w.py = S.take<real>(d.K * d.D + 1); w.pq = S.take<real>(d.K + 1);
+    w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
+    w.Jt = B.take<real>(3 * kTileMarkers * d.NCt); w.Jf = B.take<real>(3 * kTileMarkers * d.npad);
+    w.A = B.take<real>(size_t(d.n2) * d.ld);
+    w.Ld = S.take<real>(d.n2); w.g = S.take<real>(d.n2); w.Ag = S.take<real>(d.n2); w.dsd = S.take<real>(d.n2);
+    w.dgn = S.take<real>(d.n2); w.d = S.take<real>(d.n2); w.tmp = S.take<real>(d.n2); w.ds = S.take<real>(d.n2);
+    w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16);
+    w.colmap = S.take<int>(d.NX); w.isc = S.take<int>(8);
+    w.vis = S.take<uint8_t>(d.M);
+}
+
+// configuration of one minimisation (one ch.minimize call of the reference)
+template <class real>
+struct StepCfg {
+    const int *free;
+    int n;
+    real wp;          // prior weight (0: no prior term)
+    real e3;
+    bool velo, poseH, dm_terms, extrap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------------
+template <class real>
+struct Solver {
+    const Model<real> &m;
+    const Job<real> &job;
+    Work<real> &w;
+    const Cta cta;
+    const Dims d;
+    // per-frame scalars (identical in every thread)
+    real wd, wp_frame, wH, wv, wdm, wex;
+    int nvis;
+    bool has_velo, has_extrap;
+    // counters of the current frame
+    int n_iter, n_eval, n_build, n_min, frame_flags;
+
+    M2_D Solver(const Model<real> &m_, const Job<real> &j_, Work<real> &w_, Cta c_)
+        : m(m_), job(j_), w(w_), cta(c_), d(make_dims(m_)) {}
+
+#define CTA_FOR(i, n) for (int i = cta.tid; i < (n); i += cta.nthr)
+
+    // ---- forward evaluation at state xs; leaves SSE terms in w.sc[0..6], argmin component in w.isc[0]
+    M2_D void eval(const real *xs, const StepCfg<real> &c) {
+        ++n_eval;
+        const real *th = xs + 3;
+        const real *dl = xs + 3 + d.PR;
+        CTA_FOR(i, d.PF) {
+            real v;
+            if (i < m.body_dof) {
+                v = th[i];
+            } else {
+                const int cc = i - m.body_dof;
+                v = m.hands_mean[cc];
+                for (int r = 0; r < m.n_hand_red; ++r) v += th[m.body_dof + r] * m.hand_comps[r * m.n_hand_full + cc];
+            }
+            w.fullpose[i] = v;
+        }
+        CTA_FOR(i, 3 * d.nJ) {
+            real v = m.j0[i];
+            for (int q = 0; q < d.nd; ++q) v += m.jd[i * d.nd + q] * dl[q];
+            w.Jp[i] = v;
+        }
+        M2_SYNC();
+        CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + 27 * j);
+        M2_SYNC();
+        for (int lv = 0; lv < m.n_levels; ++lv) {
+            const int lo = m.level_ofs[lv], cnt = m.level_ofs[lv + 1] - lo;
+            CTA_FOR(q, cnt) {
+                const int j = m.fk_order[lo + q], a = m.parents[j];
+                if (a < 0) {
+                    for (int i = 0; i < 9; ++i) w.Rg[9 * j + i] = w.Rl[9 * j + i];
+                    for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = w.Jp[3 * j + i];
+                } else {
+                    mat3_mul(w.Rg + 9 * a, w.Rl + 9 * j, w.Rg + 9 * j);
+                    real dj[3] = {w.Jp[3 * j] - w.Jp[3 * a], w.Jp[3 * j + 1] - w.Jp[3 * a + 1], w.Jp[3 * j + 2] - w.Jp[3 * a + 2]};
+                    real o[3];
+                    mat3_vec(w.Rg + 9 * a, dj, o);
+                    for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = w.tg[3 * a + i] + o[i];
+                }
+            }
+            M2_SYNC();
+        }
+        // pose-blended rest vertices of the 3M slots
+        const int rows = 3 * d.S;
+        CTA_FOR(row, rows) {
+            real acc = m.v0[row];
+            for (int q = 0; q < d.nd; ++q) acc += m.sd[row * d.nd + q] * dl[q];
+            const real *p = m.pd + size_t(row) * 9;
+            for (int j = 1; j < d.nJ; ++j, p += size_t(rows) * 9) {
+                const real *R = w.Rl + 9 * j;
+                acc += p[0] * (R[0] - real(1)) + p[1] * R[1] + p[2] * R[2] + p[3] * R[3] + p[4] * (R[4] - real(1)) +
+                       p[5] * R[5] + p[6] * R[6] + p[7] * R[7] + p[8] * (R[8] - real(1));
+            }
+            w.vp[row] = acc;
+        }
+        M2_SYNC();
+        // skinning
+        CTA_FOR(s, d.S) {
+            real v[3] = {0, 0, 0};
+            real Rs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < d.kw; ++i) {
+                const int j = m.w_joint[s * d.kw + i];
+                real *pp = w.pj + 3 * (s * d.kw + i);
+                if (j < 0) { pp[0] = pp[1] = pp[2] = 0; continue; }
+                const real wt = m.w_val[s * d.kw + i];
+                real dv[3] = {w.vp[3 * s] - w.Jp[3 * j], w.vp[3 * s + 1] - w.Jp[3 * j + 1], w.vp[3 * s + 2] - w.Jp[3 * j + 2]};
+                real o[3];
+                mat3_vec(w.Rg + 9 * j, dv, o);
+                for (int q = 0; q < 3; ++q) {
+                    pp[q] = o[q] + w.tg[3 * j + q];
+                    v[q] += wt * pp[q];
+                }
+                for (int q = 0; q < 9; ++q) Rs[q] += wt * w.Rg[9 * j + q];
+            }
+            // skinned vertex is kept in vp's place (v_posed is not needed afterwards)
+            for (int q = 0; q < 3; ++q) w.vp[3 * s + q] = v[q] + xs[q];
+            for (int q = 0; q < 9; ++q) w.Rsk[9 * s + q] = Rs[q];
+        }
+        // max-mixture prior: y_k = Q_k (x - mu_k)
+        if (c.wp > real(0)) {
+            const int D = d.D;
+            CTA_FOR(idx, d.K * D) {
+                const int k = idx / D, i = idx - k * D;
+                const real *Q = m.prior_Q + (size_t(k) * D + i) * D;
+                const real *mu = m.prior_means + k * D;
+                real s = 0;
+                for (int l = 0; l < D; ++l) s += Q[l] * (th[m.prior_off + l] - mu[l]);
+                w.py[idx] = s;
+            }
+        }
+        M2_SYNC();
+        // simulated markers, data residual, local Jacobians (transformed_lm.py:130-159)
+        CTA_FOR(mi, d.M) {
+            const real *v0 = w.vp + 9 * mi, *v1 = v0 + 3, *v2 = v0 + 6;
+            real e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
+            real e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+            const real n1 = r_sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+            real f1[3] = {e1[0] / n1, e1[1] / n1, e1[2] / n1};
+            real nn[3];
+            cross3(e1, e2, nn);
+            const real n2 = r_sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+            real f2[3] = {nn[0] / n2, nn[1] / n2, nn[2] / n2};
+            real f3[3];
+            cross3(f1, f2, f3);
+            const real k1 = m.coefs[3 * mi], k2 = m.coefs[3 * mi + 1], k3 = m.coefs[3 * mi + 2];
+            const bool vis = w.vis[mi] != 0;
+            for (int q = 0; q < 3; ++q) {
+                const real mk = v0[q] + k1 * f1[q] + k2 * f2[q] + k3 * f3[q];
+                w.mk[3 * mi + q] = mk;
+                w.rm[3 * mi + q] = vis ? (mk - w.obs[3 * mi + q]) * wd : real(0);
+            }
+            // d marker / d(e1, e2):  N(u) = (I - uh uh^T)/|u|
+            real N1[9], Nn[9];
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q) {
+                    N1[3 * r + q] = ((r == q ? real(1) : real(0)) - f1[r] * f1[q]) / n1;
+                    Nn[3 * r + q] = ((r == q ? real(1) : real(0)) - f2[r] * f2[q]) / n2;
+                }
+            const real Se1[9] = {0, -e1[2], e1[1], e1[2], 0, -e1[0], -e1[1], e1[0], 0};
+            const real Se2[9] = {0, -e2[2], e2[1], e2[2], 0, -e2[0], -e2[1], e2[0], 0};
+            const real Sf1[9] = {0, -f1[2], f1[1], f1[2], 0, -f1[0], -f1[1], f1[0], 0};
+            const real Sf2[9] = {0, -f2[2], f2[1], f2[2], 0, -f2[0], -f2[1], f2[0], 0};
+            real df2e1[9], df2e2[9], t1[9], t2[9], df3e1[9], df3e2[9];
+            mat3_mul(Nn, Se2, df2e1);                       // d f2/d e1 = N(n) (-[e2]x)
+            for (int q = 0; q < 9; ++q) df2e1[q] = -df2e1[q];
+            mat3_mul(Nn, Se1, df2e2);                       // d f2/d e2 = N(n) [e1]x
+            mat3_mul(Sf2, N1, t1);                          // d f3/d e1 = -[f2]x N1 + [f1]x df2e1
+            mat3_mul(Sf1, df2e1, t2);
+            for (int q = 0; q < 9; ++q) df3e1[q] = t2[q] - t1[q];
+            mat3_mul(Sf1, df2e2, df3e2);
+            real *L = w.Loc + 27 * mi;
+            for (int q = 0; q < 9; ++q) {
+                const real de1 = k1 * N1[q] + k2 * df2e1[q] + k3 * df3e1[q];
+                const real de2 = k2 * df2e2[q] + k3 * df3e2[q];
+                const real id = (q == 0 || q == 4 || q == 8) ? real(1) : real(0);
+                L[q] = id - de1 - de2;
+                L[9 + q] = de1;
+                L[18 + q] = de2;
+            }
+        }
+        if (c.wp > real(0)) {
+            CTA_FOR(k, d.K) {
+                const real *mu = m.prior_means + k * d.D;
+                real s = m.prior_nlw[k];
+                for (int i = 0; i < d.D; ++i) s += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
+                w.pq[k] = s;
+            }
+        }
+        M2_SYNC();
+        real part[N_ERR] = {0, 0, 0, 0, 0, 0};
+        CTA_FOR(i, 3 * d.M) part[ERR_DATA] += w.rm[i] * w.rm[i];
+        if (c.velo) CTA_FOR(i, d.PR) { const real e = (th[i] - w.velo_tgt[i]) * wv; part[ERR_VELO] += e * e; }
+        if (c.poseH) CTA_FOR(i, m.finger_hi - m.finger_lo) { const real e = th[m.finger_lo + i] * wH; part[ERR_POSEH] += e * e; }
+        if (c.dm_terms) CTA_FOR(i, d.nd) {
+            const real e = dl[i] * wdm;
+            part[ERR_DMPL] += e * e;
+            if (c.extrap) { const real e2 = (dl[i] - w.dm_tgt[i]) * wex; part[ERR_EXTRAP] += e2 * e2; }
+        }
+        cta_reduce<real, N_ERR>(cta, part, w.red);
+        if (cta.tid == 0) {
+            int ks = 0;
+            real sp = 0;
+            if (c.wp > real(0)) {
+                for (int k = 1; k < d.K; ++k) if (w.pq[k] < w.pq[ks]) ks = k;
+                sp = c.wp * c.wp * w.pq[ks];
+            }
+            w.isc[0] = ks;
+            part[ERR_POSEB] = sp;
+            real tot = 0;
+            for (int i = 0; i < N_ERR; ++i) { w.sc[1 + i] = part[i]; tot += part[i]; }
+            w.sc[0] = tot;
+        }
+        M2_SYNC();
+    }
+
+    // ---- normal equations at the state of the latest eval():  A (upper) = J^T J, g = -J^T r
+    M2_D void build(const real *xs, const StepCfg<real> &c) {
+        ++n_build;
+        const real *th = xs + 3;
+        const real *dl = xs + 3 + d.PR;
+        const int n = c.n, ld = d.ld;
+        CTA_FOR(idx, 3 * d.nJ) {
+            const int a = idx / 3, k = idx - 3 * a;
+            const real *D = w.dRl + 27 * a + 9 * k, *R = w.Rl + 9 * a;
+            // Om = dR R^T (skew); vee(Om) = (Om21, Om02, Om10)
+            real om[3];
+            om[0] = D[6] * R[3] + D[7] * R[4] + D[8] * R[5];
+            om[1] = D[0] * R[6] + D[1] * R[7] + D[2] * R[8];
+            om[2] = D[3] * R[0] + D[4] * R[1] + D[5] * R[2];
+            const int par = m.parents[a];
+            if (par < 0) { for (int q = 0; q < 3; ++q) w.u[3 * idx + q] = om[q]; }
+            else mat3_vec(w.Rg + 9 * par, om, w.u + 3 * idx);
+        }
+        CTA_FOR(s, d.S) mat3_mul(w.Loc + 27 * (s / 3) + 9 * (s % 3), w.Rsk + 9 * s, w.MtR + 9 * s);
+        CTA_FOR(i, n * ld) w.A[i] = 0;
+        CTA_FOR(i, n) w.g[i] = 0;
+        if (d.nd) {
+            // d tg_j / d delta_i = d tg_par + Rg_par (Jd_j - Jd_par)
+            for (int lv = 0; lv < m.n_levels; ++lv) {
+                const int lo = m.level_ofs[lv], cnt = m.level_ofs[lv + 1] - lo;
+                CTA_FOR(q, cnt * d.nd) {
+                    const int j = m.fk_order[lo + q / d.nd], i = q % d.nd, a = m.parents[j];
+                    real *o = w.dtg + 3 * (j * d.nd + i);
+                    if (a < 0) { for (int r = 0; r < 3; ++r) o[r] = m.jd[(3 * j + r) * d.nd + i]; }
+                    else {
+                        real dj[3], t[3];
+                        for (int r = 0; r < 3; ++r) dj[r] = m.jd[(3 * j + r) * d.nd + i] - m.jd[(3 * a + r) * d.nd + i];
+                        mat3_vec(w.Rg + 9 * a, dj, t);
+                        for (int r = 0; r < 3; ++r) o[r] = w.dtg[3 * (a * d.nd + i) + r] + t[r];
+                    }
+                }
+                M2_SYNC();
+            }
+        }
+        M2_SYNC();
+        const int rows9 = 3 * d.S;
+        for (int t0 = 0; t0 < d.M; t0 += kTileMarkers) {
+            const int tm = (d.M - t0 < kTileMarkers) ? d.M - t0 : kTileMarkers;
+            // T1: full-pose Jacobian blocks of the tile's markers
+            CTA_FOR(it, tm * d.nJ) {
+                const int ml = it / d.nJ, a = it - ml * d.nJ, mi = t0 + ml;
+                real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // blk[r*3+k]
+                if (a >= 1) {
+                    const real *P = m.pd + (size_t(a - 1) * rows9 + 9 * mi) * 9;
+                    const real *dR = w.dRl + 27 * a;
+                    for (int t = 0; t < 3; ++t) {
+                        real E[9];
+                        for (int cc = 0; cc < 3; ++cc) {
+                            const real *p = P + (3 * t + cc) * 9;
+                            for (int k = 0; k < 3; ++k) {
+                                const real *q = dR + 9 * k;
+                                E[3 * cc + k] = p[0] * q[0] + p[1] * q[1] + p[2] * q[2] + p[3] * q[3] + p[4] * q[4] +
+                                                p[5] * q[5] + p[6] * q[6] + p[7] * q[7] + p[8] * q[8];
+                            }
+                        }
+                        const real *Mt = w.MtR + 9 * (3 * mi + t);
+                        for (int r = 0; r < 3; ++r)
+                            for (int k = 0; k < 3; ++k)
+                                blk[3 * r + k] += Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
+                    }
+                }
+                for (int t = 0; t < 3; ++t) {
+                    const int s = 3 * mi + t;
+                    const int ai = m.anc_pos[s * d.nJ + a];
+                    if (ai < 0) continue;
+                    const int mask = m.anc_mask[s * m.na + ai];
+                    real q[3] = {0, 0, 0};
+                    for (int i = 0; i < d.kw; ++i)
+                        if ((mask >> i) & 1) {
+                            const real wt = m.w_val[s * d.kw + i];
+                            const real *pp = w.pj + 3 * (s * d.kw + i);
+                            for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
+                        }
+                    const real *L = w.Loc + 27 * mi + 9 * t;
+                    for (int k = 0; k < 3; ++k) {
+                        real cr[3];
+                        cross3(w.u + 3 * (3 * a + k), q, cr);
+                        for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
+                    }
+                }
+                for (int r = 0; r < 3; ++r)
+                    for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
+            }
+            CTA_FOR(it, tm * d.nd) {
+                const int ml = it / d.nd, i = it - ml * d.nd, mi = t0 + ml;
+                real val[3] = {0, 0, 0};
+                for (int t = 0; t < 3; ++t) {
+                    const int s = 3 * mi + t;
+                    real dv[3] = {0, 0, 0};
+                    for (int kk = 0; kk < d.kw; ++kk) {
+                        const int j = m.w_joint[s * d.kw + kk];
+                        if (j < 0) continue;
+                        const real wt = m.w_val[s * d.kw + kk];
+                        real df[3], o[3];
+                        for (int r = 0; r < 3; ++r) df[r] = m.sd[(3 * s + r) * d.nd + i] - m.jd[(3 * j + r) * d.nd + i];
+                        mat3_vec(w.Rg + 9 * j, df, o);
+                        for (int r = 0; r < 3; ++r) dv[r] += wt * (o[r] + w.dtg[3 * (j * d.nd + i) + r]);
+                    }
+                    const real *L = w.Loc + 27 * mi + 9 * t;
+                    for (int r = 0; r < 3; ++r) val[r] += L[3 * r] * dv[0] + L[3 * r + 1] * dv[1] + L[3 * r + 2] * dv[2];
+                }
+                for (int r = 0; r < 3; ++r) w.Jt[(3 * ml + r) * d.NCt + d.PF + i] = val[r];
+            }
+            M2_SYNC();
+            // T2: chain through the hand PCA, keep the free columns, apply weight and visibility
+            const int trows = 3 * tm;
+            CTA_FOR(idx, trows * d.npad) {
+                const int row = idx / d.npad, cc = idx - row * d.npad;
+                real v = 0;
+                if (cc < n) {
+                    const int fv = c.free[cc];
+                    const real *Jr = w.Jt + row * d.NCt;
+                    if (fv < 3) v = (row % 3 == fv) ? real(1) : real(0);
+                    else if (fv < 3 + m.body_dof) v = Jr[fv - 3];
+                    else if (fv < 3 + d.PR) {
+                        const int r = fv - 3 - m.body_dof;
+                        const real *C = m.hand_comps + r * m.n_hand_full;
+                        for (int q = m.hand_lo[r]; q < m.hand_hi[r]; ++q) v += Jr[m.body_dof + q] * C[q];
+                    } else v = Jr[d.PF + (fv - 3 - d.PR)];
+                    v *= (w.vis[t0 + row / 3] ? wd : real(0));
+                }
+                w.Jf[row * d.npad + cc] = v;
+            }
+            M2_SYNC();
+            // T3: A += Jf^T Jf (upper blocks), g -= Jf^T r
+            const int nb = (n + kBS - 1) / kBS, nblk = nb * (nb + 1) / 2;
+            CTA_FOR(b, nblk) {
+                int bi = 0, rem = b;
+                while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+                const int bj = bi + rem;
+                real acc[kBS * kBS];
+                for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
+                for (int row = 0; row < trows; ++row) {
+                    const real *Jr = w.Jf + row * d.npad;
+                    real ai[kBS], bjv[kBS];
+                    for (int q = 0; q < kBS; ++q) { ai[q] = Jr[bi * kBS + q]; bjv[q] = Jr[bj * kBS + q]; }
+                    for (int p = 0; p < kBS; ++p)
+                        for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bjv[q];
+                }
+                for (int p = 0; p < kBS; ++p)
+                    for (int q = 0; q < kBS; ++q) {
+                        const int i = bi * kBS + p, j = bj * kBS + q;
+                        if (i < n && j < n && i <= j) w.A[i * ld + j] += acc[p * kBS + q];
+                    }
+            }
+            CTA_FOR(cc, n) {
+                real s = 0;
+                for (int row = 0; row < trows; ++row) s += w.Jf[row * d.npad + cc] * w.rm[3 * t0 + row];
+                w.g[cc] -= s;
+            }
+            M2_SYNC();
+        }
+        // closed-form terms
+        if (c.wp > real(0)) {
+            const int D = d.D, ks = w.isc[0];
+            const real w2 = c.wp * c.wp;
+            const real *Q = m.prior_Q + size_t(ks) * D * D;
+            CTA_FOR(idx, D * D) {
+                const int i = idx / D, l = idx - i * D;
+                const int ci = w.colmap[3 + m.prior_off + i], cl = w.colmap[3 + m.prior_off + l];
+                if (ci >= 0 && cl >= 0 && ci <= cl) w.A[ci * ld + cl] += w2 * Q[idx];
+            }
+            CTA_FOR(i, D) {
+                const int ci = w.colmap[3 + m.prior_off + i];
+                if (ci >= 0) w.g[ci] -= w2 * w.py[ks * D + i];
+            }
+            M2_SYNC();
+        }
+        CTA_FOR(cc, n) {
+            const int fv = c.free[cc];
+            real da = 0, dg = 0;
+            if (fv >= 3 && fv < 3 + d.PR) {
+                const int i = fv - 3;
+                if (c.velo) { da += wv * wv; dg += wv * wv * (th[i] - w.velo_tgt[i]); }
+                if (c.poseH && i >= m.finger_lo && i < m.finger_hi) { da += wH * wH; dg += wH * wH * th[i]; }
+            } else if (fv >= 3 + d.PR && c.dm_terms) {
+                const int i = fv - 3 - d.PR;
+                da += wdm * wdm;
+                dg += wdm * wdm * dl[i];
+                if (c.extrap) { da += wex * wex; dg += wex * wex * (dl[i] - w.dm_tgt[i]); }
+            }
+            w.A[cc * ld + cc] += da;
+            w.g[cc] -= dg;
+        }
+        M2_SYNC();
+    }
+
+    M2_D real Asym(int i, int j) const { return i <= j ? w.A[i * d.ld + j] : w.A[j * d.ld + i]; }
+
+    // out = A v  (A symmetric, upper stored)
+    M2_D void symv(const real *v, real *out, int n) {
+        CTA_FOR(i, n) {
+            real s = 0;
+            for (int j = 0; j < i; ++j) s += w.A[j * d.ld + i] * v[j];
+            for (int j = i; j < n; ++j) s += w.A[i * d.ld + j] * v[j];
+            out[i] = s;
+        }
+        M2_SYNC();
+    }
+
+    // Gauss-Newton step dgn = A^-1 g by Jacobi-scaled Cholesky; the factor lives in the strict lower
+    // triangle of w.A, its diagonal in w.Ld.  Returns false if A is not numerically positive definite.
+    M2_D bool gauss_newton(int n) {
+        const int ld = d.ld;
+        CTA_FOR(i, n) {
+            const real a = w.A[i * ld + i];
+            w.ds[i] = (a > real(0)) ? real(1) / r_sqrt(a) : real(0);
+            w.Ld[i] = (a > real(0)) ? real(1) : real(-1);
+        }
+        M2_SYNC();
+        const int TX = cta.nthr >= 256 ? 16 : (cta.nthr >= 16 ? 4 : 1);
+        const int TY = cta.nthr / TX, tx = cta.tid % TX, ty = cta.tid / TX;
+        for (int i = 1 + ty; i < n; i += TY)
+            for (int j = tx; j < i; j += TX) w.A[i * ld + j] = w.A[j * ld + i] * w.ds[i] * w.ds[j];
+        M2_SYNC();
+        bool ok = true;
+        for (int k = 0; k < n; ++k) {
+            const real piv = w.Ld[k];
+            if (!(piv > pivot_eps<real>())) { ok = false; break; }      // uniform: every thread reads the same value
+            const real sq = r_sqrt(piv), inv = real(1) / sq;
+            CTA_FOR(i, n - k - 1) w.A[(k + 1 + i) * ld + k] *= inv;
+            M2_SYNC();
+            if (cta.tid == 0) w.Ld[k] = sq;
+            for (int i = k + 1 + ty; i < n; i += TY) {
+                const real lik = w.A[i * ld + k];
+                for (int j = k + 1 + tx; j <= i; j += TX) {
+                    const real v = lik * w.A[j * ld + k];
+                    if (j == i) w.Ld[i] -= v; else w.A[i * ld + j] -= v;
+                }
+            }
+            M2_SYNC();
+        }
+        if (!ok) return false;
+        // solves by the first warp: L z = ds*g ; L^T y = z ; dgn = ds*y
+        const int wl = cta.nthr < 32 ? cta.nthr : 32;
+        if (cta.tid < wl) {
+            for (int i = cta.tid; i < n; i += wl) w.tmp[i] = w.g[i] * w.ds[i];
+#if M2_GPU
+            __syncwarp();
+#endif
+            for (int k = 0; k < n; ++k) {
+                const real zk = w.tmp[k] / w.Ld[k];
+#if M2_GPU
+                __syncwarp();
+#endif
+                if (cta.tid == 0) w.tmp[k] = zk;
+                for (int i = k + 1 + cta.tid; i < n; i += wl) w.tmp[i] -= w.A[i * ld + k] * zk;
+#if M2_GPU
+                __syncwarp();
+#endif
+            }
+            for (int k = n - 1; k >= 0; --k) {
+                const real yk = w.tmp[k] / w.Ld[k];
+#if M2_GPU
+                __syncwarp();
+#endif
+                if (cta.tid == 0) w.tmp[k] = yk;
+                for (int j = cta.tid; j < k; j += wl) w.tmp[j] -= w.A[k * ld + j] * yk;
+#if M2_GPU
+                __syncwarp();
+#endif
+            }
+            for (int i = cta.tid; i < n; i += wl) w.dgn[i] = w.tmp[i] * w.ds[i];
+        }
+        M2_SYNC();
+        return true;
+    }
+
+    // ---- one ch.minimize(method='dogleg') of the reference on state w.x
+    M2_D void minimize(const StepCfg<real> &c) {
+        ++n_min;
+        const int n = c.n;
+        const real e1 = real(1e-15), e2 = real(1e-15);
+        CTA_FOR(i, d.NX) w.colmap[i] = -1;
+        M2_SYNC();
+        CTA_FOR(i, n) w.colmap[c.free[i]] = i;
+        M2_SYNC();
+        eval(w.x, c);
+        build(w.x, c);
+        real sse0 = w.sc[0];
+        real delta = real(job.opt.delta_0);
+        bool done = false;
+        {
+            // chumpy stops on ||g||_inf < e_1 = 1e-15, i.e. only for a numerically zero gradient
+            real s[1] = {0};
+            CTA_FOR(i, n) s[0] += w.g[i] * w.g[i];
+            cta_reduce<real, 1>(cta, s, w.red);
+            if (r_sqrt(s[0]) < e1) done = true;
+        }
+        int iter = 0;
+        while (!done) {
+            ++iter;
+            ++n_iter;
+            symv(w.g, w.Ag, n);
+            real r2[2] = {0, 0};
+            CTA_FOR(i, n) { r2[0] += w.g[i] * w.g[i]; r2[1] += w.g[i] * w.Ag[i]; }
+            cta_reduce<real, 2>(cta, r2, w.red);
+            const real gg = r2[0], gAg = r2[1];
+            const real alpha = gg / gAg;
+            const real nsd = alpha * r_sqrt(gg);
+            bool have_gn = false, gn_ok = true;
+            real ngn2 = 0, gn_sd = 0;      // |dgn|^2, dgn . dsd
+            while (true) {
+                // ---- update_step
+                int kind;           // 0 stunted Cauchy, 1 Gauss-Newton, 2 blend
+                real beta = 0, scale_sd = 0;
+                if (nsd >= delta) { kind = 0; scale_sd = delta / nsd * alpha; }
+                else {
+                    if (!have_gn) {
+                        gn_ok = gauss_newton(n);
+                        have_gn = true;
+                        if (gn_ok) {
+                            real q[2] = {0, 0};
+                            CTA_FOR(i, n) { q[0] += w.dgn[i] * w.dgn[i]; q[1] += w.dgn[i] * w.g[i]; }
+                            cta_reduce<real, 2>(cta, q, w.red);
+                            ngn2 = q[0];
+                            gn_sd = alpha * q[1];
+                        } else frame_flags |= ST_GN_FALLBACK;
+                    }
+                    if (!gn_ok) { kind = 0; scale_sd = alpha; }         // Cauchy step (documented deviation)
+                    else if (r_sqrt(ngn2) <= delta) kind = 1;
+                    else {
+                        kind = 2;
+                        const real dsq = delta * delta, sd2 = nsd * nsd;
+                        const real diff2 = ngn2 - real(2) * gn_sd + sd2;          // |dgn - dsd|^2
+                        const real pnow = diff2 * dsq + gn_sd * gn_sd - ngn2 * sd2;
+                        beta = (dsq - sd2) / ((gn_sd - sd2) + r_sqrt(pnow));
+                    }
+                }
+                CTA_FOR(i, n) {
+                    real v;
+                    if (kind == 0) v = scale_sd * w.g[i];
+                    else if (kind == 1) v = w.dgn[i];
+                    else v = alpha * w.g[i] + beta * (w.dgn[i] - alpha * w.g[i]);
+                    w.d[i] = v;
+                }
+                M2_SYNC();
+                symv(w.d, w.tmp, n);
+                real q[4] = {0, 0, 0, 0};
+                CTA_FOR(i, n) {
+                    q[0] += w.d[i] * w.d[i];
+                    q[1] += w.g[i] * w.d[i];
+                    q[2] += w.d[i] * w.tmp[i];
+                    const real p = w.x[c.free[i]];
+                    q[3] += p * p;
+                }
+                cta_reduce<real, 4>(cta, q, w.red);
+                const real nstep = r_sqrt(q[0]), npn = r_sqrt(q[3]);
+                bool improved = false;
+                if (nstep <= e2 * npn) done = true;
+                else {
+                    CTA_FOR(i, d.NX) w.xt[i] = w.x[i];
+                    M2_SYNC();
+                    CTA_FOR(i, n) w.xt[c.free[i]] += w.d[i];
+                    M2_SYNC();
+                    eval(w.xt, c);
+                    const real sse1 = w.sc[0];
+                    real rho = sse0 - sse1;
+                    if (rho > real(0)) rho = rho / (real(2) * q[1] - q[2]);
+                    improved = rho > real(0);
+                    if (improved) {
+                        CTA_FOR(i, d.NX) w.x[i] = w.xt[i];
+                        M2_SYNC();
+                        if (c.e3 > real(0) && (sse0 - sse1) / sse0 < c.e3) done = true;
+                        else {
+                            build(w.x, c);
+                            sse0 = sse1;
+                        }
+                    }
+                    if (rho > real(0.9)) { const real cand = real(2.5) * nstep; if (cand > delta) delta = cand; }
+                    else if (rho < real(0.05)) delta *= real(0.25);
+                    if (delta <= e2 * npn) done = true;
+                }
+                if (done || improved) break;
+            }
+            if (!done && iter >= job.opt.maxiter) { done = true; frame_flags |= ST_MAXITER; }
+        }
+    }
+
+    // ---- Procrustes initialisation of root orientation and translation (rigid_transformations.py:39-83)
+    M2_D void procrustes() {
+        if (cta.tid == 0) {
+            double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+            int cnt = 0;
+            for (int mi = 0; mi < d.M; ++mi)
+                if (w.vis[mi]) {
+                    for (int q = 0; q < 3; ++q) { ca[q] += double(w.mk[3 * mi + q]); cb[q] += double(w.obs[3 * mi + q]); }
+                    ++cnt;
+                }
+            for (int q = 0; q < 3; ++q) { ca[q] /= cnt; cb[q] /= cnt; }
+            double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};          // S[r][c] = sum a_r b_c
+            for (int mi = 0; mi < d.M; ++mi)
+                if (w.vis[mi])
+                    for (int r = 0; r < 3; ++r)
+                        for (int q = 0; q < 3; ++q)
+                            S[3 * r + q] += (double(w.mk[3 * mi + r]) - ca[r]) * (double(w.obs[3 * mi + q]) - cb[q]);
+            // Horn's quaternion matrix; its top eigenvector is the optimal proper rotation a -> b,
+            // i.e. the SVD solution with the det fix of rigid_transformations.py:57-63.
+            double N[16] = {
+                S[0] + S[4] + S[8], S[5] - S[7], S[6] - S[2], S[1] - S[3],
+                S[5] - S[7], S[0] - S[4] - S[8], S[1] + S[3], S[6] + S[2],
+                S[6] - S[2], S[1] + S[3], -S[0] + S[4] - S[8], S[5] + S[7],
+                S[1] - S[3], S[6] + S[2], S[5] + S[7], -S[0] - S[4] + S[8]};
+            double V[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            for (int sweep = 0; sweep < 30; ++sweep) {
+                double off = 0;
+                for (int p = 0; p < 4; ++p)
+                    for (int q = p + 1; q < 4; ++q) off += N[4 * p + q] * N[4 * p + q];
+                if (off < 1e-30) break;
+                for (int p = 0; p < 4; ++p)
+                    for (int q = p + 1; q < 4; ++q) {
+                        const double apq = N[4 * p + q];
+                        if (fabs(apq) < 1e-300) continue;
+                        const double th = (N[4 * q + q] - N[4 * p + p]) / (2 * apq);
+                        const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1));
+                        const double cs = 1 / sqrt(t * t + 1), sn = t * cs;
+                        for (int k = 0; k < 4; ++k) {
+                            const double akp = N[4 * k + p], akq = N[4 * k + q];
+                            N[4 * k + p] = cs * akp - sn * akq;
+                            N[4 * k + q] = sn * akp + cs * akq;
+                        }
+                        for (int k = 0; k < 4; ++k) {
+                            const double apk = N[4 * p + k], aqk = N[4 * q + k];
+                            N[4 * p + k] = cs * apk - sn * aqk;
+                            N[4 * q + k] = sn * apk + cs * aqk;
+                        }
+                        for (int k = 0; k < 4; ++k) {
+                            const double vkp = V[4 * k + p], vkq = V[4 * k + q];
+                            V[4 * k + p] = cs * vkp - sn * vkq;
+                            V[4 * k + q] = sn * vkp + cs * vkq;
+                        }
+                    }
+            }
+            int best = 0;
+            for (int k = 1; k < 4; ++k) if (N[5 * k] > N[5 * best]) best = k;
+            double qw = V[best], qx = V[4 + best], qy = V[8 + best], qz = V[12 + best];
+            if (qw < 0) { qw = -qw; qx = -qx; qy = -qy; qz = -qz; }
+            const double vn = sqrt(qx * qx + qy * qy + qz * qz);
+            const double ang = 2 * atan2(vn, qw);
+            double rv[3] = {0, 0, 0};
+            if (vn > 1e-300) { rv[0] = qx / vn * ang; rv[1] = qy / vn * ang; rv[2] = qz / vn * ang; }
+            // R from the quaternion, T = b_mean - R a_mean
+            const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                                 2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                                 2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
+            for (int r = 0; r < 3; ++r) {
+                w.x[3 + r] = real(rv[r]);
+                w.x[r] = real(cb[r] - (R[3 * r] * ca[0] + R[3 * r + 1] * ca[1] + R[3 * r + 2] * ca[2]));
+            }
+        }
+        M2_SYNC();
+    }
+
+    // ---- the chunk loop
+    M2_D void run_chunk(int chunk) {
+        const Options &o = job.opt;
+        int f_emit, f_begin, f_end;
+        if (job.chunk_len <= 0) { f_emit = 0; f_begin = 0; f_end = job.n_frames; }
+        else {
+            f_emit = chunk * job.chunk_len;
+            f_begin = f_emit - job.warmup; if (f_begin < 0) f_begin = 0;
+            f_end = f_emit + job.chunk_len; if (f_end > job.n_frames) f_end = job.n_frames;
+        }
+        CTA_FOR(i, d.NX) w.x[i] = 0;
+        M2_SYNC();
+        bool first = true, have_prev = false, have_dm_prev = false;
+        wv = real(o.wt_velo); wdm = real(o.wt_dmpl); wex = real(o.wt_extrap);
+        const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd > 0;
+        const bool has_prior = d.K > 0;
+        for (int f = f_begin; f < f_end; ++f) {
+            n_iter = n_eval = n_build = n_min = 0;
+            frame_flags = 0;
+            CTA_FOR(i, d.M) w.vis[i] = job.vis[size_t(f) * d.M + i];
+            CTA_FOR(i, 3 * d.M) w.obs[i] = job.obs[size_t(f) * 3 * d.M + i];
+            M2_SYNC();
+            {
+                real cnt[1] = {0};
+                CTA_FOR(i, d.M) cnt[0] += w.vis[i] ? real(1) : real(0);
+                cta_reduce<real, 1>(cta, cnt, w.red);
+                nvis = int(cnt[0] + real(0.5));
+            }
+            if (nvis == 0) {                                   // chmosh.py:586-588
+                if (f >= f_emit && cta.tid == 0) job.status[f] = ST_SKIPPED;
+                continue;
+            }
+            real anneal = 1;
+            if (nvis < d.M) anneal += real(d.M - nvis) / real(d.M) * real(o.wt_annealing);
+            wd = real(o.wt_data) * (real(o.num_train_markers) / real(nvis));
+            wp_frame = has_prior ? real(o.wt_poseB) * anneal : real(0);
+            wH = real(o.wt_poseH) * anneal;
+            has_velo = have_prev;                              // chmosh.py:624-626
+            if (has_velo) {
+                CTA_FOR(i, d.PR) w.velo_tgt[i] = real(2) * w.x[3 + i] - w.pose_prev[i];
+                M2_SYNC();
+            }
+            StepCfg<real> c1;
+            c1.free = m.free1; c1.n = m.n1; c1.velo = has_velo; c1.poseH = false; c1.dm_terms = false; c1.extrap = false;
+            if (first) {
+                c1.wp = 0; c1.e3 = real(o.e3_first);
+                eval(w.x, c1);                                 // simulated markers at the current state
+                procrustes();                                  // chmosh.py:634
+                const real mult[3] = {10, 5, 1};
+                for (int s = 0; s < 3; ++s) { c1.wp = wp_frame * mult[s]; minimize(c1); }   // chmosh.py:637-653
+                first = false;
+            } else {
+                CTA_FOR(i, d.PR) w.pose_prev[i] = w.x[3 + i];                               // chmosh.py:656-659
+                have_prev = true;
+                if (dyn) { CTA_FOR(i, d.nd) w.dm_tgt[i] = w.x[3 + d.PR + i]; have_dm_prev = true; }
+                M2_SYNC();
+            }
+            c1.wp = wp_frame; c1.e3 = real(o.e3);
+            minimize(c1);                                      // Step 1, chmosh.py:665-671
+            StepCfg<real> c2 = c1;
+            c2.free = m.free2; c2.n = m.n2; c2.poseH = fingers; c2.dm_terms = dyn;
+            has_extrap = dyn && have_dm_prev;
+            c2.extrap = has_extrap;
+            minimize(c2);                                      // Step 2, chmosh.py:676-705
+            if (cta.tid == 0 && job.totals) {
+#if M2_GPU
+                atomicAdd(job.totals + 0, n_iter); atomicAdd(job.totals + 1, n_eval);
+                atomicAdd(job.totals + 2, n_build); atomicAdd(job.totals + 3, n_min);
+#else
+                job.totals[0] += n_iter; job.totals[1] += n_eval; job.totals[2] += n_build; job.totals[3] += n_min;
+#endif
+            }
+            if (f >= f_emit) {
+                eval(w.x, c2);                                 // per-term SSE and markers at the solution
+                CTA_FOR(i, d.PF) job.fullpose[size_t(f) * d.PF + i] = w.fullpose[i];
+                CTA_FOR(i, d.PR) job.pose[size_t(f) * d.PR + i] = w.x[3 + i];
+                CTA_FOR(i, 3) job.trans[size_t(f) * 3 + i] = w.x[i];
+                if (job.dmpls) CTA_FOR(i, d.nd) job.dmpls[size_t(f) * d.nd + i] = w.x[3 + d.PR + i];
+                CTA_FOR(i, 3 * d.M) job.markers_sim[size_t(f) * 3 * d.M + i] = w.mk[i];
+                CTA_FOR(i, N_ERR) job.errs[size_t(f) * N_ERR + i] = w.sc[1 + i];
+                if (cta.tid == 0) {
+                    job.status[f] = ST_SOLVED | frame_flags | (has_velo ? ST_HAS_VELO : 0) | (has_extrap ? ST_HAS_EXTRAP : 0);
+                    job.counters[4 * f + 0] = n_iter;
+                    job.counters[4 * f + 1] = n_eval;
+                    job.counters[4 * f + 2] = n_build;
+                    job.counters[4 * f + 3] = n_min;
+                }
+                M2_SYNC();
+            }
+        }
+    }
+#undef CTA_FOR
+};
+
+}  // namespace mosh2

@@ -1,0 +1,284 @@
+"""ctypes binding of ``libmosh2.so`` (C-ABI: include/mosh2.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``moshpp_b200/build.py``.  There is no
+CPU fallback: if the shared object or a CUDA device is missing, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from .pack import StageIIPack
+
+MOSH2_F32, MOSH2_F64 = 0, 1
+ST_SOLVED, ST_SKIPPED, ST_HAS_VELO, ST_HAS_EXTRAP, ST_GN_FALLBACK, ST_MAXITER = 1, 2, 4, 8, 16, 32
+ERR_NAMES = ('data', 'poseB', 'velo', 'poseH', 'dmpl', 'extrap_dmpl')   # column order of mosh2_result.errs
+
+_i32p = C.POINTER(C.c_int32)
+_i8p = C.POINTER(C.c_int8)
+_u8p = C.POINTER(C.c_uint8)
+_f64p = C.POINTER(C.c_double)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ('n_joints', C.c_int32), ('n_markers', C.c_int32), ('body_dof', C.c_int32), ('p_red', C.c_int32),
+        ('n_hand_red', C.c_int32), ('n_hand_full', C.c_int32), ('n_dmpl', C.c_int32),
+        ('kw', C.c_int32), ('na', C.c_int32), ('n_levels', C.c_int32),
+        ('parents', _i32p), ('fk_order', _i32p), ('level_ofs', _i32p), ('w_joint', _i32p),
+        ('anc_joint', _i32p), ('anc_mask', _i32p), ('anc_pos', _i8p),
+        ('hand_comps', _f64p), ('hands_mean', _f64p), ('v0', _f64p), ('sd', _f64p), ('pd', _f64p),
+        ('w_val', _f64p), ('j0', _f64p), ('jd', _f64p), ('coefs', _f64p),
+        ('prior_k', C.c_int32), ('prior_d', C.c_int32), ('prior_off', C.c_int32),
+        ('prior_means', _f64p), ('prior_Q', _f64p), ('prior_neglogw', _f64p),
+        ('n_free1', C.c_int32), ('n_free2', C.c_int32), ('free1', _i32p), ('free2', _i32p),
+        ('finger_lo', C.c_int32), ('finger_hi', C.c_int32),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ('wt_data', C.c_double), ('wt_poseB', C.c_double), ('wt_poseH', C.c_double), ('wt_velo', C.c_double),
+        ('wt_dmpl', C.c_double), ('wt_annealing', C.c_double), ('wt_extrap_dmpl', C.c_double),
+        ('num_train_markers', C.c_double), ('delta_0', C.c_double), ('e3_first', C.c_double), ('e3', C.c_double),
+        ('maxiter', C.c_int32), ('optimize_fingers', C.c_int32), ('optimize_dynamics', C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ('fullpose', _f64p), ('pose', _f64p), ('trans', _f64p), ('dmpls', _f64p), ('markers_sim', _f64p),
+        ('errs', _f64p), ('status', _i32p), ('counters', _i32p),
+    ]
+
+
+class Mosh2Error(RuntimeError):
+    pass
+
+
+def default_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmosh2.so')
+
+
+_LIB = None
+
+
+def load_library(path: Optional[str] = None):
+    """Loads libmosh2.so (once) and declares the prototypes of include/mosh2.h."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or default_library_path()
+    if not os.path.exists(p):
+        raise Mosh2Error(f'{p} not found: build it with `python -m moshpp_b200.build` (nvcc, sm_100a). '
+                         'moshpp_b200 has no CPU solver.')
+    lib = C.CDLL(p)
+    vp = C.c_void_p
+    lib.mosh2_version.restype = C.c_int
+    lib.mosh2_last_error.restype = C.c_char_p
+    lib.mosh2_device_count.restype = C.c_int
+    lib.mosh2_default_options.argtypes = [C.POINTER(Options)]
+    lib.mosh2_default_options.restype = None
+    lib.mosh2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(vp)]
+    lib.mosh2_model_destroy.argtypes = [vp]
+    lib.mosh2_model_destroy.restype = None
+    lib.mosh2_job_create.argtypes = [vp, C.POINTER(Options), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.mosh2_job_upload.argtypes = [vp, _f64p, _u8p]
+    lib.mosh2_job_launch.argtypes = [vp]
+    lib.mosh2_job_download.argtypes = [vp, C.POINTER(Result)]
+    lib.mosh2_job_sync.argtypes = [vp]
+    lib.mosh2_job_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.mosh2_job_num_chunks.argtypes = [vp]
+    lib.mosh2_job_totals.argtypes = [vp, _i32p]
+    lib.mosh2_job_destroy.argtypes = [vp]
+    lib.mosh2_job_destroy.restype = None
+    lib.mosh2_solve.argtypes = [vp, C.POINTER(Options), C.c_int32, _f64p, _u8p, C.c_int32, C.c_int32, C.c_int32,
+                                C.POINTER(Result)]
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    'mosh2_version', 'mosh2_last_error', 'mosh2_device_count', 'mosh2_default_options', 'mosh2_model_create',
+    'mosh2_model_destroy', 'mosh2_job_create', 'mosh2_job_upload', 'mosh2_job_launch', 'mosh2_job_download',
+    'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
+    'mosh2_solve')
+
+
+def _ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+class DescHolder:
+    """Keeps the contiguous arrays alive next to the ctypes struct that points into them."""
+
+    def __init__(self, pk: StageIIPack):
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self.arrays = dict(
+            parents=i32(pk.parents), fk_order=i32(pk.fk_order), level_ofs=i32(pk.level_ofs), w_joint=i32(pk.w_joint),
+            anc_joint=i32(pk.anc_joint), anc_mask=i32(pk.anc_mask),
+            anc_pos=np.ascontiguousarray(pk.anc_pos, dtype=np.int8),
+            hand_comps=f64(pk.hand_comps), hands_mean=f64(pk.hands_mean), v0=f64(pk.v0), sd=f64(pk.sd), pd=f64(pk.pd),
+            w_val=f64(pk.w_val), j0=f64(pk.j0), jd=f64(pk.jd), coefs=f64(pk.coefs),
+            prior_means=f64(pk.prior_means), prior_Q=f64(pk.prior_Q), prior_neglogw=f64(pk.prior_neglogw),
+            free1=i32(pk.free_step1), free2=i32(pk.free_step2))
+        a = self.arrays
+        d = ModelDesc()
+        d.n_joints, d.n_markers, d.body_dof, d.p_red = pk.n_joints, pk.n_markers, pk.body_dof, pk.p_red
+        d.n_hand_red, d.n_hand_full, d.n_dmpl = pk.n_hand_red, pk.n_hand_full, pk.n_dmpl
+        d.kw, d.na, d.n_levels = pk.kw, pk.na, pk.n_levels
+        for k in ('parents', 'fk_order', 'level_ofs', 'w_joint', 'anc_joint', 'anc_mask', 'free1', 'free2'):
+            setattr(d, k, _ptr(a[k], _i32p))
+        d.anc_pos = _ptr(a['anc_pos'], _i8p)
+        for k in ('hand_comps', 'hands_mean', 'v0', 'sd', 'pd', 'w_val', 'j0', 'jd', 'coefs', 'prior_means',
+                  'prior_Q', 'prior_neglogw'):
+            setattr(d, k, _ptr(a[k], _f64p))
+        d.prior_k, d.prior_d, d.prior_off = pk.prior_k, pk.prior_d, pk.prior_off
+        d.n_free1, d.n_free2 = len(pk.free_step1), len(pk.free_step2)
+        d.finger_lo, d.finger_hi = pk.finger_lo, pk.finger_hi
+        self.desc = d
+
+
+def make_options(weights=None, *, maxiter: int = 100, optimize_fingers: bool = False,
+                 optimize_dynamics: bool = False) -> Options:
+    """Stage-II weights (moshpp_conf.yaml:118-125) -> mosh2_options."""
+    o = Options(wt_data=400., wt_poseB=1.6, wt_poseH=1.0, wt_velo=2.5, wt_dmpl=1.0, wt_annealing=2.5,
+                wt_extrap_dmpl=6.0, num_train_markers=46., delta_0=0.5, e3_first=1e-3, e3=1e-2, maxiter=maxiter,
+                optimize_fingers=int(optimize_fingers), optimize_dynamics=int(optimize_dynamics))
+    if weights is not None:
+        g = (lambda k: weights[k])
+        o.wt_data, o.wt_poseB, o.wt_poseH = float(g('stageii_wt_data')), float(g('stageii_wt_poseB')), float(g('stageii_wt_poseH'))
+        o.wt_velo, o.wt_dmpl = float(g('stageii_wt_velo')), float(g('stageii_wt_dmpl'))
+        o.wt_annealing = float(g('stageii_wt_annealing'))
+    return o
+
+
+class ResultArrays:
+    def __init__(self, n_frames: int, pk_dims: Dict[str, int]):
+        F, M, nj, pr, nd = n_frames, pk_dims['M'], pk_dims['nJ'], pk_dims['p_red'], pk_dims['nd']
+        self.fullpose = np.zeros((F, 3 * nj))
+        self.pose = np.zeros((F, pr))
+        self.trans = np.zeros((F, 3))
+        self.dmpls = np.zeros((F, max(nd, 1)))
+        self.markers_sim = np.zeros((F, M, 3))
+        self.errs = np.zeros((F, 6))
+        self.status = np.zeros(F, dtype=np.int32)
+        self.counters = np.zeros((F, 4), dtype=np.int32)
+        self.nd = nd
+        r = Result()
+        r.fullpose, r.pose, r.trans = _ptr(self.fullpose, _f64p), _ptr(self.pose, _f64p), _ptr(self.trans, _f64p)
+        r.dmpls = _ptr(self.dmpls, _f64p)
+        r.markers_sim, r.errs = _ptr(self.markers_sim, _f64p), _ptr(self.errs, _f64p)
+        r.status, r.counters = _ptr(self.status, _i32p), _ptr(self.counters, _i32p)
+        self.c = r
+
+
+def pack_dims(pk: StageIIPack) -> Dict[str, int]:
+    return dict(M=pk.n_markers, nJ=pk.n_joints, p_red=pk.p_red, nd=pk.n_dmpl)
+
+
+class Model:
+    """Owns a ``mosh2_model`` handle on one GPU."""
+
+    def __init__(self, pk: StageIIPack, device: int = 0, library_path: Optional[str] = None):
+        self.lib = load_library(library_path)
+        self.pk = pk
+        self.holder = DescHolder(pk)
+        self.handle = C.c_void_p()
+        self.device = device
+        rc = self.lib.mosh2_model_create(C.byref(self.holder.desc), device, C.byref(self.handle))
+        if rc != 0:
+            raise Mosh2Error(f'mosh2_model_create failed ({rc}): {self.lib.mosh2_last_error().decode()}')
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise Mosh2Error(f'{what} failed ({rc}): {self.lib.mosh2_last_error().decode()}')
+
+    def solve(self, obs: np.ndarray, vis: np.ndarray, options: Options, *, chunk_len: int = 0,
+              chunk_warmup: int = 0, precision: int = MOSH2_F32) -> ResultArrays:
+        """One blocking call: H2D, kernel, D2H (mosh2_solve)."""
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
+        F = obs.shape[0]
+        assert obs.shape == (F, self.pk.n_markers, 3) and vis8.shape == (F, self.pk.n_markers)
+        res = ResultArrays(F, pack_dims(self.pk))
+        rc = self.lib.mosh2_solve(self.handle, C.byref(options), F, _ptr(obs, _f64p), _ptr(vis8, _u8p),
+                                  chunk_len, chunk_warmup, precision, C.byref(res.c))
+        self._check(rc, 'mosh2_solve')
+        return res
+
+    def job(self, n_frames: int, options: Options, *, chunk_len: int = 0, chunk_warmup: int = 0,
+            precision: int = MOSH2_F32) -> 'Job':
+        return Job(self, n_frames, options, chunk_len, chunk_warmup, precision)
+
+    def close(self):
+        if self.handle:
+            self.lib.mosh2_model_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Job:
+    """Staged upload / launch / download on device-resident buffers (used by bench.py)."""
+
+    def __init__(self, model: Model, n_frames: int, options: Options, chunk_len: int, chunk_warmup: int, precision: int):
+        self.model, self.lib, self.n_frames = model, model.lib, n_frames
+        self.handle = C.c_void_p()
+        self.options = options
+        rc = self.lib.mosh2_job_create(model.handle, C.byref(options), n_frames, chunk_len, chunk_warmup, precision,
+                                       C.byref(self.handle))
+        model._check(rc, 'mosh2_job_create')
+        self.result = ResultArrays(n_frames, pack_dims(model.pk))
+        self._keep = None
+
+    def upload(self, obs: np.ndarray, vis: np.ndarray):
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
+        self._keep = (obs, vis8)
+        self.model._check(self.lib.mosh2_job_upload(self.handle, _ptr(obs, _f64p), _ptr(vis8, _u8p)), 'mosh2_job_upload')
+
+    def launch(self):
+        self.model._check(self.lib.mosh2_job_launch(self.handle), 'mosh2_job_launch')
+
+    def sync(self):
+        self.model._check(self.lib.mosh2_job_sync(self.handle), 'mosh2_job_sync')
+
+    def download(self) -> ResultArrays:
+        self.model._check(self.lib.mosh2_job_download(self.handle, C.byref(self.result.c)), 'mosh2_job_download')
+        return self.result
+
+    def kernel_ms(self) -> float:
+        ms = C.c_float()
+        self.model._check(self.lib.mosh2_job_kernel_ms(self.handle, C.byref(ms)), 'mosh2_job_kernel_ms')
+        return float(ms.value)
+
+    def totals(self) -> Dict[str, int]:
+        """Work of the last launch over all processed frames, warm-up included."""
+        t = np.zeros(4, dtype=np.int32)
+        self.model._check(self.lib.mosh2_job_totals(self.handle, _ptr(t, _i32p)), 'mosh2_job_totals')
+        return dict(iterations=int(t[0]), evaluations=int(t[1]), builds=int(t[2]), minimisations=int(t[3]))
+
+    @property
+    def num_chunks(self) -> int:
+        return int(self.lib.mosh2_job_num_chunks(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.mosh2_job_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

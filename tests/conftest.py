@@ -1,0 +1,93 @@
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu on the GPU box)')
+
+
+# small variants of the BASELINE configs: same topology / variable layout, fewer vertices and frames,
+# so the float64 oracle finishes in seconds
+SMALL = {
+    'C1': dict(frames=12, n_verts=1200),
+    'C2': dict(frames=16, n_verts=1500),
+    'C3': dict(frames=10, n_verts=2000),
+    'C4': dict(frames=12, n_verts=None),
+}
+
+
+@pytest.fixture(scope='session')
+def case_dir(tmp_path_factory):
+    return str(tmp_path_factory.mktemp('mosh_cases'))
+
+
+@pytest.fixture(scope='session')
+def cases(case_dir):
+    from moshpp_b200 import synth
+    cache = {}
+
+    def get(name, **kw):
+        key = (name, tuple(sorted(kw.items())))
+        if key not in cache:
+            args = dict(SMALL.get(name, {}))
+            args.update(kw)
+            cache[key] = synth.make_case(case_dir, name, **args)
+        return cache[key]
+    return get
+
+
+def dense_obs(case):
+    from moshpp_b200.mocap_interface import MocapSession
+    mocap = MocapSession(case['mocap_fname'], case['cfg'].mocap.unit)
+    return mocap.frames_for_labels(case['latent_labels'], range(len(mocap)))
+
+
+@pytest.fixture(scope='session')
+def emu():
+    """TEST-ONLY single-thread host build of the device source (never part of the product)."""
+    from moshpp_b200 import build, lib
+    handle = C.CDLL(build.build_emu())
+
+    def solve(case, chunk_len=0, warmup=0, precision=None, obs_vis=None):
+        precision = lib.MOSH2_F64 if precision is None else precision
+        pk, cfg = case['pack'], case['cfg']
+        obs, vis = obs_vis if obs_vis is not None else dense_obs(case)
+        h = lib.DescHolder(pk)
+        opt = lib.make_options(cfg.opt_settings.weights, optimize_fingers=cfg.moshpp.optimize_fingers and pk.finger_hi > pk.finger_lo,
+                               optimize_dynamics=cfg.moshpp.optimize_dynamics)
+        F = obs.shape[0]
+        res = lib.ResultArrays(F, lib.pack_dims(pk))
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
+        rc = handle.mosh2_emu_solve(C.byref(h.desc), C.byref(opt), F, obs.ctypes.data_as(lib._f64p),
+                                    vis8.ctypes.data_as(lib._u8p), chunk_len, warmup, precision, C.byref(res.c))
+        assert rc == 0
+        return res
+    return solve
+
+
+def run_oracle(case, **kw):
+    from oracle import stageii
+    return stageii.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'],
+                                case['betas'], case['marker_meta'], **kw)
+
+
+def gpu_solve(case, chunk_len=0, warmup=0, precision='f32', obs_vis=None):
+    from moshpp_b200 import chmosh, lib
+    pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'],
+                                             case['betas'], case['marker_meta'])
+    obs, vis = obs_vis if obs_vis is not None else dense_obs(case)
+    model = lib.Model(pk, device=0)
+    try:
+        return model.solve(obs, vis, opts, chunk_len=chunk_len, chunk_warmup=warmup,
+                           precision={'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[precision])
+    finally:
+        model.close()

@@ -1,0 +1,98 @@
+"""Parity tests proper: the CUDA library (through the C-ABI) against the float64 oracle on a B200."""
+import numpy as np
+import pytest
+
+from conftest import dense_obs, gpu_solve, run_oracle
+from moshpp_b200 import lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+def test_f64_kernel_equals_oracle(cases, name):
+    case = cases(name)
+    out = run_oracle(case)
+    res = gpu_solve(case, precision='f64')
+    dbg = out['stageii_debug_details']
+    fid = dbg['frame_ids']
+    assert np.array_equal(np.nonzero(res.status & lib.ST_SOLVED)[0], fid)
+    assert np.abs(res.pose[fid] - out['_pose_reduced']).max() < 1e-8
+    assert np.abs(res.fullpose[fid] - out['fullpose']).max() < 1e-8
+    assert np.abs(res.trans[fid] - out['trans']).max() < 1e-9
+    if 'dmpls' in out:
+        assert np.abs(res.dmpls[fid, :out['dmpls'].shape[1]] - out['dmpls']).max() < 1e-8
+    assert res.counters[fid, 2].sum() == dbg['oracle_stats']['j_evals']
+    for k, col in zip(lib.ERR_NAMES, range(6)):
+        if k in dbg['stageii_errs'] and k not in ('velo', 'extrap_dmpl'):
+            assert np.allclose(res.errs[fid, col], dbg['stageii_errs'][k], rtol=1e-7, atol=1e-10)
+    mk = np.concatenate(dbg['markers_sim'])
+    _, vis = dense_obs(case)
+    assert np.abs(res.markers_sim[fid][vis[fid]] - mk).max() < 1e-9
+
+
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+def test_f32_kernel_within_stated_tolerance(cases, name):
+    """Tolerances of BASELINE.md section 4 for the fp32 path (sequential mode)."""
+    case = cases(name)
+    out = run_oracle(case)
+    res = gpu_solve(case, precision='f32')
+    dbg = out['stageii_debug_details']
+    fid = dbg['frame_ids']
+    bd = min(case['pack'].body_dof, 66)
+    dp = np.abs(res.pose[fid] - out['_pose_reduced'])
+    assert dp[:, :bd].max() < 1e-3                      # rad, root + body
+    assert dp.max() < 1e-2                              # weakly observed finger PCA coefficients
+    assert np.abs(res.trans[fid] - out['trans']).max() < 1e-4   # m
+    sse = dbg['stageii_errs']['data']
+    assert np.abs(res.errs[fid, 0] / sse - 1).max() < 1e-2     # final marker residual within 1 %
+    mk = np.concatenate(dbg['markers_sim'])
+    _, vis = dense_obs(case)
+    assert np.abs(res.markers_sim[fid][vis[fid]] - mk).max() < 1e-4
+
+
+def test_chunked_kernel_equals_oracle_chunked(cases):
+    case = cases('C2')
+    out = run_oracle(case, chunk=(5, 2))
+    res = gpu_solve(case, chunk_len=5, warmup=2, precision='f64')
+    fid = out['stageii_debug_details']['frame_ids']
+    assert np.abs(res.pose[fid] - out['_pose_reduced']).max() < 1e-8
+
+
+def test_chunk_warmup_converges_on_gpu(cases):
+    case = cases('C2', frames=160)
+    seq = gpu_solve(case, precision='f64')
+    ok = (seq.status & lib.ST_SOLVED) != 0
+    e = [np.abs(gpu_solve(case, chunk_len=32, warmup=W, precision='f64').pose - seq.pose)[ok].max() for W in (0, 48, 96)]
+    assert e[1] < 1e-3 and e[2] < 1e-6, e
+
+
+def test_skipped_frames_and_flags(cases):
+    case = cases('C1')
+    obs, vis = dense_obs(case)
+    vis = vis.copy()
+    vis[3] = False
+    res = gpu_solve(case, obs_vis=(obs, vis))
+    assert res.status[3] == lib.ST_SKIPPED
+    assert not (res.status[1] & lib.ST_HAS_VELO) and (res.status[2] & lib.ST_HAS_VELO)
+    assert np.all(res.fullpose[3] == 0)
+
+
+def test_full_size_c2_properties(cases):
+    """BASELINE config 2 at full size (V=6890, 500 frames): size-independent properties."""
+    case = cases('C2', frames=500, n_verts=None)
+    obs, vis = dense_obs(case)
+    res = gpu_solve(case, chunk_len=4, warmup=64, precision='f32')
+    ok = (res.status & lib.ST_SOLVED) != 0
+    assert ok.sum() == (vis.any(1)).sum()
+    # solved markers reproduce the observations to about the 1 mm noise floor
+    d = np.linalg.norm(res.markers_sim - obs, axis=-1)[vis]
+    assert np.sqrt((d ** 2).mean()) < 2.5e-3
+    # fullpose is the PCA expansion of the reduced pose (smpl_fast_derivatives.py:194-204)
+    pk = case['pack']
+    full = np.concatenate([res.pose[:, :pk.body_dof], pk.hands_mean[None] + res.pose[:, pk.body_dof:] @ pk.hand_comps], 1)
+    assert np.abs(full[ok] - res.fullpose[ok]).max() < 1e-5
+    # toes are frozen (chmosh.py:646-647)
+    assert np.abs(res.pose[ok][:, 30:36]).max() == 0
+    # chunked == sequential within the warm-up bound
+    seq = gpu_solve(case, precision='f32')
+    assert np.abs(seq.pose - res.pose)[ok][:, :66].max() < 2e-3
