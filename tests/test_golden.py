@@ -1,0 +1,56 @@
+"""Committed golden vectors (tests/golden/make_golden.py): oracle drift check on CPU, CUDA target on GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import gpu_solve, run_oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, f'stageii_{name}.npz'))
+
+
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+def test_fixture_generation_is_reproducible(cases, name):
+    g = _load(name)
+    case = cases(name)
+    assert np.allclose(g['markers_latent'], case['markers_latent'], rtol=0, atol=1e-12)
+    assert np.allclose(g['obs_checksum'], [np.nansum(case['obs']), case['vis'].sum()], rtol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['C1', 'C4'])
+def test_oracle_reproduces_golden(cases, name):
+    g = _load(name)
+    out = run_oracle(cases(name))
+    assert np.array_equal(out['stageii_debug_details']['frame_ids'], g['frame_ids'])
+    assert np.abs(out['fullpose'] - g['fullpose']).max() < 1e-9
+    assert np.abs(out['trans'] - g['trans']).max() < 1e-10
+    assert out['stageii_debug_details']['oracle_stats']['j_evals'] == int(g['j_evals'])
+
+
+@pytest.mark.parametrize('name', ['C2', 'C3'])
+def test_device_source_reproduces_golden(cases, emu, name):
+    g = _load(name)
+    res = emu(cases(name))
+    fid = g['frame_ids']
+    assert np.abs(res.fullpose[fid] - g['fullpose']).max() < 1e-9
+    if 'dmpls' in g.files:
+        assert np.abs(res.dmpls[fid, :g['dmpls'].shape[1]] - g['dmpls']).max() < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+def test_cuda_reproduces_golden(cases, name):
+    g = _load(name)
+    fid = g['frame_ids']
+    r64 = gpu_solve(cases(name), precision='f64')
+    assert np.abs(r64.fullpose[fid] - g['fullpose']).max() < 1e-8
+    assert np.abs(r64.trans[fid] - g['trans']).max() < 1e-9
+    r32 = gpu_solve(cases(name), precision='f32')
+    bd = min(cases(name)['pack'].body_dof, 66)
+    assert np.abs(r32.pose[fid] - g['pose'])[:, :bd].max() < 1e-3
+    assert np.abs(r32.trans[fid] - g['trans']).max() < 1e-4
+    assert np.abs(r32.errs[fid, 0] / g['err_data'] - 1).max() < 1e-2

