@@ -130,4 +130,4 @@ def test_library_is_the_cuda_build():
     L = lib.load_library()
     assert L.mosh2_device_count() >= 1
     maps = open('/proc/self/maps').read()
-    assert 'libmosh2.so' in maps and 'libmosh2_emu' not in maps.replace('tests/emu', 'tests/emu')  or True
+    assert 'libmosh2.so' in maps
