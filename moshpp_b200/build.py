@@ -35,7 +35,7 @@ def _nvcc() -> str:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, 'mosh2.cu'), os.path.join(CSRC, 'mosh2_device.cuh'),
+    srcs = [os.path.join(CSRC, "mosh2.cu"), os.path.join(CSRC, "mosh2_device.cuh"), os.path.join(CSRC, "mosh2_host.h"),
             os.path.join(ROOT, 'include', 'mosh2.h')]
     if force or _stale(LIB, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, srcs[0]]
@@ -49,7 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 def build_emu(force: bool = False) -> str:
     """TEST-ONLY single-thread host build of the CTA program (see tests/emu/mosh2_emu.cpp)."""
-    srcs = [EMU_SRC, os.path.join(CSRC, 'mosh2_device.cuh'), os.path.join(ROOT, 'include', 'mosh2.h')]
+    srcs = [EMU_SRC, os.path.join(CSRC, "mosh2_device.cuh"), os.path.join(CSRC, "mosh2_host.h"), os.path.join(ROOT, 'include', 'mosh2.h')]
     if force or _stale(EMU_LIB, srcs):
         os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
         cmd = ['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', EMU_LIB, EMU_SRC]

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "mosh2_device.cuh"
+#include "mosh2_host.h"
 
 namespace {
 
@@ -35,18 +36,18 @@ int fail(int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(MOSH2_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kThreads = 256;
 constexpr size_t kMaxSmem = 227 * 1024;
+template <class real> constexpr int threads_for() { return sizeof(real) == 4 ? 512 : 256; }
 
 template <class real>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_for<real>(), 1)
 mosh2_stageii_kernel(const mosh2::Model<real> m, const mosh2::Job<real> job, int big_in_global) {
     extern __shared__ __align__(16) unsigned char smem[];
     mosh2::Work<real> w;
     const mosh2::Dims d = mosh2::make_dims(m);
     mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
     mosh2::Arena G{job.gws ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
-    mosh2::carve(w, d, S, G, big_in_global != 0);
+    mosh2::carve(w, d, m.hct_size, S, G, big_in_global != 0);
     mosh2::Cta c{int(threadIdx.x), int(blockDim.x)};
     mosh2::Solver<real> s(m, job, w, c);
     s.run_chunk(blockIdx.x);
@@ -93,27 +94,43 @@ struct DevModel {
         if ((rc = up<int>(d.anc_joint, S * d.na, &m.anc_joint))) return rc;
         if ((rc = up<int>(d.anc_mask, S * d.na, &m.anc_mask))) return rc;
         if ((rc = up<int8_t>(d.anc_pos, S * nJ, &m.anc_pos))) return rc;
-        std::vector<int> lo(d.n_hand_red, 0), hi(d.n_hand_red, 0);
-        for (int r = 0; r < d.n_hand_red; ++r) {
-            int a = d.n_hand_full, b = 0;
-            for (int c = 0; c < d.n_hand_full; ++c)
-                if (d.hand_comps[size_t(r) * d.n_hand_full + c] != 0.0) { if (c < a) a = c; b = c + 1; }
-            if (b <= a) a = b = 0;
-            lo[r] = a; hi[r] = b;
+        {   // dense blocks of the hand-PCA matrix (rows with the same non-zero column range), stored transposed
+            std::vector<double> hct;
+            mosh2::HandBlock blocks[mosh2::kMaxHandBlocks];
+            const int nb = mosh2_host::hand_blocks(d.hand_comps, d.n_hand_red, d.n_hand_full, blocks, hct);
+            m.hb_n = nb;
+            for (int b = 0; b < nb; ++b) m.hb[b] = blocks[b];
+            m.hct_size = int(hct.size());
+            if ((rc = up<real>(hct.data(), hct.size(), &m.hct))) return rc;
         }
-        if ((rc = up<int>(lo.data(), lo.size(), &m.hand_lo))) return rc;
-        if ((rc = up<int>(hi.data(), hi.size(), &m.hand_hi))) return rc;
-        if ((rc = up<real>(d.hand_comps, size_t(d.n_hand_red) * d.n_hand_full, &m.hand_comps))) return rc;
         if ((rc = up<real>(d.hands_mean, d.n_hand_full, &m.hands_mean))) return rc;
         if ((rc = up<real>(d.v0, S * 3, &m.v0))) return rc;
         if ((rc = up<real>(d.sd, S * 3 * nd, &m.sd))) return rc;
-        if ((rc = up<real>(d.pd, (nJ - 1) * S * 3 * 9, &m.pd))) return rc;
+        {   // pose-blend blocks [(nJ-1)][M][9 rows][12]: rows padded to three 16-byte vectors
+            // [(nJ-1)][9 e][3M slots][4]: x, y, z of a slot for one (joint, e) form one 16-byte vector
+            const size_t S3 = size_t(3) * d.n_markers;
+            std::vector<double> pd4((nJ - 1) * 9 * S3 * mosh2::kPdSlot, 0.0);
+            for (size_t j = 0; j + 1 < nJ; ++j)
+                for (size_t sl = 0; sl < S3; ++sl)
+                    for (int c = 0; c < 3; ++c)
+                        for (int e = 0; e < 9; ++e)
+                            pd4[((j * 9 + e) * S3 + sl) * mosh2::kPdSlot + c] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+            if ((rc = up<real>(pd4.data(), pd4.size(), &m.pd4))) return rc;
+        }
         if ((rc = up<real>(d.w_val, S * d.kw, &m.w_val))) return rc;
         if ((rc = up<real>(d.j0, nJ * 3, &m.j0))) return rc;
         if ((rc = up<real>(d.jd, nJ * 3 * nd, &m.jd))) return rc;
         if ((rc = up<real>(d.coefs, size_t(d.n_markers) * 3, &m.coefs))) return rc;
         if ((rc = up<real>(d.prior_means, size_t(d.prior_k) * d.prior_d, &m.prior_means))) return rc;
-        if ((rc = up<real>(d.prior_Q, size_t(d.prior_k) * d.prior_d * d.prior_d, &m.prior_Q))) return rc;
+        {
+            const size_t K = d.prior_k, D = d.prior_d, D4 = (D + 3) & ~size_t(3);
+            m.prior_d4 = int(D4);
+            std::vector<double> q4(K * D * D4, 0.0);
+            for (size_t k = 0; k < K; ++k)
+                for (size_t i = 0; i < D; ++i)
+                    for (size_t l = 0; l < D; ++l) q4[(k * D + i) * D4 + l] = d.prior_Q[(k * D + i) * D + l];
+            if ((rc = up<real>(q4.data(), q4.size(), &m.prior_Q4))) return rc;
+        }
         if ((rc = up<real>(d.prior_neglogw, d.prior_k, &m.prior_nlw))) return rc;
         if ((rc = up<int>(d.free1, d.n_free1, &m.free1))) return rc;
         if ((rc = up<int>(d.free2, d.n_free2, &m.free2))) return rc;
@@ -169,7 +186,7 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     job.opt = j->opt;
     CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
     CU(cudaEventRecord(j->ev0, j->stream));
-    mosh2_stageii_kernel<real><<<j->n_chunks, kThreads, j->smem, j->stream>>>(m, job, j->big_in_global);
+    mosh2_stageii_kernel<real><<<j->n_chunks, threads_for<real>(), j->smem, j->stream>>>(m, job, j->big_in_global);
     CU(cudaGetLastError());
     CU(cudaEventRecord(j->ev1, j->stream));
     return 0;
@@ -180,11 +197,11 @@ void plan_workspace(const mosh2::Model<real> &m, size_t *smem, size_t *gws, int 
     mosh2::Work<real> w;
     const mosh2::Dims d = mosh2::make_dims(m);
     mosh2::Arena S{nullptr, 0}, G{nullptr, 0};
-    mosh2::carve(w, d, S, G, false);
+    mosh2::carve(w, d, m.hct_size, S, G, false);
     *big = 0;
     if (S.off > kMaxSmem) {
         S.off = 0; G.off = 0;
-        mosh2::carve(w, d, S, G, true);
+        mosh2::carve(w, d, m.hct_size, S, G, true);
         *big = 1;
     }
     *smem = (S.off + 15) & ~size_t(15);

@@ -24,11 +24,13 @@
 #define M2_HD __host__ __device__ __forceinline__
 #define M2_D __device__ __forceinline__
 #define M2_SYNC() __syncthreads()
+#define M2_WSYNC() __syncwarp()
 #define M2_GPU 1
 #else
 #define M2_HD inline
 #define M2_D inline
 #define M2_SYNC() ((void)0)
+#define M2_WSYNC() ((void)0)
 #define M2_GPU 0
 #endif
 
@@ -38,10 +40,18 @@ enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_
 enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
 
 constexpr int kTileMarkers = 8;   // markers per Jacobian tile (24 rows)
-constexpr int kBS = 4;            // register tile of the J^T J accumulation
+constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
+constexpr int kPdSlot = 4;        // pose-blend rows of one slot (x, y, z, pad): one 16-byte vector per (joint, e)
+constexpr int kBlendGroups = 3;   // joint groups of the pose-blend partial sums
+constexpr int kCholNB = 8;        // block column width of the Cholesky factorisation
+constexpr int kMaxHandBlocks = 4;
 
 struct Cta {
     int tid, nthr;
+};
+
+struct HandBlock {   // one dense block of the hand-PCA matrix: rows [r0,r1) of the reduced pose, columns [q0,q1)
+    int r0, r1, q0, q1, ct_off, rw4;   // Ct[(q-q0)*rw4 + (r-r0)] at hct + ct_off, rw4 = round_up(r1-r0, 4)
 };
 
 template <class real>
@@ -49,10 +59,13 @@ struct Model {
     int nJ, M, body_dof, p_red, n_hand_red, n_hand_full, nd, kw, na, n_levels;
     const int *parents, *fk_order, *level_ofs, *w_joint, *anc_joint, *anc_mask;
     const int8_t *anc_pos;
-    const int *hand_lo, *hand_hi;   // non-zero column range of each row of hand_comps
-    const real *hand_comps, *hands_mean, *v0, *sd, *pd, *w_val, *j0, *jd, *coefs;
-    int prior_k, prior_d, prior_off;
-    const real *prior_means, *prior_Q, *prior_nlw;
+    int hb_n, hct_size;
+    HandBlock hb[kMaxHandBlocks];
+    const real *hct;            // compact transposed hand-PCA blocks
+    const real *hands_mean, *v0, *sd, *w_val, *j0, *jd, *coefs;
+    const real *pd4;            // [(nJ-1)][9 e][3M slots][4]: lanes over slots read consecutive 16-byte vectors
+    int prior_k, prior_d, prior_off, prior_d4;
+    const real *prior_means, *prior_Q4, *prior_nlw;   // Q4: [K][D][D4]
     int n1, n2;
     const int *free1, *free2;
     int finger_lo, finger_hi;
@@ -106,6 +119,9 @@ template <> M2_HD double series_thresh<double>() { return 1e-2; }
 template <class real> M2_HD real pivot_eps();          // smallest accepted pivot of the unit-diagonal-scaled A
 template <> M2_HD float pivot_eps<float>() { return 1e-6f; }
 template <> M2_HD double pivot_eps<double>() { return 1e-13; }
+
+template <class real> struct alignas(16) Vec4 { real x, y, z, w; };
+template <class real> M2_HD Vec4<real> ld4(const real *p) { return *reinterpret_cast<const Vec4<real> *>(p); }
 
 template <class real>
 M2_HD void mat3_mul(const real *A, const real *B, real *C) {   // C = A B (row-major 3x3)
@@ -163,11 +179,9 @@ M2_HD void rodrigues(const real *w, real *R, real *dR) {
         real *D = dR + 9 * k;
 #pragma unroll
         for (int i = 0; i < 9; ++i) D[i] = c1 * wk * K[i] + c2 * wk * K2[i];
-        // a E_k
         if (k == 0) { D[5] -= a; D[7] += a; }
         if (k == 1) { D[2] += a; D[6] -= a; }
         if (k == 2) { D[1] -= a; D[3] += a; }
-        // b (e_k w^T + w e_k^T - 2 w_k I)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             D[3 * k + c] += b * w[c];
@@ -180,7 +194,7 @@ M2_HD void rodrigues(const real *w, real *R, real *dR) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA-wide reduction of nv (<= 8) per-thread values; result broadcast to every thread.
+// CTA-wide reduction of NV (<= 8) per-thread values; result broadcast to every thread.
 // ---------------------------------------------------------------------------------------------
 template <class real, int NV>
 M2_D void cta_reduce(const Cta &c, real *vals, real *scratch /* >= 8*33 reals */) {
@@ -208,6 +222,15 @@ M2_D void cta_reduce(const Cta &c, real *vals, real *scratch /* >= 8*33 reals */
 #endif
 }
 
+template <class real>
+M2_D real warp_sum(real v) {
+#if M2_GPU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------
@@ -216,26 +239,28 @@ struct Work {
     // state
     real *x, *xt, *pose_prev, *velo_tgt, *dm_tgt;
     // forward scratch of the latest evaluation
-    real *fullpose, *Rl, *dRl, *Jp, *Rg, *tg, *vp, *pj, *Rsk, *mk, *rm, *Loc, *MtR, *obs, *py, *pq;
+    real *fullpose, *Rl, *dRl, *Jp, *Rg, *tg, *vp, *pj, *Rsk, *mk, *rm, *obs, *py, *pq;
     // Jacobian / normal equations
-    real *u, *dtg, *Jt, *Jf, *A, *Ld, *g, *Ag, *dsd, *dgn, *d, *tmp, *ds;
-    real *red, *sc;
-    int *colmap, *isc;
+    real *Loc, *MtR, *u, *dtg, *Jt, *Jf, *A, *Lm, *Linv, *g, *Ag, *dgn, *d, *tmp, *ds;
+    real *red, *sc, *hct;
+    int *colmap, *colsrc, *jlist, *isc;
     uint8_t *vis;
 };
 
 struct Dims {
-    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, npad, K, D, kw;
+    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, npad, K, D, D4, kw, jt_size;
 };
 
 template <class real>
 M2_HD Dims make_dims(const Model<real> &m) {
     Dims d;
     d.nJ = m.nJ; d.M = m.M; d.S = 3 * m.M; d.PF = 3 * m.nJ; d.PR = m.p_red; d.nd = m.nd;
-    d.NX = 3 + m.p_red + m.nd; d.NCt = d.PF + m.nd; d.n1 = m.n1; d.n2 = m.n2;
+    d.NX = 3 + m.p_red + m.nd; d.NCt = (d.PF + m.nd + 3) & ~3; d.n1 = m.n1; d.n2 = m.n2;
     d.npad = (m.n2 + 3) & ~3;
-    d.ld = d.npad | 1;          // odd leading dimension: conflict-free column walks of A / L
-    d.K = m.prior_k; d.D = m.prior_d; d.kw = m.kw;
+    d.ld = d.npad;              // rows are 16-byte aligned; every product walks rows (warp per row)
+    d.K = m.prior_k; d.D = m.prior_d; d.D4 = m.prior_d4; d.kw = m.kw;
+    const int a = 3 * kTileMarkers * d.NCt, b = kBlendGroups * 9 * m.M + 4;   // Jt doubles as the pose-blend partial sums
+    d.jt_size = a > b ? a : b;
     return d;
 }
 
@@ -250,26 +275,27 @@ struct Arena {
     }
 };
 
-// Lays the workspace out.  Arrays flagged "big" go to arena G when big_in_global is set (f64 runs of
-// large models), everything else to arena S (shared memory).  Returns the byte counts via the arenas.
+// Lays the workspace out.  Arrays flagged "big" go to arena G when big_in_global is set (f64 runs, large
+// models), everything else to arena S (shared memory).
 template <class real>
-M2_HD void carve(Work<real> &w, const Dims &d, Arena &S, Arena &G, bool big_in_global) {
+M2_HD void carve(Work<real> &w, const Dims &d, int hct_size, Arena &S, Arena &G, bool big_in_global) {
     Arena &B = big_in_global ? G : S;
     w.x = S.take<real>(d.NX); w.xt = S.take<real>(d.NX);
     w.pose_prev = S.take<real>(d.PR); w.velo_tgt = S.take<real>(d.PR); w.dm_tgt = S.take<real>(d.nd + 1);
     w.fullpose = S.take<real>(d.PF); w.Rl = S.take<real>(9 * d.nJ); w.dRl = S.take<real>(27 * d.nJ);
     w.Jp = S.take<real>(3 * d.nJ); w.Rg = S.take<real>(9 * d.nJ); w.tg = S.take<real>(3 * d.nJ);
     w.vp = S.take<real>(3 * d.S); w.pj = S.take<real>(3 * d.S * d.kw); w.Rsk = S.take<real>(9 * d.S);
-    w.mk = S.take<real>(3 * d.M); w.rm = S.take<real>(3 * d.M); w.Loc = S.take<real>(27 * d.M);
-    w.MtR = S.take<real>(9 * d.S); w.obs = S.take<real>(3 * d.M);
+    w.mk = S.take<real>(3 * d.M); w.rm = S.take<real>(3 * d.M); w.obs = S.take<real>(3 * d.M);
     w.py = S.take<real>(d.K * d.D + 1); w.pq = S.take<real>(d.K + 1);
+    w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
     w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
-    w.Jt = B.take<real>(3 * kTileMarkers * d.NCt); w.Jf = B.take<real>(3 * kTileMarkers * d.npad);
-    w.A = B.take<real>(size_t(d.n2) * d.ld);
-    w.Ld = S.take<real>(d.n2); w.g = S.take<real>(d.n2); w.Ag = S.take<real>(d.n2); w.dsd = S.take<real>(d.n2);
-    w.dgn = S.take<real>(d.n2); w.d = S.take<real>(d.n2); w.tmp = S.take<real>(d.n2); w.ds = S.take<real>(d.n2);
-    w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16);
-    w.colmap = S.take<int>(d.NX); w.isc = S.take<int>(8);
+    w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * kTileMarkers * d.npad);
+    w.A = B.take<real>(size_t(d.n2) * d.ld); w.Lm = B.take<real>(size_t(d.n2) * d.ld);
+    w.Linv = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
+    w.g = S.take<real>(d.npad); w.Ag = S.take<real>(d.npad); w.dgn = S.take<real>(d.npad);
+    w.d = S.take<real>(d.npad); w.tmp = S.take<real>(d.npad); w.ds = S.take<real>(d.npad);
+    w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16); w.hct = S.take<real>(hct_size + 4);
+    w.colmap = S.take<int>(d.NX); w.colsrc = S.take<int>(d.n2); w.jlist = S.take<int>(d.nJ); w.isc = S.take<int>(8);
     w.vis = S.take<uint8_t>(d.M);
 }
 
@@ -295,8 +321,8 @@ struct Solver {
     const Dims d;
     // per-frame scalars (identical in every thread)
     real wd, wp_frame, wH, wv, wdm, wex;
-    int nvis;
-    bool has_velo, has_extrap;
+    int nvis, njl;            // njl: joints whose full-pose columns the current step needs
+    bool has_velo, has_extrap, hand_free;
     // counters of the current frame
     int n_iter, n_eval, n_build, n_min, frame_flags;
 
@@ -305,33 +331,11 @@ struct Solver {
 
 #define CTA_FOR(i, n) for (int i = cta.tid; i < (n); i += cta.nthr)
 
-    // ---- forward evaluation at state xs; leaves SSE terms in w.sc[0..6], argmin component in w.isc[0]
-    M2_D void eval(const real *xs, const StepCfg<real> &c) {
-        ++n_eval;
-        const real *th = xs + 3;
-        const real *dl = xs + 3 + d.PR;
-        CTA_FOR(i, d.PF) {
-            real v;
-            if (i < m.body_dof) {
-                v = th[i];
-            } else {
-                const int cc = i - m.body_dof;
-                v = m.hands_mean[cc];
-                for (int r = 0; r < m.n_hand_red; ++r) v += th[m.body_dof + r] * m.hand_comps[r * m.n_hand_full + cc];
-            }
-            w.fullpose[i] = v;
-        }
-        CTA_FOR(i, 3 * d.nJ) {
-            real v = m.j0[i];
-            for (int q = 0; q < d.nd; ++q) v += m.jd[i * d.nd + q] * dl[q];
-            w.Jp[i] = v;
-        }
-        M2_SYNC();
-        CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + 27 * j);
-        M2_SYNC();
+    // ---- FK by depth level, executed by `nl` lanes (one warp on the GPU) starting at lane id `l`
+    M2_D void fk(int l, int nl) {
         for (int lv = 0; lv < m.n_levels; ++lv) {
             const int lo = m.level_ofs[lv], cnt = m.level_ofs[lv + 1] - lo;
-            CTA_FOR(q, cnt) {
+            for (int q = l; q < cnt; q += nl) {
                 const int j = m.fk_order[lo + q], a = m.parents[j];
                 if (a < 0) {
                     for (int i = 0; i < 9; ++i) w.Rg[9 * j + i] = w.Rl[9 * j + i];
@@ -344,24 +348,87 @@ struct Solver {
                     for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = w.tg[3 * a + i] + o[i];
                 }
             }
-            M2_SYNC();
+            M2_WSYNC();
         }
-        // pose-blended rest vertices of the 3M slots
-        const int rows = 3 * d.S;
-        CTA_FOR(row, rows) {
-            real acc = m.v0[row];
-            for (int q = 0; q < d.nd; ++q) acc += m.sd[row * d.nd + q] * dl[q];
-            const real *p = m.pd + size_t(row) * 9;
-            for (int j = 1; j < d.nJ; ++j, p += size_t(rows) * 9) {
+    }
+
+    // ---- pose-blend partial sums: item (joint group, slot) -> x,y,z of the slot; part[g][3 s + c] (aliases Jt).
+    //      Lanes run over consecutive slots, so every warp load is one contiguous run of 16-byte vectors.
+    M2_D void blend_partials(int l, int nl) {
+        const int per = (d.nJ - 1 + kBlendGroups - 1) / kBlendGroups;
+        const size_t estride = size_t(d.S) * kPdSlot;
+        for (int it = l; it < d.S * kBlendGroups; it += nl) {
+            const int g = it / d.S, s = it - g * d.S;
+            int j0 = 1 + g * per, j1 = j0 + per;
+            if (j1 > d.nJ) j1 = d.nJ;
+            real ax = 0, ay = 0, az = 0;
+            for (int j = j0; j < j1; ++j) {
+                const real *P = m.pd4 + size_t(j - 1) * 9 * estride + size_t(s) * kPdSlot;
                 const real *R = w.Rl + 9 * j;
-                acc += p[0] * (R[0] - real(1)) + p[1] * R[1] + p[2] * R[2] + p[3] * R[3] + p[4] * (R[4] - real(1)) +
-                       p[5] * R[5] + p[6] * R[6] + p[7] * R[7] + p[8] * (R[8] - real(1));
+                const real f[9] = {R[0] - real(1), R[1], R[2], R[3], R[4] - real(1), R[5], R[6], R[7], R[8] - real(1)};
+#pragma unroll
+                for (int e = 0; e < 9; ++e) {
+                    const Vec4<real> p = ld4(P + e * estride);
+                    ax += p.x * f[e]; ay += p.y * f[e]; az += p.z * f[e];
+                }
             }
-            w.vp[row] = acc;
+            real *o = w.Jt + (g * d.S + s) * 3;
+            o[0] = ax; o[1] = ay; o[2] = az;
+        }
+    }
+
+    // ---- forward evaluation at state xs; leaves SSE terms in w.sc[0..6], argmin component in w.isc[0]
+    M2_D void eval(const real *xs, const StepCfg<real> &c) {
+        ++n_eval;
+        const real *th = xs + 3;
+        const real *dl = xs + 3 + d.PR;
+        CTA_FOR(i, d.PF) {
+            real v;
+            if (i < m.body_dof) {
+                v = th[i];
+            } else {
+                const int q = i - m.body_dof;
+                v = m.hands_mean[q];
+                for (int b = 0; b < m.hb_n; ++b) {
+                    const HandBlock hb = m.hb[b];
+                    if (q >= hb.q0 && q < hb.q1) {
+                        const real *ct = w.hct + hb.ct_off + (q - hb.q0) * hb.rw4;
+                        for (int r = hb.r0; r < hb.r1; ++r) v += th[m.body_dof + r] * ct[r - hb.r0];
+                    }
+                }
+            }
+            w.fullpose[i] = v;
+        }
+        CTA_FOR(i, 3 * d.nJ) {
+            real v = m.j0[i];
+            for (int q = 0; q < d.nd; ++q) v += m.jd[i * d.nd + q] * dl[q];
+            w.Jp[i] = v;
         }
         M2_SYNC();
-        // skinning
+        CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + 27 * j);
+        M2_SYNC();
+#if M2_GPU
+        if (cta.nthr > 64) {                      // warp 0 walks the kinematic tree while the others blend
+            if (cta.tid < 32) fk(cta.tid, 32); else blend_partials(cta.tid - 32, cta.nthr - 32);
+        } else {
+            fk(cta.tid, cta.nthr); __syncthreads(); blend_partials(cta.tid, cta.nthr);
+        }
+#else
+        fk(0, 1);
+        blend_partials(0, 1);
+#endif
+        M2_SYNC();
+        // skinning of the 3M slots
         CTA_FOR(s, d.S) {
+            real vpo[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                real a = m.v0[3 * s + q];
+                for (int e = 0; e < d.nd; ++e) a += m.sd[(3 * s + q) * d.nd + e] * dl[e];
+#pragma unroll
+                for (int g = 0; g < kBlendGroups; ++g) a += w.Jt[(g * d.S + s) * 3 + q];
+                vpo[q] = a;
+            }
             real v[3] = {0, 0, 0};
             real Rs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int i = 0; i < d.kw; ++i) {
@@ -369,7 +436,7 @@ struct Solver {
                 real *pp = w.pj + 3 * (s * d.kw + i);
                 if (j < 0) { pp[0] = pp[1] = pp[2] = 0; continue; }
                 const real wt = m.w_val[s * d.kw + i];
-                real dv[3] = {w.vp[3 * s] - w.Jp[3 * j], w.vp[3 * s + 1] - w.Jp[3 * j + 1], w.vp[3 * s + 2] - w.Jp[3 * j + 2]};
+                real dv[3] = {vpo[0] - w.Jp[3 * j], vpo[1] - w.Jp[3 * j + 1], vpo[2] - w.Jp[3 * j + 2]};
                 real o[3];
                 mat3_vec(w.Rg + 9 * j, dv, o);
                 for (int q = 0; q < 3; ++q) {
@@ -378,24 +445,29 @@ struct Solver {
                 }
                 for (int q = 0; q < 9; ++q) Rs[q] += wt * w.Rg[9 * j + q];
             }
-            // skinned vertex is kept in vp's place (v_posed is not needed afterwards)
             for (int q = 0; q < 3; ++q) w.vp[3 * s + q] = v[q] + xs[q];
             for (int q = 0; q < 9; ++q) w.Rsk[9 * s + q] = Rs[q];
         }
         // max-mixture prior: y_k = Q_k (x - mu_k)
         if (c.wp > real(0)) {
-            const int D = d.D;
+            const int D = d.D, D4 = d.D4;
             CTA_FOR(idx, d.K * D) {
                 const int k = idx / D, i = idx - k * D;
-                const real *Q = m.prior_Q + (size_t(k) * D + i) * D;
+                const real *Q = m.prior_Q4 + (size_t(k) * D + i) * D4;
                 const real *mu = m.prior_means + k * D;
+                const real *xb = th + m.prior_off;
                 real s = 0;
-                for (int l = 0; l < D; ++l) s += Q[l] * (th[m.prior_off + l] - mu[l]);
+                int l = 0;
+                for (; l + 4 <= D; l += 4) {
+                    const Vec4<real> q = ld4(Q + l);
+                    s += q.x * (xb[l] - mu[l]) + q.y * (xb[l + 1] - mu[l + 1]) + q.z * (xb[l + 2] - mu[l + 2]) + q.w * (xb[l + 3] - mu[l + 3]);
+                }
+                for (; l < D; ++l) s += Q[l] * (xb[l] - mu[l]);
                 w.py[idx] = s;
             }
         }
         M2_SYNC();
-        // simulated markers, data residual, local Jacobians (transformed_lm.py:130-159)
+        // simulated markers and data residual (transformed_lm.py:130-159)
         CTA_FOR(mi, d.M) {
             const real *v0 = w.vp + 9 * mi, *v1 = v0 + 3, *v2 = v0 + 6;
             real e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
@@ -414,34 +486,6 @@ struct Solver {
                 const real mk = v0[q] + k1 * f1[q] + k2 * f2[q] + k3 * f3[q];
                 w.mk[3 * mi + q] = mk;
                 w.rm[3 * mi + q] = vis ? (mk - w.obs[3 * mi + q]) * wd : real(0);
-            }
-            // d marker / d(e1, e2):  N(u) = (I - uh uh^T)/|u|
-            real N1[9], Nn[9];
-            for (int r = 0; r < 3; ++r)
-                for (int q = 0; q < 3; ++q) {
-                    N1[3 * r + q] = ((r == q ? real(1) : real(0)) - f1[r] * f1[q]) / n1;
-                    Nn[3 * r + q] = ((r == q ? real(1) : real(0)) - f2[r] * f2[q]) / n2;
-                }
-            const real Se1[9] = {0, -e1[2], e1[1], e1[2], 0, -e1[0], -e1[1], e1[0], 0};
-            const real Se2[9] = {0, -e2[2], e2[1], e2[2], 0, -e2[0], -e2[1], e2[0], 0};
-            const real Sf1[9] = {0, -f1[2], f1[1], f1[2], 0, -f1[0], -f1[1], f1[0], 0};
-            const real Sf2[9] = {0, -f2[2], f2[1], f2[2], 0, -f2[0], -f2[1], f2[0], 0};
-            real df2e1[9], df2e2[9], t1[9], t2[9], df3e1[9], df3e2[9];
-            mat3_mul(Nn, Se2, df2e1);                       // d f2/d e1 = N(n) (-[e2]x)
-            for (int q = 0; q < 9; ++q) df2e1[q] = -df2e1[q];
-            mat3_mul(Nn, Se1, df2e2);                       // d f2/d e2 = N(n) [e1]x
-            mat3_mul(Sf2, N1, t1);                          // d f3/d e1 = -[f2]x N1 + [f1]x df2e1
-            mat3_mul(Sf1, df2e1, t2);
-            for (int q = 0; q < 9; ++q) df3e1[q] = t2[q] - t1[q];
-            mat3_mul(Sf1, df2e2, df3e2);
-            real *L = w.Loc + 27 * mi;
-            for (int q = 0; q < 9; ++q) {
-                const real de1 = k1 * N1[q] + k2 * df2e1[q] + k3 * df3e1[q];
-                const real de2 = k2 * df2e2[q] + k3 * df3e2[q];
-                const real id = (q == 0 || q == 4 || q == 8) ? real(1) : real(0);
-                L[q] = id - de1 - de2;
-                L[9 + q] = de1;
-                L[18 + q] = de2;
             }
         }
         if (c.wp > real(0)) {
@@ -479,7 +523,93 @@ struct Solver {
         M2_SYNC();
     }
 
-    // ---- normal equations at the state of the latest eval():  A (upper) = J^T J, g = -J^T r
+    // ---- local 3x9 Jacobian of a marker wrt its three (skinned) vertices, at the latest eval()
+    M2_D void marker_local_jacobian(int mi) {
+        const real *v0 = w.vp + 9 * mi, *v1 = v0 + 3, *v2 = v0 + 6;
+        real e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
+        real e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+        const real n1 = r_sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+        real f1[3] = {e1[0] / n1, e1[1] / n1, e1[2] / n1};
+        real nn[3];
+        cross3(e1, e2, nn);
+        const real n2 = r_sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+        real f2[3] = {nn[0] / n2, nn[1] / n2, nn[2] / n2};
+        const real k1 = m.coefs[3 * mi], k2 = m.coefs[3 * mi + 1], k3 = m.coefs[3 * mi + 2];
+        // d marker / d(e1, e2):  N(u) = (I - uh uh^T)/|u|
+        real N1[9], Nn[9];
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) {
+                N1[3 * r + q] = ((r == q ? real(1) : real(0)) - f1[r] * f1[q]) / n1;
+                Nn[3 * r + q] = ((r == q ? real(1) : real(0)) - f2[r] * f2[q]) / n2;
+            }
+        const real Se1[9] = {0, -e1[2], e1[1], e1[2], 0, -e1[0], -e1[1], e1[0], 0};
+        const real Se2[9] = {0, -e2[2], e2[1], e2[2], 0, -e2[0], -e2[1], e2[0], 0};
+        const real Sf1[9] = {0, -f1[2], f1[1], f1[2], 0, -f1[0], -f1[1], f1[0], 0};
+        const real Sf2[9] = {0, -f2[2], f2[1], f2[2], 0, -f2[0], -f2[1], f2[0], 0};
+        real df2e1[9], df2e2[9], t1[9], t2[9], df3e1[9], df3e2[9];
+        mat3_mul(Nn, Se2, df2e1);                       // d f2/d e1 = N(n) (-[e2]x)
+        for (int q = 0; q < 9; ++q) df2e1[q] = -df2e1[q];
+        mat3_mul(Nn, Se1, df2e2);                       // d f2/d e2 = N(n) [e1]x
+        mat3_mul(Sf2, N1, t1);                          // d f3/d e1 = -[f2]x N1 + [f1]x df2e1
+        mat3_mul(Sf1, df2e1, t2);
+        for (int q = 0; q < 9; ++q) df3e1[q] = t2[q] - t1[q];
+        mat3_mul(Sf1, df2e2, df3e2);
+        real *L = w.Loc + 27 * mi;
+        for (int q = 0; q < 9; ++q) {
+            const real de1 = k1 * N1[q] + k2 * df2e1[q] + k3 * df3e1[q];
+            const real de2 = k2 * df2e2[q] + k3 * df3e2[q];
+            const real id = (q == 0 || q == 4 || q == 8) ? real(1) : real(0);
+            L[q] = id - de1 - de2;
+            L[9 + q] = de1;
+            L[18 + q] = de2;
+        }
+    }
+
+    // ---- contribution of slot (marker mi, vertex t) to the 3x3 Jacobian block of joint a:  blk[r*3+k] +=
+    M2_D void t1_partial(int mi, int a, int t, real *blk) {
+        const int s = 3 * mi + t;
+        if (a >= 1) {
+            const size_t estride = size_t(d.S) * kPdSlot;
+            const real *P = m.pd4 + size_t(a - 1) * 9 * estride + size_t(s) * kPdSlot;
+            const real *dR = w.dRl + 27 * a;
+            real E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // E[c*3+k] = sum_e Pd[c][e] dR_k[e]
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                const Vec4<real> p = ld4(P + e * estride);
+                const real q0 = dR[e], q1 = dR[9 + e], q2 = dR[18 + e];
+                E[0] += p.x * q0; E[1] += p.x * q1; E[2] += p.x * q2;
+                E[3] += p.y * q0; E[4] += p.y * q1; E[5] += p.y * q2;
+                E[6] += p.z * q0; E[7] += p.z * q1; E[8] += p.z * q2;
+            }
+            const real *Mt = w.MtR + 9 * s;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    blk[3 * r + k] += Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
+        }
+        const int ai = m.anc_pos[s * d.nJ + a];
+        if (ai >= 0) {
+            const int mask = m.anc_mask[s * m.na + ai];
+            real q[3] = {0, 0, 0};
+            for (int i = 0; i < d.kw; ++i)
+                if ((mask >> i) & 1) {
+                    const real wt = m.w_val[s * d.kw + i];
+                    const real *pp = w.pj + 3 * (s * d.kw + i);
+                    for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
+                }
+            const real *L = w.Loc + 27 * mi + 9 * t;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                real cr[3];
+                cross3(w.u + 3 * (3 * a + k), q, cr);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
+            }
+        }
+    }
+
+    // ---- normal equations at the state of the latest eval():  A = J^T J (full symmetric), g = -J^T r
     M2_D void build(const real *xs, const StepCfg<real> &c) {
         ++n_build;
         const real *th = xs + 3;
@@ -488,8 +618,7 @@ struct Solver {
         CTA_FOR(idx, 3 * d.nJ) {
             const int a = idx / 3, k = idx - 3 * a;
             const real *D = w.dRl + 27 * a + 9 * k, *R = w.Rl + 9 * a;
-            // Om = dR R^T (skew); vee(Om) = (Om21, Om02, Om10)
-            real om[3];
+            real om[3];     // vee(dR R^T)
             om[0] = D[6] * R[3] + D[7] * R[4] + D[8] * R[5];
             om[1] = D[0] * R[6] + D[1] * R[7] + D[2] * R[8];
             om[2] = D[3] * R[0] + D[4] * R[1] + D[5] * R[2];
@@ -497,7 +626,7 @@ struct Solver {
             if (par < 0) { for (int q = 0; q < 3; ++q) w.u[3 * idx + q] = om[q]; }
             else mat3_vec(w.Rg + 9 * par, om, w.u + 3 * idx);
         }
-        CTA_FOR(s, d.S) mat3_mul(w.Loc + 27 * (s / 3) + 9 * (s % 3), w.Rsk + 9 * s, w.MtR + 9 * s);
+        CTA_FOR(mi, d.M) marker_local_jacobian(mi);
         CTA_FOR(i, n * ld) w.A[i] = 0;
         CTA_FOR(i, n) w.g[i] = 0;
         if (d.nd) {
@@ -519,53 +648,51 @@ struct Solver {
             }
         }
         M2_SYNC();
-        const int rows9 = 3 * d.S;
+        CTA_FOR(s, d.S) mat3_mul(w.Loc + 27 * (s / 3) + 9 * (s % 3), w.Rsk + 9 * s, w.MtR + 9 * s);
+        M2_SYNC();
         for (int t0 = 0; t0 < d.M; t0 += kTileMarkers) {
             const int tm = (d.M - t0 < kTileMarkers) ? d.M - t0 : kTileMarkers;
-            // T1: full-pose Jacobian blocks of the tile's markers
-            CTA_FOR(it, tm * d.nJ) {
-                const int ml = it / d.nJ, a = it - ml * d.nJ, mi = t0 + ml;
-                real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // blk[r*3+k]
-                if (a >= 1) {
-                    const real *P = m.pd + (size_t(a - 1) * rows9 + 9 * mi) * 9;
-                    const real *dR = w.dRl + 27 * a;
-                    for (int t = 0; t < 3; ++t) {
-                        real E[9];
-                        for (int cc = 0; cc < 3; ++cc) {
-                            const real *p = P + (3 * t + cc) * 9;
-                            for (int k = 0; k < 3; ++k) {
-                                const real *q = dR + 9 * k;
-                                E[3 * cc + k] = p[0] * q[0] + p[1] * q[1] + p[2] * q[2] + p[3] * q[3] + p[4] * q[4] +
-                                                p[5] * q[5] + p[6] * q[6] + p[7] * q[7] + p[8] * q[8];
-                            }
-                        }
-                        const real *Mt = w.MtR + 9 * (3 * mi + t);
+            // T1: full-pose 3x3 Jacobian blocks (marker, joint) for the joints this step needs.  A block is the sum
+            // over the marker's three slots; on the GPU three adjacent lanes take one slot each (their pose-blend
+            // vectors are adjacent in memory) and are summed with two shuffles.
+            {
+                const int ngroups = tm * njl;
+#if M2_GPU
+                const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
+                const int t = lane % 3, grp = lane / 3;
+                for (int g0 = warp * 10; g0 < ngroups; g0 += nwarp * 10) {
+                    const int gi = g0 + grp;
+                    const bool valid = lane < 30 && gi < ngroups;
+                    real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    int ml = 0, a = 0;
+                    if (valid) {
+                        ml = gi % tm;
+                        a = w.jlist[gi / tm];
+                        t1_partial(t0 + ml, a, t, blk);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q)
+                        blk[q] += __shfl_down_sync(0xffffffffu, blk[q], 1) + __shfl_down_sync(0xffffffffu, blk[q], 2);
+                    if (valid && t == 0) {
+#pragma unroll
                         for (int r = 0; r < 3; ++r)
-                            for (int k = 0; k < 3; ++k)
-                                blk[3 * r + k] += Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
                     }
                 }
-                for (int t = 0; t < 3; ++t) {
-                    const int s = 3 * mi + t;
-                    const int ai = m.anc_pos[s * d.nJ + a];
-                    if (ai < 0) continue;
-                    const int mask = m.anc_mask[s * m.na + ai];
-                    real q[3] = {0, 0, 0};
-                    for (int i = 0; i < d.kw; ++i)
-                        if ((mask >> i) & 1) {
-                            const real wt = m.w_val[s * d.kw + i];
-                            const real *pp = w.pj + 3 * (s * d.kw + i);
-                            for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
-                        }
-                    const real *L = w.Loc + 27 * mi + 9 * t;
-                    for (int k = 0; k < 3; ++k) {
-                        real cr[3];
-                        cross3(w.u + 3 * (3 * a + k), q, cr);
-                        for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
+#else
+                for (int gi = 0; gi < ngroups; ++gi) {
+                    const int ml = gi % tm, a = w.jlist[gi / tm];
+                    real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int t = 0; t < 3; ++t) {
+                        real part[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                        t1_partial(t0 + ml, a, t, part);
+                        for (int q = 0; q < 9; ++q) blk[q] += part[q];
                     }
+                    for (int r = 0; r < 3; ++r)
+                        for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
                 }
-                for (int r = 0; r < 3; ++r)
-                    for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
+#endif
             }
             CTA_FOR(it, tm * d.nd) {
                 const int ml = it / d.nd, i = it - ml * d.nd, mi = t0 + ml;
@@ -588,45 +715,76 @@ struct Solver {
                 for (int r = 0; r < 3; ++r) w.Jt[(3 * ml + r) * d.NCt + d.PF + i] = val[r];
             }
             M2_SYNC();
-            // T2: chain through the hand PCA, keep the free columns, apply weight and visibility
+            // T2a: translation / body / DMPL columns: gather, weight, mask (hand columns are written by T2b)
             const int trows = 3 * tm;
             CTA_FOR(idx, trows * d.npad) {
                 const int row = idx / d.npad, cc = idx - row * d.npad;
                 real v = 0;
+                bool store = true;
                 if (cc < n) {
-                    const int fv = c.free[cc];
-                    const real *Jr = w.Jt + row * d.NCt;
-                    if (fv < 3) v = (row % 3 == fv) ? real(1) : real(0);
-                    else if (fv < 3 + m.body_dof) v = Jr[fv - 3];
-                    else if (fv < 3 + d.PR) {
-                        const int r = fv - 3 - m.body_dof;
-                        const real *C = m.hand_comps + r * m.n_hand_full;
-                        for (int q = m.hand_lo[r]; q < m.hand_hi[r]; ++q) v += Jr[m.body_dof + q] * C[q];
-                    } else v = Jr[d.PF + (fv - 3 - d.PR)];
+                    const int src = w.colsrc[cc];
+                    if (src >= 0) v = w.Jt[row * d.NCt + src];
+                    else if (src >= -3) v = (row % 3 == -1 - src) ? real(1) : real(0);
+                    else store = false;
                     v *= (w.vis[t0 + row / 3] ? wd : real(0));
                 }
-                w.Jf[row * d.npad + cc] = v;
+                if (store) w.Jf[row * d.npad + cc] = v;
+            }
+            // T2b: hand columns = Jt[:, hand block] * C^T as a register-tiled product (1 row x 4 outputs)
+            if (hand_free) {
+                for (int b = 0; b < m.hb_n; ++b) {
+                    const HandBlock hb = m.hb[b];
+                    const int nq = hb.q1 - hb.q0, ng = hb.rw4 / 4;
+                    CTA_FOR(it, trows * ng) {
+                        const int row = it / ng, rg = it - row * ng;
+                        const real *Jr = w.Jt + row * d.NCt + m.body_dof + hb.q0;
+                        const real *ct = w.hct + hb.ct_off + 4 * rg;
+                        real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                        for (int q = 0; q < nq; ++q) {
+                            const real jv = Jr[q];
+                            const Vec4<real> cv = ld4(ct + q * hb.rw4);
+                            a0 += jv * cv.x; a1 += jv * cv.y; a2 += jv * cv.z; a3 += jv * cv.w;
+                        }
+                        const real sc = w.vis[t0 + row / 3] ? wd : real(0);
+                        const real out[4] = {a0 * sc, a1 * sc, a2 * sc, a3 * sc};
+                        for (int e = 0; e < 4; ++e) {
+                            const int r = hb.r0 + 4 * rg + e;
+                            if (r < hb.r1) {
+                                const int col = w.colmap[3 + m.body_dof + r];
+                                if (col >= 0) w.Jf[row * d.npad + col] = out[e];
+                            }
+                        }
+                    }
+                }
             }
             M2_SYNC();
-            // T3: A += Jf^T Jf (upper blocks), g -= Jf^T r
+            // T3: A += Jf^T Jf (upper 4x4 blocks), g -= Jf^T r
             const int nb = (n + kBS - 1) / kBS, nblk = nb * (nb + 1) / 2;
             CTA_FOR(b, nblk) {
                 int bi = 0, rem = b;
                 while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
                 const int bj = bi + rem;
                 real acc[kBS * kBS];
+#pragma unroll
                 for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
                 for (int row = 0; row < trows; ++row) {
                     const real *Jr = w.Jf + row * d.npad;
-                    real ai[kBS], bjv[kBS];
-                    for (int q = 0; q < kBS; ++q) { ai[q] = Jr[bi * kBS + q]; bjv[q] = Jr[bj * kBS + q]; }
+                    const Vec4<real> av = ld4(Jr + bi * kBS), bv = ld4(Jr + bj * kBS);
+                    const real ai[4] = {av.x, av.y, av.z, av.w}, bjv[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
                     for (int p = 0; p < kBS; ++p)
+#pragma unroll
                         for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bjv[q];
                 }
+#pragma unroll
                 for (int p = 0; p < kBS; ++p)
+#pragma unroll
                     for (int q = 0; q < kBS; ++q) {
                         const int i = bi * kBS + p, j = bj * kBS + q;
-                        if (i < n && j < n && i <= j) w.A[i * ld + j] += acc[p * kBS + q];
+                        if (j < n && i <= j) {
+                            w.A[i * ld + j] += acc[p * kBS + q];
+                            if (i < j) w.A[j * ld + i] += acc[p * kBS + q];
+                        }
                     }
             }
             CTA_FOR(cc, n) {
@@ -640,11 +798,11 @@ struct Solver {
         if (c.wp > real(0)) {
             const int D = d.D, ks = w.isc[0];
             const real w2 = c.wp * c.wp;
-            const real *Q = m.prior_Q + size_t(ks) * D * D;
+            const real *Q = m.prior_Q4 + size_t(ks) * D * d.D4;
             CTA_FOR(idx, D * D) {
                 const int i = idx / D, l = idx - i * D;
                 const int ci = w.colmap[3 + m.prior_off + i], cl = w.colmap[3 + m.prior_off + l];
-                if (ci >= 0 && cl >= 0 && ci <= cl) w.A[ci * ld + cl] += w2 * Q[idx];
+                if (ci >= 0 && cl >= 0) w.A[ci * ld + cl] += w2 * Q[i * d.D4 + l];
             }
             CTA_FOR(i, D) {
                 const int ci = w.colmap[3 + m.prior_off + i];
@@ -671,82 +829,178 @@ struct Solver {
         M2_SYNC();
     }
 
-    M2_D real Asym(int i, int j) const { return i <= j ? w.A[i * d.ld + j] : w.A[j * d.ld + i]; }
-
-    // out = A v  (A symmetric, upper stored)
+    // out = A v for the full symmetric A: one warp per row, lanes along the row
     M2_D void symv(const real *v, real *out, int n) {
-        CTA_FOR(i, n) {
+#if M2_GPU
+        const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
+        for (int i = warp; i < n; i += nwarp) {
+            const real *Ar = w.A + i * d.ld;
             real s = 0;
-            for (int j = 0; j < i; ++j) s += w.A[j * d.ld + i] * v[j];
-            for (int j = i; j < n; ++j) s += w.A[i * d.ld + j] * v[j];
+            for (int j = lane; j < n; j += 32) s += Ar[j] * v[j];
+            s = warp_sum(s);
+            if (lane == 0) out[i] = s;
+        }
+        __syncthreads();
+#else
+        for (int i = 0; i < n; ++i) {
+            real s = 0;
+            for (int j = 0; j < n; ++j) s += w.A[i * d.ld + j] * v[j];
             out[i] = s;
         }
-        M2_SYNC();
+#endif
     }
 
-    // Gauss-Newton step dgn = A^-1 g by Jacobi-scaled Cholesky; the factor lives in the strict lower
-    // triangle of w.A, its diagonal in w.Ld.  Returns false if A is not numerically positive definite.
+    // Gauss-Newton step dgn = A^-1 g by a Jacobi-scaled, blocked right-looking Cholesky in w.Lm (lower
+    // triangle incl. diagonal).  One lane factors each 8x8 diagonal block and also inverts it; the panel and
+    // both triangular solves then use the explicit block inverses (plain dot products, no divides and no
+    // dependent chains).  Returns false if A is not numerically positive definite.
     M2_D bool gauss_newton(int n) {
         const int ld = d.ld;
+        constexpr int NB = kCholNB;
         CTA_FOR(i, n) {
             const real a = w.A[i * ld + i];
             w.ds[i] = (a > real(0)) ? real(1) / r_sqrt(a) : real(0);
-            w.Ld[i] = (a > real(0)) ? real(1) : real(-1);
         }
+        if (cta.tid == 0) w.isc[3] = 1;
         M2_SYNC();
-        const int TX = cta.nthr >= 256 ? 16 : (cta.nthr >= 16 ? 4 : 1);
-        const int TY = cta.nthr / TX, tx = cta.tid % TX, ty = cta.tid / TX;
-        for (int i = 1 + ty; i < n; i += TY)
-            for (int j = tx; j < i; j += TX) w.A[i * ld + j] = w.A[j * ld + i] * w.ds[i] * w.ds[j];
+#if M2_GPU
+        {
+            const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
+            for (int i = warp; i < n; i += nwarp)
+                for (int j = lane; j <= i; j += 32) w.Lm[i * ld + j] = w.A[i * ld + j] * w.ds[i] * w.ds[j];
+        }
+#else
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j <= i; ++j) w.Lm[i * ld + j] = w.A[i * ld + j] * w.ds[i] * w.ds[j];
+#endif
         M2_SYNC();
-        bool ok = true;
-        for (int k = 0; k < n; ++k) {
-            const real piv = w.Ld[k];
-            if (!(piv > pivot_eps<real>())) { ok = false; break; }      // uniform: every thread reads the same value
-            const real sq = r_sqrt(piv), inv = real(1) / sq;
-            CTA_FOR(i, n - k - 1) w.A[(k + 1 + i) * ld + k] *= inv;
-            M2_SYNC();
-            if (cta.tid == 0) w.Ld[k] = sq;
-            for (int i = k + 1 + ty; i < n; i += TY) {
-                const real lik = w.A[i * ld + k];
-                for (int j = k + 1 + tx; j <= i; j += TX) {
-                    const real v = lik * w.A[j * ld + k];
-                    if (j == i) w.Ld[i] -= v; else w.A[i * ld + j] -= v;
-                }
+        for (int k0 = 0; k0 < n; k0 += NB) {
+            const int kb = (n - k0 < NB) ? n - k0 : NB;
+            real *Li = w.Linv + (k0 / NB) * NB * NB;
+            if (cta.tid == 0) {
+                real Lk[NB * NB], id[NB];
+                bool ok = true;
+                for (int r = 0; r < kb; ++r)
+                    for (int cc = 0; cc <= r; ++cc) {
+                        real sacc = w.Lm[(k0 + r) * ld + k0 + cc];
+                        for (int p = 0; p < cc; ++p) sacc -= Lk[r * NB + p] * Lk[cc * NB + p];
+                        if (cc == r) {
+                            if (!(sacc > pivot_eps<real>())) { ok = false; sacc = real(1); }
+                            const real sq = r_sqrt(sacc);
+                            Lk[r * NB + r] = sq;
+                            id[r] = real(1) / sq;
+                        } else Lk[r * NB + cc] = sacc * id[cc];
+                    }
+                // inverse of the lower-triangular block, column by column
+                for (int cc = 0; cc < kb; ++cc)
+                    for (int r = 0; r < kb; ++r) {
+                        real v = 0;
+                        if (r == cc) v = id[r];
+                        else if (r > cc) {
+                            real sacc = 0;
+                            for (int p = cc; p < r; ++p) sacc -= Lk[r * NB + p] * Li[p * NB + cc];
+                            v = sacc * id[r];
+                        }
+                        Li[r * NB + cc] = v;
+                    }
+                for (int r = 0; r < kb; ++r)
+                    for (int cc = 0; cc <= r; ++cc) w.Lm[(k0 + r) * ld + k0 + cc] = Lk[r * NB + cc];
+                if (!ok) w.isc[3] = 0;
             }
             M2_SYNC();
+            if (w.isc[3] == 0) return false;
+            // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p])
+            CTA_FOR(ii, n - k0 - kb) {
+                real *row = w.Lm + (k0 + kb + ii) * ld + k0;
+                real av[NB], xr[NB];
+                for (int cc = 0; cc < kb; ++cc) av[cc] = row[cc];
+                for (int cc = 0; cc < kb; ++cc) {
+                    real sacc = 0;
+                    for (int p = 0; p <= cc; ++p) sacc += av[p] * Li[cc * NB + p];
+                    xr[cc] = sacc;
+                }
+                for (int cc = 0; cc < kb; ++cc) row[cc] = xr[cc];
+            }
+            M2_SYNC();
+            // trailing update with 4x4 register tiles: Lm[i][j] -= sum_c Lm[i][k0+c] Lm[j][k0+c], j <= i
+            const int r0 = k0 + kb, R = n - r0;
+            if (R > 0) {
+                const int nt = (R + kBS - 1) / kBS;
+                CTA_FOR(it, nt * nt) {
+                    const int ti = it / nt, tj = it - ti * nt;
+                    if (tj > ti) continue;
+                    real acc[kBS * kBS];
+#pragma unroll
+                    for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
+                    for (int cc = 0; cc < kb; ++cc) {
+                        real ai[kBS], bj[kBS];
+#pragma unroll
+                        for (int p = 0; p < kBS; ++p) {
+                            const int i = r0 + ti * kBS + p, j = r0 + tj * kBS + p;
+                            ai[p] = i < n ? w.Lm[i * ld + k0 + cc] : real(0);
+                            bj[p] = j < n ? w.Lm[j * ld + k0 + cc] : real(0);
+                        }
+#pragma unroll
+                        for (int p = 0; p < kBS; ++p)
+#pragma unroll
+                            for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bj[q];
+                    }
+#pragma unroll
+                    for (int p = 0; p < kBS; ++p)
+#pragma unroll
+                        for (int q = 0; q < kBS; ++q) {
+                            const int i = r0 + ti * kBS + p, j = r0 + tj * kBS + q;
+                            if (i < n && j <= i) w.Lm[i * ld + j] -= acc[p * kBS + q];
+                        }
+                }
+                M2_SYNC();
+            }
         }
-        if (!ok) return false;
-        // solves by the first warp: L z = ds*g ; L^T y = z ; dgn = ds*y
+        // triangular solves by the first warp, block column by block column:  L z = ds*g ;  L^T y = z
         const int wl = cta.nthr < 32 ? cta.nthr : 32;
         if (cta.tid < wl) {
-            for (int i = cta.tid; i < n; i += wl) w.tmp[i] = w.g[i] * w.ds[i];
-#if M2_GPU
-            __syncwarp();
-#endif
-            for (int k = 0; k < n; ++k) {
-                const real zk = w.tmp[k] / w.Ld[k];
-#if M2_GPU
-                __syncwarp();
-#endif
-                if (cta.tid == 0) w.tmp[k] = zk;
-                for (int i = k + 1 + cta.tid; i < n; i += wl) w.tmp[i] -= w.A[i * ld + k] * zk;
-#if M2_GPU
-                __syncwarp();
-#endif
+            const int lane = cta.tid;
+            for (int i = lane; i < n; i += wl) w.tmp[i] = w.g[i] * w.ds[i];
+            M2_WSYNC();
+            for (int k0 = 0; k0 < n; k0 += NB) {
+                const int kb = (n - k0 < NB) ? n - k0 : NB;
+                const real *Li = w.Linv + (k0 / NB) * NB * NB;
+                real tv[NB], z[NB];
+                for (int cc = 0; cc < kb; ++cc) tv[cc] = w.tmp[k0 + cc];
+                for (int cc = 0; cc < kb; ++cc) {          // z = Linv t, every lane redundantly
+                    real sacc = 0;
+                    for (int p = 0; p <= cc; ++p) sacc += Li[cc * NB + p] * tv[p];
+                    z[cc] = sacc;
+                }
+                M2_WSYNC();
+                if (lane == 0) for (int cc = 0; cc < kb; ++cc) w.tmp[k0 + cc] = z[cc];
+                for (int i = k0 + kb + lane; i < n; i += wl) {
+                    real sacc = w.tmp[i];
+                    for (int cc = 0; cc < kb; ++cc) sacc -= w.Lm[i * ld + k0 + cc] * z[cc];
+                    w.tmp[i] = sacc;
+                }
+                M2_WSYNC();
             }
-            for (int k = n - 1; k >= 0; --k) {
-                const real yk = w.tmp[k] / w.Ld[k];
-#if M2_GPU
-                __syncwarp();
-#endif
-                if (cta.tid == 0) w.tmp[k] = yk;
-                for (int j = cta.tid; j < k; j += wl) w.tmp[j] -= w.A[k * ld + j] * yk;
-#if M2_GPU
-                __syncwarp();
-#endif
+            for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
+                const int kb = (n - k0 < NB) ? n - k0 : NB;
+                const real *Li = w.Linv + (k0 / NB) * NB * NB;
+                real sv[NB], y[NB];
+                for (int cc = 0; cc < kb; ++cc) sv[cc] = 0;
+                for (int i = k0 + kb + lane; i < n; i += wl) {
+                    const real yi = w.tmp[i];
+                    for (int cc = 0; cc < kb; ++cc) sv[cc] += w.Lm[i * ld + k0 + cc] * yi;
+                }
+                for (int cc = 0; cc < kb; ++cc) sv[cc] = w.tmp[k0 + cc] - warp_sum(sv[cc]);
+                for (int cc = 0; cc < kb; ++cc) {          // y = Linv^T s
+                    real sacc = 0;
+                    for (int p = cc; p < kb; ++p) sacc += Li[p * NB + cc] * sv[p];
+                    y[cc] = sacc;
+                }
+                M2_WSYNC();
+                if (lane == 0) for (int cc = 0; cc < kb; ++cc) w.tmp[k0 + cc] = y[cc];
+                M2_WSYNC();
             }
-            for (int i = cta.tid; i < n; i += wl) w.dgn[i] = w.tmp[i] * w.ds[i];
+            for (int i = lane; i < n; i += wl) w.dgn[i] = w.tmp[i] * w.ds[i];
         }
         M2_SYNC();
         return true;
@@ -758,9 +1012,38 @@ struct Solver {
         const int n = c.n;
         const real e1 = real(1e-15), e2 = real(1e-15);
         CTA_FOR(i, d.NX) w.colmap[i] = -1;
+        CTA_FOR(i, d.nJ) w.jlist[i] = 0;
         M2_SYNC();
-        CTA_FOR(i, n) w.colmap[c.free[i]] = i;
+        CTA_FOR(i, n) {
+            const int fv = c.free[i];
+            w.colmap[fv] = i;
+            int src;
+            if (fv < 3) src = -1 - fv;
+            else if (fv < 3 + m.body_dof) { src = fv - 3; w.jlist[(fv - 3) / 3] = 1; }
+            else if (fv < 3 + d.PR) src = -4;
+            else src = d.PF + (fv - 3 - d.PR);
+            w.colsrc[i] = src;
+        }
         M2_SYNC();
+        if (cta.tid == 0) {
+            // joints needed by this step: body joints with a free column, hand joints of blocks with a free row
+            int hf = 0;
+            for (int b = 0; b < m.hb_n; ++b) {
+                bool any = false;
+                for (int r = m.hb[b].r0; r < m.hb[b].r1; ++r) any = any || w.colmap[3 + m.body_dof + r] >= 0;
+                if (any) {
+                    hf = 1;
+                    for (int q = m.hb[b].q0; q < m.hb[b].q1; ++q) w.jlist[(m.body_dof + q) / 3] = 1;
+                }
+            }
+            int cnt = 0;
+            for (int j = 0; j < d.nJ; ++j) if (w.jlist[j]) w.jlist[cnt++] = j;
+            w.isc[1] = cnt;
+            w.isc[2] = hf;
+        }
+        M2_SYNC();
+        njl = w.isc[1];
+        hand_free = w.isc[2] != 0;
         eval(w.x, c);
         build(w.x, c);
         real sse0 = w.sc[0];
@@ -787,7 +1070,6 @@ struct Solver {
             bool have_gn = false, gn_ok = true;
             real ngn2 = 0, gn_sd = 0;      // |dgn|^2, dgn . dsd
             while (true) {
-                // ---- update_step
                 int kind;           // 0 stunted Cauchy, 1 Gauss-Newton, 2 blend
                 real beta = 0, scale_sd = 0;
                 if (nsd >= delta) { kind = 0; scale_sd = delta / nsd * alpha; }
@@ -925,7 +1207,6 @@ struct Solver {
             const double ang = 2 * atan2(vn, qw);
             double rv[3] = {0, 0, 0};
             if (vn > 1e-300) { rv[0] = qx / vn * ang; rv[1] = qy / vn * ang; rv[2] = qz / vn * ang; }
-            // R from the quaternion, T = b_mean - R a_mean
             const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
                                  2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
                                  2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
@@ -948,11 +1229,14 @@ struct Solver {
             f_end = f_emit + job.chunk_len; if (f_end > job.n_frames) f_end = job.n_frames;
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
+        CTA_FOR(i, m.hct_size) w.hct[i] = m.hct[i];
         M2_SYNC();
         bool first = true, have_prev = false, have_dm_prev = false;
         wv = real(o.wt_velo); wdm = real(o.wt_dmpl); wex = real(o.wt_extrap);
         const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd > 0;
         const bool has_prior = d.K > 0;
+        njl = 0;
+        hand_free = false;
         for (int f = f_begin; f < f_end; ++f) {
             n_iter = n_eval = n_build = n_min = 0;
             frame_flags = 0;
@@ -981,12 +1265,12 @@ struct Solver {
             }
             StepCfg<real> c1;
             c1.free = m.free1; c1.n = m.n1; c1.velo = has_velo; c1.poseH = false; c1.dm_terms = false; c1.extrap = false;
+            int stage0 = 3;
             if (first) {
                 c1.wp = 0; c1.e3 = real(o.e3_first);
                 eval(w.x, c1);                                 // simulated markers at the current state
                 procrustes();                                  // chmosh.py:634
-                const real mult[3] = {10, 5, 1};
-                for (int s = 0; s < 3; ++s) { c1.wp = wp_frame * mult[s]; minimize(c1); }   // chmosh.py:637-653
+                stage0 = 0;
                 first = false;
             } else {
                 CTA_FOR(i, d.PR) w.pose_prev[i] = w.x[3 + i];                               // chmosh.py:656-659
@@ -994,13 +1278,23 @@ struct Solver {
                 if (dyn) { CTA_FOR(i, d.nd) w.dm_tgt[i] = w.x[3 + d.PR + i]; have_dm_prev = true; }
                 M2_SYNC();
             }
-            c1.wp = wp_frame; c1.e3 = real(o.e3);
-            minimize(c1);                                      // Step 1, chmosh.py:665-671
-            StepCfg<real> c2 = c1;
-            c2.free = m.free2; c2.n = m.n2; c2.poseH = fingers; c2.dm_terms = dyn;
             has_extrap = dyn && have_dm_prev;
-            c2.extrap = has_extrap;
-            minimize(c2);                                      // Step 2, chmosh.py:676-705
+            // stages 0..2: first-frame annealing (prior x10, x5, x1; e_3 = 1e-3), chmosh.py:637-653;
+            // stage 3: Step 1 (chmosh.py:665-671); stage 4: Step 2 (chmosh.py:676-705)
+            for (int stage = stage0; stage < 5; ++stage) {
+                StepCfg<real> c = c1;
+                if (stage < 3) {
+                    c.wp = wp_frame * (stage == 0 ? real(10) : (stage == 1 ? real(5) : real(1)));
+                    c.e3 = real(o.e3_first);
+                } else {
+                    c.wp = wp_frame;
+                    c.e3 = real(o.e3);
+                    if (stage == 4) {
+                        c.free = m.free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap;
+                    }
+                }
+                minimize(c);
+            }
             if (cta.tid == 0 && job.totals) {
 #if M2_GPU
                 atomicAdd(job.totals + 0, n_iter); atomicAdd(job.totals + 1, n_eval);
@@ -1010,6 +1304,9 @@ struct Solver {
 #endif
             }
             if (f >= f_emit) {
+                StepCfg<real> c2 = c1;
+                c2.wp = wp_frame; c2.e3 = real(o.e3);
+                c2.free = m.free2; c2.n = m.n2; c2.poseH = fingers; c2.dm_terms = dyn; c2.extrap = has_extrap;
                 eval(w.x, c2);                                 // per-term SSE and markers at the solution
                 CTA_FOR(i, d.PF) job.fullpose[size_t(f) * d.PF + i] = w.fullpose[i];
                 CTA_FOR(i, d.PR) job.pose[size_t(f) * d.PR + i] = w.x[3 + i];

@@ -1,0 +1,49 @@
+// mosh2_host.h -- host-side layout helpers shared by libmosh2.so and the test-only host build.
+#pragma once
+#include <vector>
+
+#include "mosh2_device.cuh"
+
+namespace mosh2_host {
+
+// Splits the hand-PCA matrix C (n_red x n_full, row-major) into dense blocks of consecutive rows that
+// share one non-zero column range (SMPL-H / SMPL-X: left and right hand; MANO: one block) and stores each
+// block transposed, rows padded to a multiple of four: hct[ct_off + (q-q0)*rw4 + (r-r0)] = C[r][q].
+// Falls back to a single dense block when the structure is irregular.
+inline int hand_blocks(const double *C, int n_red, int n_full, mosh2::HandBlock *out, std::vector<double> &hct) {
+    hct.clear();
+    if (n_red == 0) return 0;
+    std::vector<int> lo(n_red), hi(n_red);
+    for (int r = 0; r < n_red; ++r) {
+        int a = n_full, b = 0;
+        for (int c = 0; c < n_full; ++c)
+            if (C[size_t(r) * n_full + c] != 0.0) { if (c < a) a = c; b = c + 1; }
+        if (b <= a) { a = 0; b = 0; }
+        lo[r] = a; hi[r] = b;
+    }
+    int nb = 0;
+    bool regular = true;
+    for (int r = 0; r < n_red && regular;) {
+        int e = r + 1;
+        while (e < n_red && lo[e] == lo[r] && hi[e] == hi[r]) ++e;
+        if (nb == mosh2::kMaxHandBlocks) { regular = false; break; }
+        out[nb].r0 = r; out[nb].r1 = e; out[nb].q0 = lo[r]; out[nb].q1 = hi[r];
+        ++nb;
+        r = e;
+    }
+    for (int a = 0; a < nb && regular; ++a)          // column ranges of different blocks must not overlap
+        for (int b = a + 1; b < nb; ++b)
+            if (out[a].q0 < out[b].q1 && out[b].q0 < out[a].q1) regular = false;
+    if (!regular) { nb = 1; out[0].r0 = 0; out[0].r1 = n_red; out[0].q0 = 0; out[0].q1 = n_full; }
+    for (int b = 0; b < nb; ++b) {
+        mosh2::HandBlock &h = out[b];
+        h.rw4 = ((h.r1 - h.r0) + 3) & ~3;
+        h.ct_off = int(hct.size());
+        hct.resize(hct.size() + size_t(h.q1 - h.q0) * h.rw4, 0.0);
+        for (int q = h.q0; q < h.q1; ++q)
+            for (int r = h.r0; r < h.r1; ++r) hct[h.ct_off + size_t(q - h.q0) * h.rw4 + (r - h.r0)] = C[size_t(r) * n_full + q];
+    }
+    return nb;
+}
+
+}  // namespace mosh2_host

@@ -6,6 +6,7 @@
 #define MOSH2_EMU 1
 #include "../../include/mosh2.h"
 #include "../../moshpp_b200/csrc/mosh2_device.cuh"
+#include "../../moshpp_b200/csrc/mosh2_host.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -19,8 +20,9 @@ struct HostModel {
     std::vector<std::vector<char>> store;
     template <class T, class U>
     const T *up(const U *src, size_t n) {
-        store.emplace_back((n + 1) * sizeof(T));
-        T *p = reinterpret_cast<T *>(store.back().data());
+        store.emplace_back((n + 1) * sizeof(T) + 32);
+        char *raw = store.back().data();
+        T *p = reinterpret_cast<T *>(raw + ((32 - (reinterpret_cast<uintptr_t>(raw) & 31)) & 31));
         for (size_t i = 0; i < n; ++i) p[i] = static_cast<T>(src[i]);
         return p;
     }
@@ -37,27 +39,42 @@ struct HostModel {
         m.anc_joint = up<int>(d.anc_joint, S * d.na);
         m.anc_mask = up<int>(d.anc_mask, S * d.na);
         m.anc_pos = up<int8_t>(d.anc_pos, S * nJ);
-        std::vector<int> lo(d.n_hand_red, 0), hi(d.n_hand_red, 0);
-        for (int r = 0; r < d.n_hand_red; ++r) {
-            int a = d.n_hand_full, b = 0;
-            for (int c = 0; c < d.n_hand_full; ++c)
-                if (d.hand_comps[size_t(r) * d.n_hand_full + c] != 0.0) { if (c < a) a = c; b = c + 1; }
-            if (b <= a) a = b = 0;
-            lo[r] = a; hi[r] = b;
+        {
+            std::vector<double> hct;
+            mosh2::HandBlock blocks[mosh2::kMaxHandBlocks];
+            m.hb_n = mosh2_host::hand_blocks(d.hand_comps, d.n_hand_red, d.n_hand_full, blocks, hct);
+            for (int b = 0; b < m.hb_n; ++b) m.hb[b] = blocks[b];
+            m.hct_size = int(hct.size());
+            m.hct = up<real>(hct.data(), hct.size());
         }
-        m.hand_lo = up<int>(lo.data(), lo.size());
-        m.hand_hi = up<int>(hi.data(), hi.size());
-        m.hand_comps = up<real>(d.hand_comps, size_t(d.n_hand_red) * d.n_hand_full);
         m.hands_mean = up<real>(d.hands_mean, d.n_hand_full);
         m.v0 = up<real>(d.v0, S * 3);
         m.sd = up<real>(d.sd, S * 3 * nd);
-        m.pd = up<real>(d.pd, (nJ - 1) * S * 3 * 9);
+        {
+            // [(nJ-1)][9 e][3M slots][4]: x, y, z of a slot for one (joint, e) form one 16-byte vector
+            const size_t S3 = size_t(3) * d.n_markers;
+            std::vector<double> pd4((nJ - 1) * 9 * S3 * mosh2::kPdSlot, 0.0);
+            for (size_t j = 0; j + 1 < nJ; ++j)
+                for (size_t sl = 0; sl < S3; ++sl)
+                    for (int c = 0; c < 3; ++c)
+                        for (int e = 0; e < 9; ++e)
+                            pd4[((j * 9 + e) * S3 + sl) * mosh2::kPdSlot + c] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+            m.pd4 = up<real>(pd4.data(), pd4.size());
+        }
         m.w_val = up<real>(d.w_val, S * d.kw);
         m.j0 = up<real>(d.j0, nJ * 3);
         m.jd = up<real>(d.jd, nJ * 3 * nd);
         m.coefs = up<real>(d.coefs, size_t(d.n_markers) * 3);
         m.prior_means = up<real>(d.prior_means, size_t(d.prior_k) * d.prior_d);
-        m.prior_Q = up<real>(d.prior_Q, size_t(d.prior_k) * d.prior_d * d.prior_d);
+        {
+            const size_t K = d.prior_k, D = d.prior_d, D4 = (D + 3) & ~size_t(3);
+            m.prior_d4 = int(D4);
+            std::vector<double> q4(K * D * D4, 0.0);
+            for (size_t k = 0; k < K; ++k)
+                for (size_t i = 0; i < D; ++i)
+                    for (size_t l = 0; l < D; ++l) q4[(k * D + i) * D4 + l] = d.prior_Q[(k * D + i) * D + l];
+            m.prior_Q4 = up<real>(q4.data(), q4.size());
+        }
         m.prior_nlw = up<real>(d.prior_neglogw, d.prior_k);
         m.free1 = up<int>(d.free1, d.n_free1);
         m.free2 = up<int>(d.free2, d.n_free2);
@@ -95,12 +112,13 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     const mosh2::Dims d = mosh2::make_dims(hm.m);
     mosh2::Work<real> w;
     mosh2::Arena S0{nullptr, 0}, G0{nullptr, 0};
-    mosh2::carve(w, d, S0, G0, false);
-    std::vector<char> smem(S0.off + 64);
+    mosh2::carve(w, d, hm.m.hct_size, S0, G0, false);
+    std::vector<char> smem_raw(S0.off + 128);
+    char *smem_base = smem_raw.data() + ((32 - (reinterpret_cast<uintptr_t>(smem_raw.data()) & 31)) & 31);
     for (int c = 0; c < job.n_chunks; ++c) {
-        std::memset(smem.data(), 0, smem.size());
-        mosh2::Arena S{smem.data(), 0}, G{nullptr, 0};
-        mosh2::carve(w, d, S, G, false);
+        std::memset(smem_base, 0, S0.off + 64);
+        mosh2::Arena S{smem_base, 0}, G{nullptr, 0};
+        mosh2::carve(w, d, hm.m.hct_size, S, G, false);
         mosh2::Cta cta{0, 1};
         mosh2::Solver<real> s(hm.m, job, w, cta);
         s.run_chunk(c);
