@@ -241,7 +241,7 @@ struct Work {
     // forward scratch of the latest evaluation
     real *fullpose, *Rl, *dRl, *Jp, *Rg, *tg, *vp, *pj, *Rsk, *mk, *rm, *obs, *py, *pq;
     // Jacobian / normal equations
-    real *Loc, *MtR, *u, *dtg, *Jt, *Jf, *A, *Lm, *Linv, *g, *Ag, *dgn, *d, *tmp, *ds;
+    real *Loc, *MtR, *u, *dtg, *Jt, *Jf, *A, *Lm, *Linv, *Pn, *g, *Ag, *dgn, *d, *tmp, *ds;
     real *red, *sc, *hct;
     int *colmap, *colsrc, *jlist, *isc;
     uint8_t *vis;
@@ -292,6 +292,7 @@ M2_HD void carve(Work<real> &w, const Dims &d, int hct_size, Arena &S, Arena &G,
     w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * kTileMarkers * d.npad);
     w.A = B.take<real>(size_t(d.n2) * d.ld); w.Lm = B.take<real>(size_t(d.n2) * d.ld);
     w.Linv = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
+    w.Pn = S.take<real>(size_t(kCholNB) * d.npad);
     w.g = S.take<real>(d.npad); w.Ag = S.take<real>(d.npad); w.dgn = S.take<real>(d.npad);
     w.d = S.take<real>(d.npad); w.tmp = S.take<real>(d.npad); w.ds = S.take<real>(d.npad);
     w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16); w.hct = S.take<real>(hct_size + 4);
@@ -877,6 +878,49 @@ struct Solver {
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = (n - k0 < NB) ? n - k0 : NB;
             real *Li = w.Linv + (k0 / NB) * NB * NB;
+#if M2_GPU
+            if (cta.tid < 32) {
+                // warp 0: lane r holds row r of the diagonal block in registers; columns are finalised one by
+                // one with shuffles (no local memory, no divides besides one reciprocal per column)
+                const int lane = cta.tid;
+                const unsigned full = 0xffffffffu;
+                real a[NB], invd[NB], x[NB];
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc)
+                    a[cc] = (lane < kb && cc <= lane) ? w.Lm[(k0 + lane) * ld + k0 + cc] : ((cc == lane) ? real(1) : real(0));
+                bool ok = true;
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) {
+                    real v = a[cc];
+#pragma unroll
+                    for (int pp = 0; pp < cc; ++pp) v -= a[pp] * __shfl_sync(full, a[pp], cc);
+                    real piv = __shfl_sync(full, v, cc);
+                    if (!(piv > pivot_eps<real>())) { ok = false; piv = real(1); }
+                    const real sq = r_sqrt(piv), iv = real(1) / sq;
+                    invd[cc] = iv;
+                    a[cc] = (lane == cc) ? sq : ((lane > cc) ? v * iv : real(0));
+                }
+                // lane c computes column c of the inverse: x[r] = Linv[r][c]
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    real sacc = (r == lane) ? real(1) : real(0);
+#pragma unroll
+                    for (int pp = 0; pp < r; ++pp) {
+                        const real lrp = __shfl_sync(full, a[pp], r);
+                        if (pp >= lane) sacc -= lrp * x[pp];
+                    }
+                    x[r] = (r >= lane) ? sacc * invd[r] : real(0);
+                }
+                if (lane < kb) {
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) {
+                        if (cc <= lane) w.Lm[(k0 + lane) * ld + k0 + cc] = a[cc];
+                        if (cc < kb) Li[cc * NB + lane] = x[cc];
+                    }
+                }
+                if (!ok && lane == 0) w.isc[3] = 0;
+            }
+#else
             if (cta.tid == 0) {
                 real Lk[NB * NB], id[NB];
                 bool ok = true;
@@ -891,7 +935,6 @@ struct Solver {
                             id[r] = real(1) / sq;
                         } else Lk[r * NB + cc] = sacc * id[cc];
                     }
-                // inverse of the lower-triangular block, column by column
                 for (int cc = 0; cc < kb; ++cc)
                     for (int r = 0; r < kb; ++r) {
                         real v = 0;
@@ -907,51 +950,65 @@ struct Solver {
                     for (int cc = 0; cc <= r; ++cc) w.Lm[(k0 + r) * ld + k0 + cc] = Lk[r * NB + cc];
                 if (!ok) w.isc[3] = 0;
             }
+#endif
             M2_SYNC();
             if (w.isc[3] == 0) return false;
-            // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p])
-            CTA_FOR(ii, n - k0 - kb) {
-                real *row = w.Lm + (k0 + kb + ii) * ld + k0;
-                real av[NB], xr[NB];
-                for (int cc = 0; cc < kb; ++cc) av[cc] = row[cc];
-                for (int cc = 0; cc < kb; ++cc) {
-                    real sacc = 0;
-                    for (int p = 0; p <= cc; ++p) sacc += av[p] * Li[cc * NB + p];
-                    xr[cc] = sacc;
+            // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p]); the solved panel is
+            // also kept transposed (Pn[c][row]) so that the trailing update reads consecutive vectors
+            CTA_FOR(ii, d.npad - k0 - kb) {
+                const int i = k0 + kb + ii;
+                real xr[NB];
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) xr[cc] = 0;
+                if (i < n) {
+                    real *row = w.Lm + i * ld + k0;
+                    real av[NB];
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) av[cc] = cc < kb ? row[cc] : real(0);
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) {
+                        real sacc = 0;
+#pragma unroll
+                        for (int pp = 0; pp <= cc; ++pp) sacc += av[pp] * Li[cc * NB + pp];
+                        xr[cc] = cc < kb ? sacc : real(0);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) row[cc] = xr[cc];
                 }
-                for (int cc = 0; cc < kb; ++cc) row[cc] = xr[cc];
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.npad + i] = xr[cc];
             }
             M2_SYNC();
-            // trailing update with 4x4 register tiles: Lm[i][j] -= sum_c Lm[i][k0+c] Lm[j][k0+c], j <= i
+            // trailing update with 4x4 register tiles: Lm[i][j] -= sum_c Pn[c][i] Pn[c][j], tiles with tj <= ti
             const int r0 = k0 + kb, R = n - r0;
             if (R > 0) {
-                const int nt = (R + kBS - 1) / kBS;
-                CTA_FOR(it, nt * nt) {
-                    const int ti = it / nt, tj = it - ti * nt;
-                    if (tj > ti) continue;
+                const int nt = (R + kBS - 1) / kBS, ntri = nt * (nt + 1) / 2;
+                CTA_FOR(it, ntri) {
+                    int ti = 0, rem = it;
+                    while (rem > ti) { rem -= ti + 1; ++ti; }
+                    const int tj = rem;
                     real acc[kBS * kBS];
 #pragma unroll
                     for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
-                    for (int cc = 0; cc < kb; ++cc) {
-                        real ai[kBS], bj[kBS];
 #pragma unroll
-                        for (int p = 0; p < kBS; ++p) {
-                            const int i = r0 + ti * kBS + p, j = r0 + tj * kBS + p;
-                            ai[p] = i < n ? w.Lm[i * ld + k0 + cc] : real(0);
-                            bj[p] = j < n ? w.Lm[j * ld + k0 + cc] : real(0);
-                        }
+                    for (int cc = 0; cc < NB; ++cc) {
+                        const Vec4<real> av = ld4(w.Pn + cc * d.npad + r0 + ti * kBS), bv = ld4(w.Pn + cc * d.npad + r0 + tj * kBS);
+                        const real ai[4] = {av.x, av.y, av.z, av.w}, bj[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                         for (int p = 0; p < kBS; ++p)
 #pragma unroll
                             for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bj[q];
                     }
 #pragma unroll
-                    for (int p = 0; p < kBS; ++p)
-#pragma unroll
-                        for (int q = 0; q < kBS; ++q) {
-                            const int i = r0 + ti * kBS + p, j = r0 + tj * kBS + q;
-                            if (i < n && j <= i) w.Lm[i * ld + j] -= acc[p * kBS + q];
+                    for (int p = 0; p < kBS; ++p) {
+                        const int i = r0 + ti * kBS + p;
+                        if (i < n) {
+                            real *dst = w.Lm + i * ld + r0 + tj * kBS;
+                            Vec4<real> v = ld4(dst);
+                            v.x -= acc[p * kBS]; v.y -= acc[p * kBS + 1]; v.z -= acc[p * kBS + 2]; v.w -= acc[p * kBS + 3];
+                            *reinterpret_cast<Vec4<real> *>(dst) = v;
                         }
+                    }
                 }
                 M2_SYNC();
             }
