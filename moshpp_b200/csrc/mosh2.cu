@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -36,20 +37,26 @@ int fail(int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(MOSH2_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr size_t kMaxSmem = 227 * 1024;
+constexpr size_t kMaxSmem = 227 * 1024 - 1024;   // dynamic part; 1 KB is static (pointer table, dims)
 template <class real> constexpr int threads_for() { return sizeof(real) == 4 ? 512 : 256; }
 
 template <class real>
 __global__ void __launch_bounds__(threads_for<real>(), 1)
 mosh2_stageii_kernel(const mosh2::Model<real> m, const mosh2::Job<real> job, int big_in_global) {
     extern __shared__ __align__(16) unsigned char smem[];
-    mosh2::Work<real> w;
-    const mosh2::Dims d = mosh2::make_dims(m);
-    mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
-    mosh2::Arena G{job.gws ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
-    mosh2::carve(w, d, m.hct_size, S, G, big_in_global != 0);
+    // the workspace pointer table and the dimensions live in shared memory: one load instead of re-deriving
+    // offsets at every use (the 32 KB instruction cache makes code size a first-order cost)
+    __shared__ mosh2::Work<real> w;
+    __shared__ mosh2::Dims d;
+    if (threadIdx.x == 0) {
+        d = mosh2::make_dims(m);
+        mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
+        mosh2::Arena G{job.gws ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
+        mosh2::carve(w, d, m.hct_size, S, G, big_in_global != 0);
+    }
+    __syncthreads();
     mosh2::Cta c{int(threadIdx.x), int(blockDim.x)};
-    mosh2::Solver<real> s(m, job, w, c);
+    mosh2::Solver<real> s(m, job, w, d, c);
     s.run_chunk(blockIdx.x);
 }
 
@@ -161,6 +168,7 @@ struct mosh2_job {
     void *d_obs = nullptr, *d_out = nullptr, *d_gws = nullptr;
     uint8_t *d_vis = nullptr;
     int *d_status = nullptr, *d_counters = nullptr, *d_totals = nullptr;
+    long long *d_prof = nullptr;
     // pinned staging
     void *h_obs = nullptr, *h_out = nullptr;
     uint8_t *h_vis = nullptr;
@@ -181,31 +189,39 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     job.fullpose = out + j->o_fullpose; job.pose = out + j->o_pose; job.trans = out + j->o_trans;
     job.dmpls = j->model->n_dmpl ? out + j->o_dmpls : nullptr;
     job.markers_sim = out + j->o_mk; job.errs = out + j->o_errs;
-    job.status = j->d_status; job.counters = j->d_counters; job.totals = j->d_totals;
+    job.status = j->d_status; job.counters = j->d_counters; job.totals = j->d_totals; job.prof = j->d_prof;
     job.gws = static_cast<char *>(j->d_gws); job.gws_stride = j->gws_stride;
     job.opt = j->opt;
     CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
     CU(cudaEventRecord(j->ev0, j->stream));
-    mosh2_stageii_kernel<real><<<j->n_chunks, threads_for<real>(), j->smem, j->stream>>>(m, job, j->big_in_global);
+    int threads = threads_for<real>();
+    if (const char *e = getenv("MOSH2_DEV_THREADS")) {      // development aid: any multiple of 32 up to the launch bound
+        const int t = atoi(e);
+        if (t >= 32 && t <= threads && t % 32 == 0) threads = t;
+    }
+    mosh2_stageii_kernel<real><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job, j->big_in_global);
     CU(cudaGetLastError());
     CU(cudaEventRecord(j->ev1, j->stream));
     return 0;
 }
 
 template <class real>
-void plan_workspace(const mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) {
-    mosh2::Work<real> w;
-    const mosh2::Dims d = mosh2::make_dims(m);
-    mosh2::Arena S{nullptr, 0}, G{nullptr, 0};
-    mosh2::carve(w, d, m.hct_size, S, G, false);
-    *big = 0;
-    if (S.off > kMaxSmem) {
-        S.off = 0; G.off = 0;
-        mosh2::carve(w, d, m.hct_size, S, G, true);
-        *big = 1;
+void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) {
+    // largest Jacobian tile that still fits the shared-memory budget; the f64 / oversized case moves the
+    // big arrays to a per-CTA global workspace
+    const int tiles[2] = {16, 8};
+    for (int pass = 0; pass < 3; ++pass) {
+        m.tile_markers = pass < 2 ? tiles[pass] : 8;
+        const bool in_global = pass == 2;
+        mosh2::Work<real> w;
+        const mosh2::Dims d = mosh2::make_dims(m);
+        mosh2::Arena S{nullptr, 0}, G{nullptr, 0};
+        mosh2::carve(w, d, m.hct_size, S, G, in_global);
+        *big = in_global ? 1 : 0;
+        *smem = (S.off + 15) & ~size_t(15);
+        *gws = (G.off + 255) & ~size_t(255);
+        if (S.off <= kMaxSmem) return;
     }
-    *smem = (S.off + 15) & ~size_t(15);
-    *gws = (G.off + 255) & ~size_t(255);
 }
 
 }  // namespace
@@ -314,6 +330,7 @@ int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames,
     chk(cudaMalloc(&j->d_status, F * sizeof(int)));
     chk(cudaMalloc(&j->d_counters, F * 4 * sizeof(int)));
     chk(cudaMalloc(&j->d_totals, 4 * sizeof(int)));
+    chk(cudaMalloc(&j->d_prof, 32 * sizeof(long long)));
     if (j->gws_stride) chk(cudaMalloc(&j->d_gws, j->gws_stride * j->n_chunks));
     chk(cudaMallocHost(&j->h_obs, j->n_obs * j->esz));
     chk(cudaMallocHost(&j->h_out, j->n_out * j->esz));
@@ -350,6 +367,7 @@ int mosh2_job_launch(mosh2_job *j) {
     CU(cudaMemsetAsync(j->d_status, 0, size_t(j->n_frames) * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_counters, 0, size_t(j->n_frames) * 4 * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_totals, 0, 4 * sizeof(int), j->stream));
+    CU(cudaMemsetAsync(j->d_prof, 0, 32 * sizeof(long long), j->stream));
     if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
     return launch<float>(j, j->model->f32.m);
 }
@@ -369,6 +387,15 @@ int mosh2_job_kernel_ms(mosh2_job *j, float *ms) {
 }
 
 int mosh2_job_num_chunks(mosh2_job *j) { return j ? j->n_chunks : 0; }
+
+// development builds (-DMOSH2_PROFILE) only: 32 phase clock sums of the last launch; not part of mosh2.h
+int mosh2_dev_phase_clocks(mosh2_job *j, long long *out32) {
+    if (!j || !out32) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaStreamSynchronize(j->stream));
+    CU(cudaMemcpy(out32, j->d_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 int mosh2_job_totals(mosh2_job *j, int32_t *out4) {
     if (!j || !out4) return fail(MOSH2_E_INVALID, "null argument");
@@ -410,7 +437,7 @@ void mosh2_job_destroy(mosh2_job *j) {
     if (!j) return;
     cudaSetDevice(j->model->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
-    cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_gws);
+    cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_prof); cudaFree(j->d_gws);
     cudaFreeHost(j->h_obs); cudaFreeHost(j->h_out); cudaFreeHost(j->h_vis); cudaFreeHost(j->h_status); cudaFreeHost(j->h_counters);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);

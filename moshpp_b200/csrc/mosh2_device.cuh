@@ -23,15 +23,27 @@
 #if defined(__CUDACC__) && !defined(MOSH2_EMU)
 #define M2_HD __host__ __device__ __forceinline__
 #define M2_D __device__ __forceinline__
+#define M2_NOINLINE __device__ __noinline__
 #define M2_SYNC() __syncthreads()
 #define M2_WSYNC() __syncwarp()
 #define M2_GPU 1
 #else
 #define M2_HD inline
 #define M2_D inline
+#define M2_NOINLINE static inline
 #define M2_SYNC() ((void)0)
 #define M2_WSYNC() ((void)0)
 #define M2_GPU 0
+#endif
+
+// Optional phase timers (development builds only: -DMOSH2_PROFILE): thread 0 accumulates clock64() deltas
+// between barriers into Job::prof.  Compiled out of the product library.
+#if defined(MOSH2_PROFILE) && M2_GPU
+#define M2_T0() long long t_prev_ = clock64()
+#define M2_TACC(slot) do { if (cta.tid == 0) { const long long t_now_ = clock64(); w.prof[(slot) + prof_base] += t_now_ - t_prev_; t_prev_ = t_now_; } } while (0)
+#else
+#define M2_T0() ((void)0)
+#define M2_TACC(slot) ((void)0)
 #endif
 
 namespace mosh2 {
@@ -39,7 +51,7 @@ namespace mosh2 {
 enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32 };
 enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
 
-constexpr int kTileMarkers = 8;   // markers per Jacobian tile (24 rows)
+constexpr int kTileMarkersMax = 16;   // markers per Jacobian tile: 16 (48 rows) when shared memory allows, else 8
 constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
 constexpr int kPdSlot = 4;        // pose-blend rows of one slot (x, y, z, pad): one 16-byte vector per (joint, e)
 constexpr int kBlendGroups = 3;   // joint groups of the pose-blend partial sums
@@ -69,6 +81,7 @@ struct Model {
     int n1, n2;
     const int *free1, *free2;
     int finger_lo, finger_hi;
+    int tile_markers;           // markers per Jacobian tile (8 or 16), chosen by the host from the shared-memory budget
 };
 
 struct Options {
@@ -85,6 +98,7 @@ struct Job {
     real *fullpose, *pose, *trans, *dmpls, *markers_sim, *errs;
     int *status, *counters;
     int *totals;            // [4] iterations, evaluations, builds, minimisations over ALL processed frames (incl. warm-up)
+    long long *prof;        // [32] phase clock sums (MOSH2_PROFILE builds only, else unused)
     char *gws;              // optional per-CTA global workspace (f64 / large models)
     size_t gws_stride;
     Options opt;
@@ -120,11 +134,31 @@ template <class real> M2_HD real pivot_eps();          // smallest accepted pivo
 template <> M2_HD float pivot_eps<float>() { return 1e-6f; }
 template <> M2_HD double pivot_eps<double>() { return 1e-13; }
 
+// Acceptance slack of the dog-leg in units of the current SSE.  chumpy accepts a trial step iff the SSE decreases
+// (rho > 0).  In float64 that test is exact enough (slack 0: reference semantics).  In float32 the SSE of a
+// converged frame is only resolved to ~1e-6 relative, so the final tiny-improvement step that float64 accepts
+// (and then stops on, e_3) would be rejected at random and trigger a cascade of trust-region shrinks; a step whose
+// measured SSE change is within the slack is therefore treated like float64 would treat it: accepted, after
+// which the e_3 rule stops the minimisation.  DESIGN.md section 5.
+template <class real> M2_HD real accept_slack();
+template <> M2_HD float accept_slack<float>() { return 1e-5f; }
+template <> M2_HD double accept_slack<double>() { return 0.0; }
+
 template <class real> struct alignas(16) Vec4 { real x, y, z, w; };
 template <class real> M2_HD Vec4<real> ld4(const real *p) { return *reinterpret_cast<const Vec4<real> *>(p); }
 
 template <class real>
-M2_HD void mat3_mul(const real *A, const real *B, real *C) {   // C = A B (row-major 3x3)
+M2_NOINLINE void mat3_mul(const real *A, const real *B, real *C) {   // C = A B (row-major 3x3); C must not alias A or B
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        const real a0 = A[3 * i], a1 = A[3 * i + 1], a2 = A[3 * i + 2];
+        C[3 * i] = a0 * B[0] + a1 * B[3] + a2 * B[6];
+        C[3 * i + 1] = a0 * B[1] + a1 * B[4] + a2 * B[7];
+        C[3 * i + 2] = a0 * B[2] + a1 * B[5] + a2 * B[8];
+    }
+}
+template <class real>
+M2_HD void mat3_mul_reg(const real *A, const real *B, real *C) {   // inline variant for register arrays
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -145,7 +179,7 @@ M2_HD void cross3(const real *a, const real *b, real *o) {
 
 // R = exp([w]x) and dR[k] = dR/dw_k (cv2.Rodrigues convention), cancellation-free near 0.
 template <class real>
-M2_HD void rodrigues(const real *w, real *R, real *dR) {
+M2_NOINLINE void rodrigues(const real *w, real *R, real *dR) {
     const real x = w[0], y = w[1], z = w[2];
     const real t2 = x * x + y * y + z * z;
     real a, b, c1, c2;
@@ -173,7 +207,7 @@ M2_HD void rodrigues(const real *w, real *R, real *dR) {
     R[8] += real(1);
     if (!dR) return;
     // dR/dw_k = c1 w_k K + a E_k + c2 w_k K2 + b (E_k K + K E_k),   E_k K + K E_k = e_k w^T + w e_k^T - 2 w_k I
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 3; ++k) {
         const real wk = w[k];
         real *D = dR + 9 * k;
@@ -244,11 +278,12 @@ struct Work {
     real *Loc, *MtR, *u, *dtg, *Jt, *Jf, *A, *Lm, *Linv, *Pn, *g, *Ag, *dgn, *d, *tmp, *ds;
     real *red, *sc, *hct;
     int *colmap, *colsrc, *jlist, *isc;
+    long long *prof;
     uint8_t *vis;
 };
 
 struct Dims {
-    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, npad, K, D, D4, kw, jt_size;
+    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, lda, npad, K, D, D4, kw, jt_size, tmk;
 };
 
 template <class real>
@@ -257,9 +292,11 @@ M2_HD Dims make_dims(const Model<real> &m) {
     d.nJ = m.nJ; d.M = m.M; d.S = 3 * m.M; d.PF = 3 * m.nJ; d.PR = m.p_red; d.nd = m.nd;
     d.NX = 3 + m.p_red + m.nd; d.NCt = (d.PF + m.nd + 3) & ~3; d.n1 = m.n1; d.n2 = m.n2;
     d.npad = (m.n2 + 3) & ~3;
-    d.ld = d.npad;              // rows are 16-byte aligned; every product walks rows (warp per row)
+    d.ld = d.npad;              // Cholesky factor: rows are 16-byte aligned (vector read-modify-write of 4x4 tiles)
+    d.lda = d.npad | 1;         // A: odd leading dimension, so row-strided and transposed tile accesses spread over banks
     d.K = m.prior_k; d.D = m.prior_d; d.D4 = m.prior_d4; d.kw = m.kw;
-    const int a = 3 * kTileMarkers * d.NCt, b = kBlendGroups * 9 * m.M + 4;   // Jt doubles as the pose-blend partial sums
+    d.tmk = m.tile_markers > 0 ? m.tile_markers : 8;
+    const int a = 3 * d.tmk * d.NCt, b = kBlendGroups * 9 * m.M + 4;   // Jt doubles as the pose-blend partial sums
     d.jt_size = a > b ? a : b;
     return d;
 }
@@ -289,14 +326,15 @@ M2_HD void carve(Work<real> &w, const Dims &d, int hct_size, Arena &S, Arena &G,
     w.py = S.take<real>(d.K * d.D + 1); w.pq = S.take<real>(d.K + 1);
     w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
     w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
-    w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * kTileMarkers * d.npad);
-    w.A = B.take<real>(size_t(d.n2) * d.ld); w.Lm = B.take<real>(size_t(d.n2) * d.ld);
+    w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * d.tmk * d.npad);
+    w.A = B.take<real>(size_t(d.n2) * d.lda); w.Lm = B.take<real>(size_t(d.n2) * d.ld);
     w.Linv = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
     w.Pn = S.take<real>(size_t(kCholNB) * d.npad);
     w.g = S.take<real>(d.npad); w.Ag = S.take<real>(d.npad); w.dgn = S.take<real>(d.npad);
     w.d = S.take<real>(d.npad); w.tmp = S.take<real>(d.npad); w.ds = S.take<real>(d.npad);
     w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16); w.hct = S.take<real>(hct_size + 4);
     w.colmap = S.take<int>(d.NX); w.colsrc = S.take<int>(d.n2); w.jlist = S.take<int>(d.nJ); w.isc = S.take<int>(8);
+    w.prof = S.take<long long>(32);
     w.vis = S.take<uint8_t>(d.M);
 }
 
@@ -319,18 +357,19 @@ struct Solver {
     const Job<real> &job;
     Work<real> &w;
     const Cta cta;
-    const Dims d;
+    const Dims &d;
     // per-frame scalars (identical in every thread)
     real wd, wp_frame, wH, wv, wdm, wex;
     int nvis, njl;            // njl: joints whose full-pose columns the current step needs
     bool has_velo, has_extrap, hand_free;
     // counters of the current frame
     int n_iter, n_eval, n_build, n_min, frame_flags;
+    int prof_base = 0;        // development builds: offset of the phase-timer slots
 
-    M2_D Solver(const Model<real> &m_, const Job<real> &j_, Work<real> &w_, Cta c_)
-        : m(m_), job(j_), w(w_), cta(c_), d(make_dims(m_)) {}
+    M2_D Solver(const Model<real> &m_, const Job<real> &j_, Work<real> &w_, const Dims &d_, Cta c_)
+        : m(m_), job(j_), w(w_), cta(c_), d(d_) {}
 
-#define CTA_FOR(i, n) for (int i = cta.tid; i < (n); i += cta.nthr)
+#define CTA_FOR(i, n) _Pragma("unroll 1") for (int i = cta.tid; i < (n); i += cta.nthr)
 
     // ---- FK by depth level, executed by `nl` lanes (one warp on the GPU) starting at lane id `l`
     M2_D void fk(int l, int nl) {
@@ -381,6 +420,7 @@ struct Solver {
     // ---- forward evaluation at state xs; leaves SSE terms in w.sc[0..6], argmin component in w.isc[0]
     M2_D void eval(const real *xs, const StepCfg<real> &c) {
         ++n_eval;
+        M2_T0();
         const real *th = xs + 3;
         const real *dl = xs + 3 + d.PR;
         CTA_FOR(i, d.PF) {
@@ -406,8 +446,10 @@ struct Solver {
             w.Jp[i] = v;
         }
         M2_SYNC();
+        M2_TACC(0);
         CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + 27 * j);
         M2_SYNC();
+        M2_TACC(1);
 #if M2_GPU
         if (cta.nthr > 64) {                      // warp 0 walks the kinematic tree while the others blend
             if (cta.tid < 32) fk(cta.tid, 32); else blend_partials(cta.tid - 32, cta.nthr - 32);
@@ -419,6 +461,7 @@ struct Solver {
         blend_partials(0, 1);
 #endif
         M2_SYNC();
+        M2_TACC(2);
         // skinning of the 3M slots
         CTA_FOR(s, d.S) {
             real vpo[3];
@@ -468,6 +511,7 @@ struct Solver {
             }
         }
         M2_SYNC();
+        M2_TACC(3);
         // simulated markers and data residual (transformed_lm.py:130-159)
         CTA_FOR(mi, d.M) {
             const real *v0 = w.vp + 9 * mi, *v1 = v0 + 3, *v2 = v0 + 6;
@@ -498,6 +542,7 @@ struct Solver {
             }
         }
         M2_SYNC();
+        M2_TACC(4);
         real part[N_ERR] = {0, 0, 0, 0, 0, 0};
         CTA_FOR(i, 3 * d.M) part[ERR_DATA] += w.rm[i] * w.rm[i];
         if (c.velo) CTA_FOR(i, d.PR) { const real e = (th[i] - w.velo_tgt[i]) * wv; part[ERR_VELO] += e * e; }
@@ -522,6 +567,7 @@ struct Solver {
             w.sc[0] = tot;
         }
         M2_SYNC();
+        M2_TACC(5);
     }
 
     // ---- local 3x9 Jacobian of a marker wrt its three (skinned) vertices, at the latest eval()
@@ -548,13 +594,13 @@ struct Solver {
         const real Sf1[9] = {0, -f1[2], f1[1], f1[2], 0, -f1[0], -f1[1], f1[0], 0};
         const real Sf2[9] = {0, -f2[2], f2[1], f2[2], 0, -f2[0], -f2[1], f2[0], 0};
         real df2e1[9], df2e2[9], t1[9], t2[9], df3e1[9], df3e2[9];
-        mat3_mul(Nn, Se2, df2e1);                       // d f2/d e1 = N(n) (-[e2]x)
+        mat3_mul_reg(Nn, Se2, df2e1);                       // d f2/d e1 = N(n) (-[e2]x)
         for (int q = 0; q < 9; ++q) df2e1[q] = -df2e1[q];
-        mat3_mul(Nn, Se1, df2e2);                       // d f2/d e2 = N(n) [e1]x
-        mat3_mul(Sf2, N1, t1);                          // d f3/d e1 = -[f2]x N1 + [f1]x df2e1
-        mat3_mul(Sf1, df2e1, t2);
+        mat3_mul_reg(Nn, Se1, df2e2);                       // d f2/d e2 = N(n) [e1]x
+        mat3_mul_reg(Sf2, N1, t1);                          // d f3/d e1 = -[f2]x N1 + [f1]x df2e1
+        mat3_mul_reg(Sf1, df2e1, t2);
         for (int q = 0; q < 9; ++q) df3e1[q] = t2[q] - t1[q];
-        mat3_mul(Sf1, df2e2, df3e2);
+        mat3_mul_reg(Sf1, df2e2, df3e2);
         real *L = w.Loc + 27 * mi;
         for (int q = 0; q < 9; ++q) {
             const real de1 = k1 * N1[q] + k2 * df2e1[q] + k3 * df3e1[q];
@@ -613,9 +659,10 @@ struct Solver {
     // ---- normal equations at the state of the latest eval():  A = J^T J (full symmetric), g = -J^T r
     M2_D void build(const real *xs, const StepCfg<real> &c) {
         ++n_build;
+        M2_T0();
         const real *th = xs + 3;
         const real *dl = xs + 3 + d.PR;
-        const int n = c.n, ld = d.ld;
+        const int n = c.n, ld = d.lda;
         CTA_FOR(idx, 3 * d.nJ) {
             const int a = idx / 3, k = idx - 3 * a;
             const real *D = w.dRl + 27 * a + 9 * k, *R = w.Rl + 9 * a;
@@ -651,8 +698,9 @@ struct Solver {
         M2_SYNC();
         CTA_FOR(s, d.S) mat3_mul(w.Loc + 27 * (s / 3) + 9 * (s % 3), w.Rsk + 9 * s, w.MtR + 9 * s);
         M2_SYNC();
-        for (int t0 = 0; t0 < d.M; t0 += kTileMarkers) {
-            const int tm = (d.M - t0 < kTileMarkers) ? d.M - t0 : kTileMarkers;
+        M2_TACC(6);
+        for (int t0 = 0; t0 < d.M; t0 += d.tmk) {
+            const int tm = (d.M - t0 < d.tmk) ? d.M - t0 : d.tmk;
             // T1: full-pose 3x3 Jacobian blocks (marker, joint) for the joints this step needs.  A block is the sum
             // over the marker's three slots; on the GPU three adjacent lanes take one slot each (their pose-blend
             // vectors are adjacent in memory) and are summed with two shuffles.
@@ -716,6 +764,7 @@ struct Solver {
                 for (int r = 0; r < 3; ++r) w.Jt[(3 * ml + r) * d.NCt + d.PF + i] = val[r];
             }
             M2_SYNC();
+            M2_TACC(7);
             // T2a: translation / body / DMPL columns: gather, weight, mask (hand columns are written by T2b)
             const int trows = 3 * tm;
             CTA_FOR(idx, trows * d.npad) {
@@ -759,6 +808,7 @@ struct Solver {
                 }
             }
             M2_SYNC();
+            M2_TACC(8);
             // T3: A += Jf^T Jf (upper 4x4 blocks), g -= Jf^T r
             const int nb = (n + kBS - 1) / kBS, nblk = nb * (nb + 1) / 2;
             CTA_FOR(b, nblk) {
@@ -794,6 +844,7 @@ struct Solver {
                 w.g[cc] -= s;
             }
             M2_SYNC();
+            M2_TACC(9);
         }
         // closed-form terms
         if (c.wp > real(0)) {
@@ -828,6 +879,7 @@ struct Solver {
             w.g[cc] -= dg;
         }
         M2_SYNC();
+        M2_TACC(10);
     }
 
     // out = A v for the full symmetric A: one warp per row, lanes along the row
@@ -835,7 +887,7 @@ struct Solver {
 #if M2_GPU
         const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
         for (int i = warp; i < n; i += nwarp) {
-            const real *Ar = w.A + i * d.ld;
+            const real *Ar = w.A + i * d.lda;
             real s = 0;
             for (int j = lane; j < n; j += 32) s += Ar[j] * v[j];
             s = warp_sum(s);
@@ -845,7 +897,7 @@ struct Solver {
 #else
         for (int i = 0; i < n; ++i) {
             real s = 0;
-            for (int j = 0; j < n; ++j) s += w.A[i * d.ld + j] * v[j];
+            for (int j = 0; j < n; ++j) s += w.A[i * d.lda + j] * v[j];
             out[i] = s;
         }
 #endif
@@ -858,8 +910,9 @@ struct Solver {
     M2_D bool gauss_newton(int n) {
         const int ld = d.ld;
         constexpr int NB = kCholNB;
+        M2_T0();
         CTA_FOR(i, n) {
-            const real a = w.A[i * ld + i];
+            const real a = w.A[i * d.lda + i];
             w.ds[i] = (a > real(0)) ? real(1) / r_sqrt(a) : real(0);
         }
         if (cta.tid == 0) w.isc[3] = 1;
@@ -868,13 +921,14 @@ struct Solver {
         {
             const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
             for (int i = warp; i < n; i += nwarp)
-                for (int j = lane; j <= i; j += 32) w.Lm[i * ld + j] = w.A[i * ld + j] * w.ds[i] * w.ds[j];
+                for (int j = lane; j <= i; j += 32) w.Lm[i * ld + j] = w.A[i * d.lda + j] * w.ds[i] * w.ds[j];
         }
 #else
         for (int i = 0; i < n; ++i)
-            for (int j = 0; j <= i; ++j) w.Lm[i * ld + j] = w.A[i * ld + j] * w.ds[i] * w.ds[j];
+            for (int j = 0; j <= i; ++j) w.Lm[i * ld + j] = w.A[i * d.lda + j] * w.ds[i] * w.ds[j];
 #endif
         M2_SYNC();
+        M2_TACC(11);
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = (n - k0 < NB) ? n - k0 : NB;
             real *Li = w.Linv + (k0 / NB) * NB * NB;
@@ -911,11 +965,11 @@ struct Solver {
                     }
                     x[r] = (r >= lane) ? sacc * invd[r] : real(0);
                 }
-                if (lane < kb) {
+                if (lane < NB) {
 #pragma unroll
                     for (int cc = 0; cc < NB; ++cc) {
-                        if (cc <= lane) w.Lm[(k0 + lane) * ld + k0 + cc] = a[cc];
-                        if (cc < kb) Li[cc * NB + lane] = x[cc];
+                        if (lane < kb && cc <= lane) w.Lm[(k0 + lane) * ld + k0 + cc] = a[cc];
+                        Li[cc * NB + lane] = x[cc];       // rows/columns >= kb hold identity padding
                     }
                 }
                 if (!ok && lane == 0) w.isc[3] = 0;
@@ -948,10 +1002,14 @@ struct Solver {
                     }
                 for (int r = 0; r < kb; ++r)
                     for (int cc = 0; cc <= r; ++cc) w.Lm[(k0 + r) * ld + k0 + cc] = Lk[r * NB + cc];
+                for (int r = 0; r < NB; ++r)
+                    for (int cc = 0; cc < NB; ++cc)
+                        if (r >= kb || cc >= kb) Li[r * NB + cc] = (r == cc) ? real(1) : real(0);
                 if (!ok) w.isc[3] = 0;
             }
 #endif
             M2_SYNC();
+            M2_TACC(12);
             if (w.isc[3] == 0) return false;
             // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p]); the solved panel is
             // also kept transposed (Pn[c][row]) so that the trailing update reads consecutive vectors
@@ -979,6 +1037,7 @@ struct Solver {
                 for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.npad + i] = xr[cc];
             }
             M2_SYNC();
+            M2_TACC(13);
             // trailing update with 4x4 register tiles: Lm[i][j] -= sum_c Pn[c][i] Pn[c][j], tiles with tj <= ti
             const int r0 = k0 + kb, R = n - r0;
             if (R > 0) {
@@ -1011,9 +1070,11 @@ struct Solver {
                     }
                 }
                 M2_SYNC();
+                M2_TACC(14);
             }
         }
-        // triangular solves by the first warp, block column by block column:  L z = ds*g ;  L^T y = z
+        // triangular solves by the first warp, block column by block column:  L z = ds*g ;  L^T y = z.
+        // Fully unrolled over the block width so that every small vector lives in registers.
         const int wl = cta.nthr < 32 ? cta.nthr : 32;
         if (cta.tid < wl) {
             const int lane = cta.tid;
@@ -1023,17 +1084,25 @@ struct Solver {
                 const int kb = (n - k0 < NB) ? n - k0 : NB;
                 const real *Li = w.Linv + (k0 / NB) * NB * NB;
                 real tv[NB], z[NB];
-                for (int cc = 0; cc < kb; ++cc) tv[cc] = w.tmp[k0 + cc];
-                for (int cc = 0; cc < kb; ++cc) {          // z = Linv t, every lane redundantly
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) tv[cc] = cc < kb ? w.tmp[k0 + cc] : real(0);
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) {          // z = Linv t, every lane redundantly
                     real sacc = 0;
-                    for (int p = 0; p <= cc; ++p) sacc += Li[cc * NB + p] * tv[p];
+#pragma unroll
+                    for (int pp = 0; pp <= cc; ++pp) sacc += Li[cc * NB + pp] * tv[pp];
                     z[cc] = sacc;
                 }
                 M2_WSYNC();
-                if (lane == 0) for (int cc = 0; cc < kb; ++cc) w.tmp[k0 + cc] = z[cc];
+                if (lane == 0) {
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) w.tmp[k0 + cc] = z[cc];
+                }
                 for (int i = k0 + kb + lane; i < n; i += wl) {
+                    const real *row = w.Lm + i * ld + k0;
                     real sacc = w.tmp[i];
-                    for (int cc = 0; cc < kb; ++cc) sacc -= w.Lm[i * ld + k0 + cc] * z[cc];
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) sacc -= row[cc] * z[cc];
                     w.tmp[i] = sacc;
                 }
                 M2_WSYNC();
@@ -1042,32 +1111,41 @@ struct Solver {
                 const int kb = (n - k0 < NB) ? n - k0 : NB;
                 const real *Li = w.Linv + (k0 / NB) * NB * NB;
                 real sv[NB], y[NB];
-                for (int cc = 0; cc < kb; ++cc) sv[cc] = 0;
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) sv[cc] = 0;
                 for (int i = k0 + kb + lane; i < n; i += wl) {
+                    const real *row = w.Lm + i * ld + k0;
                     const real yi = w.tmp[i];
-                    for (int cc = 0; cc < kb; ++cc) sv[cc] += w.Lm[i * ld + k0 + cc] * yi;
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) sv[cc] += row[cc] * yi;
                 }
-                for (int cc = 0; cc < kb; ++cc) sv[cc] = w.tmp[k0 + cc] - warp_sum(sv[cc]);
-                for (int cc = 0; cc < kb; ++cc) {          // y = Linv^T s
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) sv[cc] = (cc < kb ? w.tmp[k0 + cc] : real(0)) - warp_sum(sv[cc]);
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) {          // y = Linv^T s
                     real sacc = 0;
-                    for (int p = cc; p < kb; ++p) sacc += Li[p * NB + cc] * sv[p];
+#pragma unroll
+                    for (int pp = cc; pp < NB; ++pp) sacc += Li[pp * NB + cc] * sv[pp];
                     y[cc] = sacc;
                 }
                 M2_WSYNC();
-                if (lane == 0) for (int cc = 0; cc < kb; ++cc) w.tmp[k0 + cc] = y[cc];
+                if (lane == 0) {
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) w.tmp[k0 + cc] = y[cc];
+                }
                 M2_WSYNC();
             }
             for (int i = lane; i < n; i += wl) w.dgn[i] = w.tmp[i] * w.ds[i];
         }
         M2_SYNC();
+        M2_TACC(15);
         return true;
     }
 
-    // ---- one ch.minimize(method='dogleg') of the reference on state w.x
-    M2_D void minimize(const StepCfg<real> &c) {
+    // ---- per-stage set-up of one ch.minimize call: column maps and the joints whose columns are needed
+    M2_D void stage_setup(const StepCfg<real> &c) {
         ++n_min;
         const int n = c.n;
-        const real e1 = real(1e-15), e2 = real(1e-15);
         CTA_FOR(i, d.NX) w.colmap[i] = -1;
         CTA_FOR(i, d.nJ) w.jlist[i] = 0;
         M2_SYNC();
@@ -1101,38 +1179,108 @@ struct Solver {
         M2_SYNC();
         njl = w.isc[1];
         hand_free = w.isc[2] != 0;
-        eval(w.x, c);
-        build(w.x, c);
-        real sse0 = w.sc[0];
-        real delta = real(job.opt.delta_0);
-        bool done = false;
-        {
-            // chumpy stops on ||g||_inf < e_1 = 1e-15, i.e. only for a numerically zero gradient
-            real s[1] = {0};
-            CTA_FOR(i, n) s[0] += w.g[i] * w.g[i];
-            cta_reduce<real, 1>(cta, s, w.red);
-            if (r_sqrt(s[0]) < e1) done = true;
-        }
+    }
+
+    // ---- one frame: [Procrustes] + the ch.minimize calls of the reference + the output evaluation, written as
+    //      one loop around a single eval() / build() / gauss_newton() call site each (the 32 KB instruction cache
+    //      makes code size a first-order cost).  The dog-leg control flow is chumpy's
+    //      (SURVEY.md Appendix A.6): outer iterations, inner retries until a step improves, e_3 / e_2 / maxiter.
+    M2_D void solve_frame(int f, bool emit, bool first, bool fingers, bool dyn) {
+        const Options &o = job.opt;
+        const real e1 = real(1e-15), e2 = real(1e-15);
+        enum { OP_PROCRUSTES, OP_BEGIN, OP_TRIAL, OP_OUTPUT };
+        int op = first ? OP_PROCRUSTES : OP_BEGIN;
+        int stage = first ? 0 : 3;     // 0..2 first-frame annealing (chmosh.py:637-653), 3 Step 1 (665-671), 4 Step 2 (676-705)
+        StepCfg<real> c;
+        c.free = m.free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false;
+        c.wp = 0; c.e3 = real(o.e3_first);
+        bool need_setup = !first;
+        // dog-leg state of the running minimisation
+        real sse0 = 0, delta = 0, alpha = 0, nsd = 0, ngn2 = 0, gn_sd = 0, nstep = 0, npn = 0, gd = 0, dAd = 0;
+        bool done = false, in_iter = false, have_gn = false, gn_ok = true;
         int iter = 0;
-        while (!done) {
-            ++iter;
-            ++n_iter;
-            symv(w.g, w.Ag, n);
-            real r2[2] = {0, 0};
-            CTA_FOR(i, n) { r2[0] += w.g[i] * w.g[i]; r2[1] += w.g[i] * w.Ag[i]; }
-            cta_reduce<real, 2>(cta, r2, w.red);
-            const real gg = r2[0], gAg = r2[1];
-            const real alpha = gg / gAg;
-            const real nsd = alpha * r_sqrt(gg);
-            bool have_gn = false, gn_ok = true;
-            real ngn2 = 0, gn_sd = 0;      // |dgn|^2, dgn . dsd
-            while (true) {
+        while (true) {
+            if (need_setup) {
+                // configuration of this stage
+                c.free = m.free1; c.n = m.n1; c.poseH = false; c.dm_terms = false; c.extrap = false;
+                if (stage < 3) {
+                    c.wp = wp_frame * (stage == 0 ? real(10) : (stage == 1 ? real(5) : real(1)));
+                    c.e3 = real(o.e3_first);
+                } else {
+                    c.wp = wp_frame;
+                    c.e3 = real(o.e3);
+                    if (stage == 4) { c.free = m.free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap; }
+                }
+                stage_setup(c);
+                need_setup = false;
+            }
+            const int n = c.n;
+            // ---------------- the one evaluation site
+            eval(op == OP_TRIAL ? w.xt : w.x, c);
+#if defined(MOSH2_EXP_WARM)
+            prof_base = 20; eval(op == OP_TRIAL ? w.xt : w.x, c); --n_eval; prof_base = 0;   // experiment: the same code again, now warm
+#endif
+            if (op == OP_PROCRUSTES) {                         // chmosh.py:634
+                procrustes();
+                op = OP_BEGIN;
+                need_setup = true;
+                continue;
+            }
+            if (op == OP_OUTPUT) break;
+            bool do_build = false, improved = false;
+            if (op == OP_BEGIN) {
+                sse0 = w.sc[0];
+                delta = real(o.delta_0);
+                done = false; in_iter = false; iter = 0;
+                do_build = true;
+            } else {
+                const real sse1 = w.sc[0];
+                real rho = sse0 - sse1;
+                improved = rho > real(0) || rho >= -accept_slack<real>() * sse0;
+                if (rho > real(0)) rho = rho / (real(2) * gd - dAd);
+                if (improved) {
+                    CTA_FOR(i, d.NX) w.x[i] = w.xt[i];
+                    M2_SYNC();
+                    if (c.e3 > real(0) && (sse0 - sse1) / sse0 < c.e3) done = true;
+                    else { do_build = true; sse0 = sse1; }
+                }
+                if (rho > real(0.9)) { const real cand = real(2.5) * nstep; if (cand > delta) delta = cand; }
+                else if (rho < real(0.05)) delta *= real(0.25);
+                if (delta <= e2 * npn) done = true;
+                if (done || improved) {
+                    in_iter = false;
+                    if (!done && iter >= o.maxiter) { done = true; frame_flags |= ST_MAXITER; }
+                }
+            }
+            // ---------------- the one linearisation site
+            if (do_build && !done) build(w.x, c);
+            if (op == OP_BEGIN) {
+                // chumpy stops on ||g||_inf < e_1 = 1e-15, i.e. only for a numerically zero gradient
+                real sq[1] = {0};
+                CTA_FOR(i, n) sq[0] += w.g[i] * w.g[i];
+                cta_reduce<real, 1>(cta, sq, w.red);
+                if (r_sqrt(sq[0]) < e1) done = true;
+            }
+            if (!done) {
+                if (!in_iter) {                                // start of an outer iteration
+                    ++iter;
+                    ++n_iter;
+                    symv(w.g, w.Ag, n);
+                    real r2[2] = {0, 0};
+                    CTA_FOR(i, n) { r2[0] += w.g[i] * w.g[i]; r2[1] += w.g[i] * w.Ag[i]; }
+                    cta_reduce<real, 2>(cta, r2, w.red);
+                    alpha = r2[0] / r2[1];
+                    nsd = alpha * r_sqrt(r2[0]);
+                    have_gn = false; gn_ok = true;
+                    in_iter = true;
+                }
+                // ---- update_step
                 int kind;           // 0 stunted Cauchy, 1 Gauss-Newton, 2 blend
                 real beta = 0, scale_sd = 0;
                 if (nsd >= delta) { kind = 0; scale_sd = delta / nsd * alpha; }
                 else {
                     if (!have_gn) {
-                        gn_ok = gauss_newton(n);
+                        gn_ok = gauss_newton(n);               // the one factorisation site
                         have_gn = true;
                         if (gn_ok) {
                             real q[2] = {0, 0};
@@ -1166,39 +1314,49 @@ struct Solver {
                     q[0] += w.d[i] * w.d[i];
                     q[1] += w.g[i] * w.d[i];
                     q[2] += w.d[i] * w.tmp[i];
-                    const real p = w.x[c.free[i]];
-                    q[3] += p * p;
+                    const real pv = w.x[c.free[i]];
+                    q[3] += pv * pv;
                 }
                 cta_reduce<real, 4>(cta, q, w.red);
-                const real nstep = r_sqrt(q[0]), npn = r_sqrt(q[3]);
-                bool improved = false;
+                nstep = r_sqrt(q[0]); gd = q[1]; dAd = q[2]; npn = r_sqrt(q[3]);
                 if (nstep <= e2 * npn) done = true;
                 else {
                     CTA_FOR(i, d.NX) w.xt[i] = w.x[i];
                     M2_SYNC();
                     CTA_FOR(i, n) w.xt[c.free[i]] += w.d[i];
                     M2_SYNC();
-                    eval(w.xt, c);
-                    const real sse1 = w.sc[0];
-                    real rho = sse0 - sse1;
-                    if (rho > real(0)) rho = rho / (real(2) * q[1] - q[2]);
-                    improved = rho > real(0);
-                    if (improved) {
-                        CTA_FOR(i, d.NX) w.x[i] = w.xt[i];
-                        M2_SYNC();
-                        if (c.e3 > real(0) && (sse0 - sse1) / sse0 < c.e3) done = true;
-                        else {
-                            build(w.x, c);
-                            sse0 = sse1;
-                        }
-                    }
-                    if (rho > real(0.9)) { const real cand = real(2.5) * nstep; if (cand > delta) delta = cand; }
-                    else if (rho < real(0.05)) delta *= real(0.25);
-                    if (delta <= e2 * npn) done = true;
+                    op = OP_TRIAL;
+                    continue;
                 }
-                if (done || improved) break;
             }
-            if (!done && iter >= job.opt.maxiter) { done = true; frame_flags |= ST_MAXITER; }
+            // the minimisation of this stage has terminated
+            if (stage < 4) { ++stage; op = OP_BEGIN; need_setup = true; continue; }
+            if (!emit) break;
+            op = OP_OUTPUT;                                    // per-term SSE and markers at the solution
+        }
+        if (cta.tid == 0 && job.totals) {
+#if M2_GPU
+            atomicAdd(job.totals + 0, n_iter); atomicAdd(job.totals + 1, n_eval);
+            atomicAdd(job.totals + 2, n_build); atomicAdd(job.totals + 3, n_min);
+#else
+            job.totals[0] += n_iter; job.totals[1] += n_eval; job.totals[2] += n_build; job.totals[3] += n_min;
+#endif
+        }
+        if (emit) {
+            CTA_FOR(i, d.PF) job.fullpose[size_t(f) * d.PF + i] = w.fullpose[i];
+            CTA_FOR(i, d.PR) job.pose[size_t(f) * d.PR + i] = w.x[3 + i];
+            CTA_FOR(i, 3) job.trans[size_t(f) * 3 + i] = w.x[i];
+            if (job.dmpls) CTA_FOR(i, d.nd) job.dmpls[size_t(f) * d.nd + i] = w.x[3 + d.PR + i];
+            CTA_FOR(i, 3 * d.M) job.markers_sim[size_t(f) * 3 * d.M + i] = w.mk[i];
+            CTA_FOR(i, N_ERR) job.errs[size_t(f) * N_ERR + i] = w.sc[1 + i];
+            if (cta.tid == 0) {
+                job.status[f] = ST_SOLVED | frame_flags | (has_velo ? ST_HAS_VELO : 0) | (has_extrap ? ST_HAS_EXTRAP : 0);
+                job.counters[4 * f + 0] = n_iter;
+                job.counters[4 * f + 1] = n_eval;
+                job.counters[4 * f + 2] = n_build;
+                job.counters[4 * f + 3] = n_min;
+            }
+            M2_SYNC();
         }
     }
 
@@ -1287,13 +1445,16 @@ struct Solver {
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
         CTA_FOR(i, m.hct_size) w.hct[i] = m.hct[i];
+        CTA_FOR(i, 32) w.prof[i] = 0;
         M2_SYNC();
+        M2_T0();
         bool first = true, have_prev = false, have_dm_prev = false;
         wv = real(o.wt_velo); wdm = real(o.wt_dmpl); wex = real(o.wt_extrap);
         const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd > 0;
         const bool has_prior = d.K > 0;
         njl = 0;
         hand_free = false;
+#pragma unroll 1
         for (int f = f_begin; f < f_end; ++f) {
             n_iter = n_eval = n_build = n_min = 0;
             frame_flags = 0;
@@ -1320,67 +1481,20 @@ struct Solver {
                 CTA_FOR(i, d.PR) w.velo_tgt[i] = real(2) * w.x[3 + i] - w.pose_prev[i];
                 M2_SYNC();
             }
-            StepCfg<real> c1;
-            c1.free = m.free1; c1.n = m.n1; c1.velo = has_velo; c1.poseH = false; c1.dm_terms = false; c1.extrap = false;
-            int stage0 = 3;
-            if (first) {
-                c1.wp = 0; c1.e3 = real(o.e3_first);
-                eval(w.x, c1);                                 // simulated markers at the current state
-                procrustes();                                  // chmosh.py:634
-                stage0 = 0;
-                first = false;
-            } else {
+            if (!first) {
                 CTA_FOR(i, d.PR) w.pose_prev[i] = w.x[3 + i];                               // chmosh.py:656-659
                 have_prev = true;
                 if (dyn) { CTA_FOR(i, d.nd) w.dm_tgt[i] = w.x[3 + d.PR + i]; have_dm_prev = true; }
                 M2_SYNC();
             }
             has_extrap = dyn && have_dm_prev;
-            // stages 0..2: first-frame annealing (prior x10, x5, x1; e_3 = 1e-3), chmosh.py:637-653;
-            // stage 3: Step 1 (chmosh.py:665-671); stage 4: Step 2 (chmosh.py:676-705)
-            for (int stage = stage0; stage < 5; ++stage) {
-                StepCfg<real> c = c1;
-                if (stage < 3) {
-                    c.wp = wp_frame * (stage == 0 ? real(10) : (stage == 1 ? real(5) : real(1)));
-                    c.e3 = real(o.e3_first);
-                } else {
-                    c.wp = wp_frame;
-                    c.e3 = real(o.e3);
-                    if (stage == 4) {
-                        c.free = m.free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap;
-                    }
-                }
-                minimize(c);
-            }
-            if (cta.tid == 0 && job.totals) {
-#if M2_GPU
-                atomicAdd(job.totals + 0, n_iter); atomicAdd(job.totals + 1, n_eval);
-                atomicAdd(job.totals + 2, n_build); atomicAdd(job.totals + 3, n_min);
-#else
-                job.totals[0] += n_iter; job.totals[1] += n_eval; job.totals[2] += n_build; job.totals[3] += n_min;
-#endif
-            }
-            if (f >= f_emit) {
-                StepCfg<real> c2 = c1;
-                c2.wp = wp_frame; c2.e3 = real(o.e3);
-                c2.free = m.free2; c2.n = m.n2; c2.poseH = fingers; c2.dm_terms = dyn; c2.extrap = has_extrap;
-                eval(w.x, c2);                                 // per-term SSE and markers at the solution
-                CTA_FOR(i, d.PF) job.fullpose[size_t(f) * d.PF + i] = w.fullpose[i];
-                CTA_FOR(i, d.PR) job.pose[size_t(f) * d.PR + i] = w.x[3 + i];
-                CTA_FOR(i, 3) job.trans[size_t(f) * 3 + i] = w.x[i];
-                if (job.dmpls) CTA_FOR(i, d.nd) job.dmpls[size_t(f) * d.nd + i] = w.x[3 + d.PR + i];
-                CTA_FOR(i, 3 * d.M) job.markers_sim[size_t(f) * 3 * d.M + i] = w.mk[i];
-                CTA_FOR(i, N_ERR) job.errs[size_t(f) * N_ERR + i] = w.sc[1 + i];
-                if (cta.tid == 0) {
-                    job.status[f] = ST_SOLVED | frame_flags | (has_velo ? ST_HAS_VELO : 0) | (has_extrap ? ST_HAS_EXTRAP : 0);
-                    job.counters[4 * f + 0] = n_iter;
-                    job.counters[4 * f + 1] = n_eval;
-                    job.counters[4 * f + 2] = n_build;
-                    job.counters[4 * f + 3] = n_min;
-                }
-                M2_SYNC();
-            }
+            solve_frame(f, f >= f_emit, first, fingers, dyn);
+            first = false;
         }
+        M2_TACC(17);
+#if defined(MOSH2_PROFILE) && M2_GPU
+        if (cta.tid == 0 && job.prof) for (int i = 0; i < 32; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(job.prof + i), (unsigned long long)w.prof[i]);
+#endif
     }
 #undef CTA_FOR
 };

@@ -102,6 +102,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     job.status = status.data(); job.counters = counters.data();
     int totals[4] = {0, 0, 0, 0};
     job.totals = totals;
+    job.prof = nullptr;
     job.gws = nullptr; job.gws_stride = 0;
     mosh2::Options &q = job.opt;
     q.wt_data = opt->wt_data; q.wt_poseB = opt->wt_poseB; q.wt_poseH = opt->wt_poseH; q.wt_velo = opt->wt_velo;
@@ -109,6 +110,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     q.num_train_markers = opt->num_train_markers; q.delta_0 = opt->delta_0; q.e3_first = opt->e3_first; q.e3 = opt->e3;
     q.maxiter = opt->maxiter; q.optimize_fingers = opt->optimize_fingers; q.optimize_dynamics = opt->optimize_dynamics;
 
+    hm.m.tile_markers = 16;
     const mosh2::Dims d = mosh2::make_dims(hm.m);
     mosh2::Work<real> w;
     mosh2::Arena S0{nullptr, 0}, G0{nullptr, 0};
@@ -120,7 +122,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
         mosh2::Arena S{smem_base, 0}, G{nullptr, 0};
         mosh2::carve(w, d, hm.m.hct_size, S, G, false);
         mosh2::Cta cta{0, 1};
-        mosh2::Solver<real> s(hm.m, job, w, cta);
+        mosh2::Solver<real> s(hm.m, job, w, d, cta);
         s.run_chunk(c);
     }
     auto conv = [](double *dst, const std::vector<real> &src, size_t n) {

@@ -55,3 +55,28 @@ def srcline(k):
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     st = sorted(a[3].items(), key=lambda kv: -kv[1])[:3]
     print(f'{str(k):34s} samp {100*a[1]/tot_s:5.1f}% inst {100*a[0]/tot_i:5.1f}% sass {a[2]:5d} {[(s.replace("stall_",""),v) for s,v in st]} | {srcline(k)}')
+
+# ---- optional phase summary: NCU_PHASES="name:lo-hi,name:lo-hi" groups lines of mosh2_device.cuh
+import os
+ph = os.environ.get('NCU_PHASES')
+if ph:
+    groups = []
+    for item in ph.split(','):
+        name, rng = item.split(':')
+        lo, hi = rng.split('-')
+        groups.append((name, int(lo), int(hi)))
+    tot = defaultdict(lambda: [0, 0, defaultdict(int)])
+    for k, a in agg.items():
+        nm = 'other'
+        if k and k[0] == 'mosh2_device.cuh':
+            for name, lo, hi in groups:
+                if lo <= k[1] <= hi:
+                    nm = name
+                    break
+        tot[nm][0] += a[0]; tot[nm][1] += a[1]
+        for s_, v in a[3].items():
+            tot[nm][2][s_] += v
+    print('--- phases')
+    for nm, a in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        st = sorted(a[2].items(), key=lambda kv: -kv[1])[:4]
+        print(f'{nm:14s} samp {100*a[1]/tot_s:5.1f}% inst {100*a[0]/tot_i:5.1f}%  {[(s_.replace("stall_",""), round(100*v/max(1,a[1]))) for s_, v in st]}')
