@@ -117,6 +117,11 @@ def run_reference(args, rank, world):
     host cores, a bounded sample of the workload per step."""
     if rank != 0:
         return
+    try:        # torchrun pins OMP_NUM_THREADS=1; the reference arm may use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     case, pk, opts, obs, vis = make_workload(0)
     n = args.cpu_frames
     vals = []
@@ -148,7 +153,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--chunk-len', type=int, default=None)
-    ap.add_argument('--chunk-warmup', type=int, default=64)
+    ap.add_argument('--chunk-warmup', type=int, default=None)
     ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
     ap.add_argument('--cpu-frames', type=int, default=5, help='frames of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -182,6 +187,8 @@ def main():
     case, pk, opts, obs, vis = make_workload(rank)
     F = obs.shape[0]
     chunk_len = args.chunk_len if args.chunk_len is not None else chmosh.auto_chunk_len(F)
+    if args.chunk_warmup is None:
+        args.chunk_warmup = chmosh.DEFAULT_WARMUP
     prec = {'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[args.precision]
     model = lib.Model(pk, device=local_rank)
     job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=args.chunk_warmup, precision=prec)
