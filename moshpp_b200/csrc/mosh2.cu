@@ -37,24 +37,20 @@ int fail(int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(MOSH2_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr size_t kMaxSmem = 227 * 1024 - 1024;   // dynamic part; 1 KB is static (pointer table, dims)
+constexpr size_t kMaxSmem = 227 * 1024;
 template <class real> constexpr int threads_for() { return sizeof(real) == 4 ? 512 : 256; }
 
-template <class real>
+template <class real, bool BIG>
 __global__ void __launch_bounds__(threads_for<real>(), 1)
-mosh2_stageii_kernel(const mosh2::Model<real> m, const mosh2::Job<real> job, int big_in_global) {
+mosh2_stageii_kernel(const mosh2::Model<real> m, const mosh2::Job<real> job) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // the workspace pointer table and the dimensions live in shared memory: one load instead of re-deriving
-    // offsets at every use (the 32 KB instruction cache makes code size a first-order cost)
-    __shared__ mosh2::Work<real> w;
-    __shared__ mosh2::Dims d;
-    if (threadIdx.x == 0) {
-        d = mosh2::make_dims(m);
-        mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
-        mosh2::Arena G{job.gws ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
-        mosh2::carve(w, d, m.hct_size, S, G, big_in_global != 0);
-    }
-    __syncthreads();
+    // BIG = false: the whole workspace is carved from `smem`, so every workspace access is an LDS/STS;
+    // BIG = true (f64 / oversized models): A, its factor and the Jacobian tiles live in a per-CTA global workspace
+    mosh2::Work<real> w;
+    const mosh2::Dims d = mosh2::make_dims(m);
+    mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
+    mosh2::Arena G{BIG ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
+    mosh2::carve<real, BIG>(w, d, m, S, G);
     mosh2::Cta c{int(threadIdx.x), int(blockDim.x)};
     mosh2::Solver<real> s(m, job, w, d, c);
     s.run_chunk(blockIdx.x);
@@ -192,14 +188,19 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     job.status = j->d_status; job.counters = j->d_counters; job.totals = j->d_totals; job.prof = j->d_prof;
     job.gws = static_cast<char *>(j->d_gws); job.gws_stride = j->gws_stride;
     job.opt = j->opt;
-    CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
-    CU(cudaEventRecord(j->ev0, j->stream));
     int threads = threads_for<real>();
     if (const char *e = getenv("MOSH2_DEV_THREADS")) {      // development aid: any multiple of 32 up to the launch bound
         const int t = atoi(e);
         if (t >= 32 && t <= threads && t % 32 == 0) threads = t;
     }
-    mosh2_stageii_kernel<real><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job, j->big_in_global);
+    CU(cudaEventRecord(j->ev0, j->stream));
+    if (j->big_in_global) {
+        CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
+        mosh2_stageii_kernel<real, true><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job);
+    } else {
+        CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
+        mosh2_stageii_kernel<real, false><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job);
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(j->ev1, j->stream));
     return 0;
@@ -209,14 +210,16 @@ template <class real>
 void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) {
     // largest Jacobian tile that still fits the shared-memory budget; the f64 / oversized case moves the
     // big arrays to a per-CTA global workspace
-    const int tiles[2] = {16, 8};
+    // preference order: table staging and 16-marker tiles while they fit the shared-memory budget; the f64 /
+    // oversized case moves the big arrays to a per-CTA global workspace
+    const int tries[3][2] = {{16, 0}, {8, 0}, {8, 1}};   // tile, big
     for (int pass = 0; pass < 3; ++pass) {
-        m.tile_markers = pass < 2 ? tiles[pass] : 8;
-        const bool in_global = pass == 2;
+        m.tile_markers = tries[pass][0];
+        const bool in_global = tries[pass][1] != 0;
         mosh2::Work<real> w;
         const mosh2::Dims d = mosh2::make_dims(m);
         mosh2::Arena S{nullptr, 0}, G{nullptr, 0};
-        mosh2::carve(w, d, m.hct_size, S, G, in_global);
+        if (in_global) mosh2::carve<real, true>(w, d, m, S, G); else mosh2::carve<real, false>(w, d, m, S, G);
         *big = in_global ? 1 : 0;
         *smem = (S.off + 15) & ~size_t(15);
         *gws = (G.off + 255) & ~size_t(255);

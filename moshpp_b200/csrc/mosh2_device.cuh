@@ -278,6 +278,11 @@ struct Work {
     real *Loc, *MtR, *u, *dtg, *Jt, *Jf, *A, *Lm, *Linv, *Pn, *g, *Ag, *dgn, *d, *tmp, *ds;
     real *red, *sc, *hct;
     int *colmap, *colsrc, *jlist, *isc;
+    // small per-model tables: shared-memory copies when they fit (a dependent global load costs ~600 cycles and the
+    // kinematic-tree walk alone chains three of them per level), else aliases of the global arrays
+    const int *c_parents, *c_fk_order, *c_level_ofs, *c_wj, *c_ancmask, *c_free1, *c_free2;
+    const int8_t *c_ancpos;
+    const real *c_wv, *c_v0, *c_coefs, *c_j0, *c_hmean, *c_pmeans, *c_pnlw;
     long long *prof;
     uint8_t *vis;
 };
@@ -314,9 +319,12 @@ struct Arena {
 
 // Lays the workspace out.  Arrays flagged "big" go to arena G when big_in_global is set (f64 runs, large
 // models), everything else to arena S (shared memory).
-template <class real>
-M2_HD void carve(Work<real> &w, const Dims &d, int hct_size, Arena &S, Arena &G, bool big_in_global) {
-    Arena &B = big_in_global ? G : S;
+template <class real, bool BIG>
+M2_HD void carve(Work<real> &w, const Dims &d, const Model<real> &m, Arena &S, Arena &G) {
+    // BIG is a compile-time switch so that, in the normal case, every workspace pointer provably points into
+    // shared memory and the compiler emits LDS/STS instead of generic loads and stores
+    const int hct_size = m.hct_size;
+    Arena &B = BIG ? G : S;
     w.x = S.take<real>(d.NX); w.xt = S.take<real>(d.NX);
     w.pose_prev = S.take<real>(d.PR); w.velo_tgt = S.take<real>(d.PR); w.dm_tgt = S.take<real>(d.nd + 1);
     w.fullpose = S.take<real>(d.PF); w.Rl = S.take<real>(9 * d.nJ); w.dRl = S.take<real>(27 * d.nJ);
@@ -336,6 +344,13 @@ M2_HD void carve(Work<real> &w, const Dims &d, int hct_size, Arena &S, Arena &G,
     w.colmap = S.take<int>(d.NX); w.colsrc = S.take<int>(d.n2); w.jlist = S.take<int>(d.nJ); w.isc = S.take<int>(8);
     w.prof = S.take<long long>(32);
     w.vis = S.take<uint8_t>(d.M);
+    // small per-model tables are always staged in shared memory (a dependent global load costs ~600 cycles and the
+    // kinematic-tree walk chains three of them per level); the larger ones stay in global memory / L2
+    w.c_parents = S.take<int>(d.nJ); w.c_fk_order = S.take<int>(d.nJ); w.c_level_ofs = S.take<int>(m.n_levels + 1);
+    w.c_wj = S.take<int>(d.S * d.kw); w.c_free1 = S.take<int>(d.n1); w.c_free2 = S.take<int>(d.n2);
+    w.c_wv = S.take<real>(d.S * d.kw); w.c_v0 = S.take<real>(3 * d.S); w.c_coefs = S.take<real>(3 * d.M);
+    w.c_j0 = S.take<real>(3 * d.nJ); w.c_hmean = S.take<real>(m.n_hand_full + 1);
+    w.c_ancmask = m.anc_mask; w.c_ancpos = m.anc_pos; w.c_pmeans = m.prior_means; w.c_pnlw = m.prior_nlw;
 }
 
 // configuration of one minimisation (one ch.minimize call of the reference)
@@ -374,9 +389,9 @@ struct Solver {
     // ---- FK by depth level, executed by `nl` lanes (one warp on the GPU) starting at lane id `l`
     M2_D void fk(int l, int nl) {
         for (int lv = 0; lv < m.n_levels; ++lv) {
-            const int lo = m.level_ofs[lv], cnt = m.level_ofs[lv + 1] - lo;
+            const int lo = w.c_level_ofs[lv], cnt = w.c_level_ofs[lv + 1] - lo;
             for (int q = l; q < cnt; q += nl) {
-                const int j = m.fk_order[lo + q], a = m.parents[j];
+                const int j = w.c_fk_order[lo + q], a = w.c_parents[j];
                 if (a < 0) {
                     for (int i = 0; i < 9; ++i) w.Rg[9 * j + i] = w.Rl[9 * j + i];
                     for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = w.Jp[3 * j + i];
@@ -429,7 +444,7 @@ struct Solver {
                 v = th[i];
             } else {
                 const int q = i - m.body_dof;
-                v = m.hands_mean[q];
+                v = w.c_hmean[q];
                 for (int b = 0; b < m.hb_n; ++b) {
                     const HandBlock hb = m.hb[b];
                     if (q >= hb.q0 && q < hb.q1) {
@@ -441,7 +456,7 @@ struct Solver {
             w.fullpose[i] = v;
         }
         CTA_FOR(i, 3 * d.nJ) {
-            real v = m.j0[i];
+            real v = w.c_j0[i];
             for (int q = 0; q < d.nd; ++q) v += m.jd[i * d.nd + q] * dl[q];
             w.Jp[i] = v;
         }
@@ -467,7 +482,7 @@ struct Solver {
             real vpo[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                real a = m.v0[3 * s + q];
+                real a = w.c_v0[3 * s + q];
                 for (int e = 0; e < d.nd; ++e) a += m.sd[(3 * s + q) * d.nd + e] * dl[e];
 #pragma unroll
                 for (int g = 0; g < kBlendGroups; ++g) a += w.Jt[(g * d.S + s) * 3 + q];
@@ -476,10 +491,10 @@ struct Solver {
             real v[3] = {0, 0, 0};
             real Rs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int i = 0; i < d.kw; ++i) {
-                const int j = m.w_joint[s * d.kw + i];
+                const int j = w.c_wj[s * d.kw + i];
                 real *pp = w.pj + 3 * (s * d.kw + i);
                 if (j < 0) { pp[0] = pp[1] = pp[2] = 0; continue; }
-                const real wt = m.w_val[s * d.kw + i];
+                const real wt = w.c_wv[s * d.kw + i];
                 real dv[3] = {vpo[0] - w.Jp[3 * j], vpo[1] - w.Jp[3 * j + 1], vpo[2] - w.Jp[3 * j + 2]};
                 real o[3];
                 mat3_vec(w.Rg + 9 * j, dv, o);
@@ -498,7 +513,7 @@ struct Solver {
             CTA_FOR(idx, d.K * D) {
                 const int k = idx / D, i = idx - k * D;
                 const real *Q = m.prior_Q4 + (size_t(k) * D + i) * D4;
-                const real *mu = m.prior_means + k * D;
+                const real *mu = w.c_pmeans + k * D;
                 const real *xb = th + m.prior_off;
                 real s = 0;
                 int l = 0;
@@ -525,7 +540,7 @@ struct Solver {
             real f2[3] = {nn[0] / n2, nn[1] / n2, nn[2] / n2};
             real f3[3];
             cross3(f1, f2, f3);
-            const real k1 = m.coefs[3 * mi], k2 = m.coefs[3 * mi + 1], k3 = m.coefs[3 * mi + 2];
+            const real k1 = w.c_coefs[3 * mi], k2 = w.c_coefs[3 * mi + 1], k3 = w.c_coefs[3 * mi + 2];
             const bool vis = w.vis[mi] != 0;
             for (int q = 0; q < 3; ++q) {
                 const real mk = v0[q] + k1 * f1[q] + k2 * f2[q] + k3 * f3[q];
@@ -535,8 +550,8 @@ struct Solver {
         }
         if (c.wp > real(0)) {
             CTA_FOR(k, d.K) {
-                const real *mu = m.prior_means + k * d.D;
-                real s = m.prior_nlw[k];
+                const real *mu = w.c_pmeans + k * d.D;
+                real s = w.c_pnlw[k];
                 for (int i = 0; i < d.D; ++i) s += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
                 w.pq[k] = s;
             }
@@ -581,7 +596,7 @@ struct Solver {
         cross3(e1, e2, nn);
         const real n2 = r_sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
         real f2[3] = {nn[0] / n2, nn[1] / n2, nn[2] / n2};
-        const real k1 = m.coefs[3 * mi], k2 = m.coefs[3 * mi + 1], k3 = m.coefs[3 * mi + 2];
+        const real k1 = w.c_coefs[3 * mi], k2 = w.c_coefs[3 * mi + 1], k3 = w.c_coefs[3 * mi + 2];
         // d marker / d(e1, e2):  N(u) = (I - uh uh^T)/|u|
         real N1[9], Nn[9];
         for (int r = 0; r < 3; ++r)
@@ -635,13 +650,13 @@ struct Solver {
                 for (int k = 0; k < 3; ++k)
                     blk[3 * r + k] += Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
         }
-        const int ai = m.anc_pos[s * d.nJ + a];
+        const int ai = w.c_ancpos[s * d.nJ + a];
         if (ai >= 0) {
-            const int mask = m.anc_mask[s * m.na + ai];
+            const int mask = w.c_ancmask[s * m.na + ai];
             real q[3] = {0, 0, 0};
             for (int i = 0; i < d.kw; ++i)
                 if ((mask >> i) & 1) {
-                    const real wt = m.w_val[s * d.kw + i];
+                    const real wt = w.c_wv[s * d.kw + i];
                     const real *pp = w.pj + 3 * (s * d.kw + i);
                     for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
                 }
@@ -670,7 +685,7 @@ struct Solver {
             om[0] = D[6] * R[3] + D[7] * R[4] + D[8] * R[5];
             om[1] = D[0] * R[6] + D[1] * R[7] + D[2] * R[8];
             om[2] = D[3] * R[0] + D[4] * R[1] + D[5] * R[2];
-            const int par = m.parents[a];
+            const int par = w.c_parents[a];
             if (par < 0) { for (int q = 0; q < 3; ++q) w.u[3 * idx + q] = om[q]; }
             else mat3_vec(w.Rg + 9 * par, om, w.u + 3 * idx);
         }
@@ -680,9 +695,9 @@ struct Solver {
         if (d.nd) {
             // d tg_j / d delta_i = d tg_par + Rg_par (Jd_j - Jd_par)
             for (int lv = 0; lv < m.n_levels; ++lv) {
-                const int lo = m.level_ofs[lv], cnt = m.level_ofs[lv + 1] - lo;
+                const int lo = w.c_level_ofs[lv], cnt = w.c_level_ofs[lv + 1] - lo;
                 CTA_FOR(q, cnt * d.nd) {
-                    const int j = m.fk_order[lo + q / d.nd], i = q % d.nd, a = m.parents[j];
+                    const int j = w.c_fk_order[lo + q / d.nd], i = q % d.nd, a = w.c_parents[j];
                     real *o = w.dtg + 3 * (j * d.nd + i);
                     if (a < 0) { for (int r = 0; r < 3; ++r) o[r] = m.jd[(3 * j + r) * d.nd + i]; }
                     else {
@@ -750,9 +765,9 @@ struct Solver {
                     const int s = 3 * mi + t;
                     real dv[3] = {0, 0, 0};
                     for (int kk = 0; kk < d.kw; ++kk) {
-                        const int j = m.w_joint[s * d.kw + kk];
+                        const int j = w.c_wj[s * d.kw + kk];
                         if (j < 0) continue;
-                        const real wt = m.w_val[s * d.kw + kk];
+                        const real wt = w.c_wv[s * d.kw + kk];
                         real df[3], o[3];
                         for (int r = 0; r < 3; ++r) df[r] = m.sd[(3 * s + r) * d.nd + i] - m.jd[(3 * j + r) * d.nd + i];
                         mat3_vec(w.Rg + 9 * j, df, o);
@@ -1192,7 +1207,7 @@ struct Solver {
         int op = first ? OP_PROCRUSTES : OP_BEGIN;
         int stage = first ? 0 : 3;     // 0..2 first-frame annealing (chmosh.py:637-653), 3 Step 1 (665-671), 4 Step 2 (676-705)
         StepCfg<real> c;
-        c.free = m.free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false;
+        c.free = w.c_free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false;
         c.wp = 0; c.e3 = real(o.e3_first);
         bool need_setup = !first;
         // dog-leg state of the running minimisation
@@ -1202,14 +1217,14 @@ struct Solver {
         while (true) {
             if (need_setup) {
                 // configuration of this stage
-                c.free = m.free1; c.n = m.n1; c.poseH = false; c.dm_terms = false; c.extrap = false;
+                c.free = w.c_free1; c.n = m.n1; c.poseH = false; c.dm_terms = false; c.extrap = false;
                 if (stage < 3) {
                     c.wp = wp_frame * (stage == 0 ? real(10) : (stage == 1 ? real(5) : real(1)));
                     c.e3 = real(o.e3_first);
                 } else {
                     c.wp = wp_frame;
                     c.e3 = real(o.e3);
-                    if (stage == 4) { c.free = m.free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap; }
+                    if (stage == 4) { c.free = w.c_free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap; }
                 }
                 stage_setup(c);
                 need_setup = false;
@@ -1445,6 +1460,15 @@ struct Solver {
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
         CTA_FOR(i, m.hct_size) w.hct[i] = m.hct[i];
+        CTA_FOR(i, d.nJ) { const_cast<int *>(w.c_parents)[i] = m.parents[i]; const_cast<int *>(w.c_fk_order)[i] = m.fk_order[i]; }
+        CTA_FOR(i, m.n_levels + 1) const_cast<int *>(w.c_level_ofs)[i] = m.level_ofs[i];
+        CTA_FOR(i, d.S * d.kw) { const_cast<int *>(w.c_wj)[i] = m.w_joint[i]; const_cast<real *>(w.c_wv)[i] = m.w_val[i]; }
+        CTA_FOR(i, d.n1) const_cast<int *>(w.c_free1)[i] = m.free1[i];
+        CTA_FOR(i, d.n2) const_cast<int *>(w.c_free2)[i] = m.free2[i];
+        CTA_FOR(i, 3 * d.S) const_cast<real *>(w.c_v0)[i] = m.v0[i];
+        CTA_FOR(i, 3 * d.M) const_cast<real *>(w.c_coefs)[i] = m.coefs[i];
+        CTA_FOR(i, 3 * d.nJ) const_cast<real *>(w.c_j0)[i] = m.j0[i];
+        CTA_FOR(i, m.n_hand_full) const_cast<real *>(w.c_hmean)[i] = m.hands_mean[i];
         CTA_FOR(i, 32) w.prof[i] = 0;
         M2_SYNC();
         M2_T0();

@@ -114,13 +114,13 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     const mosh2::Dims d = mosh2::make_dims(hm.m);
     mosh2::Work<real> w;
     mosh2::Arena S0{nullptr, 0}, G0{nullptr, 0};
-    mosh2::carve(w, d, hm.m.hct_size, S0, G0, false);
+    mosh2::carve<real, false>(w, d, hm.m, S0, G0);
     std::vector<char> smem_raw(S0.off + 128);
     char *smem_base = smem_raw.data() + ((32 - (reinterpret_cast<uintptr_t>(smem_raw.data()) & 31)) & 31);
     for (int c = 0; c < job.n_chunks; ++c) {
         std::memset(smem_base, 0, S0.off + 64);
         mosh2::Arena S{smem_base, 0}, G{nullptr, 0};
-        mosh2::carve(w, d, hm.m.hct_size, S, G, false);
+        mosh2::carve<real, false>(w, d, hm.m, S, G);
         mosh2::Cta cta{0, 1};
         mosh2::Solver<real> s(hm.m, job, w, d, cta);
         s.run_chunk(c);
