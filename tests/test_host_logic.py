@@ -1,0 +1,91 @@
+"""Host-side logic that needs no GPU: result assembly (chmosh.py:712-741), chunk sizing, bench bookkeeping."""
+import importlib.util
+import os
+
+import numpy as np
+
+from conftest import dense_obs, run_oracle
+from moshpp_b200 import chmosh, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_result_assembly_matches_reference_layout(cases, emu):
+    """The dictionary builder is fed with the device-source result arrays (host build) and compared, key by key,
+    with the oracle's restatement of chmosh.py:712-741."""
+    case = cases('C3')
+    obs, vis = dense_obs(case)
+    vis = vis.copy()
+    vis[4] = False                                   # a frame without markers is dropped from every list
+    res = emu(case, obs_vis=(obs, vis))
+    pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
+    data = chmosh.assemble_stageii_data(res, obs, vis, case['latent_labels'], pk, flags, dyn=True)
+    n = int(vis.any(1).sum())
+    assert data['fullpose'].shape == (n, 165) and data['trans'].shape == (n, 3) and data['dmpls'].shape == (n, 8)
+    dbg = data['stageii_debug_details']
+    assert len(dbg['markers_sim']) == len(dbg['markers_obs']) == len(dbg['labels_obs']) == n
+    for mk, ob, lb in zip(dbg['markers_sim'], dbg['markers_obs'], dbg['labels_obs']):
+        assert mk.shape == ob.shape == (len(lb), 3)
+    e = dbg['stageii_errs']
+    assert list(e.keys()) == ['data', 'poseB', 'poseH', 'dmpl', 'extrap_dmpl', 'velo']
+    assert len(e['data']) == n and len(e['extrap_dmpl']) == n - 1 and len(e['velo']) == n - 2
+    # same numbers as the oracle on the unmodified visibility
+    ref = run_oracle(case)
+    res2 = emu(case)
+    d2 = chmosh.assemble_stageii_data(res2, *dense_obs(case), case['latent_labels'], pk, flags, dyn=True)
+    for k, v in ref['stageii_debug_details']['stageii_errs'].items():
+        assert np.allclose(d2['stageii_debug_details']['stageii_errs'][k], v, rtol=1e-8, atol=1e-12)
+    assert np.abs(d2['fullpose'] - ref['fullpose']).max() < 1e-9
+
+
+def test_auto_chunk_len():
+    assert chmosh.auto_chunk_len(500) == 4 and chmosh.auto_chunk_len(4000) == 28 and chmosh.auto_chunk_len(12) == 4
+    assert chmosh.auto_chunk_len(4000, sm_budget=37) == 109
+
+
+def test_options_follow_the_config(cases):
+    case = cases('C2')
+    pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
+    assert (opts.wt_data, opts.wt_poseB, opts.wt_velo, opts.wt_annealing, opts.maxiter) == (400.0, 1.6, 2.5, 2.5, 100)
+    assert opts.optimize_fingers == 1 and opts.optimize_dynamics == 0
+    # fingers are switched off when the layout has no finger markers (chmosh.py:475-486)
+    c1 = cases('C1')
+    c1['cfg'].moshpp.optimize_fingers = True
+    _, o1, f1 = chmosh.prepare_stageii(c1['cfg'], c1['markers_latent'], c1['latent_labels'], c1['betas'], c1['marker_meta'])
+    assert not f1['optimize_fingers'] and o1.optimize_fingers == 0 and c1['cfg'].moshpp.optimize_fingers is False
+
+
+def test_bench_algorithmic_bytes_match_baseline_table(cases):
+    """C2 R=385 n=111 B_K1=174.1 KB B_K2=197.8 KB."""
+    spec = importlib.util.spec_from_file_location('bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ab = bench.algorithmic_bytes(cases('C2')['pack'])
+    assert (ab['R'], ab['n']) == (385, 111)
+    assert round(ab['B_K1'] / 1000, 1) == 174.1 and round(ab['B_K2'] / 1000, 1) == 197.8
+    ab3 = bench.algorithmic_bytes(cases('C3')['pack'])
+    assert (ab3['R'], ab3['n']) == (452, 119)
+
+
+def test_amass_writer_round_trip(cases, emu, tmp_path):
+    """pkl merge + AMASS npz layout (mosh_head.py:289-295,444-541; run_tools.py:70-85)."""
+    from moshpp_b200 import amass_io
+    case = cases('C3')
+    obs, vis = dense_obs(case)
+    pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
+    data = chmosh.assemble_stageii_data(emu(case), obs, vis, case['latent_labels'], pk, flags, dyn=True)
+    data['stageii_debug_details'].update(markers_orig=obs, labels_orig=case['latent_labels'], mocap_frame_rate=120.0,
+                                         mocap_time_length=len(obs) / 120.0)
+    stagei = dict(markers_latent=case['markers_latent'], latent_labels=case['latent_labels'], betas=case['betas'],
+                  marker_meta=case['marker_meta'], markers_latent_vids={l: 0 for l in case['latent_labels']})
+    merged = amass_io.merge_stageii(data, stagei, case['cfg'], 1.5, str(tmp_path / 'x_stageii.pkl'))
+    assert merged['stageii_debug_details']['stageii_elapsed_time'] == 1.5 and 'betas' in merged
+    npz = amass_io.load_as_amass_npz(str(tmp_path / 'x_stageii.pkl'), str(tmp_path / 'x_stageii.npz'), include_markers=True)
+    n = len(merged['fullpose'])
+    assert npz['poses'].shape == (n, 165) and npz['root_orient'].shape == (n, 3) and npz['pose_body'].shape == (n, 63)
+    assert npz['pose_jaw'].shape == (n, 3) and npz['pose_eye'].shape == (n, 6) and npz['pose_hand'].shape == (n, 90)
+    assert npz['dmpls'].shape == (n, 8) and npz['betas'].shape == (16,) and npz['surface_model_type'] == 'smplx'
+    back = np.load(str(tmp_path / 'x_stageii.npz'), allow_pickle=True)
+    assert np.array_equal(back['trans'], merged['trans']) and back['num_markers'] == 67
+    parts = amass_io.turn_fullpose_into_parts(np.zeros((2, 48)), 'mano')
+    assert parts['pose_hand'].shape == (2, 45) and 'pose_body' not in parts
