@@ -288,7 +288,7 @@ struct Work {
 };
 
 struct Dims {
-    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, lda, npad, K, D, D4, kw, jt_size, tmk;
+    int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, lda, ldp, npad, K, D, D4, kw, jt_size, tmk;
 };
 
 template <class real>
@@ -298,6 +298,7 @@ M2_HD Dims make_dims(const Model<real> &m) {
     d.NX = 3 + m.p_red + m.nd; d.NCt = (d.PF + m.nd + 3) & ~3; d.n1 = m.n1; d.n2 = m.n2;
     d.npad = (m.n2 + 3) & ~3;
     d.ld = d.npad;              // Cholesky factor: rows are 16-byte aligned (vector read-modify-write of 4x4 tiles)
+    d.ldp = d.npad + 4;         // row length of the transposed panel (one extra row: the right-hand side)
     d.lda = d.npad | 1;         // A: odd leading dimension, so row-strided and transposed tile accesses spread over banks
     d.K = m.prior_k; d.D = m.prior_d; d.D4 = m.prior_d4; d.kw = m.kw;
     d.tmk = m.tile_markers > 0 ? m.tile_markers : 8;
@@ -335,9 +336,9 @@ M2_HD void carve(Work<real> &w, const Dims &d, const Model<real> &m, Arena &S, A
     w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
     w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
     w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * d.tmk * d.npad);
-    w.A = B.take<real>(size_t(d.n2) * d.lda); w.Lm = B.take<real>(size_t(d.n2) * d.ld);
+    w.A = B.take<real>(size_t(d.n2) * d.lda); w.Lm = B.take<real>(size_t(d.n2 + 1) * d.ld);
     w.Linv = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
-    w.Pn = S.take<real>(size_t(kCholNB) * d.npad);
+    w.Pn = S.take<real>(size_t(kCholNB) * d.ldp);
     w.g = S.take<real>(d.npad); w.Ag = S.take<real>(d.npad); w.dgn = S.take<real>(d.npad);
     w.d = S.take<real>(d.npad); w.tmp = S.take<real>(d.npad); w.ds = S.take<real>(d.npad);
     w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16); w.hct = S.take<real>(hct_size + 4);
@@ -507,27 +508,9 @@ struct Solver {
             for (int q = 0; q < 3; ++q) w.vp[3 * s + q] = v[q] + xs[q];
             for (int q = 0; q < 9; ++q) w.Rsk[9 * s + q] = Rs[q];
         }
-        // max-mixture prior: y_k = Q_k (x - mu_k)
-        if (c.wp > real(0)) {
-            const int D = d.D, D4 = d.D4;
-            CTA_FOR(idx, d.K * D) {
-                const int k = idx / D, i = idx - k * D;
-                const real *Q = m.prior_Q4 + (size_t(k) * D + i) * D4;
-                const real *mu = w.c_pmeans + k * D;
-                const real *xb = th + m.prior_off;
-                real s = 0;
-                int l = 0;
-                for (; l + 4 <= D; l += 4) {
-                    const Vec4<real> q = ld4(Q + l);
-                    s += q.x * (xb[l] - mu[l]) + q.y * (xb[l + 1] - mu[l + 1]) + q.z * (xb[l + 2] - mu[l + 2]) + q.w * (xb[l + 3] - mu[l + 3]);
-                }
-                for (; l < D; ++l) s += Q[l] * (xb[l] - mu[l]);
-                w.py[idx] = s;
-            }
-        }
         M2_SYNC();
         M2_TACC(3);
-        // simulated markers and data residual (transformed_lm.py:130-159)
+        // simulated markers and data residual (transformed_lm.py:130-159); the prior products share the phase
         CTA_FOR(mi, d.M) {
             const real *v0 = w.vp + 9 * mi, *v1 = v0 + 3, *v2 = v0 + 6;
             real e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
@@ -548,6 +531,28 @@ struct Solver {
                 w.rm[3 * mi + q] = vis ? (mk - w.obs[3 * mi + q]) * wd : real(0);
             }
         }
+        // max-mixture prior: y_k = Q_k (x - mu_k)
+        if (c.wp > real(0)) {
+            const int D = d.D, D4 = d.D4;
+            // items are dealt from the last thread downwards so that they overlap the 3M/3 marker threads
+#pragma unroll 1
+            for (int idx = cta.nthr - 1 - cta.tid; idx < d.K * D; idx += cta.nthr) {
+                const int k = idx / D, i = idx - k * D;
+                const real *Q = m.prior_Q4 + (size_t(k) * D + i) * D4;
+                const real *mu = w.c_pmeans + k * D;
+                const real *xb = th + m.prior_off;
+                real s = 0;
+                int l = 0;
+                for (; l + 4 <= D; l += 4) {
+                    const Vec4<real> q = ld4(Q + l);
+                    s += q.x * (xb[l] - mu[l]) + q.y * (xb[l + 1] - mu[l + 1]) + q.z * (xb[l + 2] - mu[l + 2]) + q.w * (xb[l + 3] - mu[l + 3]);
+                }
+                for (; l < D; ++l) s += Q[l] * (xb[l] - mu[l]);
+                w.py[idx] = s;
+            }
+        }
+        M2_SYNC();
+        M2_TACC(4);
         if (c.wp > real(0)) {
             CTA_FOR(k, d.K) {
                 const real *mu = w.c_pmeans + k * d.D;
@@ -556,8 +561,6 @@ struct Solver {
                 w.pq[k] = s;
             }
         }
-        M2_SYNC();
-        M2_TACC(4);
         real part[N_ERR] = {0, 0, 0, 0, 0, 0};
         CTA_FOR(i, 3 * d.M) part[ERR_DATA] += w.rm[i] * w.rm[i];
         if (c.velo) CTA_FOR(i, d.PR) { const real e = (th[i] - w.velo_tgt[i]) * wv; part[ERR_VELO] += e * e; }
@@ -671,6 +674,27 @@ struct Solver {
         }
     }
 
+    // ---- a finished 3x3 block of T1: body joints go straight to their free columns of the tile (weighted and
+    //      masked); hand joints go to the full-pose tile for the PCA chain (T2b)
+    M2_D void t1_store(int ml, int mi, int a, const real *blk) {
+        if (3 * a < m.body_dof) {
+            const real sc = w.vis[mi] ? wd : real(0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int col = w.colmap[3 + 3 * a + k];
+                if (col >= 0) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) w.Jf[(3 * ml + r) * d.npad + col] = blk[3 * r + k] * sc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
+        }
+    }
+
     // ---- normal equations at the state of the latest eval():  A = J^T J (full symmetric), g = -J^T r
     M2_D void build(const real *xs, const StepCfg<real> &c) {
         ++n_build;
@@ -737,12 +761,7 @@ struct Solver {
 #pragma unroll
                     for (int q = 0; q < 9; ++q)
                         blk[q] += __shfl_down_sync(0xffffffffu, blk[q], 1) + __shfl_down_sync(0xffffffffu, blk[q], 2);
-                    if (valid && t == 0) {
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
-                    }
+                    if (valid && t == 0) t1_store(ml, t0 + ml, a, blk);
                 }
 #else
                 for (int gi = 0; gi < ngroups; ++gi) {
@@ -753,8 +772,7 @@ struct Solver {
                         t1_partial(t0 + ml, a, t, part);
                         for (int q = 0; q < 9; ++q) blk[q] += part[q];
                     }
-                    for (int r = 0; r < 3; ++r)
-                        for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
+                    t1_store(ml, t0 + ml, a, blk);
                 }
 #endif
             }
@@ -776,25 +794,24 @@ struct Solver {
                     const real *L = w.Loc + 27 * mi + 9 * t;
                     for (int r = 0; r < 3; ++r) val[r] += L[3 * r] * dv[0] + L[3 * r + 1] * dv[1] + L[3 * r + 2] * dv[2];
                 }
-                for (int r = 0; r < 3; ++r) w.Jt[(3 * ml + r) * d.NCt + d.PF + i] = val[r];
+                const int col = w.colmap[3 + d.PR + i];
+                const real sc = w.vis[mi] ? wd : real(0);
+                if (col >= 0) for (int r = 0; r < 3; ++r) w.Jf[(3 * ml + r) * d.npad + col] = val[r] * sc;
+            }
+            // translation columns (identity) and the zero padding of the tile
+            const int trows = 3 * tm;
+            {
+                const int npadc = d.npad - n, per = 3 + npadc;
+                CTA_FOR(idx, trows * per) {
+                    const int row = idx / per, q = idx - row * per;
+                    if (q < 3) {
+                        const int col = w.colmap[q];
+                        if (col >= 0) w.Jf[row * d.npad + col] = (row % 3 == q) ? (w.vis[t0 + row / 3] ? wd : real(0)) : real(0);
+                    } else w.Jf[row * d.npad + n + (q - 3)] = 0;
+                }
             }
             M2_SYNC();
             M2_TACC(7);
-            // T2a: translation / body / DMPL columns: gather, weight, mask (hand columns are written by T2b)
-            const int trows = 3 * tm;
-            CTA_FOR(idx, trows * d.npad) {
-                const int row = idx / d.npad, cc = idx - row * d.npad;
-                real v = 0;
-                bool store = true;
-                if (cc < n) {
-                    const int src = w.colsrc[cc];
-                    if (src >= 0) v = w.Jt[row * d.NCt + src];
-                    else if (src >= -3) v = (row % 3 == -1 - src) ? real(1) : real(0);
-                    else store = false;
-                    v *= (w.vis[t0 + row / 3] ? wd : real(0));
-                }
-                if (store) w.Jf[row * d.npad + cc] = v;
-            }
             // T2b: hand columns = Jt[:, hand block] * C^T as a register-tiled product (1 row x 4 outputs)
             if (hand_free) {
                 for (int b = 0; b < m.hb_n; ++b) {
@@ -942,6 +959,8 @@ struct Solver {
         for (int i = 0; i < n; ++i)
             for (int j = 0; j <= i; ++j) w.Lm[i * ld + j] = w.A[i * d.lda + j] * w.ds[i] * w.ds[j];
 #endif
+        // the scaled right-hand side rides along as row n: after the factorisation it holds z = L^-1 (ds*g)
+        CTA_FOR(j, n) w.Lm[n * ld + j] = w.g[j] * w.ds[j];
         M2_SYNC();
         M2_TACC(11);
         for (int k0 = 0; k0 < n; k0 += NB) {
@@ -1028,12 +1047,12 @@ struct Solver {
             if (w.isc[3] == 0) return false;
             // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p]); the solved panel is
             // also kept transposed (Pn[c][row]) so that the trailing update reads consecutive vectors
-            CTA_FOR(ii, d.npad - k0 - kb) {
+            CTA_FOR(ii, d.ldp - k0 - kb) {
                 const int i = k0 + kb + ii;
                 real xr[NB];
 #pragma unroll
                 for (int cc = 0; cc < NB; ++cc) xr[cc] = 0;
-                if (i < n) {
+                if (i <= n) {
                     real *row = w.Lm + i * ld + k0;
                     real av[NB];
 #pragma unroll
@@ -1049,12 +1068,12 @@ struct Solver {
                     for (int cc = 0; cc < NB; ++cc) if (cc < kb) row[cc] = xr[cc];
                 }
 #pragma unroll
-                for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.npad + i] = xr[cc];
+                for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.ldp + i] = xr[cc];
             }
             M2_SYNC();
             M2_TACC(13);
             // trailing update with 4x4 register tiles: Lm[i][j] -= sum_c Pn[c][i] Pn[c][j], tiles with tj <= ti
-            const int r0 = k0 + kb, R = n - r0;
+            const int r0 = k0 + kb, R = r0 < n ? n + 1 - r0 : 0;   // rows r0..n (row n = right-hand side), columns r0..n-1
             if (R > 0) {
                 const int nt = (R + kBS - 1) / kBS, ntri = nt * (nt + 1) / 2;
                 CTA_FOR(it, ntri) {
@@ -1066,7 +1085,7 @@ struct Solver {
                     for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
 #pragma unroll
                     for (int cc = 0; cc < NB; ++cc) {
-                        const Vec4<real> av = ld4(w.Pn + cc * d.npad + r0 + ti * kBS), bv = ld4(w.Pn + cc * d.npad + r0 + tj * kBS);
+                        const Vec4<real> av = ld4(w.Pn + cc * d.ldp + r0 + ti * kBS), bv = ld4(w.Pn + cc * d.ldp + r0 + tj * kBS);
                         const real ai[4] = {av.x, av.y, av.z, av.w}, bj[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                         for (int p = 0; p < kBS; ++p)
@@ -1076,7 +1095,7 @@ struct Solver {
 #pragma unroll
                     for (int p = 0; p < kBS; ++p) {
                         const int i = r0 + ti * kBS + p;
-                        if (i < n) {
+                        if (i <= n && r0 + tj * kBS < n) {
                             real *dst = w.Lm + i * ld + r0 + tj * kBS;
                             Vec4<real> v = ld4(dst);
                             v.x -= acc[p * kBS]; v.y -= acc[p * kBS + 1]; v.z -= acc[p * kBS + 2]; v.w -= acc[p * kBS + 3];
@@ -1088,40 +1107,14 @@ struct Solver {
                 M2_TACC(14);
             }
         }
-        // triangular solves by the first warp, block column by block column:  L z = ds*g ;  L^T y = z.
+        // backward solve L^T y = z by the first warp, block column by block column (the forward solve happened
+        // inside the factorisation).
         // Fully unrolled over the block width so that every small vector lives in registers.
         const int wl = cta.nthr < 32 ? cta.nthr : 32;
         if (cta.tid < wl) {
             const int lane = cta.tid;
-            for (int i = lane; i < n; i += wl) w.tmp[i] = w.g[i] * w.ds[i];
+            for (int i = lane; i < n; i += wl) w.tmp[i] = w.Lm[n * ld + i];     // z = L^-1 (ds*g), see above
             M2_WSYNC();
-            for (int k0 = 0; k0 < n; k0 += NB) {
-                const int kb = (n - k0 < NB) ? n - k0 : NB;
-                const real *Li = w.Linv + (k0 / NB) * NB * NB;
-                real tv[NB], z[NB];
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) tv[cc] = cc < kb ? w.tmp[k0 + cc] : real(0);
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) {          // z = Linv t, every lane redundantly
-                    real sacc = 0;
-#pragma unroll
-                    for (int pp = 0; pp <= cc; ++pp) sacc += Li[cc * NB + pp] * tv[pp];
-                    z[cc] = sacc;
-                }
-                M2_WSYNC();
-                if (lane == 0) {
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) w.tmp[k0 + cc] = z[cc];
-                }
-                for (int i = k0 + kb + lane; i < n; i += wl) {
-                    const real *row = w.Lm + i * ld + k0;
-                    real sacc = w.tmp[i];
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) sacc -= row[cc] * z[cc];
-                    w.tmp[i] = sacc;
-                }
-                M2_WSYNC();
-            }
             for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
                 const int kb = (n - k0 < NB) ? n - k0 : NB;
                 const real *Li = w.Linv + (k0 / NB) * NB * NB;
