@@ -38,7 +38,10 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr size_t kMaxSmem = 227 * 1024;
-template <class real> constexpr int threads_for() { return sizeof(real) == 4 ? 512 : 256; }
+#ifndef MOSH2_F32_THREADS
+#define MOSH2_F32_THREADS 384      // 168 registers per thread: measured best of 256 / 320 / 384 / 512 (profiles/)
+#endif
+template <class real> constexpr int threads_for() { return sizeof(real) == 4 ? MOSH2_F32_THREADS : 256; }
 
 template <class real, bool BIG>
 __global__ void __launch_bounds__(threads_for<real>(), 1)

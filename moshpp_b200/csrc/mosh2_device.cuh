@@ -146,7 +146,6 @@ template <> M2_HD double accept_slack<double>() { return 0.0; }
 
 template <class real> struct alignas(16) Vec4 { real x, y, z, w; };
 template <class real> M2_HD Vec4<real> ld4(const real *p) { return *reinterpret_cast<const Vec4<real> *>(p); }
-
 template <class real>
 M2_NOINLINE void mat3_mul(const real *A, const real *B, real *C) {   // C = A B (row-major 3x3); C must not alias A or B
 #pragma unroll 1
@@ -630,21 +629,26 @@ struct Solver {
         }
     }
 
+    // ---- pose-blend vectors of slot (marker mi, vertex t) for joint a (nine 16-byte loads, issued together)
+    M2_D void t1_load(int mi, int a, int t, Vec4<real> *p) {
+        const size_t estride = size_t(d.S) * kPdSlot;
+        const real *P = m.pd4 + size_t(a >= 1 ? a - 1 : 0) * 9 * estride + size_t(3 * mi + t) * kPdSlot;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) p[e] = ld4(P + e * estride);
+    }
+
     // ---- contribution of slot (marker mi, vertex t) to the 3x3 Jacobian block of joint a:  blk[r*3+k] +=
-    M2_D void t1_partial(int mi, int a, int t, real *blk) {
+    M2_D void t1_compute(int mi, int a, int t, const Vec4<real> *p, real *blk) {
         const int s = 3 * mi + t;
         if (a >= 1) {
-            const size_t estride = size_t(d.S) * kPdSlot;
-            const real *P = m.pd4 + size_t(a - 1) * 9 * estride + size_t(s) * kPdSlot;
             const real *dR = w.dRl + 27 * a;
             real E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // E[c*3+k] = sum_e Pd[c][e] dR_k[e]
 #pragma unroll
             for (int e = 0; e < 9; ++e) {
-                const Vec4<real> p = ld4(P + e * estride);
                 const real q0 = dR[e], q1 = dR[9 + e], q2 = dR[18 + e];
-                E[0] += p.x * q0; E[1] += p.x * q1; E[2] += p.x * q2;
-                E[3] += p.y * q0; E[4] += p.y * q1; E[5] += p.y * q2;
-                E[6] += p.z * q0; E[7] += p.z * q1; E[8] += p.z * q2;
+                E[0] += p[e].x * q0; E[1] += p[e].x * q1; E[2] += p[e].x * q2;
+                E[3] += p[e].y * q0; E[4] += p[e].y * q1; E[5] += p[e].y * q2;
+                E[6] += p[e].z * q0; E[7] += p[e].z * q1; E[8] += p[e].z * q2;
             }
             const real *Mt = w.MtR + 9 * s;
 #pragma unroll
@@ -748,6 +752,7 @@ struct Solver {
 #if M2_GPU
                 const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
                 const int t = lane % 3, grp = lane / 3;
+#pragma unroll 1
                 for (int g0 = warp * 10; g0 < ngroups; g0 += nwarp * 10) {
                     const int gi = g0 + grp;
                     const bool valid = lane < 30 && gi < ngroups;
@@ -756,7 +761,9 @@ struct Solver {
                     if (valid) {
                         ml = gi % tm;
                         a = w.jlist[gi / tm];
-                        t1_partial(t0 + ml, a, t, blk);
+                        Vec4<real> pv[9];
+                        t1_load(t0 + ml, a, t, pv);
+                        t1_compute(t0 + ml, a, t, pv, blk);
                     }
 #pragma unroll
                     for (int q = 0; q < 9; ++q)
@@ -769,7 +776,9 @@ struct Solver {
                     real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                     for (int t = 0; t < 3; ++t) {
                         real part[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                        t1_partial(t0 + ml, a, t, part);
+                        Vec4<real> pv[9];
+                        t1_load(t0 + ml, a, t, pv);
+                        t1_compute(t0 + ml, a, t, pv, part);
                         for (int q = 0; q < 9; ++q) blk[q] += part[q];
                     }
                     t1_store(ml, t0 + ml, a, blk);
