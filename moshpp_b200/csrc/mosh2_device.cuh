@@ -332,10 +332,25 @@ M2_HD void carve(Work<real> &w, const Dims &d, const Model<real> &m, Arena &S, A
     w.vp = S.take<real>(3 * d.S); w.pj = S.take<real>(3 * d.S * d.kw); w.Rsk = S.take<real>(9 * d.S);
     w.mk = S.take<real>(3 * d.M); w.rm = S.take<real>(3 * d.M); w.obs = S.take<real>(3 * d.M);
     w.py = S.take<real>(d.K * d.D + 1); w.pq = S.take<real>(d.K + 1);
-    w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
-    w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
-    w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * d.tmk * d.npad);
-    w.A = B.take<real>(size_t(d.n2) * d.lda); w.Lm = B.take<real>(size_t(d.n2 + 1) * d.ld);
+    // The Cholesky factor is alive only inside gauss_newton(); the Jacobian tiles and the other scratch of build()
+    // (and the pose-blend partial sums of eval(), which live in Jt) are dead there, so they share its storage.
+    w.A = B.take<real>(size_t(d.n2) * d.lda);
+    {
+        const size_t mark_b = B.off;
+        w.Lm = B.take<real>(size_t(d.n2 + 1) * d.ld);
+        const size_t end_b = B.off;
+        B.off = mark_b;
+        w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * d.tmk * d.npad);
+        if (!BIG) {
+            w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
+            w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
+        }
+        if (B.off < end_b) B.off = end_b;
+    }
+    if (BIG) {
+        w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
+        w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
+    }
     w.Linv = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
     w.Pn = S.take<real>(size_t(kCholNB) * d.ldp);
     w.g = S.take<real>(d.npad); w.Ag = S.take<real>(d.npad); w.dgn = S.take<real>(d.npad);
