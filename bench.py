@@ -21,7 +21,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -45,27 +44,36 @@ def algorithmic_bytes(pk, has_velo=True, fingers=True):
     return dict(R=R, n=n, B_K1=b_k1, B_K2=b_k2)
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms 100` child process from the warm-up to the end of the end-to-end leg."""
 
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.15)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            for line in out.strip().splitlines():
+                r = [x.strip() for x in line.split(',')]
+                if len(r) >= 7:
+                    self.rows.append(r)
+        except Exception:
+            pass
 
     def summary(self):
         if not self.rows:
@@ -200,13 +208,13 @@ def main():
         flush_buf.add_(1)
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         flush_l2()
         job.launch()
         job.sync()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     dev_ms = []
@@ -251,8 +259,7 @@ def main():
         mine = torch.from_numpy(res.pose.astype(np.float32)).to(f'cuda:{local_rank}')
         gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, gathered, dst=0)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
 
     solved = int(((res.status & lib.ST_SOLVED) != 0).sum())
     ab = algorithmic_bytes(pk)
