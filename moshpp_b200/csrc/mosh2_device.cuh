@@ -54,7 +54,7 @@ enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, E
 constexpr int kTileMarkersMax = 16;   // markers per Jacobian tile: 16 (48 rows) when shared memory allows, else 8
 constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
 constexpr int kPdSlot = 4;        // pose-blend rows of one slot (x, y, z, pad): one 16-byte vector per (joint, e)
-constexpr int kBlendGroups = 3;   // joint groups of the pose-blend partial sums
+constexpr int kBlendGroups = 3;   // upper bound of the joint groups of the pose-blend partial sums (run time: 1..3, one round of threads)
 constexpr int kCholNB = 8;        // block column width of the Cholesky factorisation
 constexpr int kMaxHandBlocks = 4;
 
@@ -109,6 +109,16 @@ struct Job {
 // ---------------------------------------------------------------------------------------------
 M2_HD float r_sqrt(float x) { return sqrtf(x); }
 M2_HD double r_sqrt(double x) { return sqrt(x); }
+// reciprocal square root: MUFU.RSQ plus one Newton step on the device (f32), exact division elsewhere
+M2_HD float r_rsqrt(float x) {
+#if M2_GPU
+    const float y = rsqrtf(x);
+    return y * (1.5f - 0.5f * x * y * y);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+M2_HD double r_rsqrt(double x) { return 1.0 / sqrt(x); }
 M2_HD float r_abs(float x) { return fabsf(x); }
 M2_HD double r_abs(double x) { return fabs(x); }
 M2_HD void r_sincos(float x, float *s, float *c) {
@@ -279,8 +289,8 @@ struct Work {
     int *colmap, *colsrc, *jlist, *isc;
     // small per-model tables: shared-memory copies when they fit (a dependent global load costs ~600 cycles and the
     // kinematic-tree walk alone chains three of them per level), else aliases of the global arrays
-    const int *c_parents, *c_fk_order, *c_level_ofs, *c_wj, *c_ancmask, *c_free1, *c_free2;
-    const int8_t *c_ancpos;
+    const int *c_parents, *c_fk_order, *c_level_ofs, *c_wj, *c_free1, *c_free2;
+    int *c_tin, *c_tsz;       // pre-order index and subtree size of every joint: j in subtree(a) <=> tin[j]-tin[a] in [0, tsz[a])
     const real *c_wv, *c_v0, *c_coefs, *c_j0, *c_hmean, *c_pmeans, *c_pnlw;
     long long *prof;
     uint8_t *vis;
@@ -365,7 +375,8 @@ M2_HD void carve(Work<real> &w, const Dims &d, const Model<real> &m, Arena &S, A
     w.c_wj = S.take<int>(d.S * d.kw); w.c_free1 = S.take<int>(d.n1); w.c_free2 = S.take<int>(d.n2);
     w.c_wv = S.take<real>(d.S * d.kw); w.c_v0 = S.take<real>(3 * d.S); w.c_coefs = S.take<real>(3 * d.M);
     w.c_j0 = S.take<real>(3 * d.nJ); w.c_hmean = S.take<real>(m.n_hand_full + 1);
-    w.c_ancmask = m.anc_mask; w.c_ancpos = m.anc_pos; w.c_pmeans = m.prior_means; w.c_pnlw = m.prior_nlw;
+    w.c_tin = S.take<int>(d.nJ); w.c_tsz = S.take<int>(d.nJ);
+    w.c_pmeans = S.take<real>(d.K * d.D + 1); w.c_pnlw = S.take<real>(d.K + 1);
 }
 
 // configuration of one minimisation (one ch.minimize call of the reference)
@@ -424,10 +435,15 @@ struct Solver {
 
     // ---- pose-blend partial sums: item (joint group, slot) -> x,y,z of the slot; part[g][3 s + c] (aliases Jt).
     //      Lanes run over consecutive slots, so every warp load is one contiguous run of 16-byte vectors.
+    M2_D int blend_groups(int nl) const {      // as many joint groups as fit one round of the nl blending threads
+        int g = nl / d.S;
+        return g < 1 ? 1 : (g > kBlendGroups ? kBlendGroups : g);
+    }
     M2_D void blend_partials(int l, int nl) {
-        const int per = (d.nJ - 1 + kBlendGroups - 1) / kBlendGroups;
+        const int G = blend_groups(nl);
+        const int per = (d.nJ - 1 + G - 1) / G;
         const size_t estride = size_t(d.S) * kPdSlot;
-        for (int it = l; it < d.S * kBlendGroups; it += nl) {
+        for (int it = l; it < d.S * G; it += nl) {
             const int g = it / d.S, s = it - g * d.S;
             int j0 = 1 + g * per, j1 = j0 + per;
             if (j1 > d.nJ) j1 = d.nJ;
@@ -481,17 +497,39 @@ struct Solver {
         M2_SYNC();
         M2_TACC(1);
 #if M2_GPU
+        const int nblend = cta.nthr > 64 ? cta.nthr - 32 : cta.nthr;
         if (cta.nthr > 64) {                      // warp 0 walks the kinematic tree while the others blend
-            if (cta.tid < 32) fk(cta.tid, 32); else blend_partials(cta.tid - 32, cta.nthr - 32);
+            if (cta.tid < 32) fk(cta.tid, 32); else blend_partials(cta.tid - 32, nblend);
         } else {
-            fk(cta.tid, cta.nthr); __syncthreads(); blend_partials(cta.tid, cta.nthr);
+            fk(cta.tid, cta.nthr); __syncthreads(); blend_partials(cta.tid, nblend);
         }
 #else
+        const int nblend = 1;
         fk(0, 1);
         blend_partials(0, 1);
 #endif
+        const int nbg = blend_groups(nblend);
         M2_SYNC();
         M2_TACC(2);
+        // max-mixture prior: y_k = Q_k (x - mu_k), one row of Q per item.  The items are dealt from the last thread
+        // downwards so that the second round falls on threads that do not skin.
+        if (c.wp > real(0)) {
+            const int D = d.D, D4 = d.D4;
+            const real *xb = th + m.prior_off;
+#pragma unroll 1
+            for (int idx = cta.nthr - 1 - cta.tid; idx < d.K * D; idx += cta.nthr) {
+                const int k = idx / D;
+                const real *Q = m.prior_Q4 + size_t(idx) * D4, *mu = w.c_pmeans + k * D;
+                real s = 0;
+                int l = 0;
+                for (; l + 4 <= D; l += 4) {
+                    const Vec4<real> q = ld4(Q + l);
+                    s += q.x * (xb[l] - mu[l]) + q.y * (xb[l + 1] - mu[l + 1]) + q.z * (xb[l + 2] - mu[l + 2]) + q.w * (xb[l + 3] - mu[l + 3]);
+                }
+                for (; l < D; ++l) s += Q[l] * (xb[l] - mu[l]);
+                w.py[idx] = s;
+            }
+        }
         // skinning of the 3M slots
         CTA_FOR(s, d.S) {
             real vpo[3];
@@ -499,8 +537,7 @@ struct Solver {
             for (int q = 0; q < 3; ++q) {
                 real a = w.c_v0[3 * s + q];
                 for (int e = 0; e < d.nd; ++e) a += m.sd[(3 * s + q) * d.nd + e] * dl[e];
-#pragma unroll
-                for (int g = 0; g < kBlendGroups; ++g) a += w.Jt[(g * d.S + s) * 3 + q];
+                for (int g = 0; g < nbg; ++g) a += w.Jt[(g * d.S + s) * 3 + q];
                 vpo[q] = a;
             }
             real v[3] = {0, 0, 0};
@@ -545,35 +582,26 @@ struct Solver {
                 w.rm[3 * mi + q] = vis ? (mk - w.obs[3 * mi + q]) * wd : real(0);
             }
         }
-        // max-mixture prior: y_k = Q_k (x - mu_k)
-        if (c.wp > real(0)) {
-            const int D = d.D, D4 = d.D4;
-            // items are dealt from the last thread downwards so that they overlap the 3M/3 marker threads
-#pragma unroll 1
-            for (int idx = cta.nthr - 1 - cta.tid; idx < d.K * D; idx += cta.nthr) {
-                const int k = idx / D, i = idx - k * D;
-                const real *Q = m.prior_Q4 + (size_t(k) * D + i) * D4;
-                const real *mu = w.c_pmeans + k * D;
-                const real *xb = th + m.prior_off;
-                real s = 0;
-                int l = 0;
-                for (; l + 4 <= D; l += 4) {
-                    const Vec4<real> q = ld4(Q + l);
-                    s += q.x * (xb[l] - mu[l]) + q.y * (xb[l + 1] - mu[l + 1]) + q.z * (xb[l + 2] - mu[l + 2]) + q.w * (xb[l + 3] - mu[l + 3]);
-                }
-                for (; l < D; ++l) s += Q[l] * (xb[l] - mu[l]);
-                w.py[idx] = s;
-            }
-        }
         M2_SYNC();
         M2_TACC(4);
-        if (c.wp > real(0)) {
-            CTA_FOR(k, d.K) {
+        if (c.wp > real(0)) {                  // q_k = (x - mu_k)^T y_k - log w_k, one warp per component
+#if M2_GPU
+            const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
+            for (int k = warp; k < d.K; k += nwarp) {
                 const real *mu = w.c_pmeans + k * d.D;
-                real s = w.c_pnlw[k];
-                for (int i = 0; i < d.D; ++i) s += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
-                w.pq[k] = s;
+                real sacc = 0;
+                for (int i = lane; i < d.D; i += 32) sacc += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
+                sacc = warp_sum(sacc);
+                if (lane == 0) w.pq[k] = sacc + w.c_pnlw[k];
             }
+#else
+            for (int k = 0; k < d.K; ++k) {
+                const real *mu = w.c_pmeans + k * d.D;
+                real sacc = w.c_pnlw[k];
+                for (int i = 0; i < d.D; ++i) sacc += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
+                w.pq[k] = sacc;
+            }
+#endif
         }
         real part[N_ERR] = {0, 0, 0, 0, 0, 0};
         CTA_FOR(i, 3 * d.M) part[ERR_DATA] += w.rm[i] * w.rm[i];
@@ -653,7 +681,34 @@ struct Solver {
     }
 
     // ---- contribution of slot (marker mi, vertex t) to the 3x3 Jacobian block of joint a:  blk[r*3+k] +=
-    M2_D void t1_compute(int mi, int a, int t, const Vec4<real> *p, real *blk) {
+    M2_D void t1_rigid(int mi, int a, int t, real *blk) {
+        const int s = 3 * mi + t;
+        real q[3] = {0, 0, 0};                       // sum of w_j (p_j - t_a) over the slot's joints below a
+        bool any = false;
+        {
+            const int ta = w.c_tin[a], na = w.c_tsz[a];
+            for (int i = 0; i < d.kw; ++i) {
+                const int j = w.c_wj[s * d.kw + i];
+                if (j >= 0 && unsigned(w.c_tin[j] - ta) < unsigned(na)) {
+                    const real wt = w.c_wv[s * d.kw + i];
+                    const real *pp = w.pj + 3 * (s * d.kw + i);
+                    for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
+                    any = true;
+                }
+            }
+        }
+        if (any) {
+            const real *L = w.Loc + 27 * mi + 9 * t;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                real cr[3];
+                cross3(w.u + 3 * (3 * a + k), q, cr);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
+            }
+        }
+    }
+    M2_D void t1_blend(int mi, int a, int t, const Vec4<real> *p, real *blk) {
         const int s = 3 * mi + t;
         if (a >= 1) {
             const real *dR = w.dRl + 27 * a;
@@ -672,25 +727,10 @@ struct Solver {
                 for (int k = 0; k < 3; ++k)
                     blk[3 * r + k] += Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
         }
-        const int ai = w.c_ancpos[s * d.nJ + a];
-        if (ai >= 0) {
-            const int mask = w.c_ancmask[s * m.na + ai];
-            real q[3] = {0, 0, 0};
-            for (int i = 0; i < d.kw; ++i)
-                if ((mask >> i) & 1) {
-                    const real wt = w.c_wv[s * d.kw + i];
-                    const real *pp = w.pj + 3 * (s * d.kw + i);
-                    for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
-                }
-            const real *L = w.Loc + 27 * mi + 9 * t;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                real cr[3];
-                cross3(w.u + 3 * (3 * a + k), q, cr);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
-            }
-        }
+    }
+    M2_D void t1_compute(int mi, int a, int t, const Vec4<real> *p, real *blk) {
+        t1_blend(mi, a, t, p, blk);
+        t1_rigid(mi, a, t, blk);
     }
 
     // ---- a finished 3x3 block of T1: body joints go straight to their free columns of the tile (weighted and
@@ -838,27 +878,29 @@ struct Solver {
             M2_TACC(7);
             // T2b: hand columns = Jt[:, hand block] * C^T as a register-tiled product (1 row x 4 outputs)
             if (hand_free) {
-                for (int b = 0; b < m.hb_n; ++b) {
+                int ngt = 0;                                  // output groups of 4 over all blocks
+                for (int b = 0; b < m.hb_n; ++b) ngt += m.hb[b].rw4 / 4;
+                CTA_FOR(it, trows * ngt) {
+                    const int row = it / ngt;
+                    int rg = it - row * ngt, b = 0;
+                    while (rg >= m.hb[b].rw4 / 4) { rg -= m.hb[b].rw4 / 4; ++b; }
                     const HandBlock hb = m.hb[b];
-                    const int nq = hb.q1 - hb.q0, ng = hb.rw4 / 4;
-                    CTA_FOR(it, trows * ng) {
-                        const int row = it / ng, rg = it - row * ng;
-                        const real *Jr = w.Jt + row * d.NCt + m.body_dof + hb.q0;
-                        const real *ct = w.hct + hb.ct_off + 4 * rg;
-                        real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                        for (int q = 0; q < nq; ++q) {
-                            const real jv = Jr[q];
-                            const Vec4<real> cv = ld4(ct + q * hb.rw4);
-                            a0 += jv * cv.x; a1 += jv * cv.y; a2 += jv * cv.z; a3 += jv * cv.w;
-                        }
-                        const real sc = w.vis[t0 + row / 3] ? wd : real(0);
-                        const real out[4] = {a0 * sc, a1 * sc, a2 * sc, a3 * sc};
-                        for (int e = 0; e < 4; ++e) {
-                            const int r = hb.r0 + 4 * rg + e;
-                            if (r < hb.r1) {
-                                const int col = w.colmap[3 + m.body_dof + r];
-                                if (col >= 0) w.Jf[row * d.npad + col] = out[e];
-                            }
+                    const int nq = hb.q1 - hb.q0;
+                    const real *Jr = w.Jt + row * d.NCt + m.body_dof + hb.q0;
+                    const real *ct = w.hct + hb.ct_off + 4 * rg;
+                    real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    for (int q = 0; q < nq; ++q) {
+                        const real jv = Jr[q];
+                        const Vec4<real> cv = ld4(ct + q * hb.rw4);
+                        a0 += jv * cv.x; a1 += jv * cv.y; a2 += jv * cv.z; a3 += jv * cv.w;
+                    }
+                    const real sc = w.vis[t0 + row / 3] ? wd : real(0);
+                    const real out[4] = {a0 * sc, a1 * sc, a2 * sc, a3 * sc};
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = hb.r0 + 4 * rg + e;
+                        if (r < hb.r1) {
+                            const int col = w.colmap[3 + m.body_dof + r];
+                            if (col >= 0) w.Jf[row * d.npad + col] = out[e];
                         }
                     }
                 }
@@ -992,44 +1034,51 @@ struct Solver {
             real *Li = w.Linv + (k0 / NB) * NB * NB;
 #if M2_GPU
             if (cta.tid < 32) {
-                // warp 0: lane r holds row r of the diagonal block in registers; columns are finalised one by
-                // one with shuffles (no local memory, no divides besides one reciprocal per column)
+                // warp 0: every lane factors the whole 8x8 block in registers (36 values, all loops unrolled: no
+                // shuffles, no local memory; the dependent chain is one FMA + one reciprocal square root per
+                // column); lane c then forward-substitutes column c of the inverse.
                 const int lane = cta.tid;
-                const unsigned full = 0xffffffffu;
-                real a[NB], invd[NB], x[NB];
+                real Lb[NB][NB], invd[NB], x[NB];
 #pragma unroll
-                for (int cc = 0; cc < NB; ++cc)
-                    a[cc] = (lane < kb && cc <= lane) ? w.Lm[(k0 + lane) * ld + k0 + cc] : ((cc == lane) ? real(1) : real(0));
+                for (int r = 0; r < NB; ++r)
+#pragma unroll
+                    for (int cc = 0; cc <= r; ++cc)
+                        Lb[r][cc] = (r < kb) ? w.Lm[(k0 + r) * ld + k0 + cc] : ((cc == r) ? real(1) : real(0));
                 bool ok = true;
 #pragma unroll
                 for (int cc = 0; cc < NB; ++cc) {
-                    real v = a[cc];
+                    real piv = Lb[cc][cc];
 #pragma unroll
-                    for (int pp = 0; pp < cc; ++pp) v -= a[pp] * __shfl_sync(full, a[pp], cc);
-                    real piv = __shfl_sync(full, v, cc);
+                    for (int pp = 0; pp < cc; ++pp) piv -= Lb[cc][pp] * Lb[cc][pp];
                     if (!(piv > pivot_eps<real>())) { ok = false; piv = real(1); }
-                    const real sq = r_sqrt(piv), iv = real(1) / sq;
+                    const real iv = r_rsqrt(piv);
+                    Lb[cc][cc] = piv * iv;
                     invd[cc] = iv;
-                    a[cc] = (lane == cc) ? sq : ((lane > cc) ? v * iv : real(0));
-                }
-                // lane c computes column c of the inverse: x[r] = Linv[r][c]
 #pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    real sacc = (r == lane) ? real(1) : real(0);
+                    for (int r = cc + 1; r < NB; ++r) {
+                        real t = Lb[r][cc];
 #pragma unroll
-                    for (int pp = 0; pp < r; ++pp) {
-                        const real lrp = __shfl_sync(full, a[pp], r);
-                        if (pp >= lane) sacc -= lrp * x[pp];
+                        for (int pp = 0; pp < cc; ++pp) t -= Lb[r][pp] * Lb[cc][pp];
+                        Lb[r][cc] = t * iv;
                     }
-                    x[r] = (r >= lane) ? sacc * invd[r] : real(0);
+                }
+                const int c = lane & (NB - 1);
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {                 // x[r] = Linv[r][c]
+                    real sacc = (r == c) ? real(1) : real(0);
+#pragma unroll
+                    for (int pp = 0; pp < r; ++pp) sacc -= Lb[r][pp] * x[pp];
+                    x[r] = sacc * invd[r];
                 }
                 if (lane < NB) {
 #pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) {
-                        if (lane < kb && cc <= lane) w.Lm[(k0 + lane) * ld + k0 + cc] = a[cc];
-                        Li[cc * NB + lane] = x[cc];       // rows/columns >= kb hold identity padding
-                    }
+                    for (int r = 0; r < NB; ++r) Li[r * NB + lane] = x[r];   // rows/columns >= kb hold identity padding
                 }
+#pragma unroll
+                for (int r = 0; r < NB; ++r)
+#pragma unroll
+                    for (int cc = 0; cc <= r; ++cc)
+                        if (r < kb && lane == ((r * (r + 1) / 2 + cc) & 31)) w.Lm[(k0 + r) * ld + k0 + cc] = Lb[r][cc];
                 if (!ok && lane == 0) w.isc[3] = 0;
             }
 #else
@@ -1486,7 +1535,25 @@ struct Solver {
         CTA_FOR(i, 3 * d.M) const_cast<real *>(w.c_coefs)[i] = m.coefs[i];
         CTA_FOR(i, 3 * d.nJ) const_cast<real *>(w.c_j0)[i] = m.j0[i];
         CTA_FOR(i, m.n_hand_full) const_cast<real *>(w.c_hmean)[i] = m.hands_mean[i];
+        CTA_FOR(i, d.K * d.D) const_cast<real *>(w.c_pmeans)[i] = m.prior_means[i];
+        CTA_FOR(i, d.K) const_cast<real *>(w.c_pnlw)[i] = m.prior_nlw[i];
         CTA_FOR(i, 32) w.prof[i] = 0;
+        M2_SYNC();
+        if (cta.tid == 0) {                                    // pre-order numbering of the kinematic tree
+            int *cur = w.jlist;
+            for (int i = 0; i < d.nJ; ++i) w.c_tsz[i] = 1;
+            for (int i = d.nJ - 1; i >= 0; --i) {              // fk_order lists parents before children
+                const int j = w.c_fk_order[i], a = w.c_parents[j];
+                if (a >= 0) w.c_tsz[a] += w.c_tsz[j];
+            }
+            int next_root = 0;
+            for (int i = 0; i < d.nJ; ++i) {
+                const int j = w.c_fk_order[i], a = w.c_parents[j];
+                if (a < 0) { w.c_tin[j] = next_root; next_root += w.c_tsz[j]; }
+                else { w.c_tin[j] = cur[a]; cur[a] += w.c_tsz[j]; }
+                cur[j] = w.c_tin[j] + 1;
+            }
+        }
         M2_SYNC();
         M2_T0();
         bool first = true, have_prev = false, have_dm_prev = false;

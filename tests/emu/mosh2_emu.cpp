@@ -9,6 +9,7 @@
 #include "../../moshpp_b200/csrc/mosh2_host.h"
 
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -115,6 +116,17 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     mosh2::Work<real> w;
     mosh2::Arena S0{nullptr, 0}, G0{nullptr, 0};
     mosh2::carve<real, false>(w, d, hm.m, S0, G0);
+    if (std::getenv("MOSH2_EMU_PLAN")) {        // development aid: shared-memory footprint of this model
+        for (int tile : {16, 8}) {
+            hm.m.tile_markers = tile;
+            const mosh2::Dims dd = mosh2::make_dims(hm.m);
+            mosh2::Work<real> ww;
+            mosh2::Arena Sa{nullptr, 0}, Ga{nullptr, 0};
+            mosh2::carve<real, false>(ww, dd, hm.m, Sa, Ga);
+            std::fprintf(stderr, "plan: sizeof(real)=%zu tile=%d smem=%zu bytes (limit %d)\n", sizeof(real), tile, Sa.off, 227 * 1024);
+        }
+        hm.m.tile_markers = 16;
+    }
     std::vector<char> smem_raw(S0.off + 128);
     char *smem_base = smem_raw.data() + ((32 - (reinterpret_cast<uintptr_t>(smem_raw.data()) & 31)) & 31);
     for (int c = 0; c < job.n_chunks; ++c) {

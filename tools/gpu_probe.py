@@ -32,9 +32,9 @@ def main():
     F = obs.shape[0]
     print(json.dumps(dict(setup_s=round(time.time() - t0, 2), config=name, frames=F, markers=pk.n_markers,
                           n1=len(pk.free_step1), n2=len(pk.free_step2), kw=pk.kw, na=pk.na)), flush=True)
-    model = lib.Model(pk, device=0)
+    model = lib.Model(pk, device=0, library_path=os.environ.get('MOSH2_PROBE_LIB'))   # development: variant builds
     ref = None
-    for prec_name, prec in (('f32', lib.MOSH2_F32), ('f64', lib.MOSH2_F64)):
+    for prec_name, prec in (('f32', lib.MOSH2_F32), ('f64', lib.MOSH2_F64))[:1 if os.environ.get('MOSH2_PROBE_F32_ONLY') else 2]:
         for (L, W) in scheds:
             if prec == lib.MOSH2_F64 and (L, W) not in ((0, 0), (8, 64)):
                 continue
