@@ -45,18 +45,34 @@ template <class real> constexpr int threads_for() { return sizeof(real) == 4 ? M
 
 template <class real, bool BIG>
 __global__ void __launch_bounds__(threads_for<real>(), 1)
-mosh2_stageii_kernel(const mosh2::Model<real> m, const mosh2::Job<real> job) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    // BIG = false: the whole workspace is carved from `smem`, so every workspace access is an LDS/STS;
-    // BIG = true (f64 / oversized models): A, its factor and the Jacobian tiles live in a per-CTA global workspace
-    mosh2::Work<real> w;
-    const mosh2::Dims d = mosh2::make_dims(m);
-    mosh2::Arena S{reinterpret_cast<char *>(smem), 0};
-    mosh2::Arena G{BIG ? job.gws + size_t(blockIdx.x) * job.gws_stride : nullptr, 0};
-    mosh2::carve<real, BIG>(w, d, m, S, G);
+mosh2_stageii_kernel(const __grid_constant__ mosh2::Model<real> m, const __grid_constant__ mosh2::Job<real> job,
+                     const __grid_constant__ mosh2::Work<real, BIG> w, const __grid_constant__ mosh2::Dims d) {
+    // The workspace layout `w` was computed on the host (mosh2::carve) and arrives in the constant bank: every array
+    // is shared-memory base + a parameter word.  BIG = true (f64 / oversized models): A, its factor and the Jacobian
+    // tiles live in a per-CTA global workspace whose base is parked in the shared-memory header.
+    if (BIG) {
+        if (threadIdx.x == 0) *reinterpret_cast<char **>(mosh2::m2_smem()) = job.gws + size_t(blockIdx.x) * job.gws_stride;
+        __syncthreads();
+    }
     mosh2::Cta c{int(threadIdx.x), int(blockDim.x)};
-    mosh2::Solver<real> s(m, job, w, d, c);
+    mosh2::Solver<real, BIG> s(m, job, w, d, c);
+    // f32 with the workspace in shared memory: J^T J accumulates on the tensor cores (tcgen05, accumulator in
+    // tensor memory); warp 0 owns the allocation
+    if (w.tc) {
+        if (threadIdx.x < 32) mosh2::tc::tmem_alloc(mosh2::tc::smem_u32(w.tmem_slot), mosh2::kTcCols);
+        if (threadIdx.x == 32) mosh2::tc::mbar_init(mosh2::tc::smem_u32(w.mbar), 1);
+        mosh2::tc::fence_before();
+        __syncthreads();
+        mosh2::tc::fence_after();
+        s.tc_tmem = *w.tmem_slot;
+        s.tc_kt = 3 * d.tmk;
+    }
     s.run_chunk(blockIdx.x);
+    if (w.tc) {
+        mosh2::tc::fence_before();
+        __syncthreads();
+        if (threadIdx.x < 32) mosh2::tc::tmem_dealloc(s.tc_tmem, mosh2::kTcCols);
+    }
 }
 
 // device copy of every model array in one precision
@@ -178,6 +194,17 @@ struct mosh2_job {
 
 namespace {
 
+template <class real, bool BIG>
+void launch_kernel(mosh2_job *j, const mosh2::Model<real> &m, const mosh2::Job<real> &job, int threads, bool no_tc) {
+    const mosh2::Dims d = mosh2::make_dims(m);
+    mosh2::Work<real, BIG> w{};
+    mosh2::Arena S{mosh2::kSmemHeader}, G{0};
+    mosh2::carve<real, BIG>(w, d, m, S, G);
+    w.tc = (w.tc_ok && !no_tc && threads >= 128) ? 1 : 0;
+    cudaFuncSetAttribute(mosh2_stageii_kernel<real, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem));
+    mosh2_stageii_kernel<real, BIG><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job, w, d);
+}
+
 template <class real>
 int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     mosh2::Job<real> job{};
@@ -197,13 +224,9 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
         if (t >= 32 && t <= threads && t % 32 == 0) threads = t;
     }
     CU(cudaEventRecord(j->ev0, j->stream));
-    if (j->big_in_global) {
-        CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
-        mosh2_stageii_kernel<real, true><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job);
-    } else {
-        CU(cudaFuncSetAttribute(mosh2_stageii_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem)));
-        mosh2_stageii_kernel<real, false><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job);
-    }
+    const bool no_tc = getenv("MOSH2_DEV_NO_TC") != nullptr;    // development aid: J^T J on the CUDA cores
+    if (j->big_in_global) launch_kernel<real, true>(j, m, job, threads, no_tc);
+    else launch_kernel<real, false>(j, m, job, threads, no_tc);
     CU(cudaGetLastError());
     CU(cudaEventRecord(j->ev1, j->stream));
     return 0;
@@ -219,10 +242,10 @@ void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) 
     for (int pass = 0; pass < 3; ++pass) {
         m.tile_markers = tries[pass][0];
         const bool in_global = tries[pass][1] != 0;
-        mosh2::Work<real> w;
         const mosh2::Dims d = mosh2::make_dims(m);
-        mosh2::Arena S{nullptr, 0}, G{nullptr, 0};
-        if (in_global) mosh2::carve<real, true>(w, d, m, S, G); else mosh2::carve<real, false>(w, d, m, S, G);
+        mosh2::Arena S{mosh2::kSmemHeader}, G{0};
+        if (in_global) { mosh2::Work<real, true> w{}; mosh2::carve<real, true>(w, d, m, S, G); }
+        else { mosh2::Work<real, false> w{}; mosh2::carve<real, false>(w, d, m, S, G); }
         *big = in_global ? 1 : 0;
         *smem = (S.off + 15) & ~size_t(15);
         *gws = (G.off + 255) & ~size_t(255);

@@ -47,6 +47,38 @@
 #endif
 
 namespace mosh2 {
+// ---------------------------------------------------------------------------------------------
+// workspace addressing
+// ---------------------------------------------------------------------------------------------
+// The workspace layout (struct Work below) is computed once on the host and travels as a kernel parameter: every
+// array is a 32-bit offset into the block's dynamic shared memory.  An address is therefore "shared-memory base +
+// a constant-bank word": it costs no long-lived register (the dominant source of spills when the layout was
+// carved inside the kernel) and the compiler still knows the address space (LDS/STS).
+#if M2_GPU
+extern __shared__ __align__(16) unsigned char m2_dyn_smem[];
+M2_D unsigned char *m2_smem() { return m2_dyn_smem; }
+#else
+inline unsigned char *&m2_smem_ref() { static thread_local unsigned char *base = nullptr; return base; }
+inline unsigned char *m2_smem() { return m2_smem_ref(); }
+#endif
+constexpr unsigned kSmemHeader = 16;     // first bytes of the dynamic shared memory: base of the per-CTA global workspace
+
+template <class T>
+struct SPtr {                            // array in shared memory
+    uint32_t ofs;
+    M2_D operator T *() const { return reinterpret_cast<T *>(m2_smem() + ofs); }
+};
+template <class T, bool BIG>
+struct BPtr {                            // array in shared memory, or (BIG: f64 / oversized models) in the per-CTA global workspace
+    uint32_t ofs;
+    M2_D operator T *() const {
+        if (BIG) return reinterpret_cast<T *>(*reinterpret_cast<char *const *>(m2_smem()) + ofs);
+        return reinterpret_cast<T *>(m2_smem() + ofs);
+    }
+};
+}  // namespace mosh2
+
+namespace mosh2 {
 
 enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32 };
 enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
@@ -277,24 +309,97 @@ M2_D real warp_sum(real v) {
 // ---------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------
-template <class real>
+template <class real, bool BIG = false>
 struct Work {
     // state
-    real *x, *xt, *pose_prev, *velo_tgt, *dm_tgt;
+    SPtr<real> x, xt, pose_prev, velo_tgt, dm_tgt;
     // forward scratch of the latest evaluation
-    real *fullpose, *Rl, *dRl, *Jp, *Rg, *tg, *vp, *pj, *Rsk, *mk, *rm, *obs, *py, *pq;
+    SPtr<real> fullpose, Rl, dRl, Jp, Rg, tg, vp, pj, Rsk, mk, rm, obs, py, pq;
     // Jacobian / normal equations
-    real *Loc, *MtR, *u, *dtg, *Jt, *Jf, *A, *Lm, *Linv, *Pn, *g, *Ag, *dgn, *d, *tmp, *ds;
-    real *red, *sc, *hct;
-    int *colmap, *colsrc, *jlist, *isc;
-    // small per-model tables: shared-memory copies when they fit (a dependent global load costs ~600 cycles and the
-    // kinematic-tree walk alone chains three of them per level), else aliases of the global arrays
-    const int *c_parents, *c_fk_order, *c_level_ofs, *c_wj, *c_free1, *c_free2;
-    int *c_tin, *c_tsz;       // pre-order index and subtree size of every joint: j in subtree(a) <=> tin[j]-tin[a] in [0, tsz[a])
-    const real *c_wv, *c_v0, *c_coefs, *c_j0, *c_hmean, *c_pmeans, *c_pnlw;
-    long long *prof;
-    uint8_t *vis;
+    SPtr<real> Loc, MtR, u, dtg, Linv, Pn, g, Ag, dgn, d, tmp, ds;
+    BPtr<real, BIG> Jt, Jf, A, Lm;
+    SPtr<real> red, sc, hct;
+    SPtr<int> colmap, colsrc, jlist, isc;
+    // small per-model tables staged in shared memory (a dependent global load costs several hundred cycles and the
+    // kinematic-tree walk alone chains three of them per level)
+    SPtr<int> c_parents, c_fk_order, c_level_ofs, c_wj, c_free1, c_free2;
+    SPtr<int> c_tin, c_tsz;   // pre-order index and subtree size of every joint: j in subtree(a) <=> tin[j]-tin[a] in [0, tsz[a])
+    SPtr<real> c_wv, c_v0, c_coefs, c_j0, c_hmean, c_pmeans, c_pnlw;
+    SPtr<long long> prof;
+    SPtr<uint8_t> vis;
+    // tensor-core J^T J (f32, shared-memory workspace only): operand buffers (they alias A, which is idle while the
+    // tiles accumulate in tensor memory), completion barrier, tensor-memory address slot
+    SPtr<float> Xhi, Xlo;
+    SPtr<unsigned long long> mbar;
+    SPtr<unsigned int> tmem_slot;
+    int tc_ok;                // the model qualifies (f32, workspace in shared memory, n2 <= kTcM)
+    int tc;                   // set by the launcher: tensor cores in use
 };
+
+// ---------------------------------------------------------------------------------------------
+// 5th-generation tensor cores (tcgen05) for the J^T J accumulation of the f32 kernel
+// ---------------------------------------------------------------------------------------------
+// The Jacobian tile is kept transposed, X[i][k] = Jf[k][i] (i: free variable, k: residual row of the tile), in
+// the canonical K-major no-swizzle operand layout (8 x 16-byte core matrices), split into a TF32 "hi" part and
+// a TF32 "lo" remainder.  A = sum over tiles of (hi hi^T + lo hi^T + hi lo^T) accumulates in tensor memory at
+// close to fp32 accuracy (3xTF32) while the threads already assemble the next tile.
+constexpr int kTcM = 128;            // UMMA M: free variables, zero/garbage padded (rows >= n are never read back)
+constexpr int kTcCols = 128;         // tensor-memory columns of the accumulator
+M2_HD int tc_xidx(int i, int k, int kt) {        // float index of X[i][k] inside a [kTcM][kt] operand buffer
+    return (i >> 3) * (kt >> 2) * 32 + (k >> 2) * 32 + (i & 7) * 4 + (k & 3);
+}
+#if M2_GPU
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float to_tf32(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); }
+// shared-memory matrix descriptor, K-major, no swizzle: LBO = byte distance of the two core matrices along K,
+// SBO = byte distance of consecutive 8-row groups; version field 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return uint64_t((addr & 0x3FFFF) >> 4) | (uint64_t((lbo >> 4) & 0x3FFF) << 16) | (uint64_t((sbo >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46);
+}
+// instruction descriptor: D f32, A and B tf32, both K-major, M x N
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {       // 16 consecutive columns of this thread's lane
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+}  // namespace tc
+#endif
 
 struct Dims {
     int nJ, M, S, PF, PR, nd, NX, NCt, n1, n2, ld, lda, ldp, npad, K, D, D4, kw, jt_size, tmk;
@@ -317,66 +422,76 @@ M2_HD Dims make_dims(const Model<real> &m) {
 }
 
 struct Arena {
-    char *base;
     size_t off;
-    template <class T> M2_HD T *take(size_t n) {
+    template <class T> M2_HD uint32_t take(size_t n) {
         off = (off + 15) & ~size_t(15);
-        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        const size_t o = off;
         off += n * sizeof(T);
-        return p;
+        return uint32_t(o);
     }
 };
 
 // Lays the workspace out.  Arrays flagged "big" go to arena G when big_in_global is set (f64 runs, large
 // models), everything else to arena S (shared memory).
 template <class real, bool BIG>
-M2_HD void carve(Work<real> &w, const Dims &d, const Model<real> &m, Arena &S, Arena &G) {
+M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena &S, Arena &G) {
     // BIG is a compile-time switch so that, in the normal case, every workspace pointer provably points into
     // shared memory and the compiler emits LDS/STS instead of generic loads and stores
     const int hct_size = m.hct_size;
     Arena &B = BIG ? G : S;
-    w.x = S.take<real>(d.NX); w.xt = S.take<real>(d.NX);
-    w.pose_prev = S.take<real>(d.PR); w.velo_tgt = S.take<real>(d.PR); w.dm_tgt = S.take<real>(d.nd + 1);
-    w.fullpose = S.take<real>(d.PF); w.Rl = S.take<real>(9 * d.nJ); w.dRl = S.take<real>(27 * d.nJ);
-    w.Jp = S.take<real>(3 * d.nJ); w.Rg = S.take<real>(9 * d.nJ); w.tg = S.take<real>(3 * d.nJ);
-    w.vp = S.take<real>(3 * d.S); w.pj = S.take<real>(3 * d.S * d.kw); w.Rsk = S.take<real>(9 * d.S);
-    w.mk = S.take<real>(3 * d.M); w.rm = S.take<real>(3 * d.M); w.obs = S.take<real>(3 * d.M);
-    w.py = S.take<real>(d.K * d.D + 1); w.pq = S.take<real>(d.K + 1);
+    w.x.ofs = S.take<real>(d.NX); w.xt.ofs = S.take<real>(d.NX);
+    w.pose_prev.ofs = S.take<real>(d.PR); w.velo_tgt.ofs = S.take<real>(d.PR); w.dm_tgt.ofs = S.take<real>(d.nd + 1);
+    w.fullpose.ofs = S.take<real>(d.PF); w.Rl.ofs = S.take<real>(9 * d.nJ); w.dRl.ofs = S.take<real>(27 * d.nJ);
+    w.Jp.ofs = S.take<real>(3 * d.nJ); w.Rg.ofs = S.take<real>(9 * d.nJ); w.tg.ofs = S.take<real>(3 * d.nJ);
+    w.vp.ofs = S.take<real>(3 * d.S); w.pj.ofs = S.take<real>(3 * d.S * d.kw); w.Rsk.ofs = S.take<real>(9 * d.S);
+    w.mk.ofs = S.take<real>(3 * d.M); w.rm.ofs = S.take<real>(3 * d.M); w.obs.ofs = S.take<real>(3 * d.M);
+    w.py.ofs = S.take<real>(d.K * d.D + 1); w.pq.ofs = S.take<real>(d.K + 1);
     // The Cholesky factor is alive only inside gauss_newton(); the Jacobian tiles and the other scratch of build()
     // (and the pose-blend partial sums of eval(), which live in Jt) are dead there, so they share its storage.
-    w.A = B.take<real>(size_t(d.n2) * d.lda);
+    {
+        size_t a_elems = size_t(d.n2) * d.lda;
+        const size_t x_elems = size_t(2) * kTcM * 3 * d.tmk;
+        const bool tc_ok = sizeof(real) == 4 && !BIG && d.n2 <= kTcM;
+        if (tc_ok && a_elems < x_elems) a_elems = x_elems;
+        w.A.ofs = B.take<real>(a_elems);
+        w.Xhi.ofs = w.A.ofs;
+        w.Xlo.ofs = w.A.ofs + uint32_t(sizeof(float) * size_t(kTcM) * 3 * d.tmk);
+        w.tc_ok = tc_ok ? 1 : 0;
+        w.tc = 0;
+    }
     {
         const size_t mark_b = B.off;
-        w.Lm = B.take<real>(size_t(d.n2 + 1) * d.ld);
+        w.Lm.ofs = B.take<real>(size_t(d.n2 + 1) * d.ld);
         const size_t end_b = B.off;
         B.off = mark_b;
-        w.Jt = B.take<real>(d.jt_size); w.Jf = B.take<real>(3 * d.tmk * d.npad);
+        w.Jt.ofs = B.take<real>(d.jt_size); w.Jf.ofs = B.take<real>(3 * d.tmk * d.npad);
         if (!BIG) {
-            w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
-            w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
+            w.Loc.ofs = S.take<real>(27 * d.M); w.MtR.ofs = S.take<real>(9 * d.S);
+            w.u.ofs = S.take<real>(9 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
         }
         if (B.off < end_b) B.off = end_b;
     }
     if (BIG) {
-        w.Loc = S.take<real>(27 * d.M); w.MtR = S.take<real>(9 * d.S);
-        w.u = S.take<real>(9 * d.nJ); w.dtg = S.take<real>(3 * d.nJ * d.nd + 1);
+        w.Loc.ofs = S.take<real>(27 * d.M); w.MtR.ofs = S.take<real>(9 * d.S);
+        w.u.ofs = S.take<real>(9 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
     }
-    w.Linv = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
-    w.Pn = S.take<real>(size_t(kCholNB) * d.ldp);
-    w.g = S.take<real>(d.npad); w.Ag = S.take<real>(d.npad); w.dgn = S.take<real>(d.npad);
-    w.d = S.take<real>(d.npad); w.tmp = S.take<real>(d.npad); w.ds = S.take<real>(d.npad);
-    w.red = S.take<real>(8 * 33); w.sc = S.take<real>(16); w.hct = S.take<real>(hct_size + 4);
-    w.colmap = S.take<int>(d.NX); w.colsrc = S.take<int>(d.n2); w.jlist = S.take<int>(d.nJ); w.isc = S.take<int>(8);
-    w.prof = S.take<long long>(32);
-    w.vis = S.take<uint8_t>(d.M);
+    w.Linv.ofs = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
+    w.Pn.ofs = S.take<real>(size_t(kCholNB) * d.ldp);
+    w.g.ofs = S.take<real>(d.npad); w.Ag.ofs = S.take<real>(d.npad); w.dgn.ofs = S.take<real>(d.npad);
+    w.d.ofs = S.take<real>(d.npad); w.tmp.ofs = S.take<real>(d.npad); w.ds.ofs = S.take<real>(d.npad);
+    w.red.ofs = S.take<real>(8 * 33); w.sc.ofs = S.take<real>(16); w.hct.ofs = S.take<real>(hct_size + 4);
+    w.colmap.ofs = S.take<int>(d.NX); w.colsrc.ofs = S.take<int>(d.n2); w.jlist.ofs = S.take<int>(d.nJ); w.isc.ofs = S.take<int>(8);
+    w.prof.ofs = S.take<long long>(32);
+    w.mbar.ofs = S.take<unsigned long long>(1); w.tmem_slot.ofs = S.take<unsigned int>(2);
+    w.vis.ofs = S.take<uint8_t>(d.M);
     // small per-model tables are always staged in shared memory (a dependent global load costs ~600 cycles and the
     // kinematic-tree walk chains three of them per level); the larger ones stay in global memory / L2
-    w.c_parents = S.take<int>(d.nJ); w.c_fk_order = S.take<int>(d.nJ); w.c_level_ofs = S.take<int>(m.n_levels + 1);
-    w.c_wj = S.take<int>(d.S * d.kw); w.c_free1 = S.take<int>(d.n1); w.c_free2 = S.take<int>(d.n2);
-    w.c_wv = S.take<real>(d.S * d.kw); w.c_v0 = S.take<real>(3 * d.S); w.c_coefs = S.take<real>(3 * d.M);
-    w.c_j0 = S.take<real>(3 * d.nJ); w.c_hmean = S.take<real>(m.n_hand_full + 1);
-    w.c_tin = S.take<int>(d.nJ); w.c_tsz = S.take<int>(d.nJ);
-    w.c_pmeans = S.take<real>(d.K * d.D + 1); w.c_pnlw = S.take<real>(d.K + 1);
+    w.c_parents.ofs = S.take<int>(d.nJ); w.c_fk_order.ofs = S.take<int>(d.nJ); w.c_level_ofs.ofs = S.take<int>(m.n_levels + 1);
+    w.c_wj.ofs = S.take<int>(d.S * d.kw); w.c_free1.ofs = S.take<int>(d.n1); w.c_free2.ofs = S.take<int>(d.n2);
+    w.c_wv.ofs = S.take<real>(d.S * d.kw); w.c_v0.ofs = S.take<real>(3 * d.S); w.c_coefs.ofs = S.take<real>(3 * d.M);
+    w.c_j0.ofs = S.take<real>(3 * d.nJ); w.c_hmean.ofs = S.take<real>(m.n_hand_full + 1);
+    w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ);
+    w.c_pmeans.ofs = S.take<real>(d.K * d.D + 1); w.c_pnlw.ofs = S.take<real>(d.K + 1);
 }
 
 // configuration of one minimisation (one ch.minimize call of the reference)
@@ -392,11 +507,11 @@ struct StepCfg {
 // ---------------------------------------------------------------------------------------------
 // the solver
 // ---------------------------------------------------------------------------------------------
-template <class real>
+template <class real, bool BIG = false>
 struct Solver {
     const Model<real> &m;
     const Job<real> &job;
-    Work<real> &w;
+    const Work<real, BIG> &w;
     const Cta cta;
     const Dims &d;
     // per-frame scalars (identical in every thread)
@@ -406,8 +521,10 @@ struct Solver {
     // counters of the current frame
     int n_iter, n_eval, n_build, n_min, frame_flags;
     int prof_base = 0;        // development builds: offset of the phase-timer slots
+    unsigned int tc_tmem = 0, tc_phase = 0;   // tensor-memory base address, parity of the MMA completion barrier
+    int tc_kt = 0;            // rows per Jacobian tile (K extent of one tile's MMAs)
 
-    M2_D Solver(const Model<real> &m_, const Job<real> &j_, Work<real> &w_, const Dims &d_, Cta c_)
+    M2_D Solver(const Model<real> &m_, const Job<real> &j_, const Work<real, BIG> &w_, const Dims &d_, Cta c_)
         : m(m_), job(j_), w(w_), cta(c_), d(d_) {}
 
 #define CTA_FOR(i, n) _Pragma("unroll 1") for (int i = cta.tid; i < (n); i += cta.nthr)
@@ -733,6 +850,26 @@ struct Solver {
         t1_rigid(mi, a, t, blk);
     }
 
+    // ---- one entry of the weighted Jacobian tile (row = residual row inside the tile, col = free variable)
+    M2_D void jf_store(int row, int col, real v) {
+#if M2_GPU
+        if (w.tc) {
+            const float hi = tc::to_tf32(float(v)), lo = tc::to_tf32(float(v) - hi);
+            const int q = tc_xidx(col, row, tc_kt);
+            w.Xhi[q] = hi;
+            w.Xlo[q] = lo;
+            return;
+        }
+#endif
+        w.Jf[row * d.npad + col] = v;
+    }
+    M2_D real jf_load(int row, int col) const {
+#if M2_GPU
+        if (w.tc) { const int q = tc_xidx(col, row, tc_kt); return real(w.Xhi[q] + w.Xlo[q]); }
+#endif
+        return w.Jf[row * d.npad + col];
+    }
+
     // ---- a finished 3x3 block of T1: body joints go straight to their free columns of the tile (weighted and
     //      masked); hand joints go to the full-pose tile for the PCA chain (T2b)
     M2_D void t1_store(int ml, int mi, int a, const real *blk) {
@@ -743,7 +880,7 @@ struct Solver {
                 const int col = w.colmap[3 + 3 * a + k];
                 if (col >= 0) {
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) w.Jf[(3 * ml + r) * d.npad + col] = blk[3 * r + k] * sc;
+                    for (int r = 0; r < 3; ++r) jf_store(3 * ml + r, col, blk[3 * r + k] * sc);
                 }
             }
         } else {
@@ -773,7 +910,7 @@ struct Solver {
             else mat3_vec(w.Rg + 9 * par, om, w.u + 3 * idx);
         }
         CTA_FOR(mi, d.M) marker_local_jacobian(mi);
-        CTA_FOR(i, n * ld) w.A[i] = 0;
+        if (!w.tc) CTA_FOR(i, n * ld) w.A[i] = 0;      // (tensor-core mode: A's storage holds the operand tiles for now)
         CTA_FOR(i, n) w.g[i] = 0;
         if (d.nd) {
             // d tg_j / d delta_i = d tg_par + Rg_par (Jd_j - Jd_par)
@@ -860,18 +997,22 @@ struct Solver {
                 }
                 const int col = w.colmap[3 + d.PR + i];
                 const real sc = w.vis[mi] ? wd : real(0);
-                if (col >= 0) for (int r = 0; r < 3; ++r) w.Jf[(3 * ml + r) * d.npad + col] = val[r] * sc;
+                if (col >= 0) for (int r = 0; r < 3; ++r) jf_store(3 * ml + r, col, val[r] * sc);
             }
             // translation columns (identity) and the zero padding of the tile
             const int trows = 3 * tm;
             {
-                const int npadc = d.npad - n, per = 3 + npadc;
+                const int npadc = w.tc ? 0 : d.npad - n, per = 3 + npadc;
                 CTA_FOR(idx, trows * per) {
                     const int row = idx / per, q = idx - row * per;
                     if (q < 3) {
                         const int col = w.colmap[q];
-                        if (col >= 0) w.Jf[row * d.npad + col] = (row % 3 == q) ? (w.vis[t0 + row / 3] ? wd : real(0)) : real(0);
+                        if (col >= 0) jf_store(row, col, (row % 3 == q) ? (w.vis[t0 + row / 3] ? wd : real(0)) : real(0));
                     } else w.Jf[row * d.npad + n + (q - 3)] = 0;
+                }
+                if (w.tc && trows < tc_kt) {                  // short last tile: the missing rows must not contribute
+                    const int miss = tc_kt - trows;
+                    CTA_FOR(idx, n * miss) jf_store(trows + idx % miss, idx / miss, real(0));
                 }
             }
             M2_SYNC();
@@ -900,50 +1041,103 @@ struct Solver {
                         const int r = hb.r0 + 4 * rg + e;
                         if (r < hb.r1) {
                             const int col = w.colmap[3 + m.body_dof + r];
-                            if (col >= 0) w.Jf[row * d.npad + col] = out[e];
+                            if (col >= 0) jf_store(row, col, out[e]);
                         }
                     }
                 }
             }
+#if M2_GPU
+            if (w.tc) tc::fence_async_smem();                // this thread's operand stores -> visible to the async proxy
+#endif
             M2_SYNC();
             M2_TACC(8);
-            // T3: A += Jf^T Jf (upper 4x4 blocks), g -= Jf^T r
-            const int nb = (n + kBS - 1) / kBS, nblk = nb * (nb + 1) / 2;
-            CTA_FOR(b, nblk) {
-                int bi = 0, rem = b;
-                while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
-                const int bj = bi + rem;
-                real acc[kBS * kBS];
+            // T3: A += Jf^T Jf, g -= Jf^T r
+#if M2_GPU
+            if (w.tc) {
+                // tensor cores: one thread issues the tile's MMAs (hi hi^T + lo hi^T + hi lo^T per K step of 8 rows);
+                // they accumulate in tensor memory while the other threads go on with g
+                if (cta.tid == 0) {
+                    tc::fence_after();
+                    const uint32_t lbo = 128, sbo = uint32_t(tc_kt >> 2) * 128;
+                    const uint32_t ahi = tc::smem_u32(w.Xhi), alo = tc::smem_u32(w.Xlo);
+                    const uint32_t idesc = tc::idesc_tf32(kTcM, (n + 15) & ~15);
+                    for (int ks = 0; ks < (tc_kt >> 3); ++ks) {
+                        const uint64_t dhi = tc::smem_desc(ahi + ks * 2 * lbo, lbo, sbo), dlo = tc::smem_desc(alo + ks * 2 * lbo, lbo, sbo);
+                        tc::mma_tf32(tc_tmem, dhi, dhi, idesc, (t0 > 0 || ks > 0) ? 1u : 0u);
+                        tc::mma_tf32(tc_tmem, dlo, dhi, idesc, 1u);
+                        tc::mma_tf32(tc_tmem, dhi, dlo, idesc, 1u);
+                    }
+                    tc::commit(tc::smem_u32(w.mbar));
+                }
+            } else
+#endif
+            {
+                const int nb = (n + kBS - 1) / kBS, nblk = nb * (nb + 1) / 2;
+                CTA_FOR(b, nblk) {
+                    int bi = 0, rem = b;
+                    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+                    const int bj = bi + rem;
+                    real acc[kBS * kBS];
 #pragma unroll
-                for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
-                for (int row = 0; row < trows; ++row) {
-                    const real *Jr = w.Jf + row * d.npad;
-                    const Vec4<real> av = ld4(Jr + bi * kBS), bv = ld4(Jr + bj * kBS);
-                    const real ai[4] = {av.x, av.y, av.z, av.w}, bjv[4] = {bv.x, bv.y, bv.z, bv.w};
+                    for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
+                    for (int row = 0; row < trows; ++row) {
+                        const real *Jr = w.Jf + row * d.npad;
+                        const Vec4<real> av = ld4(Jr + bi * kBS), bv = ld4(Jr + bj * kBS);
+                        const real ai[4] = {av.x, av.y, av.z, av.w}, bjv[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int p = 0; p < kBS; ++p)
+#pragma unroll
+                            for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bjv[q];
+                    }
 #pragma unroll
                     for (int p = 0; p < kBS; ++p)
 #pragma unroll
-                        for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bjv[q];
-                }
-#pragma unroll
-                for (int p = 0; p < kBS; ++p)
-#pragma unroll
-                    for (int q = 0; q < kBS; ++q) {
-                        const int i = bi * kBS + p, j = bj * kBS + q;
-                        if (j < n && i <= j) {
-                            w.A[i * ld + j] += acc[p * kBS + q];
-                            if (i < j) w.A[j * ld + i] += acc[p * kBS + q];
+                        for (int q = 0; q < kBS; ++q) {
+                            const int i = bi * kBS + p, j = bj * kBS + q;
+                            if (j < n && i <= j) {
+                                w.A[i * ld + j] += acc[p * kBS + q];
+                                if (i < j) w.A[j * ld + i] += acc[p * kBS + q];
+                            }
                         }
-                    }
+                }
             }
             CTA_FOR(cc, n) {
                 real s = 0;
-                for (int row = 0; row < trows; ++row) s += w.Jf[row * d.npad + cc] * w.rm[3 * t0 + row];
+                for (int row = 0; row < trows; ++row) s += jf_load(row, cc) * w.rm[3 * t0 + row];
                 w.g[cc] -= s;
             }
+#if M2_GPU
+            if (w.tc) {                                      // the tile buffers may be rewritten once its MMAs are done
+                tc::mbar_wait(tc::smem_u32(w.mbar), tc_phase);
+                tc_phase ^= 1;
+            }
+#endif
             M2_SYNC();
             M2_TACC(9);
         }
+#if M2_GPU
+        if (w.tc) {
+            // accumulator (tensor memory, row i = lane i) -> A, mirrored from the upper triangle so that A is exactly
+            // symmetric; warps 0..3 own the four lane quarters
+            tc::fence_after();
+            if (cta.tid < 128) {
+                const int i = cta.tid, nc = (n + 15) & ~15;
+                for (int c0 = 0; c0 < nc; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + c0, v);
+                    if (i < n) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int j = c0 + q;
+                            if (j >= i && j < n) { w.A[i * ld + j] = real(v[q]); w.A[j * ld + i] = real(v[q]); }
+                        }
+                    }
+                }
+            }
+            tc::fence_before();
+            __syncthreads();
+        }
+#endif
         // closed-form terms
         if (c.wp > real(0)) {
             const int D = d.D, ks = w.isc[0];
@@ -1526,17 +1720,17 @@ struct Solver {
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
         CTA_FOR(i, m.hct_size) w.hct[i] = m.hct[i];
-        CTA_FOR(i, d.nJ) { const_cast<int *>(w.c_parents)[i] = m.parents[i]; const_cast<int *>(w.c_fk_order)[i] = m.fk_order[i]; }
-        CTA_FOR(i, m.n_levels + 1) const_cast<int *>(w.c_level_ofs)[i] = m.level_ofs[i];
-        CTA_FOR(i, d.S * d.kw) { const_cast<int *>(w.c_wj)[i] = m.w_joint[i]; const_cast<real *>(w.c_wv)[i] = m.w_val[i]; }
-        CTA_FOR(i, d.n1) const_cast<int *>(w.c_free1)[i] = m.free1[i];
-        CTA_FOR(i, d.n2) const_cast<int *>(w.c_free2)[i] = m.free2[i];
-        CTA_FOR(i, 3 * d.S) const_cast<real *>(w.c_v0)[i] = m.v0[i];
-        CTA_FOR(i, 3 * d.M) const_cast<real *>(w.c_coefs)[i] = m.coefs[i];
-        CTA_FOR(i, 3 * d.nJ) const_cast<real *>(w.c_j0)[i] = m.j0[i];
-        CTA_FOR(i, m.n_hand_full) const_cast<real *>(w.c_hmean)[i] = m.hands_mean[i];
-        CTA_FOR(i, d.K * d.D) const_cast<real *>(w.c_pmeans)[i] = m.prior_means[i];
-        CTA_FOR(i, d.K) const_cast<real *>(w.c_pnlw)[i] = m.prior_nlw[i];
+        CTA_FOR(i, d.nJ) { w.c_parents[i] = m.parents[i]; w.c_fk_order[i] = m.fk_order[i]; }
+        CTA_FOR(i, m.n_levels + 1) w.c_level_ofs[i] = m.level_ofs[i];
+        CTA_FOR(i, d.S * d.kw) { w.c_wj[i] = m.w_joint[i]; w.c_wv[i] = m.w_val[i]; }
+        CTA_FOR(i, d.n1) w.c_free1[i] = m.free1[i];
+        CTA_FOR(i, d.n2) w.c_free2[i] = m.free2[i];
+        CTA_FOR(i, 3 * d.S) w.c_v0[i] = m.v0[i];
+        CTA_FOR(i, 3 * d.M) w.c_coefs[i] = m.coefs[i];
+        CTA_FOR(i, 3 * d.nJ) w.c_j0[i] = m.j0[i];
+        CTA_FOR(i, m.n_hand_full) w.c_hmean[i] = m.hands_mean[i];
+        CTA_FOR(i, d.K * d.D) w.c_pmeans[i] = m.prior_means[i];
+        CTA_FOR(i, d.K) w.c_pnlw[i] = m.prior_nlw[i];
         CTA_FOR(i, 32) w.prof[i] = 0;
         M2_SYNC();
         if (cta.tid == 0) {                                    // pre-order numbering of the kinematic tree

@@ -113,15 +113,15 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
 
     hm.m.tile_markers = 16;
     const mosh2::Dims d = mosh2::make_dims(hm.m);
-    mosh2::Work<real> w;
-    mosh2::Arena S0{nullptr, 0}, G0{nullptr, 0};
+    mosh2::Work<real, false> w{};
+    mosh2::Arena S0{mosh2::kSmemHeader}, G0{0};
     mosh2::carve<real, false>(w, d, hm.m, S0, G0);
     if (std::getenv("MOSH2_EMU_PLAN")) {        // development aid: shared-memory footprint of this model
         for (int tile : {16, 8}) {
             hm.m.tile_markers = tile;
             const mosh2::Dims dd = mosh2::make_dims(hm.m);
-            mosh2::Work<real> ww;
-            mosh2::Arena Sa{nullptr, 0}, Ga{nullptr, 0};
+            mosh2::Work<real, false> ww{};
+            mosh2::Arena Sa{mosh2::kSmemHeader}, Ga{0};
             mosh2::carve<real, false>(ww, dd, hm.m, Sa, Ga);
             std::fprintf(stderr, "plan: sizeof(real)=%zu tile=%d smem=%zu bytes (limit %d)\n", sizeof(real), tile, Sa.off, 227 * 1024);
         }
@@ -129,12 +129,11 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     }
     std::vector<char> smem_raw(S0.off + 128);
     char *smem_base = smem_raw.data() + ((32 - (reinterpret_cast<uintptr_t>(smem_raw.data()) & 31)) & 31);
+    mosh2::m2_smem_ref() = reinterpret_cast<unsigned char *>(smem_base);
     for (int c = 0; c < job.n_chunks; ++c) {
         std::memset(smem_base, 0, S0.off + 64);
-        mosh2::Arena S{smem_base, 0}, G{nullptr, 0};
-        mosh2::carve<real, false>(w, d, hm.m, S, G);
         mosh2::Cta cta{0, 1};
-        mosh2::Solver<real> s(hm.m, job, w, d, cta);
+        mosh2::Solver<real, false> s(hm.m, job, w, d, cta);
         s.run_chunk(c);
     }
     auto conv = [](double *dst, const std::vector<real> &src, size_t n) {

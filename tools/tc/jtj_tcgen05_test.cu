@@ -37,6 +37,7 @@ __device__ __forceinline__ void commit(uint32_t mbar) {
 }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
