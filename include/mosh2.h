@@ -51,7 +51,7 @@ enum {
  * "slot" = 3*marker + t, t = 0..2 the three attachment vertices of a marker. */
 typedef struct mosh2_model_desc {
     int32_t n_joints, n_markers, body_dof, p_red, n_hand_red, n_hand_full, n_dmpl;
-    int32_t kw, na, n_levels;
+    int32_t kw, na, n_levels; /* kw: skinning weights kept per slot, 1..8 (SMPL-family models: 4) */
     const int32_t *parents;   /* [n_joints], -1 for the root                                 */
     const int32_t *fk_order;  /* [n_joints] joints sorted by depth                           */
     const int32_t *level_ofs; /* [n_levels+1] offsets into fk_order                          */

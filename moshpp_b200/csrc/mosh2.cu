@@ -65,7 +65,7 @@ mosh2_stageii_kernel(const __grid_constant__ mosh2::Model<real> m, const __grid_
         __syncthreads();
         mosh2::tc::fence_after();
         s.tc_tmem = *w.tmem_slot;
-        s.tc_kt = 3 * d.tmk;
+        s.tc_kt = 4 * d.tmk;
     }
     s.run_chunk(blockIdx.x);
     if (w.tc) {
@@ -195,12 +195,12 @@ struct mosh2_job {
 namespace {
 
 template <class real, bool BIG>
-void launch_kernel(mosh2_job *j, const mosh2::Model<real> &m, const mosh2::Job<real> &job, int threads, bool no_tc) {
+void launch_kernel(mosh2_job *j, const mosh2::Model<real> &m, const mosh2::Job<real> &job, int threads) {
     const mosh2::Dims d = mosh2::make_dims(m);
     mosh2::Work<real, BIG> w{};
     mosh2::Arena S{mosh2::kSmemHeader}, G{0};
     mosh2::carve<real, BIG>(w, d, m, S, G);
-    w.tc = (w.tc_ok && !no_tc && threads >= 128) ? 1 : 0;
+    w.tc = (w.tc_ok && threads >= 128) ? 1 : 0;
     cudaFuncSetAttribute(mosh2_stageii_kernel<real, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem));
     mosh2_stageii_kernel<real, BIG><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job, w, d);
 }
@@ -219,14 +219,13 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     job.gws = static_cast<char *>(j->d_gws); job.gws_stride = j->gws_stride;
     job.opt = j->opt;
     int threads = threads_for<real>();
-    if (const char *e = getenv("MOSH2_DEV_THREADS")) {      // development aid: any multiple of 32 up to the launch bound
+    if (const char *e = getenv("MOSH2_DEV_THREADS")) {      // development aid: any multiple of 32 from 128 up to the launch bound
         const int t = atoi(e);
-        if (t >= 32 && t <= threads && t % 32 == 0) threads = t;
+        if (t >= 128 && t <= threads && t % 32 == 0) threads = t;
     }
     CU(cudaEventRecord(j->ev0, j->stream));
-    const bool no_tc = getenv("MOSH2_DEV_NO_TC") != nullptr;    // development aid: J^T J on the CUDA cores
-    if (j->big_in_global) launch_kernel<real, true>(j, m, job, threads, no_tc);
-    else launch_kernel<real, false>(j, m, job, threads, no_tc);
+    if (j->big_in_global) launch_kernel<real, true>(j, m, job, threads);
+    else launch_kernel<real, false>(j, m, job, threads);
     CU(cudaGetLastError());
     CU(cudaEventRecord(j->ev1, j->stream));
     return 0;
@@ -241,6 +240,7 @@ void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) 
     const int tries[3][2] = {{16, 0}, {8, 0}, {8, 1}};   // tile, big
     for (int pass = 0; pass < 3; ++pass) {
         m.tile_markers = tries[pass][0];
+        m.dev_no_tc = getenv("MOSH2_DEV_NO_TC") ? 1 : 0;      // development aid: J^T J on the CUDA cores
         const bool in_global = tries[pass][1] != 0;
         const mosh2::Dims d = mosh2::make_dims(m);
         mosh2::Arena S{mosh2::kSmemHeader}, G{0};
@@ -278,7 +278,7 @@ void mosh2_default_options(mosh2_options *o) {
 int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out) {
     if (!d || !out) return fail(MOSH2_E_INVALID, "null argument");
     *out = nullptr;
-    if (d->n_joints < 1 || d->n_markers < 1 || d->kw < 1 || d->kw > 30 || d->n_free1 < 1 || d->n_free2 < d->n_free1)
+    if (d->n_joints < 1 || d->n_markers < 1 || d->kw < 1 || d->kw > 8 || d->n_free1 < 1 || d->n_free2 < d->n_free1)
         return fail(MOSH2_E_INVALID, "inconsistent model sizes");
     if (d->body_dof + d->n_hand_full != 3 * d->n_joints || d->body_dof + d->n_hand_red != d->p_red)
         return fail(MOSH2_E_INVALID, "pose layout mismatch: body_dof=%d hand_full=%d hand_red=%d p_red=%d joints=%d",

@@ -114,6 +114,7 @@ struct Model {
     const int *free1, *free2;
     int finger_lo, finger_hi;
     int tile_markers;           // markers per Jacobian tile (8 or 16), chosen by the host from the shared-memory budget
+    int dev_no_tc;              // development switch (host): 1 = J^T J stays on the CUDA cores
 };
 
 struct Options {
@@ -327,6 +328,7 @@ struct Work {
     SPtr<real> c_wv, c_v0, c_coefs, c_j0, c_hmean, c_pmeans, c_pnlw;
     SPtr<long long> prof;
     SPtr<uint8_t> vis;
+    SPtr<uint8_t> c_amask;    // [slot][joint]: bit i set <=> the slot's i-th skinning joint lies in the subtree of the joint
     // tensor-core J^T J (f32, shared-memory workspace only): operand buffers (they alias A, which is idle while the
     // tiles accumulate in tensor memory), completion barrier, tensor-memory address slot
     SPtr<float> Xhi, Xlo;
@@ -343,6 +345,8 @@ struct Work {
 // the canonical K-major no-swizzle operand layout (8 x 16-byte core matrices), split into a TF32 "hi" part and
 // a TF32 "lo" remainder.  A = sum over tiles of (hi hi^T + lo hi^T + hi lo^T) accumulates in tensor memory at
 // close to fp32 accuracy (3xTF32) while the threads already assemble the next tile.
+constexpr int kDR = 28;              // floats per joint in dRl: three 3x3 derivative matrices (27) padded to 16-byte vectors
+constexpr int kM3 = 12;              // floats per padded 3x3 matrix (MtR per slot, Loc per marker vertex) and per joint in u (3 x 4)
 constexpr int kTcM = 128;            // UMMA M: free variables, zero/garbage padded (rows >= n are never read back)
 constexpr int kTcCols = 128;         // tensor-memory columns of the accumulator
 M2_HD int tc_xidx(int i, int k, int kt) {        // float index of X[i][k] inside a [kTcM][kt] operand buffer
@@ -441,39 +445,41 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     Arena &B = BIG ? G : S;
     w.x.ofs = S.take<real>(d.NX); w.xt.ofs = S.take<real>(d.NX);
     w.pose_prev.ofs = S.take<real>(d.PR); w.velo_tgt.ofs = S.take<real>(d.PR); w.dm_tgt.ofs = S.take<real>(d.nd + 1);
-    w.fullpose.ofs = S.take<real>(d.PF); w.Rl.ofs = S.take<real>(9 * d.nJ); w.dRl.ofs = S.take<real>(27 * d.nJ);
+    w.fullpose.ofs = S.take<real>(d.PF); w.Rl.ofs = S.take<real>(9 * d.nJ); w.dRl.ofs = S.take<real>(kDR * d.nJ);
     w.Jp.ofs = S.take<real>(3 * d.nJ); w.Rg.ofs = S.take<real>(9 * d.nJ); w.tg.ofs = S.take<real>(3 * d.nJ);
     w.vp.ofs = S.take<real>(3 * d.S); w.pj.ofs = S.take<real>(3 * d.S * d.kw); w.Rsk.ofs = S.take<real>(9 * d.S);
     w.mk.ofs = S.take<real>(3 * d.M); w.rm.ofs = S.take<real>(3 * d.M); w.obs.ofs = S.take<real>(3 * d.M);
     w.py.ofs = S.take<real>(d.K * d.D + 1); w.pq.ofs = S.take<real>(d.K + 1);
     // The Cholesky factor is alive only inside gauss_newton(); the Jacobian tiles and the other scratch of build()
     // (and the pose-blend partial sums of eval(), which live in Jt) are dead there, so they share its storage.
+    // A and the Cholesky factor Lm are adjacent.  The factor is alive only inside gauss_newton(); the scratch of
+    // build() (and the pose-blend partial sums of eval(), which live in Jt) is dead there and is laid over it.  In
+    // tensor-core mode the operand tiles X start at A (idle until the accumulator is read back at the end of
+    // build()) and may run on into the factor's storage; the Jacobian tile Jf is not needed at all.
     {
-        size_t a_elems = size_t(d.n2) * d.lda;
-        const size_t x_elems = size_t(2) * kTcM * 3 * d.tmk;
-        const bool tc_ok = sizeof(real) == 4 && !BIG && d.n2 <= kTcM;
-        if (tc_ok && a_elems < x_elems) a_elems = x_elems;
-        w.A.ofs = B.take<real>(a_elems);
+        const bool tc_ok = sizeof(real) == 4 && !BIG && d.n2 <= kTcM && !m.dev_no_tc;
+        const size_t x_bytes = sizeof(float) * size_t(2) * kTcM * 4 * d.tmk;   // hi and lo tiles, 4 rows per marker (3 + 1 zero)
+        w.A.ofs = B.take<real>(size_t(d.n2) * d.lda);
         w.Xhi.ofs = w.A.ofs;
-        w.Xlo.ofs = w.A.ofs + uint32_t(sizeof(float) * size_t(kTcM) * 3 * d.tmk);
+        w.Xlo.ofs = w.A.ofs + uint32_t(x_bytes / 2);
         w.tc_ok = tc_ok ? 1 : 0;
         w.tc = 0;
-    }
-    {
         const size_t mark_b = B.off;
         w.Lm.ofs = B.take<real>(size_t(d.n2 + 1) * d.ld);
         const size_t end_b = B.off;
         B.off = mark_b;
-        w.Jt.ofs = B.take<real>(d.jt_size); w.Jf.ofs = B.take<real>(3 * d.tmk * d.npad);
+        if (tc_ok && w.A.ofs + x_bytes > B.off) B.off = w.A.ofs + x_bytes;
+        w.Jt.ofs = B.take<real>(d.jt_size);
+        w.Jf.ofs = tc_ok ? w.Jt.ofs : B.take<real>(3 * d.tmk * d.npad);
         if (!BIG) {
-            w.Loc.ofs = S.take<real>(27 * d.M); w.MtR.ofs = S.take<real>(9 * d.S);
-            w.u.ofs = S.take<real>(9 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
+            w.Loc.ofs = S.take<real>(3 * kM3 * d.M); w.MtR.ofs = S.take<real>(kM3 * d.S);
+            w.u.ofs = S.take<real>(kM3 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
         }
         if (B.off < end_b) B.off = end_b;
     }
     if (BIG) {
-        w.Loc.ofs = S.take<real>(27 * d.M); w.MtR.ofs = S.take<real>(9 * d.S);
-        w.u.ofs = S.take<real>(9 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
+        w.Loc.ofs = S.take<real>(3 * kM3 * d.M); w.MtR.ofs = S.take<real>(kM3 * d.S);
+        w.u.ofs = S.take<real>(kM3 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
     }
     w.Linv.ofs = S.take<real>(size_t((d.n2 + kCholNB - 1) / kCholNB) * kCholNB * kCholNB);
     w.Pn.ofs = S.take<real>(size_t(kCholNB) * d.ldp);
@@ -490,7 +496,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.c_wj.ofs = S.take<int>(d.S * d.kw); w.c_free1.ofs = S.take<int>(d.n1); w.c_free2.ofs = S.take<int>(d.n2);
     w.c_wv.ofs = S.take<real>(d.S * d.kw); w.c_v0.ofs = S.take<real>(3 * d.S); w.c_coefs.ofs = S.take<real>(3 * d.M);
     w.c_j0.ofs = S.take<real>(3 * d.nJ); w.c_hmean.ofs = S.take<real>(m.n_hand_full + 1);
-    w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ);
+    w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ); w.c_amask.ofs = S.take<uint8_t>(size_t(d.S) * d.nJ);
     w.c_pmeans.ofs = S.take<real>(d.K * d.D + 1); w.c_pnlw.ofs = S.take<real>(d.K + 1);
 }
 
@@ -610,7 +616,7 @@ struct Solver {
         }
         M2_SYNC();
         M2_TACC(0);
-        CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + 27 * j);
+        CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + kDR * j);
         M2_SYNC();
         M2_TACC(1);
 #if M2_GPU
@@ -778,14 +784,14 @@ struct Solver {
         mat3_mul_reg(Sf1, df2e1, t2);
         for (int q = 0; q < 9; ++q) df3e1[q] = t2[q] - t1[q];
         mat3_mul_reg(Sf1, df2e2, df3e2);
-        real *L = w.Loc + 27 * mi;
+        real *L = w.Loc + 3 * kM3 * mi;                    // three padded 3x3 blocks: d marker / d vertex t
         for (int q = 0; q < 9; ++q) {
             const real de1 = k1 * N1[q] + k2 * df2e1[q] + k3 * df3e1[q];
             const real de2 = k2 * df2e2[q] + k3 * df3e2[q];
             const real id = (q == 0 || q == 4 || q == 8) ? real(1) : real(0);
             L[q] = id - de1 - de2;
-            L[9 + q] = de1;
-            L[18 + q] = de2;
+            L[kM3 + q] = de1;
+            L[2 * kM3 + q] = de2;
         }
     }
 
@@ -798,76 +804,80 @@ struct Solver {
     }
 
     // ---- contribution of slot (marker mi, vertex t) to the 3x3 Jacobian block of joint a:  blk[r*3+k] +=
-    M2_D void t1_rigid(int mi, int a, int t, real *blk) {
-        const int s = 3 * mi + t;
-        real q[3] = {0, 0, 0};                       // sum of w_j (p_j - t_a) over the slot's joints below a
-        bool any = false;
-        {
-            const int ta = w.c_tin[a], na = w.c_tsz[a];
-            for (int i = 0; i < d.kw; ++i) {
-                const int j = w.c_wj[s * d.kw + i];
-                if (j >= 0 && unsigned(w.c_tin[j] - ta) < unsigned(na)) {
-                    const real wt = w.c_wv[s * d.kw + i];
-                    const real *pp = w.pj + 3 * (s * d.kw + i);
-                    for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
-                    any = true;
-                }
-            }
-        }
-        if (any) {
-            const real *L = w.Loc + 27 * mi + 9 * t;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                real cr[3];
-                cross3(w.u + 3 * (3 * a + k), q, cr);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
-            }
-        }
-    }
-    M2_D void t1_blend(int mi, int a, int t, const Vec4<real> *p, real *blk) {
+    M2_D void t1_compute(int mi, int a, int t, const Vec4<real> *p, real *blk) {
         const int s = 3 * mi + t;
         if (a >= 1) {
-            const real *dR = w.dRl + 27 * a;
-            real E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // E[c*3+k] = sum_e Pd[c][e] dR_k[e]
+            // pose-blend part: E[c][k] = sum_e Pd[c][e] dR_k[e], then blk += (Loc_t Rsk_s) E
+            const real *dR = w.dRl + kDR * a;
+            real dr[kDR];
+#pragma unroll
+            for (int v = 0; v < kDR / 4; ++v) {
+                const Vec4<real> q4 = ld4(dR + 4 * v);
+                dr[4 * v] = q4.x; dr[4 * v + 1] = q4.y; dr[4 * v + 2] = q4.z; dr[4 * v + 3] = q4.w;
+            }
+            real E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int e = 0; e < 9; ++e) {
-                const real q0 = dR[e], q1 = dR[9 + e], q2 = dR[18 + e];
+                const real q0 = dr[e], q1 = dr[9 + e], q2 = dr[18 + e];
                 E[0] += p[e].x * q0; E[1] += p[e].x * q1; E[2] += p[e].x * q2;
                 E[3] += p[e].y * q0; E[4] += p[e].y * q1; E[5] += p[e].y * q2;
                 E[6] += p[e].z * q0; E[7] += p[e].z * q1; E[8] += p[e].z * q2;
             }
-            const real *Mt = w.MtR + 9 * s;
+            const real *Mp = w.MtR + kM3 * s;
+            const Vec4<real> m0 = ld4(Mp), m1 = ld4(Mp + 4), m2 = ld4(Mp + 8);
+            const real Mt[9] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x};
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     blk[3 * r + k] += Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
         }
-    }
-    M2_D void t1_compute(int mi, int a, int t, const Vec4<real> *p, real *blk) {
-        t1_blend(mi, a, t, p, blk);
-        t1_rigid(mi, a, t, blk);
+        // rigid part: the slot's skinning joints below a turn about a:  d v / d omega_{a,k} = u_{a,k} x q
+        const int mask = w.c_amask[s * d.nJ + a];
+        if (mask) {
+            real q[3] = {0, 0, 0};
+            for (int i = 0; i < d.kw; ++i)
+                if ((mask >> i) & 1) {
+                    const real wt = w.c_wv[s * d.kw + i];
+                    const real *pp = w.pj + 3 * (s * d.kw + i);
+                    for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
+                }
+            const real *Lp = w.Loc + kM3 * s;
+            const Vec4<real> l0 = ld4(Lp), l1 = ld4(Lp + 4), l2 = ld4(Lp + 8);
+            const real L[9] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const Vec4<real> uk = ld4(w.u + kM3 * a + 4 * k);
+                const real uv[3] = {uk.x, uk.y, uk.z};
+                real cr[3];
+                cross3(uv, q, cr);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) blk[3 * r + k] += L[3 * r] * cr[0] + L[3 * r + 1] * cr[1] + L[3 * r + 2] * cr[2];
+            }
+        }
     }
 
-    // ---- one entry of the weighted Jacobian tile (row = residual row inside the tile, col = free variable)
-    M2_D void jf_store(int row, int col, real v) {
+    // ---- the three residual rows of marker `ml` of the tile (already weighted) in free-variable column `col`.
+    //      Tensor-core mode keeps the tile transposed and split (see tc_xidx): one marker's rows are one 16-byte
+    //      vector of the hi and of the lo operand (4th row zero).
+    M2_D void jf_store3(int ml, int col, real v0, real v1, real v2) {
 #if M2_GPU
         if (w.tc) {
-            const float hi = tc::to_tf32(float(v)), lo = tc::to_tf32(float(v) - hi);
-            const int q = tc_xidx(col, row, tc_kt);
-            w.Xhi[q] = hi;
-            w.Xlo[q] = lo;
+            const float h0 = tc::to_tf32(float(v0)), h1 = tc::to_tf32(float(v1)), h2 = tc::to_tf32(float(v2));
+            const int q = tc_xidx(col, 4 * ml, tc_kt);
+            *reinterpret_cast<float4 *>(w.Xhi + q) = make_float4(h0, h1, h2, 0.f);
+            *reinterpret_cast<float4 *>(w.Xlo + q) = make_float4(tc::to_tf32(float(v0) - h0), tc::to_tf32(float(v1) - h1), tc::to_tf32(float(v2) - h2), 0.f);
             return;
         }
 #endif
-        w.Jf[row * d.npad + col] = v;
+        real *J = w.Jf + 3 * ml * d.npad + col;
+        J[0] = v0; J[d.npad] = v1; J[2 * d.npad] = v2;
     }
-    M2_D real jf_load(int row, int col) const {
+    M2_D real jf_load(int ml, int r, int col) const {
 #if M2_GPU
-        if (w.tc) { const int q = tc_xidx(col, row, tc_kt); return real(w.Xhi[q] + w.Xlo[q]); }
+        if (w.tc) { const int q = tc_xidx(col, 4 * ml + r, tc_kt); return real(w.Xhi[q] + w.Xlo[q]); }
 #endif
-        return w.Jf[row * d.npad + col];
+        return w.Jf[(3 * ml + r) * d.npad + col];
     }
 
     // ---- a finished 3x3 block of T1: body joints go straight to their free columns of the tile (weighted and
@@ -878,10 +888,7 @@ struct Solver {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int col = w.colmap[3 + 3 * a + k];
-                if (col >= 0) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) jf_store(3 * ml + r, col, blk[3 * r + k] * sc);
-                }
+                if (col >= 0) jf_store3(ml, col, blk[k] * sc, blk[3 + k] * sc, blk[6 + k] * sc);
             }
         } else {
 #pragma unroll
@@ -900,14 +907,15 @@ struct Solver {
         const int n = c.n, ld = d.lda;
         CTA_FOR(idx, 3 * d.nJ) {
             const int a = idx / 3, k = idx - 3 * a;
-            const real *D = w.dRl + 27 * a + 9 * k, *R = w.Rl + 9 * a;
+            const real *D = w.dRl + kDR * a + 9 * k, *R = w.Rl + 9 * a;
             real om[3];     // vee(dR R^T)
             om[0] = D[6] * R[3] + D[7] * R[4] + D[8] * R[5];
             om[1] = D[0] * R[6] + D[1] * R[7] + D[2] * R[8];
             om[2] = D[3] * R[0] + D[4] * R[1] + D[5] * R[2];
             const int par = w.c_parents[a];
-            if (par < 0) { for (int q = 0; q < 3; ++q) w.u[3 * idx + q] = om[q]; }
-            else mat3_vec(w.Rg + 9 * par, om, w.u + 3 * idx);
+            real *uo = w.u + kM3 * a + 4 * k;
+            if (par < 0) { for (int q = 0; q < 3; ++q) uo[q] = om[q]; }
+            else mat3_vec(w.Rg + 9 * par, om, uo);
         }
         CTA_FOR(mi, d.M) marker_local_jacobian(mi);
         if (!w.tc) CTA_FOR(i, n * ld) w.A[i] = 0;      // (tensor-core mode: A's storage holds the operand tiles for now)
@@ -931,7 +939,7 @@ struct Solver {
             }
         }
         M2_SYNC();
-        CTA_FOR(s, d.S) mat3_mul(w.Loc + 27 * (s / 3) + 9 * (s % 3), w.Rsk + 9 * s, w.MtR + 9 * s);
+        CTA_FOR(s, d.S) mat3_mul(w.Loc + kM3 * s, w.Rsk + 9 * s, w.MtR + kM3 * s);
         M2_SYNC();
         M2_TACC(6);
         for (int t0 = 0; t0 < d.M; t0 += d.tmk) {
@@ -992,56 +1000,56 @@ struct Solver {
                         mat3_vec(w.Rg + 9 * j, df, o);
                         for (int r = 0; r < 3; ++r) dv[r] += wt * (o[r] + w.dtg[3 * (j * d.nd + i) + r]);
                     }
-                    const real *L = w.Loc + 27 * mi + 9 * t;
+                    const real *L = w.Loc + kM3 * s;
                     for (int r = 0; r < 3; ++r) val[r] += L[3 * r] * dv[0] + L[3 * r + 1] * dv[1] + L[3 * r + 2] * dv[2];
                 }
                 const int col = w.colmap[3 + d.PR + i];
                 const real sc = w.vis[mi] ? wd : real(0);
-                if (col >= 0) for (int r = 0; r < 3; ++r) jf_store(3 * ml + r, col, val[r] * sc);
+                if (col >= 0) jf_store3(ml, col, val[0] * sc, val[1] * sc, val[2] * sc);
             }
-            // translation columns (identity) and the zero padding of the tile
+            // translation columns (identity); zero padding of the tile
             const int trows = 3 * tm;
-            {
-                const int npadc = w.tc ? 0 : d.npad - n, per = 3 + npadc;
-                CTA_FOR(idx, trows * per) {
-                    const int row = idx / per, q = idx - row * per;
-                    if (q < 3) {
-                        const int col = w.colmap[q];
-                        if (col >= 0) jf_store(row, col, (row % 3 == q) ? (w.vis[t0 + row / 3] ? wd : real(0)) : real(0));
-                    } else w.Jf[row * d.npad + n + (q - 3)] = 0;
-                }
-                if (w.tc && trows < tc_kt) {                  // short last tile: the missing rows must not contribute
-                    const int miss = tc_kt - trows;
-                    CTA_FOR(idx, n * miss) jf_store(trows + idx % miss, idx / miss, real(0));
-                }
+            CTA_FOR(idx, tm * 3) {
+                const int ml = idx / 3, q = idx - 3 * ml, col = w.colmap[q];
+                const real v = w.vis[t0 + ml] ? wd : real(0);
+                if (col >= 0) jf_store3(ml, col, q == 0 ? v : real(0), q == 1 ? v : real(0), q == 2 ? v : real(0));
+            }
+            if (w.tc) {
+                // short last tile: the markers that are not there must not contribute
+                CTA_FOR(idx, n * (d.tmk - tm)) jf_store3(tm + idx / n, idx % n, real(0), real(0), real(0));
+            } else {
+                const int npadc = d.npad - n;
+                CTA_FOR(idx, trows * npadc) w.Jf[(idx / npadc) * d.npad + n + idx % npadc] = 0;
             }
             M2_SYNC();
             M2_TACC(7);
-            // T2b: hand columns = Jt[:, hand block] * C^T as a register-tiled product (1 row x 4 outputs)
+            // T2b: hand columns = Jt[:, hand block] * C^T as a register-tiled product (one marker's 3 rows x 4 outputs)
             if (hand_free) {
                 int ngt = 0;                                  // output groups of 4 over all blocks
                 for (int b = 0; b < m.hb_n; ++b) ngt += m.hb[b].rw4 / 4;
-                CTA_FOR(it, trows * ngt) {
-                    const int row = it / ngt;
-                    int rg = it - row * ngt, b = 0;
+                CTA_FOR(it, tm * ngt) {
+                    const int ml = it / ngt;
+                    int rg = it - ml * ngt, b = 0;
                     while (rg >= m.hb[b].rw4 / 4) { rg -= m.hb[b].rw4 / 4; ++b; }
                     const HandBlock hb = m.hb[b];
                     const int nq = hb.q1 - hb.q0;
-                    const real *Jr = w.Jt + row * d.NCt + m.body_dof + hb.q0;
+                    const real *J0 = w.Jt + 3 * ml * d.NCt + m.body_dof + hb.q0, *J1 = J0 + d.NCt, *J2 = J1 + d.NCt;
                     const real *ct = w.hct + hb.ct_off + 4 * rg;
-                    real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
                     for (int q = 0; q < nq; ++q) {
-                        const real jv = Jr[q];
+                        const real j0 = J0[q], j1 = J1[q], j2 = J2[q];
                         const Vec4<real> cv = ld4(ct + q * hb.rw4);
-                        a0 += jv * cv.x; a1 += jv * cv.y; a2 += jv * cv.z; a3 += jv * cv.w;
+                        acc[0] += j0 * cv.x; acc[1] += j0 * cv.y; acc[2] += j0 * cv.z; acc[3] += j0 * cv.w;
+                        acc[4] += j1 * cv.x; acc[5] += j1 * cv.y; acc[6] += j1 * cv.z; acc[7] += j1 * cv.w;
+                        acc[8] += j2 * cv.x; acc[9] += j2 * cv.y; acc[10] += j2 * cv.z; acc[11] += j2 * cv.w;
                     }
-                    const real sc = w.vis[t0 + row / 3] ? wd : real(0);
-                    const real out[4] = {a0 * sc, a1 * sc, a2 * sc, a3 * sc};
+                    const real sc = w.vis[t0 + ml] ? wd : real(0);
+#pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int r = hb.r0 + 4 * rg + e;
                         if (r < hb.r1) {
                             const int col = w.colmap[3 + m.body_dof + r];
-                            if (col >= 0) jf_store(row, col, out[e]);
+                            if (col >= 0) jf_store3(ml, col, acc[e] * sc, acc[4 + e] * sc, acc[8 + e] * sc);
                         }
                     }
                 }
@@ -1103,7 +1111,8 @@ struct Solver {
             }
             CTA_FOR(cc, n) {
                 real s = 0;
-                for (int row = 0; row < trows; ++row) s += jf_load(row, cc) * w.rm[3 * t0 + row];
+                for (int ml = 0; ml < tm; ++ml)
+                    for (int r = 0; r < 3; ++r) s += jf_load(ml, r, cc) * w.rm[3 * (t0 + ml) + r];
                 w.g[cc] -= s;
             }
 #if M2_GPU
@@ -1747,6 +1756,17 @@ struct Solver {
                 else { w.c_tin[j] = cur[a]; cur[a] += w.c_tsz[j]; }
                 cur[j] = w.c_tin[j] + 1;
             }
+        }
+        M2_SYNC();
+        CTA_FOR(idx, d.S * d.nJ) {                             // which of a slot's skinning joints hang below joint a
+            const int sl = idx / d.nJ, a = idx - sl * d.nJ;
+            const int ta = w.c_tin[a], na = w.c_tsz[a];
+            int mask = 0;
+            for (int i = 0; i < d.kw; ++i) {
+                const int j = w.c_wj[sl * d.kw + i];
+                if (j >= 0 && unsigned(w.c_tin[j] - ta) < unsigned(na)) mask |= 1 << i;
+            }
+            w.c_amask[idx] = uint8_t(mask);
         }
         M2_SYNC();
         M2_T0();

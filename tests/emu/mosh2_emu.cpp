@@ -112,6 +112,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     q.maxiter = opt->maxiter; q.optimize_fingers = opt->optimize_fingers; q.optimize_dynamics = opt->optimize_dynamics;
 
     hm.m.tile_markers = 16;
+    hm.m.dev_no_tc = 1;                          // the host build runs the CUDA-core formulation
     const mosh2::Dims d = mosh2::make_dims(hm.m);
     mosh2::Work<real, false> w{};
     mosh2::Arena S0{mosh2::kSmemHeader}, G0{0};
@@ -119,6 +120,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     if (std::getenv("MOSH2_EMU_PLAN")) {        // development aid: shared-memory footprint of this model
         for (int tile : {16, 8}) {
             hm.m.tile_markers = tile;
+            hm.m.dev_no_tc = sizeof(real) == 4 ? 0 : 1;   // what the GPU launch would lay out
             const mosh2::Dims dd = mosh2::make_dims(hm.m);
             mosh2::Work<real, false> ww{};
             mosh2::Arena Sa{mosh2::kSmemHeader}, Ga{0};
@@ -126,6 +128,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
             std::fprintf(stderr, "plan: sizeof(real)=%zu tile=%d smem=%zu bytes (limit %d)\n", sizeof(real), tile, Sa.off, 227 * 1024);
         }
         hm.m.tile_markers = 16;
+        hm.m.dev_no_tc = 1;
     }
     std::vector<char> smem_raw(S0.off + 128);
     char *smem_base = smem_raw.data() + ((32 - (reinterpret_cast<uintptr_t>(smem_raw.data()) & 31)) & 31);
