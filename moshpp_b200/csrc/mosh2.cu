@@ -128,16 +128,15 @@ struct DevModel {
         if ((rc = up<real>(d.hands_mean, d.n_hand_full, &m.hands_mean))) return rc;
         if ((rc = up<real>(d.v0, S * 3, &m.v0))) return rc;
         if ((rc = up<real>(d.sd, S * 3 * nd, &m.sd))) return rc;
-        {   // pose-blend blocks [(nJ-1)][M][9 rows][12]: rows padded to three 16-byte vectors
-            // [(nJ-1)][9 e][3M slots][4]: x, y, z of a slot for one (joint, e) form one 16-byte vector
+        {   // pose-blend table [(nJ-1)][9 e][3 c][3M slots]: lanes over slots read consecutive words, no padding
             const size_t S3 = size_t(3) * d.n_markers;
-            std::vector<double> pd4((nJ - 1) * 9 * S3 * mosh2::kPdSlot, 0.0);
+            std::vector<double> pdc((nJ - 1) * 27 * S3, 0.0);
             for (size_t j = 0; j + 1 < nJ; ++j)
                 for (size_t sl = 0; sl < S3; ++sl)
                     for (int c = 0; c < 3; ++c)
                         for (int e = 0; e < 9; ++e)
-                            pd4[((j * 9 + e) * S3 + sl) * mosh2::kPdSlot + c] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
-            if ((rc = up<real>(pd4.data(), pd4.size(), &m.pd4))) return rc;
+                            pdc[((j * 9 + e) * 3 + c) * S3 + sl] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+            if ((rc = up<real>(pdc.data(), pdc.size(), &m.pdc))) return rc;
         }
         if ((rc = up<real>(d.w_val, S * d.kw, &m.w_val))) return rc;
         if ((rc = up<real>(d.j0, nJ * 3, &m.j0))) return rc;
@@ -237,8 +236,9 @@ void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) 
     // big arrays to a per-CTA global workspace
     // preference order: table staging and 16-marker tiles while they fit the shared-memory budget; the f64 /
     // oversized case moves the big arrays to a per-CTA global workspace
-    const int tries[3][2] = {{16, 0}, {8, 0}, {8, 1}};   // tile, big
-    for (int pass = 0; pass < 3; ++pass) {
+    const int tries[3][2] = {{20, 0}, {10, 0}, {10, 1}};   // markers per tile (a warp owns ten), big
+    const char *dev_tile = getenv("MOSH2_DEV_TILE");      // development aid: 10 = skip the 20-marker tile
+    for (int pass = (dev_tile && atoi(dev_tile) == 10) ? 1 : 0; pass < 3; ++pass) {
         m.tile_markers = tries[pass][0];
         m.dev_no_tc = getenv("MOSH2_DEV_NO_TC") ? 1 : 0;      // development aid: J^T J on the CUDA cores
         const bool in_global = tries[pass][1] != 0;

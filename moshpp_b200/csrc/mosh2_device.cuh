@@ -83,9 +83,7 @@ namespace mosh2 {
 enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32 };
 enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
 
-constexpr int kTileMarkersMax = 16;   // markers per Jacobian tile: 16 (48 rows) when shared memory allows, else 8
 constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
-constexpr int kPdSlot = 4;        // pose-blend rows of one slot (x, y, z, pad): one 16-byte vector per (joint, e)
 constexpr int kBlendGroups = 3;   // upper bound of the joint groups of the pose-blend partial sums (run time: 1..3, one round of threads)
 constexpr int kCholNB = 8;        // block column width of the Cholesky factorisation
 constexpr int kMaxHandBlocks = 4;
@@ -107,13 +105,13 @@ struct Model {
     HandBlock hb[kMaxHandBlocks];
     const real *hct;            // compact transposed hand-PCA blocks
     const real *hands_mean, *v0, *sd, *w_val, *j0, *jd, *coefs;
-    const real *pd4;            // [(nJ-1)][9 e][3M slots][4]: lanes over slots read consecutive 16-byte vectors
+    const real *pdc;            // pose-blend table [(nJ-1)][9 e][3 c][3M slots]: lanes over slots read consecutive words
     int prior_k, prior_d, prior_off, prior_d4;
     const real *prior_means, *prior_Q4, *prior_nlw;   // Q4: [K][D][D4]
     int n1, n2;
     const int *free1, *free2;
     int finger_lo, finger_hi;
-    int tile_markers;           // markers per Jacobian tile (8 or 16), chosen by the host from the shared-memory budget
+    int tile_markers;           // markers per Jacobian tile (20 or 10: a warp owns ten), chosen by the host from the shared-memory budget
     int dev_no_tc;              // development switch (host): 1 = J^T J stays on the CUDA cores
 };
 
@@ -348,7 +346,7 @@ struct Work {
 constexpr int kDR = 28;              // floats per joint in dRl: three 3x3 derivative matrices (27) padded to 16-byte vectors
 constexpr int kM3 = 12;              // floats per padded 3x3 matrix (MtR per slot, Loc per marker vertex) and per joint in u (3 x 4)
 constexpr int kTcM = 128;            // UMMA M: free variables, zero/garbage padded (rows >= n are never read back)
-constexpr int kTcCols = 128;         // tensor-memory columns of the accumulator
+constexpr int kTcCols = 512;         // tensor-memory columns: hi*hi accumulators at 0 and 128 (alternating K steps), cross terms at 256
 M2_HD int tc_xidx(int i, int k, int kt) {        // float index of X[i][k] inside a [kTcM][kt] operand buffer
     return (i >> 3) * (kt >> 2) * 32 + (k >> 2) * 32 + (i & 7) * 4 + (k & 3);
 }
@@ -413,13 +411,13 @@ template <class real>
 M2_HD Dims make_dims(const Model<real> &m) {
     Dims d;
     d.nJ = m.nJ; d.M = m.M; d.S = 3 * m.M; d.PF = 3 * m.nJ; d.PR = m.p_red; d.nd = m.nd;
-    d.NX = 3 + m.p_red + m.nd; d.NCt = (d.PF + m.nd + 3) & ~3; d.n1 = m.n1; d.n2 = m.n2;
+    d.NX = 3 + m.p_red + m.nd; d.NCt = (m.n_hand_full + 3) & ~3;   /* columns of the full-pose hand tile Jt */ d.n1 = m.n1; d.n2 = m.n2;
     d.npad = (m.n2 + 3) & ~3;
     d.ld = d.npad;              // Cholesky factor: rows are 16-byte aligned (vector read-modify-write of 4x4 tiles)
     d.ldp = d.npad + 4;         // row length of the transposed panel (one extra row: the right-hand side)
     d.lda = d.npad | 1;         // A: odd leading dimension, so row-strided and transposed tile accesses spread over banks
     d.K = m.prior_k; d.D = m.prior_d; d.D4 = m.prior_d4; d.kw = m.kw;
-    d.tmk = m.tile_markers > 0 ? m.tile_markers : 8;
+    d.tmk = m.tile_markers > 0 ? m.tile_markers : 10;
     const int a = 3 * d.tmk * d.NCt, b = kBlendGroups * 9 * m.M + 4;   // Jt doubles as the pose-blend partial sums
     d.jt_size = a > b ? a : b;
     return d;
@@ -470,7 +468,11 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
         B.off = mark_b;
         if (tc_ok && w.A.ofs + x_bytes > B.off) B.off = w.A.ofs + x_bytes;
         w.Jt.ofs = B.take<real>(d.jt_size);
+#ifdef MOSH2_TC_CHECK
+        w.Jf.ofs = B.take<real>(3 * d.tmk * d.npad);      // development check: the plain tile is kept next to the operand tiles
+#else
         w.Jf.ofs = tc_ok ? w.Jt.ofs : B.take<real>(3 * d.tmk * d.npad);
+#endif
         if (!BIG) {
             w.Loc.ofs = S.take<real>(3 * kM3 * d.M); w.MtR.ofs = S.take<real>(kM3 * d.S);
             w.u.ofs = S.take<real>(kM3 * d.nJ); w.dtg.ofs = S.take<real>(3 * d.nJ * d.nd + 1);
@@ -565,20 +567,30 @@ struct Solver {
     M2_D void blend_partials(int l, int nl) {
         const int G = blend_groups(nl);
         const int per = (d.nJ - 1 + G - 1) / G;
-        const size_t estride = size_t(d.S) * kPdSlot;
+        const size_t cs = size_t(d.S);                  // stride between the 27 (e, c) rows of a joint
         for (int it = l; it < d.S * G; it += nl) {
             const int g = it / d.S, s = it - g * d.S;
             int j0 = 1 + g * per, j1 = j0 + per;
             if (j1 > d.nJ) j1 = d.nJ;
             real ax = 0, ay = 0, az = 0;
-            for (int j = j0; j < j1; ++j) {
-                const real *P = m.pd4 + size_t(j - 1) * 9 * estride + size_t(s) * kPdSlot;
-                const real *R = w.Rl + 9 * j;
-                const real f[9] = {R[0] - real(1), R[1], R[2], R[3], R[4] - real(1), R[5], R[6], R[7], R[8] - real(1)};
+            // two joints per trip: 54 independent 4-byte loads in flight per thread
+            for (int j = j0; j < j1; j += 2) {
+                const bool two = j + 1 < j1;
+                const real *P = m.pdc + size_t(j - 1) * 27 * cs + s, *Q = P + (two ? 27 * cs : 0);
+                real pa[27], pb[27];
+#pragma unroll
+                for (int q = 0; q < 27; ++q) pa[q] = P[q * cs];
+#pragma unroll
+                for (int q = 0; q < 27; ++q) pb[q] = Q[q * cs];
+                const real *R = w.Rl + 9 * j, *R2 = R + (two ? 9 : 0);
+                const real tw = two ? real(1) : real(0);
 #pragma unroll
                 for (int e = 0; e < 9; ++e) {
-                    const Vec4<real> p = ld4(P + e * estride);
-                    ax += p.x * f[e]; ay += p.y * f[e]; az += p.z * f[e];
+                    const real id = (e == 0 || e == 4 || e == 8) ? real(1) : real(0);
+                    const real fa = R[e] - id, fb = (R2[e] - id) * tw;
+                    ax += pa[3 * e] * fa + pb[3 * e] * fb;
+                    ay += pa[3 * e + 1] * fa + pb[3 * e + 1] * fb;
+                    az += pa[3 * e + 2] * fa + pb[3 * e + 2] * fb;
                 }
             }
             real *o = w.Jt + (g * d.S + s) * 3;
@@ -795,16 +807,16 @@ struct Solver {
         }
     }
 
-    // ---- pose-blend vectors of slot (marker mi, vertex t) for joint a (nine 16-byte loads, issued together)
-    M2_D void t1_load(int mi, int a, int t, Vec4<real> *p) {
-        const size_t estride = size_t(d.S) * kPdSlot;
-        const real *P = m.pd4 + size_t(a >= 1 ? a - 1 : 0) * 9 * estride + size_t(3 * mi + t) * kPdSlot;
+    // ---- pose-blend vectors of slot (marker mi, vertex t) for joint a: p[3 e + c], 27 coalesced 4-byte loads
+    M2_D void t1_load(int mi, int a, int t, real *p) {
+        const size_t cs = size_t(d.S);
+        const real *P = m.pdc + size_t(a >= 1 ? a - 1 : 0) * 27 * cs + (3 * mi + t);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) p[e] = ld4(P + e * estride);
+        for (int q = 0; q < 27; ++q) p[q] = P[q * cs];
     }
 
     // ---- contribution of slot (marker mi, vertex t) to the 3x3 Jacobian block of joint a:  blk[r*3+k] +=
-    M2_D void t1_compute(int mi, int a, int t, const Vec4<real> *p, real *blk) {
+    M2_D void t1_compute(int mi, int a, int t, const real *p, real *blk) {
         const int s = 3 * mi + t;
         if (a >= 1) {
             // pose-blend part: E[c][k] = sum_e Pd[c][e] dR_k[e], then blk += (Loc_t Rsk_s) E
@@ -819,9 +831,9 @@ struct Solver {
 #pragma unroll
             for (int e = 0; e < 9; ++e) {
                 const real q0 = dr[e], q1 = dr[9 + e], q2 = dr[18 + e];
-                E[0] += p[e].x * q0; E[1] += p[e].x * q1; E[2] += p[e].x * q2;
-                E[3] += p[e].y * q0; E[4] += p[e].y * q1; E[5] += p[e].y * q2;
-                E[6] += p[e].z * q0; E[7] += p[e].z * q1; E[8] += p[e].z * q2;
+                E[0] += p[3 * e] * q0; E[1] += p[3 * e] * q1; E[2] += p[3 * e] * q2;
+                E[3] += p[3 * e + 1] * q0; E[4] += p[3 * e + 1] * q1; E[5] += p[3 * e + 1] * q2;
+                E[6] += p[3 * e + 2] * q0; E[7] += p[3 * e + 2] * q1; E[8] += p[3 * e + 2] * q2;
             }
             const real *Mp = w.MtR + kM3 * s;
             const Vec4<real> m0 = ld4(Mp), m1 = ld4(Mp + 4), m2 = ld4(Mp + 8);
@@ -867,7 +879,9 @@ struct Solver {
             const int q = tc_xidx(col, 4 * ml, tc_kt);
             *reinterpret_cast<float4 *>(w.Xhi + q) = make_float4(h0, h1, h2, 0.f);
             *reinterpret_cast<float4 *>(w.Xlo + q) = make_float4(tc::to_tf32(float(v0) - h0), tc::to_tf32(float(v1) - h1), tc::to_tf32(float(v2) - h2), 0.f);
+#ifndef MOSH2_TC_CHECK
             return;
+#endif
         }
 #endif
         real *J = w.Jf + 3 * ml * d.npad + col;
@@ -894,7 +908,7 @@ struct Solver {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + 3 * a + k] = blk[3 * r + k];
+                for (int k = 0; k < 3; ++k) w.Jt[(3 * ml + r) * d.NCt + (3 * a - m.body_dof) + k] = blk[3 * r + k];
         }
     }
 
@@ -948,35 +962,110 @@ struct Solver {
             // over the marker's three slots; on the GPU three adjacent lanes take one slot each (their pose-blend
             // vectors are adjacent in memory) and are summed with two shuffles.
             {
-                const int ngroups = tm * njl;
 #if M2_GPU
+                // A warp owns up to ten markers of the tile (lane = marker vertex: 30 lanes) and walks a strided share
+                // of the joints, so everything that belongs to the slot stays in registers.  The three partial 3x3
+                // blocks of a marker are summed by rotation -- lane t ends up with column t -- and every lane stores
+                // its own column.
                 const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
                 const int t = lane % 3, grp = lane / 3;
-#pragma unroll 1
-                for (int g0 = warp * 10; g0 < ngroups; g0 += nwarp * 10) {
-                    const int gi = g0 + grp;
-                    const bool valid = lane < 30 && gi < ngroups;
-                    real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    int ml = 0, a = 0;
-                    if (valid) {
-                        ml = gi % tm;
-                        a = w.jlist[gi / tm];
-                        Vec4<real> pv[9];
-                        t1_load(t0 + ml, a, t, pv);
-                        t1_compute(t0 + ml, a, t, pv, blk);
+                const int nmg = (tm + 9) / 10, nch = nwarp / nmg;         // marker groups, joint shares
+                const int mg = warp % nmg, ch = warp / nmg;
+                const int ml = mg * 10 + grp;
+                const bool valid = lane < 30 && ml < tm;
+                if (ch < nch) {
+                    const int mi = t0 + (valid ? ml : 0), sl = 3 * mi + t;
+                    const real sc = (valid && w.vis[mi]) ? wd : real(0);
+                    // slot constants
+                    real Mt[9], Lc[9];
+                    {
+                        const real *Mp = w.MtR + kM3 * sl, *Lp = w.Loc + kM3 * sl;
+                        const Vec4<real> m0 = ld4(Mp), m1 = ld4(Mp + 4), m2 = ld4(Mp + 8), l0 = ld4(Lp), l1 = ld4(Lp + 4), l2 = ld4(Lp + 8);
+                        Mt[0] = m0.x; Mt[1] = m0.y; Mt[2] = m0.z; Mt[3] = m0.w; Mt[4] = m1.x; Mt[5] = m1.y; Mt[6] = m1.z; Mt[7] = m1.w; Mt[8] = m2.x;
+                        Lc[0] = l0.x; Lc[1] = l0.y; Lc[2] = l0.z; Lc[3] = l0.w; Lc[4] = l1.x; Lc[5] = l1.y; Lc[6] = l1.z; Lc[7] = l1.w; Lc[8] = l2.x;
                     }
+                    const size_t cs = size_t(d.S);
+                    const real *Pslot = m.pdc + sl;
+                    const uint8_t *mrow = w.c_amask + sl * d.nJ;
+                    const int src1 = lane - t + (t + 2) % 3, src2 = lane - t + (t + 1) % 3;   // lanes whose t is t-1, t-2 (mod 3)
+#pragma unroll 1
+                    for (int ji = ch; ji < njl; ji += nch) {
+                        const int a = w.jlist[ji];
+                        real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                        if (a >= 1) {
+                            const real *P = Pslot + size_t(a - 1) * 27 * cs;
+                            real pv[27];
 #pragma unroll
-                    for (int q = 0; q < 9; ++q)
-                        blk[q] += __shfl_down_sync(0xffffffffu, blk[q], 1) + __shfl_down_sync(0xffffffffu, blk[q], 2);
-                    if (valid && t == 0) t1_store(ml, t0 + ml, a, blk);
+                            for (int q = 0; q < 27; ++q) pv[q] = P[q * cs];
+                            const real *dR = w.dRl + kDR * a;
+                            real dr[kDR];
+#pragma unroll
+                            for (int v = 0; v < kDR / 4; ++v) {
+                                const Vec4<real> q4 = ld4(dR + 4 * v);
+                                dr[4 * v] = q4.x; dr[4 * v + 1] = q4.y; dr[4 * v + 2] = q4.z; dr[4 * v + 3] = q4.w;
+                            }
+                            real E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                            for (int e = 0; e < 9; ++e) {
+                                const real q0 = dr[e], q1 = dr[9 + e], q2 = dr[18 + e];
+                                E[0] += pv[3 * e] * q0; E[1] += pv[3 * e] * q1; E[2] += pv[3 * e] * q2;
+                                E[3] += pv[3 * e + 1] * q0; E[4] += pv[3 * e + 1] * q1; E[5] += pv[3 * e + 1] * q2;
+                                E[6] += pv[3 * e + 2] * q0; E[7] += pv[3 * e + 2] * q1; E[8] += pv[3 * e + 2] * q2;
+                            }
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    blk[3 * r + k] = Mt[3 * r] * E[k] + Mt[3 * r + 1] * E[3 + k] + Mt[3 * r + 2] * E[6 + k];
+                        }
+                        const int mask = mrow[a];
+                        if (mask) {                                  // rigid part: u_{a,k} x q
+                            real q[3] = {0, 0, 0};
+                            for (int i = 0; i < d.kw; ++i)
+                                if ((mask >> i) & 1) {
+                                    const real wt = w.c_wv[sl * d.kw + i];
+                                    const real *pp = w.pj + 3 * (sl * d.kw + i);
+                                    for (int r = 0; r < 3; ++r) q[r] += wt * (pp[r] - w.tg[3 * a + r]);
+                                }
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const Vec4<real> uk = ld4(w.u + kM3 * a + 4 * k);
+                                const real uv[3] = {uk.x, uk.y, uk.z};
+                                real cr[3];
+                                cross3(uv, q, cr);
+#pragma unroll
+                                for (int r = 0; r < 3; ++r) blk[3 * r + k] += Lc[3 * r] * cr[0] + Lc[3 * r + 1] * cr[1] + Lc[3 * r + 2] * cr[2];
+                            }
+                        }
+                        // lane t collects column t of the marker's block: own part + the parts of the two other vertices
+                        real col3[3];
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const real b0 = blk[3 * r], b1 = blk[3 * r + 1], b2 = blk[3 * r + 2];
+                            const real own = t == 0 ? b0 : (t == 1 ? b1 : b2);
+                            const real to1 = t == 0 ? b1 : (t == 1 ? b2 : b0);   // what the lane with t+1 wants: column t+1
+                            const real to2 = t == 0 ? b2 : (t == 1 ? b0 : b1);   // column t+2
+                            col3[r] = own + __shfl_sync(0xffffffffu, to1, src1) + __shfl_sync(0xffffffffu, to2, src2);
+                        }
+                        if (valid) {
+                            if (3 * a < m.body_dof) {
+                                const int col = w.colmap[3 + 3 * a + t];
+                                if (col >= 0) jf_store3(ml, col, col3[0] * sc, col3[1] * sc, col3[2] * sc);
+                            } else {
+                                real *Jr = w.Jt + 3 * ml * d.NCt + (3 * a - m.body_dof) + t;
+                                Jr[0] = col3[0]; Jr[d.NCt] = col3[1]; Jr[2 * d.NCt] = col3[2];
+                            }
+                        }
+                    }
                 }
 #else
+                const int ngroups = tm * njl;
                 for (int gi = 0; gi < ngroups; ++gi) {
                     const int ml = gi % tm, a = w.jlist[gi / tm];
                     real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                     for (int t = 0; t < 3; ++t) {
                         real part[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                        Vec4<real> pv[9];
+                        real pv[27];
                         t1_load(t0 + ml, a, t, pv);
                         t1_compute(t0 + ml, a, t, pv, part);
                         for (int q = 0; q < 9; ++q) blk[q] += part[q];
@@ -1033,7 +1122,7 @@ struct Solver {
                     while (rg >= m.hb[b].rw4 / 4) { rg -= m.hb[b].rw4 / 4; ++b; }
                     const HandBlock hb = m.hb[b];
                     const int nq = hb.q1 - hb.q0;
-                    const real *J0 = w.Jt + 3 * ml * d.NCt + m.body_dof + hb.q0, *J1 = J0 + d.NCt, *J2 = J1 + d.NCt;
+                    const real *J0 = w.Jt + 3 * ml * d.NCt + hb.q0, *J1 = J0 + d.NCt, *J2 = J1 + d.NCt;
                     const real *ct = w.hct + hb.ct_off + 4 * rg;
                     real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
                     for (int q = 0; q < nq; ++q) {
@@ -1058,6 +1147,17 @@ struct Solver {
             if (w.tc) tc::fence_async_smem();                // this thread's operand stores -> visible to the async proxy
 #endif
             M2_SYNC();
+#ifdef MOSH2_TC_CHECK
+            if (w.tc) {
+                CTA_FOR(idx, tm * 3 * n) {
+                    const int cc = idx % n, row = idx / n, ml = row / 3, r = row - 3 * ml;
+                    const int q = tc_xidx(cc, 4 * ml + r, tc_kt);
+                    const float xv = w.Xhi[q] + w.Xlo[q], jv = float(w.Jf[row * d.npad + cc]);
+                    if (fabsf(xv - jv) > 1e-4f * (fabsf(jv) + 1e-3f)) printf("X MISMATCH build %d n %d tile %d ml %d r %d col %d: X %g Jf %g\n", n_build, n, t0, ml, r, cc, xv, jv);
+                }
+                __syncthreads();
+            }
+#endif
             M2_TACC(8);
             // T3: A += Jf^T Jf, g -= Jf^T r
 #if M2_GPU
@@ -1069,11 +1169,16 @@ struct Solver {
                     const uint32_t lbo = 128, sbo = uint32_t(tc_kt >> 2) * 128;
                     const uint32_t ahi = tc::smem_u32(w.Xhi), alo = tc::smem_u32(w.Xlo);
                     const uint32_t idesc = tc::idesc_tf32(kTcM, (n + 15) & ~15);
+                    // The tensor core adds every K step into the accumulator with a truncation, so the error grows
+                    // with the number of steps into one accumulator and with its magnitude: the dominant hi*hi term
+                    // alternates between two accumulators, the (2^-11 smaller) cross terms have their own.
                     for (int ks = 0; ks < (tc_kt >> 3); ++ks) {
                         const uint64_t dhi = tc::smem_desc(ahi + ks * 2 * lbo, lbo, sbo), dlo = tc::smem_desc(alo + ks * 2 * lbo, lbo, sbo);
-                        tc::mma_tf32(tc_tmem, dhi, dhi, idesc, (t0 > 0 || ks > 0) ? 1u : 0u);
-                        tc::mma_tf32(tc_tmem, dlo, dhi, idesc, 1u);
-                        tc::mma_tf32(tc_tmem, dhi, dlo, idesc, 1u);
+                        const bool first = t0 == 0 && ks == 0, second = t0 == 0 && ks == 1;
+                        tc::mma_tf32(tc_tmem + 128 * (ks & 1), dhi, dhi, idesc, (first || second) ? 0u : 1u);
+                        tc::mma_tf32(tc_tmem + 256, dlo, dhi, idesc, first ? 0u : 1u);
+                        tc::mma_tf32(tc_tmem + 256, dhi, dlo, idesc, 1u);
+                        tc::mma_tf32(tc_tmem + 256, dlo, dlo, idesc, 1u);
                     }
                     tc::commit(tc::smem_u32(w.mbar));
                 }
@@ -1132,8 +1237,12 @@ struct Solver {
             if (cta.tid < 128) {
                 const int i = cta.tid, nc = (n + 15) & ~15;
                 for (int c0 = 0; c0 < nc; c0 += 16) {
-                    float v[16];
+                    float v[16], v1[16], v2[16];
                     tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + c0, v);
+                    tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + 128 + c0, v1);
+                    tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + 256 + c0, v2);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = (v[q] + v1[q]) + v2[q];
                     if (i < n) {
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
@@ -1277,6 +1386,7 @@ struct Solver {
 #pragma unroll
                     for (int r = 0; r < NB; ++r) Li[r * NB + lane] = x[r];   // rows/columns >= kb hold identity padding
                 }
+                __syncwarp();                               // every lane has read the block before any lane rewrites it
 #pragma unroll
                 for (int r = 0; r < NB; ++r)
 #pragma unroll

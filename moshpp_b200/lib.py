@@ -60,7 +60,8 @@ class Mosh2Error(RuntimeError):
 
 
 def default_library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmosh2.so')
+    # MOSH2_LIBRARY: development override (instrumented builds of the same CUDA source)
+    return os.environ.get('MOSH2_LIBRARY') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmosh2.so')
 
 
 _LIB = None

@@ -54,13 +54,13 @@ struct HostModel {
         {
             // [(nJ-1)][9 e][3M slots][4]: x, y, z of a slot for one (joint, e) form one 16-byte vector
             const size_t S3 = size_t(3) * d.n_markers;
-            std::vector<double> pd4((nJ - 1) * 9 * S3 * mosh2::kPdSlot, 0.0);
+            std::vector<double> pdc((nJ - 1) * 27 * S3, 0.0);
             for (size_t j = 0; j + 1 < nJ; ++j)
                 for (size_t sl = 0; sl < S3; ++sl)
                     for (int c = 0; c < 3; ++c)
                         for (int e = 0; e < 9; ++e)
-                            pd4[((j * 9 + e) * S3 + sl) * mosh2::kPdSlot + c] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
-            m.pd4 = up<real>(pd4.data(), pd4.size());
+                            pdc[((j * 9 + e) * 3 + c) * S3 + sl] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+            m.pdc = up<real>(pdc.data(), pdc.size());
         }
         m.w_val = up<real>(d.w_val, S * d.kw);
         m.j0 = up<real>(d.j0, nJ * 3);
@@ -111,14 +111,14 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     q.num_train_markers = opt->num_train_markers; q.delta_0 = opt->delta_0; q.e3_first = opt->e3_first; q.e3 = opt->e3;
     q.maxiter = opt->maxiter; q.optimize_fingers = opt->optimize_fingers; q.optimize_dynamics = opt->optimize_dynamics;
 
-    hm.m.tile_markers = 16;
+    hm.m.tile_markers = 20;
     hm.m.dev_no_tc = 1;                          // the host build runs the CUDA-core formulation
     const mosh2::Dims d = mosh2::make_dims(hm.m);
     mosh2::Work<real, false> w{};
     mosh2::Arena S0{mosh2::kSmemHeader}, G0{0};
     mosh2::carve<real, false>(w, d, hm.m, S0, G0);
     if (std::getenv("MOSH2_EMU_PLAN")) {        // development aid: shared-memory footprint of this model
-        for (int tile : {16, 8}) {
+        for (int tile : {20, 10}) {
             hm.m.tile_markers = tile;
             hm.m.dev_no_tc = sizeof(real) == 4 ? 0 : 1;   // what the GPU launch would lay out
             const mosh2::Dims dd = mosh2::make_dims(hm.m);
@@ -126,8 +126,10 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
             mosh2::Arena Sa{mosh2::kSmemHeader}, Ga{0};
             mosh2::carve<real, false>(ww, dd, hm.m, Sa, Ga);
             std::fprintf(stderr, "plan: sizeof(real)=%zu tile=%d smem=%zu bytes (limit %d)\n", sizeof(real), tile, Sa.off, 227 * 1024);
+            std::fprintf(stderr, "      A=%u Lm=%u Xhi=%u Xlo=%u Jt=%u Jf=%u Loc=%u MtR=%u u=%u dtg=%u Linv=%u tc_ok=%d\n", ww.A.ofs, ww.Lm.ofs, ww.Xhi.ofs,
+                         ww.Xlo.ofs, ww.Jt.ofs, ww.Jf.ofs, ww.Loc.ofs, ww.MtR.ofs, ww.u.ofs, ww.dtg.ofs, ww.Linv.ofs, ww.tc_ok);
         }
-        hm.m.tile_markers = 16;
+        hm.m.tile_markers = 20;
         hm.m.dev_no_tc = 1;
     }
     std::vector<char> smem_raw(S0.off + 128);

@@ -66,24 +66,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 }  // namespace tc
 
-constexpr int KT = 48;          // rows of J per tile (the K extent of one batch of MMAs)
 constexpr int MM = 128;         // UMMA M (free variables, zero padded)
 
 // X[i][k] (i: column of J, k: row of J within the tile) -> float index inside a [MM][KT] canonical buffer
-__device__ __host__ inline int xidx(int i, int k) {
+__device__ __host__ inline int xidx(int i, int k, int KT) {
     // core matrices along K are adjacent (LBO = 128 B); 8-row groups are KT/4 core matrices apart (SBO)
     return (i >> 3) * (KT / 4) * 32 + (k >> 2) * 32 + (i & 7) * 4 + (k & 3);
 }
 
-__global__ void __launch_bounds__(384, 1) jtj_kernel(const float *J, int rows, int n, float *D, int mode) {
+__global__ void __launch_bounds__(384, 1) jtj_kernel(const float *J, int rows, int n, float *D, int mode, int KT, int skew) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *Xhi = reinterpret_cast<float *>(smem_raw);
+    float *Xhi = reinterpret_cast<float *>(smem_raw + skew);      // skew: operand base not 128-byte aligned
     float *Xlo = Xhi + MM * KT;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(Xlo + MM * KT);
+    float *Xl2 = Xlo + MM * KT;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 3 * MM * KT * 4 + 128);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = (n + 15) & ~15;
-    if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 128);
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
     if (tid == 32) tc::mbar_init(tc::smem_u32(mbar), 1);
     tc::fence_before();
     __syncthreads();
@@ -91,28 +91,42 @@ __global__ void __launch_bounds__(384, 1) jtj_kernel(const float *J, int rows, i
     const uint32_t tmem = *tmem_slot;
     uint32_t phase = 0;
     const uint32_t idesc = tc::idesc_tf32(MM, N);
-    int tiles = 0;
+    int tiles = 0, kstep = 0;
     for (int r0 = 0; r0 < rows; r0 += KT, ++tiles) {
         for (int e = tid; e < MM * KT; e += blockDim.x) {
             const int i = e / KT, k = e - i * KT;
             float v = 0.f;
             if (i < n && r0 + k < rows) v = J[(r0 + k) * n + i];
-            const float hi = tc::to_tf32(v), lo = tc::to_tf32(v - hi);
-            Xhi[xidx(i, k)] = hi;
-            Xlo[xidx(i, k)] = lo;
+            const float hi = tc::to_tf32(v), lo = tc::to_tf32(v - hi), l2 = (v - hi) - lo;
+            Xhi[xidx(i, k, KT)] = hi;
+            Xlo[xidx(i, k, KT)] = lo;
+            Xl2[xidx(i, k, KT)] = l2;
         }
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc::fence_after();
-            const uint32_t ahi = tc::smem_u32(Xhi), alo = tc::smem_u32(Xlo);
+            const uint32_t ahi = tc::smem_u32(Xhi), alo = tc::smem_u32(Xlo), al2 = tc::smem_u32(Xl2);
             const uint32_t LBO = 128, SBO = (KT / 4) * 128;
             for (int ks = 0; ks < KT / 8; ++ks) {
                 const uint64_t dhi = tc::smem_desc(ahi + ks * 2 * LBO, LBO, SBO), dlo = tc::smem_desc(alo + ks * 2 * LBO, LBO, SBO);
-                tc::mma_tf32(tmem, dhi, dhi, idesc, (tiles > 0 || ks > 0) ? 1u : 0u);
-                if (mode == 3) {
-                    tc::mma_tf32(tmem, dlo, dhi, idesc, 1u);
-                    tc::mma_tf32(tmem, dhi, dlo, idesc, 1u);
+                if (mode <= 3) {
+                    tc::mma_tf32(tmem, dhi, dhi, idesc, (tiles > 0 || ks > 0) ? 1u : 0u);
+                    if (mode == 3) {
+                        tc::mma_tf32(tmem, dlo, dhi, idesc, 1u);
+                        tc::mma_tf32(tmem, dhi, dlo, idesc, 1u);
+                    }
+                } else {
+                    // mode 6/7: hi*hi alternates between two (mode 7: three) accumulators, the small cross terms go to their own
+                    const uint64_t dl2 = tc::smem_desc(al2 + ks * 2 * LBO, LBO, SBO);
+                    const int nacc = mode == 7 ? 3 : 2, which = kstep % nacc;
+                    tc::mma_tf32(tmem + 128 * which, dhi, dhi, idesc, kstep >= nacc ? 1u : 0u);
+                    tc::mma_tf32(tmem + 384, dlo, dhi, idesc, kstep > 0 ? 1u : 0u);
+                    tc::mma_tf32(tmem + 384, dhi, dlo, idesc, 1u);
+                    tc::mma_tf32(tmem + 384, dlo, dlo, idesc, 1u);
+                    tc::mma_tf32(tmem + 384, dl2, dhi, idesc, 1u);
+                    tc::mma_tf32(tmem + 384, dhi, dl2, idesc, 1u);
+                    ++kstep;
                 }
             }
             tc::commit(tc::smem_u32(mbar));
@@ -126,16 +140,22 @@ __global__ void __launch_bounds__(384, 1) jtj_kernel(const float *J, int rows, i
         for (int c0 = 0; c0 < N; c0 += 16) {
             float v[16];
             tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + c0, v);
+            if (mode >= 6) {
+                float v1[16], v2[16], v3[16];
+                tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + 128 + c0, v1);
+                tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + 384 + c0, v3);
+                if (mode == 7) tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + 256 + c0, v2);
+                for (int q = 0; q < 16; ++q) v[q] = ((v[q] + v1[q]) + (mode == 7 ? v2[q] : 0.f)) + v3[q];
+            }
             if (i < n) for (int q = 0; q < 16; ++q) if (c0 + q < n) D[i * n + c0 + q] = v[q];
         }
     }
     tc::fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-int main() {
-    const int rows = 159, n = 111;
+static int run(int rows, int n, int KT, int skew) {
     std::vector<float> J(rows * n);
     srand(1);
     for (auto &v : J) v = (rand() / float(RAND_MAX) - 0.5f) * ((rand() % 7 == 0) ? 40.f : 1.f);
@@ -143,25 +163,38 @@ int main() {
     for (int r = 0; r < rows; ++r)
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) ref[i * n + j] += double(J[r * n + i]) * double(J[r * n + j]);
-    std::vector<float> f32(n * n, 0.f);
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) { float s = 0; for (int r = 0; r < rows; ++r) s += J[r * n + i] * J[r * n + j]; f32[i * n + j] = s; }
     float *dJ, *dD;
     CK(cudaMalloc(&dJ, J.size() * 4)); CK(cudaMalloc(&dD, n * n * 4));
     CK(cudaMemcpy(dJ, J.data(), J.size() * 4, cudaMemcpyHostToDevice));
-    const size_t smem = 2 * MM * KT * 4 + 64;
+    const size_t smem = 3 * MM * KT * 4 + 256;
     CK(cudaFuncSetAttribute(jtj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     double scale = 0;
     for (int i = 0; i < n; ++i) scale = fmax(scale, ref[i * n + i]);
-    for (int mode : {1, 3}) {
+    int bad = 0;
+    for (int mode : {3, 6, 7}) {
         CK(cudaMemset(dD, 0, n * n * 4));
-        jtj_kernel<<<1, 384, smem>>>(dJ, rows, n, dD, mode);
+        jtj_kernel<<<1, 384, smem>>>(dJ, rows, n, dD, mode, KT, skew);
         CK(cudaDeviceSynchronize());
         std::vector<float> D(n * n);
         CK(cudaMemcpy(D.data(), dD, n * n * 4, cudaMemcpyDeviceToHost));
-        double e = 0, ef = 0;
-        for (int i = 0; i < n * n; ++i) { e = fmax(e, fabs(D[i] - ref[i])); ef = fmax(ef, fabs(f32[i] - ref[i])); }
-        printf("mode %dxTF32: max |D - ref| / max diag = %.3e   (plain fp32 loop: %.3e)\n", mode, e / scale, ef / scale);
+        double e = 0;
+        for (int i = 0; i < n * n; ++i) e = fmax(e, fabs(D[i] - ref[i]));
+        printf("rows %3d n %3d KT %2d skew %3d  %dxTF32: max |D - ref| / max diag = %.3e\n", rows, n, KT, skew, mode, e / scale);
+        if (!(e / scale < 1e-5)) bad = 1;
     }
-    return 0;
+    cudaFree(dJ); cudaFree(dD);
+    return bad;
+}
+
+int main() {
+    int bad = 0;
+    bad |= run(159, 111, 48, 0);
+    bad |= run(159, 111, 64, 0);
+    bad |= run(80, 30, 80, 0);
+    bad |= run(80, 30, 80, 48);
+    bad |= run(80, 6, 80, 48);
+    bad |= run(40, 30, 40, 48);
+    bad |= run(212, 111, 80, 0);
+    printf(bad ? "FAILED\n" : "OK\n");
+    return bad;
 }
