@@ -128,15 +128,21 @@ struct DevModel {
         if ((rc = up<real>(d.hands_mean, d.n_hand_full, &m.hands_mean))) return rc;
         if ((rc = up<real>(d.v0, S * 3, &m.v0))) return rc;
         if ((rc = up<real>(d.sd, S * 3 * nd, &m.sd))) return rc;
-        {   // pose-blend table [(nJ-1)][9 e][3 c][3M slots]: lanes over slots read consecutive words, no padding
+        {   // pose-blend table twice: [(nJ-1)][9 e][3 c][Sp] (eval: four slots per 16-byte load, no padding) and
+            // [(nJ-1)][9 e][3M slots][x y z -] (build: one slot per 16-byte load)
             const size_t S3 = size_t(3) * d.n_markers;
-            std::vector<double> pdc((nJ - 1) * 27 * S3, 0.0);
+            const size_t Sp = (S3 + 3) & ~size_t(3);
+            std::vector<double> pdc((nJ - 1) * 27 * Sp, 0.0), pd4((nJ - 1) * 9 * S3 * 4, 0.0);
             for (size_t j = 0; j + 1 < nJ; ++j)
                 for (size_t sl = 0; sl < S3; ++sl)
                     for (int c = 0; c < 3; ++c)
-                        for (int e = 0; e < 9; ++e)
-                            pdc[((j * 9 + e) * 3 + c) * S3 + sl] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+                        for (int e = 0; e < 9; ++e) {
+                            const double v = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+                            pdc[((j * 9 + e) * 3 + c) * Sp + sl] = v;
+                            pd4[((j * 9 + e) * S3 + sl) * 4 + c] = v;
+                        }
             if ((rc = up<real>(pdc.data(), pdc.size(), &m.pdc))) return rc;
+            if ((rc = up<real>(pd4.data(), pd4.size(), &m.pd4))) return rc;
         }
         if ((rc = up<real>(d.w_val, S * d.kw, &m.w_val))) return rc;
         if ((rc = up<real>(d.j0, nJ * 3, &m.j0))) return rc;
@@ -280,6 +286,9 @@ int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out)
     *out = nullptr;
     if (d->n_joints < 1 || d->n_markers < 1 || d->kw < 1 || d->kw > 8 || d->n_free1 < 1 || d->n_free2 < d->n_free1)
         return fail(MOSH2_E_INVALID, "inconsistent model sizes");
+    if (d->n_levels < 1 || d->n_levels > mosh2::kMaxDepth || d->n_joints > 254)
+        return fail(MOSH2_E_TOO_LARGE, "kinematic tree too deep or too large: %d levels (max %d), %d joints (max 254)", d->n_levels,
+                    mosh2::kMaxDepth, d->n_joints);
     if (d->body_dof + d->n_hand_full != 3 * d->n_joints || d->body_dof + d->n_hand_red != d->p_red)
         return fail(MOSH2_E_INVALID, "pose layout mismatch: body_dof=%d hand_full=%d hand_red=%d p_red=%d joints=%d",
                     d->body_dof, d->n_hand_full, d->n_hand_red, d->p_red, d->n_joints);

@@ -84,7 +84,7 @@ enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_
 enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
 
 constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
-constexpr int kBlendGroups = 3;   // upper bound of the joint groups of the pose-blend partial sums (run time: 1..3, one round of threads)
+constexpr int kBlendGroups = 4;   // upper bound of the joint groups of the pose-blend partial sums (run time: 1..3, one round of threads)
 constexpr int kCholNB = 8;        // block column width of the Cholesky factorisation
 constexpr int kMaxHandBlocks = 4;
 
@@ -105,7 +105,8 @@ struct Model {
     HandBlock hb[kMaxHandBlocks];
     const real *hct;            // compact transposed hand-PCA blocks
     const real *hands_mean, *v0, *sd, *w_val, *j0, *jd, *coefs;
-    const real *pdc;            // pose-blend table [(nJ-1)][9 e][3 c][3M slots]: lanes over slots read consecutive words
+    const real *pdc;            // pose-blend table [(nJ-1)][9 e][3 c][Sp], Sp = 3M rounded up to 4: no padding; eval() reads four slots per 16-byte load
+    const real *pd4;            // the same table as [(nJ-1)][9 e][3M slots][x y z -]: build() reads one slot (all three coordinates) per 16-byte load
     int prior_k, prior_d, prior_off, prior_d4;
     const real *prior_means, *prior_Q4, *prior_nlw;   // Q4: [K][D][D4]
     int n1, n2;
@@ -326,6 +327,7 @@ struct Work {
     SPtr<real> c_wv, c_v0, c_coefs, c_j0, c_hmean, c_pmeans, c_pnlw;
     SPtr<long long> prof;
     SPtr<uint8_t> vis;
+    SPtr<uint32_t> c_chain;   // [joint][4 words]: the joint's ancestor chain, root first, one byte per joint id, 255-padded
     SPtr<uint8_t> c_amask;    // [slot][joint]: bit i set <=> the slot's i-th skinning joint lies in the subtree of the joint
     // tensor-core J^T J (f32, shared-memory workspace only): operand buffers (they alias A, which is idle while the
     // tiles accumulate in tensor memory), completion barrier, tensor-memory address slot
@@ -343,6 +345,7 @@ struct Work {
 // the canonical K-major no-swizzle operand layout (8 x 16-byte core matrices), split into a TF32 "hi" part and
 // a TF32 "lo" remainder.  A = sum over tiles of (hi hi^T + lo hi^T + hi lo^T) accumulates in tensor memory at
 // close to fp32 accuracy (3xTF32) while the threads already assemble the next tile.
+constexpr int kMaxDepth = 16;         // deepest kinematic chain the tree walk unrolls (checked at model creation)
 constexpr int kDR = 28;              // floats per joint in dRl: three 3x3 derivative matrices (27) padded to 16-byte vectors
 constexpr int kM3 = 12;              // floats per padded 3x3 matrix (MtR per slot, Loc per marker vertex) and per joint in u (3 x 4)
 constexpr int kTcM = 128;            // UMMA M: free variables, zero/garbage padded (rows >= n are never read back)
@@ -418,7 +421,7 @@ M2_HD Dims make_dims(const Model<real> &m) {
     d.lda = d.npad | 1;         // A: odd leading dimension, so row-strided and transposed tile accesses spread over banks
     d.K = m.prior_k; d.D = m.prior_d; d.D4 = m.prior_d4; d.kw = m.kw;
     d.tmk = m.tile_markers > 0 ? m.tile_markers : 10;
-    const int a = 3 * d.tmk * d.NCt, b = kBlendGroups * 9 * m.M + 4;   // Jt doubles as the pose-blend partial sums
+    const int a = 3 * d.tmk * d.NCt, b = kBlendGroups * 9 * m.M + 16;   // Jt doubles as the pose-blend partial sums
     d.jt_size = a > b ? a : b;
     return d;
 }
@@ -499,6 +502,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.c_wv.ofs = S.take<real>(d.S * d.kw); w.c_v0.ofs = S.take<real>(3 * d.S); w.c_coefs.ofs = S.take<real>(3 * d.M);
     w.c_j0.ofs = S.take<real>(3 * d.nJ); w.c_hmean.ofs = S.take<real>(m.n_hand_full + 1);
     w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ); w.c_amask.ofs = S.take<uint8_t>(size_t(d.S) * d.nJ);
+    w.c_chain.ofs = S.take<uint32_t>(size_t(d.nJ) * (kMaxDepth / 4));
     w.c_pmeans.ofs = S.take<real>(d.K * d.D + 1); w.c_pnlw.ofs = S.take<real>(d.K + 1);
 }
 
@@ -537,64 +541,90 @@ struct Solver {
 
 #define CTA_FOR(i, n) _Pragma("unroll 1") for (int i = cta.tid; i < (n); i += cta.nthr)
 
-    // ---- FK by depth level, executed by `nl` lanes (one warp on the GPU) starting at lane id `l`
+    // ---- FK, executed by `nl` lanes (one warp on the GPU) starting at lane id `l`.  Every lane multiplies down the
+    //      ancestor chain of its own joint (root first), which it reads as four words: no level-by-level hand-over
+    //      through shared memory -- under the load of the pose-blend stream of the other warps a dependent shared-
+    //      memory hop costs hundreds of cycles, and the level-wise walk chained three of them per level.  Same
+    //      products in the same order as the level-wise recursion.
     M2_D void fk(int l, int nl) {
-        for (int lv = 0; lv < m.n_levels; ++lv) {
-            const int lo = w.c_level_ofs[lv], cnt = w.c_level_ofs[lv + 1] - lo;
-            for (int q = l; q < cnt; q += nl) {
-                const int j = w.c_fk_order[lo + q], a = w.c_parents[j];
-                if (a < 0) {
-                    for (int i = 0; i < 9; ++i) w.Rg[9 * j + i] = w.Rl[9 * j + i];
-                    for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = w.Jp[3 * j + i];
-                } else {
-                    mat3_mul(w.Rg + 9 * a, w.Rl + 9 * j, w.Rg + 9 * j);
-                    real dj[3] = {w.Jp[3 * j] - w.Jp[3 * a], w.Jp[3 * j + 1] - w.Jp[3 * a + 1], w.Jp[3 * j + 2] - w.Jp[3 * a + 2]};
-                    real o[3];
-                    mat3_vec(w.Rg + 9 * a, dj, o);
-                    for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = w.tg[3 * a + i] + o[i];
+        for (int j = l; j < d.nJ; j += nl) {
+            uint32_t cw[kMaxDepth / 4];
+#pragma unroll
+            for (int q = 0; q < kMaxDepth / 4; ++q) cw[q] = w.c_chain[j * (kMaxDepth / 4) + q];
+            int prev = int(cw[0] & 255u);
+            real R[9], t[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = w.Rl[9 * prev + i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) t[i] = w.Jp[3 * prev + i];
+#pragma unroll
+            for (int k = 1; k < kMaxDepth; ++k) {
+                const int c = int((cw[k >> 2] >> (8 * (k & 3))) & 255u);
+                if (c != 255) {
+                    const real *Rc = w.Rl + 9 * c;
+                    const real dj[3] = {w.Jp[3 * c] - w.Jp[3 * prev], w.Jp[3 * c + 1] - w.Jp[3 * prev + 1], w.Jp[3 * c + 2] - w.Jp[3 * prev + 2]};
+                    real rc[9], o[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) rc[i] = Rc[i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) t[i] += R[3 * i] * dj[0] + R[3 * i + 1] * dj[1] + R[3 * i + 2] * dj[2];
+                    mat3_mul_reg(R, rc, o);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) R[i] = o[i];
+                    prev = c;
                 }
             }
-            M2_WSYNC();
+#pragma unroll
+            for (int i = 0; i < 9; ++i) w.Rg[9 * j + i] = R[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) w.tg[3 * j + i] = t[i];
         }
     }
 
     // ---- pose-blend partial sums: item (joint group, slot) -> x,y,z of the slot; part[g][3 s + c] (aliases Jt).
     //      Lanes run over consecutive slots, so every warp load is one contiguous run of 16-byte vectors.
     M2_D int blend_groups(int nl) const {      // as many joint groups as fit one round of the nl blending threads
-        int g = nl / d.S;
+        const int per_group = 3 * ((d.S + 3) >> 2);
+        int g = nl / per_group;
         return g < 1 ? 1 : (g > kBlendGroups ? kBlendGroups : g);
     }
+    // item = (joint group, coordinate c, four consecutive slots): nine 16-byte loads per joint, no padding bytes; two
+    // joints are in flight per thread
     M2_D void blend_partials(int l, int nl) {
         const int G = blend_groups(nl);
         const int per = (d.nJ - 1 + G - 1) / G;
-        const size_t cs = size_t(d.S);                  // stride between the 27 (e, c) rows of a joint
-        for (int it = l; it < d.S * G; it += nl) {
-            const int g = it / d.S, s = it - g * d.S;
+        const int Sq = (d.S + 3) >> 2;
+        const size_t cs = size_t(Sq) * 4;               // stride between the 27 (e, c) rows of a joint
+        for (int it = l; it < 3 * Sq * G; it += nl) {
+            const int g = it / (3 * Sq), rem = it - g * 3 * Sq, c = rem / Sq, sq = rem - c * Sq;
             int j0 = 1 + g * per, j1 = j0 + per;
             if (j1 > d.nJ) j1 = d.nJ;
-            real ax = 0, ay = 0, az = 0;
-            // two joints per trip: 54 independent 4-byte loads in flight per thread
+            real acc[4] = {0, 0, 0, 0};
             for (int j = j0; j < j1; j += 2) {
                 const bool two = j + 1 < j1;
-                const real *P = m.pdc + size_t(j - 1) * 27 * cs + s, *Q = P + (two ? 27 * cs : 0);
-                real pa[27], pb[27];
+                const real *P = m.pdc + (size_t(j - 1) * 27 + c) * cs + 4 * sq, *Q = P + (two ? 27 * cs : 0);
+                Vec4<real> pa[9], pb[9];
 #pragma unroll
-                for (int q = 0; q < 27; ++q) pa[q] = P[q * cs];
+                for (int e = 0; e < 9; ++e) pa[e] = ld4(P + 3 * e * cs);
 #pragma unroll
-                for (int q = 0; q < 27; ++q) pb[q] = Q[q * cs];
+                for (int e = 0; e < 9; ++e) pb[e] = ld4(Q + 3 * e * cs);
                 const real *R = w.Rl + 9 * j, *R2 = R + (two ? 9 : 0);
                 const real tw = two ? real(1) : real(0);
 #pragma unroll
                 for (int e = 0; e < 9; ++e) {
                     const real id = (e == 0 || e == 4 || e == 8) ? real(1) : real(0);
                     const real fa = R[e] - id, fb = (R2[e] - id) * tw;
-                    ax += pa[3 * e] * fa + pb[3 * e] * fb;
-                    ay += pa[3 * e + 1] * fa + pb[3 * e + 1] * fb;
-                    az += pa[3 * e + 2] * fa + pb[3 * e + 2] * fb;
+                    acc[0] += pa[e].x * fa + pb[e].x * fb;
+                    acc[1] += pa[e].y * fa + pb[e].y * fb;
+                    acc[2] += pa[e].z * fa + pb[e].z * fb;
+                    acc[3] += pa[e].w * fa + pb[e].w * fb;
                 }
             }
-            real *o = w.Jt + (g * d.S + s) * 3;
-            o[0] = ax; o[1] = ay; o[2] = az;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int sl = 4 * sq + q;
+                if (sl < d.S) w.Jt[(g * d.S + sl) * 3 + c] = acc[q];
+            }
         }
     }
 
@@ -634,7 +664,12 @@ struct Solver {
 #if M2_GPU
         const int nblend = cta.nthr > 64 ? cta.nthr - 32 : cta.nthr;
         if (cta.nthr > 64) {                      // warp 0 walks the kinematic tree while the others blend
-            if (cta.tid < 32) fk(cta.tid, 32); else blend_partials(cta.tid - 32, nblend);
+            if (cta.tid < 32) {
+                fk(cta.tid, 32);
+#if defined(MOSH2_PROFILE)
+                if (cta.tid == 0) w.prof[18 + prof_base] += clock64() - t_prev_;      // the kinematic-tree walk alone
+#endif
+            } else blend_partials(cta.tid - 32, nblend);
         } else {
             fk(cta.tid, cta.nthr); __syncthreads(); blend_partials(cta.tid, nblend);
         }
@@ -807,12 +842,15 @@ struct Solver {
         }
     }
 
-    // ---- pose-blend vectors of slot (marker mi, vertex t) for joint a: p[3 e + c], 27 coalesced 4-byte loads
+    // ---- pose-blend vectors of slot (marker mi, vertex t) for joint a: p[3 e + c] (nine 16-byte loads, issued together)
     M2_D void t1_load(int mi, int a, int t, real *p) {
-        const size_t cs = size_t(d.S);
-        const real *P = m.pdc + size_t(a >= 1 ? a - 1 : 0) * 27 * cs + (3 * mi + t);
+        const size_t es = size_t(d.S) * 4;
+        const real *P = m.pd4 + size_t(a >= 1 ? a - 1 : 0) * 9 * es + size_t(3 * mi + t) * 4;
 #pragma unroll
-        for (int q = 0; q < 27; ++q) p[q] = P[q * cs];
+        for (int e = 0; e < 9; ++e) {
+            const Vec4<real> v = ld4(P + e * es);
+            p[3 * e] = v.x; p[3 * e + 1] = v.y; p[3 * e + 2] = v.z;
+        }
     }
 
     // ---- contribution of slot (marker mi, vertex t) to the 3x3 Jacobian block of joint a:  blk[r*3+k] +=
@@ -984,8 +1022,8 @@ struct Solver {
                         Mt[0] = m0.x; Mt[1] = m0.y; Mt[2] = m0.z; Mt[3] = m0.w; Mt[4] = m1.x; Mt[5] = m1.y; Mt[6] = m1.z; Mt[7] = m1.w; Mt[8] = m2.x;
                         Lc[0] = l0.x; Lc[1] = l0.y; Lc[2] = l0.z; Lc[3] = l0.w; Lc[4] = l1.x; Lc[5] = l1.y; Lc[6] = l1.z; Lc[7] = l1.w; Lc[8] = l2.x;
                     }
-                    const size_t cs = size_t(d.S);
-                    const real *Pslot = m.pdc + sl;
+                    const size_t es = size_t(d.S) * 4;
+                    const real *Pslot = m.pd4 + size_t(sl) * 4;
                     const uint8_t *mrow = w.c_amask + sl * d.nJ;
                     const int src1 = lane - t + (t + 2) % 3, src2 = lane - t + (t + 1) % 3;   // lanes whose t is t-1, t-2 (mod 3)
 #pragma unroll 1
@@ -993,10 +1031,10 @@ struct Solver {
                         const int a = w.jlist[ji];
                         real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                         if (a >= 1) {
-                            const real *P = Pslot + size_t(a - 1) * 27 * cs;
-                            real pv[27];
+                            const real *P = Pslot + size_t(a - 1) * 9 * es;
+                            Vec4<real> pv[9];
 #pragma unroll
-                            for (int q = 0; q < 27; ++q) pv[q] = P[q * cs];
+                            for (int e = 0; e < 9; ++e) pv[e] = ld4(P + e * es);
                             const real *dR = w.dRl + kDR * a;
                             real dr[kDR];
 #pragma unroll
@@ -1008,9 +1046,9 @@ struct Solver {
 #pragma unroll
                             for (int e = 0; e < 9; ++e) {
                                 const real q0 = dr[e], q1 = dr[9 + e], q2 = dr[18 + e];
-                                E[0] += pv[3 * e] * q0; E[1] += pv[3 * e] * q1; E[2] += pv[3 * e] * q2;
-                                E[3] += pv[3 * e + 1] * q0; E[4] += pv[3 * e + 1] * q1; E[5] += pv[3 * e + 1] * q2;
-                                E[6] += pv[3 * e + 2] * q0; E[7] += pv[3 * e + 2] * q1; E[8] += pv[3 * e + 2] * q2;
+                                E[0] += pv[e].x * q0; E[1] += pv[e].x * q1; E[2] += pv[e].x * q2;
+                                E[3] += pv[e].y * q0; E[4] += pv[e].y * q1; E[5] += pv[e].y * q2;
+                                E[6] += pv[e].z * q0; E[7] += pv[e].z * q1; E[8] += pv[e].z * q2;
                             }
 #pragma unroll
                             for (int r = 0; r < 3; ++r)
@@ -1868,6 +1906,17 @@ struct Solver {
             }
         }
         M2_SYNC();
+        CTA_FOR(j, d.nJ) {                                     // ancestor chain of every joint, root first
+            int chain[kMaxDepth], depth = 0;
+            for (int a = j; a >= 0 && depth < kMaxDepth; a = w.c_parents[a]) chain[depth++] = a;
+            uint32_t cw[kMaxDepth / 4];
+            for (int q = 0; q < kMaxDepth / 4; ++q) cw[q] = 0xffffffffu;
+            for (int k = 0; k < depth; ++k) {
+                const int c = chain[depth - 1 - k];
+                cw[k >> 2] = (cw[k >> 2] & ~(255u << (8 * (k & 3)))) | (uint32_t(c) << (8 * (k & 3)));
+            }
+            for (int q = 0; q < kMaxDepth / 4; ++q) w.c_chain[j * (kMaxDepth / 4) + q] = cw[q];
+        }
         CTA_FOR(idx, d.S * d.nJ) {                             // which of a slot's skinning joints hang below joint a
             const int sl = idx / d.nJ, a = idx - sl * d.nJ;
             const int ta = w.c_tin[a], na = w.c_tsz[a];

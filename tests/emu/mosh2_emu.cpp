@@ -54,13 +54,18 @@ struct HostModel {
         {
             // [(nJ-1)][9 e][3M slots][4]: x, y, z of a slot for one (joint, e) form one 16-byte vector
             const size_t S3 = size_t(3) * d.n_markers;
-            std::vector<double> pdc((nJ - 1) * 27 * S3, 0.0);
+            const size_t Sp = (S3 + 3) & ~size_t(3);
+            std::vector<double> pdc((nJ - 1) * 27 * Sp, 0.0), pd4((nJ - 1) * 9 * S3 * 4, 0.0);
             for (size_t j = 0; j + 1 < nJ; ++j)
                 for (size_t sl = 0; sl < S3; ++sl)
                     for (int c = 0; c < 3; ++c)
-                        for (int e = 0; e < 9; ++e)
-                            pdc[((j * 9 + e) * 3 + c) * S3 + sl] = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+                        for (int e = 0; e < 9; ++e) {
+                            const double v = d.pd[(j * 3 * S3 + 3 * sl + c) * 9 + e];
+                            pdc[((j * 9 + e) * 3 + c) * Sp + sl] = v;
+                            pd4[((j * 9 + e) * S3 + sl) * 4 + c] = v;
+                        }
             m.pdc = up<real>(pdc.data(), pdc.size());
+            m.pd4 = up<real>(pd4.data(), pd4.size());
         }
         m.w_val = up<real>(d.w_val, S * d.kw);
         m.j0 = up<real>(d.j0, nJ * 3);
