@@ -157,6 +157,11 @@ struct DevModel {
                 for (size_t i = 0; i < D; ++i)
                     for (size_t l = 0; l < D; ++l) q4[(k * D + i) * D4 + l] = d.prior_Q[(k * D + i) * D + l];
             if ((rc = up<real>(q4.data(), q4.size(), &m.prior_Q4))) return rc;
+            std::vector<double> qt(K * D * D4, 0.0);
+            for (size_t k = 0; k < K; ++k)
+                for (size_t i = 0; i < D; ++i)
+                    for (size_t l = 0; l < D; ++l) qt[(k * D + l) * D4 + i] = d.prior_Q[(k * D + i) * D + l];
+            if ((rc = up<real>(qt.data(), qt.size(), &m.prior_Qt))) return rc;
         }
         if ((rc = up<real>(d.prior_neglogw, d.prior_k, &m.prior_nlw))) return rc;
         if ((rc = up<int>(d.free1, d.n_free1, &m.free1))) return rc;

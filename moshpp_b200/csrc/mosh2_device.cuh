@@ -109,6 +109,7 @@ struct Model {
     const real *pd4;            // the same table as [(nJ-1)][9 e][3M slots][x y z -]: build() reads one slot (all three coordinates) per 16-byte load
     int prior_k, prior_d, prior_off, prior_d4;
     const real *prior_means, *prior_Q4, *prior_nlw;   // Q4: [K][D][D4]
+    const real *prior_Qt;       // Q transposed per component, [K][D l][D4 i]: threads over rows i read consecutive words
     int n1, n2;
     const int *free1, *free2;
     int finger_lo, finger_hi;
@@ -681,25 +682,65 @@ struct Solver {
         const int nbg = blend_groups(nblend);
         M2_SYNC();
         M2_TACC(2);
-        // max-mixture prior: y_k = Q_k (x - mu_k), one row of Q per item.  The items are dealt from the last thread
-        // downwards so that the second round falls on threads that do not skin.
+        // max-mixture prior: y_k = Q_k (x - mu_k).  GPU: an item is four rows of one component times a quarter of the
+        // columns -- sixteen independent 16-byte loads down the transposed copy of Q, all in flight at once (the
+        // product is bound by load latency, not by bytes); four adjacent lanes then add their quarters by shuffles.
         if (c.wp > real(0)) {
             const int D = d.D, D4 = d.D4;
             const real *xb = th + m.prior_off;
+#if M2_GPU
+            const int nq = D4 >> 2, lchunk = (D + 3) >> 2;          // row quads per component, columns per quarter
+            const int nitem = d.K * nq * 4, nround = (nitem + cta.nthr - 1) / cta.nthr;
 #pragma unroll 1
-            for (int idx = cta.nthr - 1 - cta.tid; idx < d.K * D; idx += cta.nthr) {
-                const int k = idx / D;
-                const real *Q = m.prior_Q4 + size_t(idx) * D4, *mu = w.c_pmeans + k * D;
-                real s = 0;
-                int l = 0;
-                for (; l + 4 <= D; l += 4) {
-                    const Vec4<real> q = ld4(Q + l);
-                    s += q.x * (xb[l] - mu[l]) + q.y * (xb[l + 1] - mu[l + 1]) + q.z * (xb[l + 2] - mu[l + 2]) + q.w * (xb[l + 3] - mu[l + 3]);
+            for (int rd = 0; rd < nround; ++rd) {
+                const int it = rd * cta.nthr + cta.tid, lr = it & 3, kq = it >> 2;
+                const bool on = it < nitem;
+                const int k = on ? kq / nq : 0, quad = on ? kq - k * nq : 0;
+                const int l0 = lr * lchunk, l1 = (l0 + lchunk < D) ? l0 + lchunk : D;
+                const real *Q = m.prior_Qt + (size_t(k) * D + l0) * D4 + 4 * quad, *mu = w.c_pmeans + k * D;
+                real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                for (int lb = l0; on && lb < l1; lb += 16) {        // blocks of sixteen columns: a fixed trip count, so the
+                    Vec4<real> q4[16];                              // sixteen loads issue back to back (predicated tail)
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (lb + u < l1) q4[u] = ld4(Q + size_t(lb + u - l0) * D4);
+                        else q4[u].x = q4[u].y = q4[u].z = q4[u].w = 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int l = (lb + u < l1) ? lb + u : l0;
+                        const real dx = xb[l] - mu[l];
+                        s0 += q4[u].x * dx; s1 += q4[u].y * dx; s2 += q4[u].z * dx; s3 += q4[u].w * dx;
+                    }
                 }
-                for (; l < D; ++l) s += Q[l] * (xb[l] - mu[l]);
+#pragma unroll
+                for (int off = 1; off <= 2; off <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, off); s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+                }
+                if (on && lr == 0) {
+                    const int i0 = 4 * quad;
+                    real *o = w.py + k * D + i0;
+                    if (i0 < D) o[0] = s0;
+                    if (i0 + 1 < D) o[1] = s1;
+                    if (i0 + 2 < D) o[2] = s2;
+                    if (i0 + 3 < D) o[3] = s3;
+                }
+            }
+#else
+            for (int idx = 0; idx < d.K * D; ++idx) {
+                const int k = idx / D, i = idx - k * D;
+                const real *Q = m.prior_Qt + size_t(k) * D * D4 + i, *mu = w.c_pmeans + k * D;
+                real s = 0;
+                for (int l = 0; l < D; ++l) s += Q[size_t(l) * D4] * (xb[l] - mu[l]);
                 w.py[idx] = s;
             }
+#endif
         }
+#if defined(MOSH2_PROFILE) && M2_GPU
+        __syncthreads();
+        M2_TACC(19);                                   // development: the prior products alone
+#endif
         // skinning of the 3M slots
         CTA_FOR(s, d.S) {
             real vpo[3];

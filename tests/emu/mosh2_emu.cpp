@@ -80,6 +80,11 @@ struct HostModel {
                 for (size_t i = 0; i < D; ++i)
                     for (size_t l = 0; l < D; ++l) q4[(k * D + i) * D4 + l] = d.prior_Q[(k * D + i) * D + l];
             m.prior_Q4 = up<real>(q4.data(), q4.size());
+            std::vector<double> qt(K * D * D4, 0.0);
+            for (size_t k = 0; k < K; ++k)
+                for (size_t i = 0; i < D; ++i)
+                    for (size_t l = 0; l < D; ++l) qt[(k * D + l) * D4 + i] = d.prior_Q[(k * D + i) * D + l];
+            m.prior_Qt = up<real>(qt.data(), qt.size());
         }
         m.prior_nlw = up<real>(d.prior_neglogw, d.prior_k);
         m.free1 = up<int>(d.free1, d.n_free1);

@@ -15,7 +15,7 @@ from moshpp_b200.mocap_interface import MocapSession  # noqa: E402
 
 NAMES = ['ev.fullpose', 'ev.rodrigues', 'ev.fk||blend', 'ev.skin+prior', 'ev.markers', 'ev.reduce', 'bd.pre', 'bd.T1',
          'bd.T2', 'bd.T3', 'bd.closed', 'gn.init', 'gn.diag', 'gn.panel', 'gn.trailing', 'gn.solves', 'minimize(all)',
-         'chunk(all)', 'ev.fk alone', '-', 'warm.fullpose', 'warm.rodrigues', 'warm.fk||blend', 'warm.skin+prior', 'warm.markers', 'warm.reduce']
+         'chunk(all)', 'ev.fk alone', 'ev.prior alone', 'warm.fullpose', 'warm.rodrigues', 'warm.fk||blend', 'warm.skin+prior', 'warm.markers', 'warm.reduce']
 
 
 def main():
