@@ -1392,6 +1392,131 @@ struct Solver {
 #endif
     }
 
+    // ---- factor and invert the 8x8 diagonal block at k0 (GPU: the calling warp, all 32 lanes; host: one thread)
+    M2_D void chol_diag(int k0, int n) {
+        const int ld = d.ld;
+        constexpr int NB = kCholNB;
+        const int kb = (n - k0 < NB) ? n - k0 : NB;
+        real *Li = w.Linv + (k0 / NB) * NB * NB;
+#if M2_GPU
+        {
+
+            // warp 0: every lane factors the whole 8x8 block in registers (36 values, all loops unrolled: no
+            // shuffles, no local memory; the dependent chain is one FMA + one reciprocal square root per
+            // column); lane c then forward-substitutes column c of the inverse.
+            const int lane = cta.tid;
+            real Lb[NB][NB], invd[NB], x[NB];
+#pragma unroll
+            for (int r = 0; r < NB; ++r)
+#pragma unroll
+                for (int cc = 0; cc <= r; ++cc)
+                    Lb[r][cc] = (r < kb) ? w.Lm[(k0 + r) * ld + k0 + cc] : ((cc == r) ? real(1) : real(0));
+            bool ok = true;
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) {
+                real piv = Lb[cc][cc];
+#pragma unroll
+                for (int pp = 0; pp < cc; ++pp) piv -= Lb[cc][pp] * Lb[cc][pp];
+                if (!(piv > pivot_eps<real>())) { ok = false; piv = real(1); }
+                const real iv = r_rsqrt(piv);
+                Lb[cc][cc] = piv * iv;
+                invd[cc] = iv;
+#pragma unroll
+                for (int r = cc + 1; r < NB; ++r) {
+                    real t = Lb[r][cc];
+#pragma unroll
+                    for (int pp = 0; pp < cc; ++pp) t -= Lb[r][pp] * Lb[cc][pp];
+                    Lb[r][cc] = t * iv;
+                }
+            }
+            const int c = lane & (NB - 1);
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {                 // x[r] = Linv[r][c]
+                real sacc = (r == c) ? real(1) : real(0);
+#pragma unroll
+                for (int pp = 0; pp < r; ++pp) sacc -= Lb[r][pp] * x[pp];
+                x[r] = sacc * invd[r];
+            }
+            if (lane < NB) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) Li[r * NB + lane] = x[r];   // rows/columns >= kb hold identity padding
+            }
+            __syncwarp();                               // every lane has read the block before any lane rewrites it
+#pragma unroll
+            for (int r = 0; r < NB; ++r)
+#pragma unroll
+                for (int cc = 0; cc <= r; ++cc)
+                    if (r < kb && lane == ((r * (r + 1) / 2 + cc) & 31)) w.Lm[(k0 + r) * ld + k0 + cc] = Lb[r][cc];
+            if (!ok && lane == 0) w.isc[3] = 0;
+                }
+#else
+        {
+
+            real Lk[NB * NB], id[NB];
+            bool ok = true;
+            for (int r = 0; r < kb; ++r)
+                for (int cc = 0; cc <= r; ++cc) {
+                    real sacc = w.Lm[(k0 + r) * ld + k0 + cc];
+                    for (int p = 0; p < cc; ++p) sacc -= Lk[r * NB + p] * Lk[cc * NB + p];
+                    if (cc == r) {
+                        if (!(sacc > pivot_eps<real>())) { ok = false; sacc = real(1); }
+                        const real sq = r_sqrt(sacc);
+                        Lk[r * NB + r] = sq;
+                        id[r] = real(1) / sq;
+                    } else Lk[r * NB + cc] = sacc * id[cc];
+                }
+            for (int cc = 0; cc < kb; ++cc)
+                for (int r = 0; r < kb; ++r) {
+                    real v = 0;
+                    if (r == cc) v = id[r];
+                    else if (r > cc) {
+                        real sacc = 0;
+                        for (int p = cc; p < r; ++p) sacc -= Lk[r * NB + p] * Li[p * NB + cc];
+                        v = sacc * id[r];
+                    }
+                    Li[r * NB + cc] = v;
+                }
+            for (int r = 0; r < kb; ++r)
+                for (int cc = 0; cc <= r; ++cc) w.Lm[(k0 + r) * ld + k0 + cc] = Lk[r * NB + cc];
+            for (int r = 0; r < NB; ++r)
+                for (int cc = 0; cc < NB; ++cc)
+                    if (r >= kb || cc >= kb) Li[r * NB + cc] = (r == cc) ? real(1) : real(0);
+            if (!ok) w.isc[3] = 0;
+                }
+#endif
+    }
+
+    // ---- one 4x4 tile of the trailing update after the panel of block k0:  Lm[i][j] -= sum_c Pn[c][i] Pn[c][j]
+    M2_D void chol_tile(int it, int r0, int n) {
+        const int ld = d.ld;
+        constexpr int NB = kCholNB;
+        int ti = 0, rem = it;
+        while (rem > ti) { rem -= ti + 1; ++ti; }
+        const int tj = rem;
+        real acc[kBS * kBS];
+#pragma unroll
+        for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) {
+            const Vec4<real> av = ld4(w.Pn + cc * d.ldp + r0 + ti * kBS), bv = ld4(w.Pn + cc * d.ldp + r0 + tj * kBS);
+            const real ai[4] = {av.x, av.y, av.z, av.w}, bj[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int p = 0; p < kBS; ++p)
+#pragma unroll
+                for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bj[q];
+        }
+#pragma unroll
+        for (int p = 0; p < kBS; ++p) {
+            const int i = r0 + ti * kBS + p;
+            if (i <= n && r0 + tj * kBS < n) {
+                real *dst = w.Lm + i * ld + r0 + tj * kBS;
+                Vec4<real> v = ld4(dst);
+                v.x -= acc[p * kBS]; v.y -= acc[p * kBS + 1]; v.z -= acc[p * kBS + 2]; v.w -= acc[p * kBS + 3];
+                *reinterpret_cast<Vec4<real> *>(dst) = v;
+            }
+        }
+    }
+
     // Gauss-Newton step dgn = A^-1 g by a Jacobi-scaled, blocked right-looking Cholesky in w.Lm (lower
     // triangle incl. diagonal).  One lane factors each 8x8 diagonal block and also inverts it; the panel and
     // both triangular solves then use the explicit block inverses (plain dot products, no divides and no
@@ -1420,96 +1545,16 @@ struct Solver {
         CTA_FOR(j, n) w.Lm[n * ld + j] = w.g[j] * w.ds[j];
         M2_SYNC();
         M2_TACC(11);
+        // Right-looking with a one-block look-ahead: while the other warps apply the trailing update of block k0,
+        // warp 0 updates the next diagonal block first (tiles 0..2 of the update) and factors it, so the serial
+        // 8x8 factorisation is off the critical path and a block costs two barriers instead of three.
+        if (cta.tid < 32) chol_diag(0, n);
+        M2_SYNC();
+        M2_TACC(12);
+        if (w.isc[3] == 0) return false;
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = (n - k0 < NB) ? n - k0 : NB;
             real *Li = w.Linv + (k0 / NB) * NB * NB;
-#if M2_GPU
-            if (cta.tid < 32) {
-                // warp 0: every lane factors the whole 8x8 block in registers (36 values, all loops unrolled: no
-                // shuffles, no local memory; the dependent chain is one FMA + one reciprocal square root per
-                // column); lane c then forward-substitutes column c of the inverse.
-                const int lane = cta.tid;
-                real Lb[NB][NB], invd[NB], x[NB];
-#pragma unroll
-                for (int r = 0; r < NB; ++r)
-#pragma unroll
-                    for (int cc = 0; cc <= r; ++cc)
-                        Lb[r][cc] = (r < kb) ? w.Lm[(k0 + r) * ld + k0 + cc] : ((cc == r) ? real(1) : real(0));
-                bool ok = true;
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) {
-                    real piv = Lb[cc][cc];
-#pragma unroll
-                    for (int pp = 0; pp < cc; ++pp) piv -= Lb[cc][pp] * Lb[cc][pp];
-                    if (!(piv > pivot_eps<real>())) { ok = false; piv = real(1); }
-                    const real iv = r_rsqrt(piv);
-                    Lb[cc][cc] = piv * iv;
-                    invd[cc] = iv;
-#pragma unroll
-                    for (int r = cc + 1; r < NB; ++r) {
-                        real t = Lb[r][cc];
-#pragma unroll
-                        for (int pp = 0; pp < cc; ++pp) t -= Lb[r][pp] * Lb[cc][pp];
-                        Lb[r][cc] = t * iv;
-                    }
-                }
-                const int c = lane & (NB - 1);
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {                 // x[r] = Linv[r][c]
-                    real sacc = (r == c) ? real(1) : real(0);
-#pragma unroll
-                    for (int pp = 0; pp < r; ++pp) sacc -= Lb[r][pp] * x[pp];
-                    x[r] = sacc * invd[r];
-                }
-                if (lane < NB) {
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) Li[r * NB + lane] = x[r];   // rows/columns >= kb hold identity padding
-                }
-                __syncwarp();                               // every lane has read the block before any lane rewrites it
-#pragma unroll
-                for (int r = 0; r < NB; ++r)
-#pragma unroll
-                    for (int cc = 0; cc <= r; ++cc)
-                        if (r < kb && lane == ((r * (r + 1) / 2 + cc) & 31)) w.Lm[(k0 + r) * ld + k0 + cc] = Lb[r][cc];
-                if (!ok && lane == 0) w.isc[3] = 0;
-            }
-#else
-            if (cta.tid == 0) {
-                real Lk[NB * NB], id[NB];
-                bool ok = true;
-                for (int r = 0; r < kb; ++r)
-                    for (int cc = 0; cc <= r; ++cc) {
-                        real sacc = w.Lm[(k0 + r) * ld + k0 + cc];
-                        for (int p = 0; p < cc; ++p) sacc -= Lk[r * NB + p] * Lk[cc * NB + p];
-                        if (cc == r) {
-                            if (!(sacc > pivot_eps<real>())) { ok = false; sacc = real(1); }
-                            const real sq = r_sqrt(sacc);
-                            Lk[r * NB + r] = sq;
-                            id[r] = real(1) / sq;
-                        } else Lk[r * NB + cc] = sacc * id[cc];
-                    }
-                for (int cc = 0; cc < kb; ++cc)
-                    for (int r = 0; r < kb; ++r) {
-                        real v = 0;
-                        if (r == cc) v = id[r];
-                        else if (r > cc) {
-                            real sacc = 0;
-                            for (int p = cc; p < r; ++p) sacc -= Lk[r * NB + p] * Li[p * NB + cc];
-                            v = sacc * id[r];
-                        }
-                        Li[r * NB + cc] = v;
-                    }
-                for (int r = 0; r < kb; ++r)
-                    for (int cc = 0; cc <= r; ++cc) w.Lm[(k0 + r) * ld + k0 + cc] = Lk[r * NB + cc];
-                for (int r = 0; r < NB; ++r)
-                    for (int cc = 0; cc < NB; ++cc)
-                        if (r >= kb || cc >= kb) Li[r * NB + cc] = (r == cc) ? real(1) : real(0);
-                if (!ok) w.isc[3] = 0;
-            }
-#endif
-            M2_SYNC();
-            M2_TACC(12);
-            if (w.isc[3] == 0) return false;
             // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p]); the solved panel is
             // also kept transposed (Pn[c][row]) so that the trailing update reads consecutive vectors
             CTA_FOR(ii, d.ldp - k0 - kb) {
@@ -1537,39 +1582,31 @@ struct Solver {
             }
             M2_SYNC();
             M2_TACC(13);
-            // trailing update with 4x4 register tiles: Lm[i][j] -= sum_c Pn[c][i] Pn[c][j], tiles with tj <= ti
+            // trailing update with 4x4 register tiles, tiles with tj <= ti
             const int r0 = k0 + kb, R = r0 < n ? n + 1 - r0 : 0;   // rows r0..n (row n = right-hand side), columns r0..n-1
             if (R > 0) {
                 const int nt = (R + kBS - 1) / kBS, ntri = nt * (nt + 1) / 2;
-                CTA_FOR(it, ntri) {
-                    int ti = 0, rem = it;
-                    while (rem > ti) { rem -= ti + 1; ++ti; }
-                    const int tj = rem;
-                    real acc[kBS * kBS];
-#pragma unroll
-                    for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) {
-                        const Vec4<real> av = ld4(w.Pn + cc * d.ldp + r0 + ti * kBS), bv = ld4(w.Pn + cc * d.ldp + r0 + tj * kBS);
-                        const real ai[4] = {av.x, av.y, av.z, av.w}, bj[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                        for (int p = 0; p < kBS; ++p)
-#pragma unroll
-                            for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bj[q];
+#if M2_GPU
+                if (cta.nthr >= 64) {
+                    if (cta.tid < 32) {
+                        if (cta.tid < 3 && cta.tid < ntri) chol_tile(cta.tid, r0, n);   // the next diagonal block
+                        __syncwarp();
+                        chol_diag(r0, n);
+                    } else {
+                        for (int it = 3 + cta.tid - 32; it < ntri; it += cta.nthr - 32) chol_tile(it, r0, n);
                     }
-#pragma unroll
-                    for (int p = 0; p < kBS; ++p) {
-                        const int i = r0 + ti * kBS + p;
-                        if (i <= n && r0 + tj * kBS < n) {
-                            real *dst = w.Lm + i * ld + r0 + tj * kBS;
-                            Vec4<real> v = ld4(dst);
-                            v.x -= acc[p * kBS]; v.y -= acc[p * kBS + 1]; v.z -= acc[p * kBS + 2]; v.w -= acc[p * kBS + 3];
-                            *reinterpret_cast<Vec4<real> *>(dst) = v;
-                        }
-                    }
+                } else {
+                    CTA_FOR(it, ntri) chol_tile(it, r0, n);
+                    __syncthreads();
+                    if (cta.tid < 32) chol_diag(r0, n);
                 }
+#else
+                for (int it = 0; it < ntri; ++it) chol_tile(it, r0, n);
+                chol_diag(r0, n);
+#endif
                 M2_SYNC();
                 M2_TACC(14);
+                if (w.isc[3] == 0) return false;
             }
         }
         // backward solve L^T y = z by the first warp, block column by block column (the forward solve happened
