@@ -31,7 +31,9 @@ def _worker(rank, world, port, case_dir, q):
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     n_seq, F = 3, 6
-    cases = [synth.make_case(case_dir, 'C4', frames=F, seq_idx=i) for i in range(n_seq)]     # same files on both ranks
+    rank_dir = os.path.join(case_dir, f'rank{rank}')     # seeded generator: identical content, no concurrent writes to one file
+    os.makedirs(rank_dir, exist_ok=True)
+    cases = [synth.make_case(rank_dir, 'C4', frames=F, seq_idx=i) for i in range(n_seq)]
     emu = C.CDLL(build.build_emu())
 
     def solve(i, obs, vis):
@@ -66,7 +68,10 @@ def _worker(rank, world, port, case_dir, q):
 def test_scatter_solve_gather_world2(tmp_path):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:                          # a free rendezvous port
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
