@@ -30,7 +30,7 @@ enum {
     MOSH2_E_INVALID = -1,   /* bad argument / inconsistent sizes            */
     MOSH2_E_CUDA = -2,      /* CUDA runtime error (message in last_error)   */
     MOSH2_E_NO_DEVICE = -3, /* no usable sm_100 device                      */
-    MOSH2_E_TOO_LARGE = -4  /* model does not fit the kernel's shared memory */
+    MOSH2_E_TOO_LARGE = -4  /* model does not fit the kernel (shared memory, tree depth > 16, > 254 joints) */
 };
 
 enum { MOSH2_F32 = 0, MOSH2_F64 = 1 };
