@@ -1340,10 +1340,24 @@ struct Solver {
             const int D = d.D, ks = w.isc[0];
             const real w2 = c.wp * c.wp;
             const real *Q = m.prior_Q4 + size_t(ks) * D * d.D4;
-            CTA_FOR(idx, D * D) {
-                const int i = idx / D, l = idx - i * D;
-                const int ci = w.colmap[3 + m.prior_off + i], cl = w.colmap[3 + m.prior_off + l];
-                if (ci >= 0 && cl >= 0) w.A[ci * ld + cl] += w2 * Q[i * d.D4 + l];
+            // blocks of eight entries per thread with a fixed trip count: the (L2) loads of a block issue back to back
+#pragma unroll 1
+            for (int base = cta.tid; base < D * D; base += 8 * cta.nthr) {
+                real qv[8];
+                int dst[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * cta.nthr;
+                    dst[u] = -1;
+                    qv[u] = 0;
+                    if (idx < D * D) {
+                        const int i = idx / D, l = idx - i * D;
+                        const int ci = w.colmap[3 + m.prior_off + i], cl = w.colmap[3 + m.prior_off + l];
+                        if (ci >= 0 && cl >= 0) { dst[u] = ci * ld + cl; qv[u] = Q[i * d.D4 + l]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (dst[u] >= 0) w.A[dst[u]] += w2 * qv[u];
             }
             CTA_FOR(i, D) {
                 const int ci = w.colmap[3 + m.prior_off + i];
@@ -1609,9 +1623,10 @@ struct Solver {
                 if (w.isc[3] == 0) return false;
             }
         }
-        // backward solve L^T y = z by the first warp, block column by block column (the forward solve happened
-        // inside the factorisation).
-        // Fully unrolled over the block width so that every small vector lives in registers.
+        // backward solve L^T y = z by the first warp (the forward solve happened inside the factorisation), column
+        // oriented: once the block y_k = Linv_k^T z_k is known, every lane subtracts its contribution from the entries
+        // z_i, i < k0, it owns -- that reads rows of L (consecutive words) and needs no reduction across lanes, where
+        // the row-oriented form read columns (16-way bank conflicts at ld = 112) and eight warp reductions per block.
         const int wl = cta.nthr < 32 ? cta.nthr : 32;
         if (cta.tid < wl) {
             const int lane = cta.tid;
@@ -1620,25 +1635,23 @@ struct Solver {
             for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
                 const int kb = (n - k0 < NB) ? n - k0 : NB;
                 const real *Li = w.Linv + (k0 / NB) * NB * NB;
-                real sv[NB], y[NB];
+                real zv[NB], y[NB];
 #pragma unroll
-                for (int cc = 0; cc < NB; ++cc) sv[cc] = 0;
-                for (int i = k0 + kb + lane; i < n; i += wl) {
-                    const real *row = w.Lm + i * ld + k0;
-                    const real yi = w.tmp[i];
+                for (int cc = 0; cc < NB; ++cc) zv[cc] = cc < kb ? w.tmp[k0 + cc] : real(0);
 #pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) sv[cc] += row[cc] * yi;
-                }
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) sv[cc] = (cc < kb ? w.tmp[k0 + cc] : real(0)) - warp_sum(sv[cc]);
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) {          // y = Linv^T s
+                for (int cc = 0; cc < NB; ++cc) {          // y = Linv^T z (every lane, redundantly)
                     real sacc = 0;
 #pragma unroll
-                    for (int pp = cc; pp < NB; ++pp) sacc += Li[pp * NB + cc] * sv[pp];
+                    for (int pp = cc; pp < NB; ++pp) sacc += Li[pp * NB + cc] * zv[pp];
                     y[cc] = sacc;
                 }
-                M2_WSYNC();
+                for (int i = lane; i < k0; i += wl) {
+                    real zi = w.tmp[i];
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) zi -= w.Lm[(k0 + cc) * ld + i] * y[cc];
+                    w.tmp[i] = zi;
+                }
+                M2_WSYNC();                                // (all lanes have read z_k before lane 0 overwrites it)
                 if (lane == 0) {
 #pragma unroll
                     for (int cc = 0; cc < NB; ++cc) if (cc < kb) w.tmp[k0 + cc] = y[cc];
