@@ -15,6 +15,8 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmosh2.so')
 EMU_SRC = os.path.join(ROOT, 'tests', 'emu', 'mosh2_emu.cpp')
 EMU_LIB = os.path.join(ROOT, 'tests', 'emu', '_build', 'libmosh2_emu.so')
+TC_SRC = os.path.join(ROOT, 'tests', 'tc', 'jtj_tcgen05_test.cu')
+TC_BIN = os.path.join(ROOT, 'tests', 'tc', '_build', 'jtj_test')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -57,6 +59,17 @@ def build_emu(force: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError('g++ failed:\n' + r.stdout + r.stderr)
     return EMU_LIB
+
+
+def build_tc_test(force: bool = False) -> str:
+    """TEST-ONLY stand-alone check of the tcgen05 J^T J building block (tests/tc/jtj_tcgen05_test.cu)."""
+    if force or _stale(TC_BIN, [TC_SRC]):
+        os.makedirs(os.path.dirname(TC_BIN), exist_ok=True)
+        cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O2', '-o', TC_BIN, TC_SRC]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
+    return TC_BIN
 
 
 if __name__ == '__main__':

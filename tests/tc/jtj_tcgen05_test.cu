@@ -1,7 +1,7 @@
 // Development test (GPU): A = J^T J on the 5th-generation tensor cores with the 3xTF32 split (hi*hi + lo*hi + hi*lo),
 // operands written by ordinary threads into the canonical no-swizzle K-major shared-memory layout, accumulator in
 // tensor memory.  Validates the descriptor encodings used by the Stage-II kernel before they go into it.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o jtj_test jtj_tcgen05_test.cu && ./jtj_test
+//   built by moshpp_b200.build.build_tc_test(), run by tests/test_gpu_parity.py::test_tcgen05_jtj_building_block
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -117,15 +117,18 @@ __global__ void __launch_bounds__(384, 1) jtj_kernel(const float *J, int rows, i
                         tc::mma_tf32(tmem, dhi, dlo, idesc, 1u);
                     }
                 } else {
-                    // mode 6/7: hi*hi alternates between two (mode 7: three) accumulators, the small cross terms go to their own
+                    // mode 5 (the Stage-II kernel's scheme), 6, 7: hi*hi alternates between two (mode 7: three) accumulators,
+                    // the small cross terms go to their own
                     const uint64_t dl2 = tc::smem_desc(al2 + ks * 2 * LBO, LBO, SBO);
                     const int nacc = mode == 7 ? 3 : 2, which = kstep % nacc;
                     tc::mma_tf32(tmem + 128 * which, dhi, dhi, idesc, kstep >= nacc ? 1u : 0u);
                     tc::mma_tf32(tmem + 384, dlo, dhi, idesc, kstep > 0 ? 1u : 0u);
                     tc::mma_tf32(tmem + 384, dhi, dlo, idesc, 1u);
                     tc::mma_tf32(tmem + 384, dlo, dlo, idesc, 1u);
-                    tc::mma_tf32(tmem + 384, dl2, dhi, idesc, 1u);
-                    tc::mma_tf32(tmem + 384, dhi, dl2, idesc, 1u);
+                    if (mode >= 6) {                                // 6, 7: a third split level (not used by the Stage-II kernel)
+                        tc::mma_tf32(tmem + 384, dl2, dhi, idesc, 1u);
+                        tc::mma_tf32(tmem + 384, dhi, dl2, idesc, 1u);
+                    }
                     ++kstep;
                 }
             }
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(384, 1) jtj_kernel(const float *J, int rows, i
         for (int c0 = 0; c0 < N; c0 += 16) {
             float v[16];
             tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + c0, v);
-            if (mode >= 6) {
+            if (mode >= 5) {
                 float v1[16], v2[16], v3[16];
                 tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + 128 + c0, v1);
                 tc::tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + 384 + c0, v3);
@@ -171,7 +174,7 @@ static int run(int rows, int n, int KT, int skew) {
     double scale = 0;
     for (int i = 0; i < n; ++i) scale = fmax(scale, ref[i * n + i]);
     int bad = 0;
-    for (int mode : {3, 6, 7}) {
+    for (int mode : {3, 5, 6, 7}) {
         CK(cudaMemset(dD, 0, n * n * 4));
         jtj_kernel<<<1, 384, smem>>>(dJ, rows, n, dD, mode, KT, skew);
         CK(cudaDeviceSynchronize());
@@ -180,7 +183,7 @@ static int run(int rows, int n, int KT, int skew) {
         double e = 0;
         for (int i = 0; i < n * n; ++i) e = fmax(e, fabs(D[i] - ref[i]));
         printf("rows %3d n %3d KT %2d skew %3d  %dxTF32: max |D - ref| / max diag = %.3e\n", rows, n, KT, skew, mode, e / scale);
-        if (!(e / scale < 1e-5)) bad = 1;
+        if (!(e / scale < (mode == 3 ? 1e-5 : 1.5e-6))) bad = 1;
     }
     cudaFree(dJ); cudaFree(dD);
     return bad;

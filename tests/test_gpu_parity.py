@@ -131,3 +131,13 @@ def test_library_is_the_cuda_build():
     assert L.mosh2_device_count() >= 1
     maps = open('/proc/self/maps').read()
     assert 'libmosh2.so' in maps
+
+
+def test_tcgen05_jtj_building_block():
+    """Stand-alone kernel (tests/tc): J^T J on the tensor cores with the split-TF32 / separate-accumulator scheme the
+    Stage-II kernel uses, against a float64 product, for the operand shapes of all model families (incl. N = 16)."""
+    import subprocess
+    from moshpp_b200 import build
+    exe = build.build_tc_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith('OK'), r.stdout + r.stderr
