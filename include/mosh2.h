@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOSH2_VERSION 100
+#define MOSH2_VERSION 101
 
 enum {
     MOSH2_OK = 0,
@@ -75,6 +75,10 @@ typedef struct mosh2_model_desc {
     int32_t n_free1, n_free2;    /* free variables of Step 1 / Step 2 (chmosh.py:645-649,676-699) */
     const int32_t *free1, *free2; /* indices into x = [trans(3) | pose(p_red) | dmpl(n_dmpl)] */
     int32_t finger_lo, finger_hi; /* reduced-pose ids penalised by poseH in Step 2            */
+    /* optimize_face (SMPL-X; chmosh.py:560-566,685-689): the last n_expr of the n_dmpl linear coefficients are
+     * expression coefficients (sd / jd hold their directions after the DMPL ones); [face_lo, face_hi) are the
+     * reduced-pose ids of the jaw, penalised by poseF in Step 2 */
+    int32_t n_expr, face_lo, face_hi;
 } mosh2_model_desc;
 
 /* Stage-II weights and dog-leg options (support_data/conf/moshpp_conf.yaml:95-125,
@@ -85,6 +89,8 @@ typedef struct mosh2_options {
     double delta_0, e3_first, e3;
     int32_t maxiter;
     int32_t optimize_fingers, optimize_dynamics;
+    double wt_poseF, wt_expr;  /* moshpp_conf.yaml: stageii_wt_poseF (annealed), stageii_wt_expr */
+    int32_t optimize_face;
 } mosh2_options;
 
 /* Outputs, one row per input frame (rows of skipped frames are zero). */
@@ -92,9 +98,9 @@ typedef struct mosh2_result {
     double *fullpose;    /* [F * 3*n_joints]            chmosh.py:719   */
     double *pose;        /* [F * p_red]   reduced pose (debug)          */
     double *trans;       /* [F * 3]                      chmosh.py:720   */
-    double *dmpls;       /* [F * n_dmpl] or NULL         chmosh.py:722   */
+    double *dmpls;       /* [F * n_dmpl] or NULL: DMPL, then expression coefficients   chmosh.py:722,724 */
     double *markers_sim; /* [F * M * 3]                  chmosh.py:716   */
-    double *errs;        /* [F * 6] SSE of data,poseB,velo,poseH,dmpl,extrap_dmpl  chmosh.py:712-714 */
+    double *errs;        /* [F * 8] SSE of data,poseB,velo,poseH,dmpl,extrap_dmpl,poseF,expr  chmosh.py:712-714 */
     int32_t *status;     /* [F] MOSH2_ST_* bits                           */
     int32_t *counters;   /* [F * 4] dog-leg iterations, residual evals, Jacobian builds, minimisations */
 } mosh2_result;

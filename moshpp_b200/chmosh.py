@@ -101,8 +101,8 @@ def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_te
                 except Exception:
                     pass
         flags[key] = on
-    if flags['optimize_face']:
-        raise NotImplementedError('optimize_face (expressions / jaw) is not built yet (SURVEY.md 8(f-4))')
+    if flags['optimize_face'] and sm.type != 'smplx':
+        flags['optimize_face'] = False          # only SMPL-X has face pose ids / expression components (chmosh.py:560-566)
 
     v_template = _read_vertices(v_template_fname) if v_template_fname else None
     model = _pack.load_surface_model(sm.fname, pose_hand_prior_fname=_get(mp, 'pose_hand_prior_fname'),
@@ -126,10 +126,15 @@ def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_te
                           num_betas=int(sm.num_betas), prior=prior, dmpl_dirs=dmpl_dirs,
                           num_dmpls=int(sm.num_dmpls) if dyn else 0,
                           optimize_fingers=flags['optimize_fingers'],
-                          optimize_toes=bool(_get(mp, 'optimize_toes', False)))
+                          optimize_toes=bool(_get(mp, 'optimize_toes', False)),
+                          optimize_face=flags['optimize_face'],
+                          expr_start=int(_get(sm, 'betas_expr_start_id', 0) or 0),
+                          num_expressions=int(_get(sm, 'num_expressions', 0) or 0) if flags['optimize_face'] else 0)
+    flags['n_betas_model'] = int(model.shapedirs.shape[-1])
+    flags['expr_start'] = int(_get(sm, 'betas_expr_start_id', 0) or 0)
     opts = _lib.make_options(cfg.opt_settings.weights, maxiter=int(cfg.opt_settings.maxiter),
                              optimize_fingers=flags['optimize_fingers'] and pk.finger_hi > pk.finger_lo,
-                             optimize_dynamics=dyn)
+                             optimize_dynamics=dyn, optimize_face=flags['optimize_face'] and pk.n_expr > 0)
     return pk, opts, flags
 
 
@@ -144,18 +149,29 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         errs['poseB'] = res.errs[fid, 1]
     if flags['optimize_fingers'] and pk.finger_hi > pk.finger_lo:
         errs['poseH'] = res.errs[fid, 3]
+    face = bool(flags.get('optimize_face')) and pk.n_expr > 0
+    if face:
+        errs['poseF'] = res.errs[fid, 6]
+        errs['expr'] = res.errs[fid, 7]
     if dyn:
         errs['dmpl'] = res.errs[fid, 4]
         errs['extrap_dmpl'] = res.errs[fid, 5][(st & _lib.ST_HAS_EXTRAP) != 0]
     errs['velo'] = res.errs[fid, 2][(st & _lib.ST_HAS_VELO) != 0]
-    errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseH', 'dmpl') or len(v)}
+    errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseH', 'dmpl', 'poseF', 'expr') or len(v)}
     labels = np.asarray(latent_labels, dtype=object)
     data = {
         'fullpose': res.fullpose[fid].copy(),
         'trans': res.trans[fid].copy(),
     }
     if dyn:
-        data['dmpls'] = res.dmpls[fid, :pk.n_dmpl].copy()
+        data['dmpls'] = res.dmpls[fid, :pk.n_dmpl - pk.n_expr].copy()
+    if face:
+        # chmosh.py:724 stores betas[exp_start:], i.e. the optimised coefficients followed by the model's remaining
+        # (untouched, zero) shape components
+        tail = max(pk.n_expr, int(flags.get('n_betas_model', 0)) - int(flags.get('expr_start', 0)))
+        expr = np.zeros((len(fid), tail))
+        expr[:, :pk.n_expr] = res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl]
+        data['expression'] = expr
     data['stageii_debug_details'] = {
         'stageii_errs': errs,
         'markers_sim': [res.markers_sim[f][vis[f]] for f in fid],

@@ -108,6 +108,7 @@ struct DevModel {
         m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw; m.na = d.na;
         m.n_levels = d.n_levels; m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
+        m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
         int rc;
         if ((rc = up<int>(d.parents, nJ, &m.parents))) return rc;
         if ((rc = up<int>(d.fk_order, nJ, &m.fk_order))) return rc;
@@ -284,6 +285,7 @@ void mosh2_default_options(mosh2_options *o) {
     o->wt_annealing = 2.5; o->wt_extrap_dmpl = 6.0; o->num_train_markers = 46;
     o->delta_0 = 0.5; o->e3_first = 1e-3; o->e3 = 1e-2; o->maxiter = 100;
     o->optimize_fingers = 0; o->optimize_dynamics = 0;
+    o->wt_poseF = 1.0; o->wt_expr = 1.0; o->optimize_face = 0;
 }
 
 int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out) {
@@ -291,6 +293,9 @@ int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out)
     *out = nullptr;
     if (d->n_joints < 1 || d->n_markers < 1 || d->kw < 1 || d->kw > 8 || d->n_free1 < 1 || d->n_free2 < d->n_free1)
         return fail(MOSH2_E_INVALID, "inconsistent model sizes");
+    if (d->n_expr < 0 || d->n_expr > d->n_dmpl || d->face_lo < 0 || d->face_hi < d->face_lo || d->face_hi > d->p_red)
+        return fail(MOSH2_E_INVALID, "inconsistent face description: n_expr=%d of %d linear coefficients, jaw ids [%d, %d)", d->n_expr,
+                    d->n_dmpl, d->face_lo, d->face_hi);
     if (d->n_levels < 1 || d->n_levels > mosh2::kMaxDepth || d->n_joints > 254)
         return fail(MOSH2_E_TOO_LARGE, "kinematic tree too deep or too large: %d levels (max %d), %d joints (max 254)", d->n_levels,
                     mosh2::kMaxDepth, d->n_joints);
@@ -341,6 +346,7 @@ int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames,
     o.wt_dmpl = opt->wt_dmpl; o.wt_annealing = opt->wt_annealing; o.wt_extrap = opt->wt_extrap_dmpl;
     o.num_train_markers = opt->num_train_markers; o.delta_0 = opt->delta_0; o.e3_first = opt->e3_first; o.e3 = opt->e3;
     o.maxiter = opt->maxiter; o.optimize_fingers = opt->optimize_fingers; o.optimize_dynamics = opt->optimize_dynamics;
+    o.wt_poseF = opt->wt_poseF; o.wt_expr = opt->wt_expr; o.optimize_face = opt->optimize_face;
 
     size_t gws = 0;
     if (precision == MOSH2_F64) plan_workspace(m->f64.m, &j->smem, &gws, &j->big_in_global);

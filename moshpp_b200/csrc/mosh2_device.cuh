@@ -81,7 +81,7 @@ struct BPtr {                            // array in shared memory, or (BIG: f64
 namespace mosh2 {
 
 enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32 };
-enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, N_ERR = 6 };
+enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, ERR_POSEF = 6, ERR_EXPR = 7, N_ERR = 8 };
 
 constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
 constexpr int kBlendGroups = 4;   // upper bound of the joint groups of the pose-blend partial sums (run time: 1..3, one round of threads)
@@ -113,6 +113,7 @@ struct Model {
     int n1, n2;
     const int *free1, *free2;
     int finger_lo, finger_hi;
+    int n_expr, face_lo, face_hi;   // optimize_face: the last n_expr linear coefficients are expressions; jaw pose ids
     int tile_markers;           // markers per Jacobian tile (20 or 10: a warp owns ten), chosen by the host from the shared-memory budget
     int dev_no_tc;              // development switch (host): 1 = J^T J stays on the CUDA cores
 };
@@ -121,6 +122,8 @@ struct Options {
     double wt_data, wt_poseB, wt_poseH, wt_velo, wt_dmpl, wt_annealing, wt_extrap;
     double num_train_markers, delta_0, e3_first, e3;
     int maxiter, optimize_fingers, optimize_dynamics;
+    double wt_poseF, wt_expr;
+    int optimize_face;
 };
 
 template <class real>
@@ -515,6 +518,7 @@ struct StepCfg {
     real wp;          // prior weight (0: no prior term)
     real e3;
     bool velo, poseH, dm_terms, extrap;
+    bool face;        // poseF (jaw) and expr terms (chmosh.py:685-687)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -528,7 +532,7 @@ struct Solver {
     const Cta cta;
     const Dims &d;
     // per-frame scalars (identical in every thread)
-    real wd, wp_frame, wH, wv, wdm, wex;
+    real wd, wp_frame, wH, wv, wdm, wex, wF, wxp;
     int nvis, njl;            // njl: joints whose full-pose columns the current step needs
     bool has_velo, has_extrap, hand_free;
     // counters of the current frame
@@ -814,11 +818,16 @@ struct Solver {
             }
 #endif
         }
-        real part[N_ERR] = {0, 0, 0, 0, 0, 0};
+        real part[N_ERR] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int nd_dm = d.nd - m.n_expr;             // DMPL coefficients come first, expressions after them
         CTA_FOR(i, 3 * d.M) part[ERR_DATA] += w.rm[i] * w.rm[i];
         if (c.velo) CTA_FOR(i, d.PR) { const real e = (th[i] - w.velo_tgt[i]) * wv; part[ERR_VELO] += e * e; }
         if (c.poseH) CTA_FOR(i, m.finger_hi - m.finger_lo) { const real e = th[m.finger_lo + i] * wH; part[ERR_POSEH] += e * e; }
-        if (c.dm_terms) CTA_FOR(i, d.nd) {
+        if (c.face) {
+            CTA_FOR(i, m.face_hi - m.face_lo) { const real e = th[m.face_lo + i] * wF; part[ERR_POSEF] += e * e; }
+            CTA_FOR(i, m.n_expr) { const real e = dl[nd_dm + i] * wxp; part[ERR_EXPR] += e * e; }
+        }
+        if (c.dm_terms) CTA_FOR(i, nd_dm) {
             const real e = dl[i] * wdm;
             part[ERR_DMPL] += e * e;
             if (c.extrap) { const real e2 = (dl[i] - w.dm_tgt[i]) * wex; part[ERR_EXTRAP] += e2 * e2; }
@@ -1372,11 +1381,16 @@ struct Solver {
                 const int i = fv - 3;
                 if (c.velo) { da += wv * wv; dg += wv * wv * (th[i] - w.velo_tgt[i]); }
                 if (c.poseH && i >= m.finger_lo && i < m.finger_hi) { da += wH * wH; dg += wH * wH * th[i]; }
-            } else if (fv >= 3 + d.PR && c.dm_terms) {
+                if (c.face && i >= m.face_lo && i < m.face_hi) { da += wF * wF; dg += wF * wF * th[i]; }
+            } else if (fv >= 3 + d.PR) {
                 const int i = fv - 3 - d.PR;
-                da += wdm * wdm;
-                dg += wdm * wdm * dl[i];
-                if (c.extrap) { da += wex * wex; dg += wex * wex * (dl[i] - w.dm_tgt[i]); }
+                if (i < d.nd - m.n_expr) {
+                    if (c.dm_terms) {
+                        da += wdm * wdm;
+                        dg += wdm * wdm * dl[i];
+                        if (c.extrap) { da += wex * wex; dg += wex * wex * (dl[i] - w.dm_tgt[i]); }
+                    }
+                } else if (c.face) { da += wxp * wxp; dg += wxp * wxp * dl[i]; }
             }
             w.A[cc * ld + cc] += da;
             w.g[cc] -= dg;
@@ -1708,14 +1722,14 @@ struct Solver {
     //      one loop around a single eval() / build() / gauss_newton() call site each (the 32 KB instruction cache
     //      makes code size a first-order cost).  The dog-leg control flow is chumpy's
     //      (SURVEY.md Appendix A.6): outer iterations, inner retries until a step improves, e_3 / e_2 / maxiter.
-    M2_D void solve_frame(int f, bool emit, bool first, bool fingers, bool dyn) {
+    M2_D void solve_frame(int f, bool emit, bool first, bool fingers, bool dyn, bool face) {
         const Options &o = job.opt;
         const real e1 = real(1e-15), e2 = real(1e-15);
         enum { OP_PROCRUSTES, OP_BEGIN, OP_TRIAL, OP_OUTPUT };
         int op = first ? OP_PROCRUSTES : OP_BEGIN;
         int stage = first ? 0 : 3;     // 0..2 first-frame annealing (chmosh.py:637-653), 3 Step 1 (665-671), 4 Step 2 (676-705)
         StepCfg<real> c;
-        c.free = w.c_free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false;
+        c.free = w.c_free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false; c.face = false;
         c.wp = 0; c.e3 = real(o.e3_first);
         bool need_setup = !first;
         // dog-leg state of the running minimisation
@@ -1725,14 +1739,14 @@ struct Solver {
         while (true) {
             if (need_setup) {
                 // configuration of this stage
-                c.free = w.c_free1; c.n = m.n1; c.poseH = false; c.dm_terms = false; c.extrap = false;
+                c.free = w.c_free1; c.n = m.n1; c.poseH = false; c.dm_terms = false; c.extrap = false; c.face = false;
                 if (stage < 3) {
                     c.wp = wp_frame * (stage == 0 ? real(10) : (stage == 1 ? real(5) : real(1)));
                     c.e3 = real(o.e3_first);
                 } else {
                     c.wp = wp_frame;
                     c.e3 = real(o.e3);
-                    if (stage == 4) { c.free = w.c_free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap; }
+                    if (stage == 4) { c.free = w.c_free2; c.n = m.n2; c.poseH = fingers; c.dm_terms = dyn; c.extrap = has_extrap; c.face = face; }
                 }
                 stage_setup(c);
                 need_setup = false;
@@ -2022,7 +2036,9 @@ struct Solver {
         M2_T0();
         bool first = true, have_prev = false, have_dm_prev = false;
         wv = real(o.wt_velo); wdm = real(o.wt_dmpl); wex = real(o.wt_extrap);
-        const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd > 0;
+        wxp = real(o.wt_expr);
+        const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd - m.n_expr > 0;
+        const bool face = o.optimize_face != 0 && m.face_hi > m.face_lo;
         const bool has_prior = d.K > 0;
         njl = 0;
         hand_free = false;
@@ -2048,6 +2064,7 @@ struct Solver {
             wd = real(o.wt_data) * (real(o.num_train_markers) / real(nvis));
             wp_frame = has_prior ? real(o.wt_poseB) * anneal : real(0);
             wH = real(o.wt_poseH) * anneal;
+            wF = real(o.wt_poseF) * anneal;
             has_velo = have_prev;                              // chmosh.py:624-626
             if (has_velo) {
                 CTA_FOR(i, d.PR) w.velo_tgt[i] = real(2) * w.x[3 + i] - w.pose_prev[i];
@@ -2056,11 +2073,11 @@ struct Solver {
             if (!first) {
                 CTA_FOR(i, d.PR) w.pose_prev[i] = w.x[3 + i];                               // chmosh.py:656-659
                 have_prev = true;
-                if (dyn) { CTA_FOR(i, d.nd) w.dm_tgt[i] = w.x[3 + d.PR + i]; have_dm_prev = true; }
+                if (dyn) { CTA_FOR(i, d.nd - m.n_expr) w.dm_tgt[i] = w.x[3 + d.PR + i]; have_dm_prev = true; }
                 M2_SYNC();
             }
             has_extrap = dyn && have_dm_prev;
-            solve_frame(f, f >= f_emit, first, fingers, dyn);
+            solve_frame(f, f >= f_emit, first, fingers, dyn, face);
             first = false;
         }
         M2_TACC(17);

@@ -15,7 +15,7 @@ from .pack import StageIIPack
 
 MOSH2_F32, MOSH2_F64 = 0, 1
 ST_SOLVED, ST_SKIPPED, ST_HAS_VELO, ST_HAS_EXTRAP, ST_GN_FALLBACK, ST_MAXITER = 1, 2, 4, 8, 16, 32
-ERR_NAMES = ('data', 'poseB', 'velo', 'poseH', 'dmpl', 'extrap_dmpl')   # column order of mosh2_result.errs
+ERR_NAMES = ('data', 'poseB', 'velo', 'poseH', 'dmpl', 'extrap_dmpl', 'poseF', 'expr')   # column order of mosh2_result.errs
 
 _i32p = C.POINTER(C.c_int32)
 _i8p = C.POINTER(C.c_int8)
@@ -36,6 +36,7 @@ class ModelDesc(C.Structure):
         ('prior_means', _f64p), ('prior_Q', _f64p), ('prior_neglogw', _f64p),
         ('n_free1', C.c_int32), ('n_free2', C.c_int32), ('free1', _i32p), ('free2', _i32p),
         ('finger_lo', C.c_int32), ('finger_hi', C.c_int32),
+        ('n_expr', C.c_int32), ('face_lo', C.c_int32), ('face_hi', C.c_int32),
     ]
 
 
@@ -45,6 +46,7 @@ class Options(C.Structure):
         ('wt_dmpl', C.c_double), ('wt_annealing', C.c_double), ('wt_extrap_dmpl', C.c_double),
         ('num_train_markers', C.c_double), ('delta_0', C.c_double), ('e3_first', C.c_double), ('e3', C.c_double),
         ('maxiter', C.c_int32), ('optimize_fingers', C.c_int32), ('optimize_dynamics', C.c_int32),
+        ('wt_poseF', C.c_double), ('wt_expr', C.c_double), ('optimize_face', C.c_int32),
     ]
 
 
@@ -142,20 +144,27 @@ class DescHolder:
         d.prior_k, d.prior_d, d.prior_off = pk.prior_k, pk.prior_d, pk.prior_off
         d.n_free1, d.n_free2 = len(pk.free_step1), len(pk.free_step2)
         d.finger_lo, d.finger_hi = pk.finger_lo, pk.finger_hi
+        d.n_expr, d.face_lo, d.face_hi = pk.n_expr, pk.face_lo, pk.face_hi
         self.desc = d
 
 
 def make_options(weights=None, *, maxiter: int = 100, optimize_fingers: bool = False,
-                 optimize_dynamics: bool = False) -> Options:
+                 optimize_dynamics: bool = False, optimize_face: bool = False) -> Options:
     """Stage-II weights (moshpp_conf.yaml:118-125) -> mosh2_options."""
     o = Options(wt_data=400., wt_poseB=1.6, wt_poseH=1.0, wt_velo=2.5, wt_dmpl=1.0, wt_annealing=2.5,
                 wt_extrap_dmpl=6.0, num_train_markers=46., delta_0=0.5, e3_first=1e-3, e3=1e-2, maxiter=maxiter,
-                optimize_fingers=int(optimize_fingers), optimize_dynamics=int(optimize_dynamics))
+                optimize_fingers=int(optimize_fingers), optimize_dynamics=int(optimize_dynamics),
+                wt_poseF=1.0, wt_expr=1.0, optimize_face=int(optimize_face))
     if weights is not None:
         g = (lambda k: weights[k])
         o.wt_data, o.wt_poseB, o.wt_poseH = float(g('stageii_wt_data')), float(g('stageii_wt_poseB')), float(g('stageii_wt_poseH'))
         o.wt_velo, o.wt_dmpl = float(g('stageii_wt_velo')), float(g('stageii_wt_dmpl'))
         o.wt_annealing = float(g('stageii_wt_annealing'))
+        for key, attr in (('stageii_wt_poseF', 'wt_poseF'), ('stageii_wt_expr', 'wt_expr')):
+            try:
+                setattr(o, attr, float(weights[key]))
+            except (KeyError, AttributeError):
+                pass
     return o
 
 
@@ -167,7 +176,7 @@ class ResultArrays:
         self.trans = np.zeros((F, 3))
         self.dmpls = np.zeros((F, max(nd, 1)))
         self.markers_sim = np.zeros((F, M, 3))
-        self.errs = np.zeros((F, 6))
+        self.errs = np.zeros((F, len(ERR_NAMES)))
         self.status = np.zeros(F, dtype=np.int32)
         self.counters = np.zeros((F, 4), dtype=np.int32)
         self.nd = nd

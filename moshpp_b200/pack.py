@@ -222,7 +222,7 @@ class StageIIPack:
     p_full: int
     n_hand_red: int
     n_hand_full: int
-    n_dmpl: int
+    n_dmpl: int              # per-frame linear coefficients in all: DMPL first, then expressions
     kw: int                  # skinning weights kept per slot (ELL width)
     na: int                  # ancestor-list width per slot
     n_levels: int
@@ -257,6 +257,9 @@ class StageIIPack:
     free_step2: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     finger_lo: int = 0       # reduced-pose ids [lo, hi) penalised by poseH in step 2
     finger_hi: int = 0
+    face_lo: int = 0         # reduced-pose ids [lo, hi) penalised by poseF in step 2 (the jaw)
+    face_hi: int = 0
+    n_expr: int = 0          # how many of the n_dmpl linear coefficients (the last ones) are expression coefficients
     # ---- host-only bookkeeping
     closest: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int64))
     can_verts_sel: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
@@ -349,9 +352,9 @@ def _subtree_matrix(parents: np.ndarray) -> np.ndarray:
 def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarray, *,
                num_betas: int, prior: Optional[BodyPrior], dmpl_dirs: Optional[np.ndarray] = None,
                num_dmpls: int = 0, optimize_fingers: bool = False, optimize_toes: bool = False,
-               optimize_face: bool = False) -> StageIIPack:
-    if optimize_face:
-        raise NotImplementedError('optimize_face (expression / jaw) is a "next" row (SURVEY.md 8(f-4)); not built yet')
+               optimize_face: bool = False, expr_start: int = 0, num_expressions: int = 0) -> StageIIPack:
+    """``optimize_face`` (SMPL-X, chmosh.py:560-566,685-689): the ``num_expressions`` shape components from
+    ``expr_start`` become per-frame linear coefficients after the DMPL ones, and the jaw joins the free pose."""
     nj = model.n_joints
     betas = np.asarray(betas, dtype=np.float64).ravel()
     nb = min(num_betas, model.shapedirs.shape[-1], betas.shape[0])
@@ -370,6 +373,19 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
     else:
         sd = np.zeros((3 * M, 3, 0))
         jd = np.zeros((nj, 3, 0))
+    n_expr = 0
+    if optimize_face:
+        if model.model_type != 'smplx':
+            optimize_face = False                                               # chmosh.py:560: only SMPL-X has face ids
+        else:
+            n_expr = int(num_expressions)
+            if expr_start + n_expr > model.shapedirs.shape[-1]:
+                raise ValueError(f'the model has {model.shapedirs.shape[-1]} shape components; expressions '
+                                 f'{expr_start}..{expr_start + n_expr} do not exist')
+            ex = np.asarray(model.shapedirs[:, :, expr_start:expr_start + n_expr], dtype=np.float64)
+            sd = np.concatenate([sd, ex[slot_vid]], axis=2)
+            jd = np.concatenate([jd, np.einsum('jv,vcd->jcd', model.J_regressor, ex)], axis=2)
+    nd_dm, nd = nd, nd + n_expr
 
     # pose-blend slabs: pd[j-1, 3*slot + c, e] = posedirs[vid(slot), c, 9(j-1)+e]
     pdsel = model.posedirs[slot_vid].reshape(3 * M, 3, nj - 1, 9)
@@ -422,11 +438,14 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
     finger = parts['finger']
     f_lo, f_hi = (finger[0], finger[-1] + 1) if finger else (0, 0)
     assert not finger or finger == list(range(f_lo, f_hi))
+    face = parts['face']
+    c_lo, c_hi = (face[0], face[-1] + 1) if face else (0, 0)
+    assert not face or face == list(range(c_lo, c_hi))
 
     pack = StageIIPack(
         model_type=model.model_type, n_joints=nj, n_markers=M, body_dof=model.body_dof, p_red=p_red,
         p_full=model.p_full, n_hand_red=model.hand_comps.shape[0], n_hand_full=model.hands_mean.shape[0],
-        n_dmpl=nd, kw=kw, na=na, n_levels=n_levels,
+        n_dmpl=nd, n_expr=n_expr, kw=kw, na=na, n_levels=n_levels,
         parents=model.parents.astype(np.int32), fk_order=fk_order, level_ofs=level_ofs,
         slot_vid=slot_vid.astype(np.int32), w_joint=w_joint, anc_joint=anc_joint, anc_mask=anc_mask,
         anc_pos=anc_pos,
@@ -435,7 +454,7 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
         w_val=np.ascontiguousarray(w_val), j0=np.ascontiguousarray(j0), jd=np.ascontiguousarray(jd),
         coefs=coefs,
         free_step1=np.asarray(step1, dtype=np.int32), free_step2=np.asarray(step2, dtype=np.int32),
-        finger_lo=int(f_lo), finger_hi=int(f_hi),
+        finger_lo=int(f_lo), finger_hi=int(f_hi), face_lo=int(c_lo), face_hi=int(c_hi),
         closest=closest, can_verts_sel=np.ascontiguousarray(can_verts[slot_vid]),
     )
     if len(parts['body']):

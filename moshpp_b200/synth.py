@@ -279,7 +279,7 @@ def _fps(points: np.ndarray, n: int, rng) -> np.ndarray:
 
 
 def make_layout(model: Dict, model_type: str, n_body: int, n_finger: int, seed: int = SEED_LAYOUT,
-                hand_side: str = 'left'):
+                hand_side: str = 'left', n_face: int = 0):
     """Returns (latent_labels, vids, marker_meta) with the reference's ordering
     (types sorted, labels sorted within type; marker_layout/edit_tools.py:136,148)."""
     rng = np.random.default_rng(seed)
@@ -313,6 +313,11 @@ def make_layout(model: Dict, model_type: str, n_body: int, n_finger: int, seed: 
                 fsel = cand[_fps(verts[cand], n_finger, rng)]
                 pref = 'L' if side == 'left' else 'R'
                 groups.append((f'finger_{side}', sorted(zip([pref + n for n in fl], fsel))))
+    if n_face and model_type == 'smplx':                 # markers on the head / jaw region, type 'face'
+        cand = np.nonzero(np.isin(dom, (15, 22)))[0]
+        cand = cand[cand < _pack.SMPLX_FIRST_EYEBALL_VID]
+        fsel = cand[_fps(verts[cand], n_face, rng)]
+        groups.append(('face', sorted(zip([f'FACE{i:02d}' for i in range(n_face)], fsel))))
     groups.sort(key=lambda g: g[0])
     labels, vids, mtypes = [], [], []
     for t, items in groups:
@@ -392,7 +397,11 @@ def make_motion(p: _pack.StageIIPack, n_frames: int, seed: int, fps: float = 120
     if p.model_type in ('smpl', 'smplh', 'smplx'):
         pose[:, 30:36] *= 0.0            # toes are frozen in Stage II unless optimize_toes
     if p.model_type == 'smplx':
-        pose[:, 66:75] = 0.0             # jaw / eyes are not optimised without optimize_face
+        if p.face_hi > p.face_lo:
+            pose[:, 69:75] = 0.0         # eyes are never optimised; the jaw is, with optimize_face
+            pose[:, 66:69] *= 0.3
+        else:
+            pose[:, 66:75] = 0.0         # jaw / eyes are not optimised without optimize_face
     trans = np.stack([0.5 * np.sin(2 * np.pi * 0.1 * t + 0.3), 0.03 * np.sin(2 * np.pi * 1.1 * t) + 0.9,
                       0.8 * t / max(t[-1], 1e-9) * min(1.0, t[-1]) + 0.2 * np.sin(2 * np.pi * 0.07 * t)], axis=1)
     dm = np.zeros((n_frames, p.n_dmpl))
@@ -464,6 +473,9 @@ CONFIGS = {
     'C3': dict(model_type='smplx', frames=4000, n_body=47, n_finger=10, optimize_fingers=True, optimize_dynamics=True, mocap_ext='npz'),
     'C4': dict(model_type='mano', frames=2000, n_body=0, n_finger=20, optimize_fingers=True, optimize_dynamics=False, mocap_ext='npz'),
     'C5': dict(model_type='smplh', frames=4000, n_body=41, n_finger=6, optimize_fingers=True, optimize_dynamics=False, mocap_ext='npz'),
+    # widening row: SMPL-X with face markers, jaw + expression coefficients free in Step 2
+    'CF': dict(model_type='smplx', frames=200, n_body=41, n_finger=6, n_face=12, optimize_fingers=True, optimize_dynamics=False,
+               optimize_face=True, mocap_ext='npz'),
 }
 
 
@@ -503,7 +515,7 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
     rng = np.random.default_rng(SEED_MODEL + 100 + seq_idx)
     betas = np.zeros(model['shapedirs'].shape[-1])
     betas[:16] = rng.standard_normal(16)
-    labels, vids, marker_meta = make_layout(model, mt, c['n_body'], c['n_finger'], hand_side=hand_side)
+    labels, vids, marker_meta = make_layout(model, mt, c['n_body'], c['n_finger'], hand_side=hand_side, n_face=c.get('n_face', 0))
     markers_latent = make_markers_latent(model, mt, betas, 16, vids, marker_meta)
 
     cfg = default_cfg(**{
@@ -512,6 +524,11 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
         'moshpp.optimize_fingers': c['optimize_fingers'], 'moshpp.optimize_dynamics': c['optimize_dynamics'],
         'moshpp.verbosity': 0,
     })
+    face = bool(c.get('optimize_face', False))
+    if face:                 # the fixture model has 24 shape components: 16 betas, then 8 used as expressions
+        cfg.moshpp.optimize_face = True
+        cfg.surface_model.betas_expr_start_id = 16
+        cfg.surface_model.num_expressions = 8
 
     sm = _pack.load_surface_model(model_fname, pose_hand_prior_fname=hand_prior_fname,
                                   use_hands_mean=cfg.surface_model.use_hands_mean,
@@ -525,7 +542,8 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
             dm_dirs = pickle.load(f)['eigvec']
     pk = _pack.build_pack(sm, betas, markers_latent, num_betas=16, prior=prior, dmpl_dirs=dm_dirs,
                           num_dmpls=8 if c['optimize_dynamics'] else 0,
-                          optimize_fingers=c['optimize_fingers'])
+                          optimize_fingers=c['optimize_fingers'], optimize_face=face,
+                          expr_start=16 if face else 0, num_expressions=8 if face else 0)
     cfg_idx = list(CONFIGS).index(config)
     pose, trans, dm = make_motion(pk, F, seed=SEED_MOTION + cfg_idx + 1000 * seq_idx)
     if not c['optimize_fingers'] and pk.n_hand_red:

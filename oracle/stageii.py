@@ -46,13 +46,13 @@ class _Objective:
         self.terms = terms                # ordered list of (name, payload)
         self.pose_ids = np.asarray(free_pose_ids, dtype=np.int64)
         self.free_dmpl = free_dmpl
-        self.n = 3 + len(self.pose_ids) + (solver.nd if free_dmpl else 0)
+        self.n = 3 + len(self.pose_ids) + (solver.nd if free_dmpl else 0)   # free_dmpl: the whole linear block (DMPL, expressions)
 
     def x0(self):
         s = self.s
         parts = [s.trans, s.pose[self.pose_ids]]
         if self.free_dmpl:
-            parts.append(s.betas[s.dmpl_ids])
+            parts.append(s.betas[s.lin_ids])
         return np.concatenate(parts)
 
     def assign(self, x):
@@ -60,7 +60,7 @@ class _Objective:
         s.trans = x[:3].copy()
         s.pose[self.pose_ids] = x[3:3 + len(self.pose_ids)]
         if self.free_dmpl:
-            s.betas[s.dmpl_ids] = x[3 + len(self.pose_ids):]
+            s.betas[s.lin_ids] = x[3 + len(self.pose_ids):]
 
     def __call__(self, x, want_jac):
         s = self.s
@@ -111,14 +111,30 @@ class _Objective:
                 if want_jac:
                     J = np.zeros((r.size, self.n))
                     if self.free_dmpl:
-                        J[:, 3 + npi:] = np.eye(s.nd) * wt
+                        J[:, 3 + npi:3 + npi + s.n_dm] = np.eye(s.n_dm) * wt
             elif name == 'dmpl':
                 wt = payload
                 r = s.betas[s.dmpl_ids] * wt
                 if want_jac:
                     J = np.zeros((r.size, self.n))
                     if self.free_dmpl:
-                        J[:, 3 + npi:] = np.eye(s.nd) * wt
+                        J[:, 3 + npi:3 + npi + s.n_dm] = np.eye(s.n_dm) * wt
+            elif name == 'poseF':                                                                  # chmosh.py:685-686
+                wt = payload
+                r = s.pose[s.face_ids] * wt
+                if want_jac:
+                    J = np.zeros((r.size, self.n))
+                    col = {pid: c for c, pid in enumerate(self.pose_ids)}
+                    for ri, pid in enumerate(s.face_ids):
+                        if pid in col:
+                            J[ri, 3 + col[pid]] = wt
+            elif name == 'expr':                                                                   # chmosh.py:687
+                wt = payload
+                r = s.betas[s.expr_ids] * wt
+                if want_jac:
+                    J = np.zeros((r.size, self.n))
+                    if self.free_dmpl:
+                        J[:, 3 + npi + s.n_dm:] = np.eye(len(s.expr_ids)) * wt
             else:
                 raise KeyError(name)
             rs.append(r)
@@ -146,6 +162,10 @@ class _Objective:
                 out[name] = float((((s.betas[s.dmpl_ids] - payload[1]) * payload[0]) ** 2).sum())
             elif name == 'dmpl':
                 out[name] = float(((s.betas[s.dmpl_ids] * payload) ** 2).sum())
+            elif name == 'poseF':
+                out[name] = float(((s.pose[s.face_ids] * payload) ** 2).sum())
+            elif name == 'expr':
+                out[name] = float(((s.betas[s.expr_ids] * payload) ** 2).sum())
         return out
 
 
@@ -159,9 +179,13 @@ class StageIISolver:
         self.mode = mode
         self.latent_labels = list(latent_labels)
         self.optimize_fingers = bool(mp.optimize_fingers)
-        if mp.optimize_face:
-            raise NotImplementedError('optimize_face is not restated by this oracle (SURVEY.md 8(f-4))')
-        # chmosh.py:475-486: gate finger optimisation on the layout / available labels
+        self.optimize_face = bool(mp.optimize_face)
+        # chmosh.py:475-486: gate finger / face optimisation on the layout / available labels
+        if self.optimize_face:
+            if not np.any(['face' in m for m in marker_meta['marker_type_mask'].keys()]):
+                self.optimize_face = False
+            elif not np.any([('face' in t) and l in self.latent_labels for l, t in marker_meta['marker_type'].items()]):
+                self.optimize_face = False
         if self.optimize_fingers:
             if not np.any(['finger' in m for m in marker_meta['marker_type_mask'].keys()]):
                 self.optimize_fingers = False
@@ -197,6 +221,16 @@ class StageIISolver:
             m.shapedirs[:, :, sm.num_betas:total] = dmpl_pcs[:, :, :sm.num_dmpls]
             self.nd = int(sm.num_dmpls)
             self.dmpl_ids = np.arange(sm.num_betas, total)
+        self.n_dm = self.nd
+        # expression coefficients (chmosh.py:560-566): betas[exp_start : exp_start + num_expressions], free in Step 2
+        self.expr_ids = np.zeros(0, dtype=np.int64)
+        self.exp_start = 0
+        if self.optimize_face and sm.type == 'smplx':
+            self.exp_start = int(sm.betas_expr_start_id)
+            self.expr_ids = np.arange(self.exp_start, self.exp_start + int(sm.num_expressions))
+            assert self.expr_ids[-1] < m.n_betas_model, 'the model has no such expression components'
+        self.lin_ids = np.concatenate([self.dmpl_ids, self.expr_ids]).astype(np.int64)
+        self.nd = len(self.lin_ids)
 
         if mode == 'lean':
             self.vids = self.tc.vids
@@ -214,6 +248,7 @@ class StageIISolver:
         self.root_ids = all_ids[:3]
         self.body_ids: List[int] = []
         self.finger_ids: List[int] = []
+        self.face_ids: List[int] = []
         if sm.type == 'smpl':
             self.body_ids = all_ids[3:]
         elif sm.type == 'smplh':
@@ -222,6 +257,8 @@ class StageIISolver:
                 self.finger_ids = all_ids[66:]
         elif sm.type == 'smplx':
             self.body_ids = all_ids[3:66]
+            if self.optimize_face:
+                self.face_ids = all_ids[66:69]                                                   # jaw only (line 564)
             if self.optimize_fingers:
                 self.finger_ids = all_ids[75:]
         elif sm.type == 'mano':
@@ -235,6 +272,8 @@ class StageIISolver:
         ids2 = list(ids)
         if self.optimize_fingers:
             ids2 += self.finger_ids
+        if self.optimize_face:
+            ids2 += self.face_ids                                                                # line 689
         self.step2_ids = sorted(set(ids2))                                                      # line 691
         self.wts = cfg.opt_settings.weights
         self.maxiter = int(cfg.opt_settings.maxiter)
@@ -242,7 +281,7 @@ class StageIISolver:
 
     # ---- one evaluation of opt_model.r / markers_sim (and Jacobians)
     def evaluate(self, want_jac):
-        res = self.lbs(self.pose, self.betas, self.trans, want_jac, beta_ids=self.dmpl_ids)
+        res = self.lbs(self.pose, self.betas, self.trans, want_jac, beta_ids=self.lin_ids)
         verts = res[0] if want_jac else res
         t = self.tri
         if not want_jac:
@@ -271,7 +310,7 @@ class StageIISolver:
         self.pose[:] = 0.0
         self.trans[:] = 0.0
         if self.nd:
-            self.betas[self.dmpl_ids] = 0.0
+            self.betas[self.lin_ids] = 0.0
 
     def solve_range(self, obs_frames: List[Optional[Tuple[np.ndarray, np.ndarray]]], emit_from: int = 0):
         """The frame loop chmosh.py:584-724 over ``obs_frames`` (each ``(vis_idx, obs m x 3)`` or None for a
@@ -293,6 +332,8 @@ class StageIISolver:
             wt_data = w['stageii_wt_data'] * (NUM_TRAIN_MARKERS / obs.shape[0])
             wt_pose = w['stageii_wt_poseB'] * anneal
             wt_poseH = w['stageii_wt_poseH'] * anneal
+            wt_poseF = w['stageii_wt_poseF'] * anneal
+            wt_expr = w['stageii_wt_expr']
             wt_dmpl = w['stageii_wt_dmpl']
             wt_velo = w['stageii_wt_velo']
 
@@ -321,12 +362,15 @@ class StageIISolver:
 
             if self.optimize_fingers:
                 terms.append(['poseH', wt_poseH])
+            if self.optimize_face and len(self.face_ids):
+                terms.append(['poseF', wt_poseF])
+                terms.append(['expr', wt_expr])
             if self.optimize_dynamics:
                 if dmpl_prev is not None:
                     cur = self.betas[self.dmpl_ids]
                     terms.append(['extrap_dmpl', (6.0, cur + (cur - dmpl_prev))])                # line 697 (App. B-1)
                 terms.append(['dmpl', wt_dmpl])
-            obj2 = _Objective(self, obs, vis, terms, self.step2_ids, self.optimize_dynamics)
+            obj2 = _Objective(self, obs, vis, terms, self.step2_ids, self.nd > 0)
             self._minimize(obj2, 1e-2)                                                           # Step 2
 
             if fi >= emit_from:
@@ -335,7 +379,8 @@ class StageIISolver:
                 out.append(dict(fidx=fi, errs=errs, markers_sim=mk.copy(), markers_obs=obs.copy(), vis=vis,
                                 fullpose=self.model.fullpose(self.pose), pose=self.pose.copy(),
                                 trans=self.trans.copy(),
-                                dmpls=self.betas[self.dmpl_ids].copy() if self.optimize_dynamics else None))
+                                dmpls=self.betas[self.dmpl_ids].copy() if self.optimize_dynamics else None,
+                                expression=self.betas[self.exp_start:].copy() if len(self.expr_ids) else None))   # line 724: the whole tail
         return out
 
 
@@ -407,6 +452,8 @@ def mosh_stageii(mocap_fname, cfg, markers_latent, latent_labels, betas, marker_
     data = {'fullpose': np.array([r['fullpose'] for r in per]), 'trans': np.array([r['trans'] for r in per])}
     if solver.optimize_dynamics:
         data['dmpls'] = np.array([r['dmpls'] for r in per])
+    if len(solver.expr_ids):                                                                    # chmosh.py:723-724,736
+        data['expression'] = np.array([r['expression'] for r in per])
     data['stageii_debug_details'] = dbg
     data['_pose_reduced'] = np.array([r['pose'] for r in per])
     return data

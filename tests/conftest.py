@@ -21,6 +21,7 @@ SMALL = {
     'C2': dict(frames=16, n_verts=1500),
     'C3': dict(frames=10, n_verts=2000),
     'C4': dict(frames=12, n_verts=None),
+    'CF': dict(frames=8, n_verts=2000),       # SMPL-X with face markers: jaw + expressions
 }
 
 
@@ -62,7 +63,8 @@ def emu():
         obs, vis = obs_vis if obs_vis is not None else dense_obs(case)
         h = lib.DescHolder(pk)
         opt = lib.make_options(cfg.opt_settings.weights, optimize_fingers=cfg.moshpp.optimize_fingers and pk.finger_hi > pk.finger_lo,
-                               optimize_dynamics=cfg.moshpp.optimize_dynamics)
+                               optimize_dynamics=cfg.moshpp.optimize_dynamics,
+                               optimize_face=bool(cfg.moshpp.optimize_face) and pk.n_expr > 0)
         F = obs.shape[0]
         res = lib.ResultArrays(F, lib.pack_dims(pk))
         obs = np.ascontiguousarray(obs, dtype=np.float64)

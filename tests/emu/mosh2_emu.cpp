@@ -33,6 +33,7 @@ struct HostModel {
         m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw; m.na = d.na;
         m.n_levels = d.n_levels; m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
+        m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
         m.parents = up<int>(d.parents, nJ);
         m.fk_order = up<int>(d.fk_order, nJ);
         m.level_ofs = up<int>(d.level_ofs, size_t(d.n_levels) + 1);
@@ -100,7 +101,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     const size_t F = n_frames, M = desc->n_markers, PF = size_t(3) * desc->n_joints, PR = desc->p_red, nd = desc->n_dmpl;
     std::vector<real> o(F * M * 3);
     for (size_t i = 0; i < o.size(); ++i) o[i] = real(obs[i]);
-    std::vector<real> fullpose(F * PF), pose(F * PR), trans(F * 3), dmpls(F * nd + 1), mk(F * M * 3), errs(F * 6);
+    std::vector<real> fullpose(F * PF), pose(F * PR), trans(F * 3), dmpls(F * nd + 1), mk(F * M * 3), errs(F * mosh2::N_ERR);
     mosh2::Job<real> job{};
     job.n_frames = n_frames;
     job.chunk_len = chunk_len > 0 ? chunk_len : 0;
@@ -120,6 +121,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     q.wt_dmpl = opt->wt_dmpl; q.wt_annealing = opt->wt_annealing; q.wt_extrap = opt->wt_extrap_dmpl;
     q.num_train_markers = opt->num_train_markers; q.delta_0 = opt->delta_0; q.e3_first = opt->e3_first; q.e3 = opt->e3;
     q.maxiter = opt->maxiter; q.optimize_fingers = opt->optimize_fingers; q.optimize_dynamics = opt->optimize_dynamics;
+    q.wt_poseF = opt->wt_poseF; q.wt_expr = opt->wt_expr; q.optimize_face = opt->optimize_face;
 
     hm.m.tile_markers = 20;
     hm.m.dev_no_tc = 1;                          // the host build runs the CUDA-core formulation
@@ -159,7 +161,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     conv(res->trans, trans, F * 3);
     if (nd) conv(res->dmpls, dmpls, F * nd);
     conv(res->markers_sim, mk, F * M * 3);
-    conv(res->errs, errs, F * 6);
+    conv(res->errs, errs, F * mosh2::N_ERR);
     if (res->status) std::memcpy(res->status, status.data(), F * sizeof(int));
     if (res->counters) std::memcpy(res->counters, counters.data(), F * 4 * sizeof(int));
     return 0;

@@ -2,7 +2,7 @@
 procedural cases of tests/conftest.py.  The reference itself cannot be run here (chumpy / psbody absent,
 SURVEY.md 8(c)), so these vectors pin the oracle against drift and give the GPU tests a fixed target.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [C1 CF ...]
 """
 import os
 import sys
@@ -22,7 +22,10 @@ from oracle import stageii  # noqa: E402
 
 def main():
     d = tempfile.mkdtemp(prefix='mosh_golden_')
+    only = sys.argv[1:]
     for name, kw in SMALL.items():
+        if only and name not in only:
+            continue
         case = synth.make_case(d, name, **kw)
         out = stageii.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'],
                                    case['betas'], case['marker_meta'])
@@ -33,6 +36,8 @@ def main():
                     markers_latent=case['markers_latent'])
         if 'dmpls' in out:
             arrs['dmpls'] = out['dmpls']
+        if 'expression' in out:
+            arrs['expression'] = out['expression']
         np.savez_compressed(os.path.join(HERE, f'stageii_{name}.npz'), **arrs)
         print(name, out['fullpose'].shape, 'written')
 

@@ -23,7 +23,7 @@ def test_header_symbols_are_exported(library):
     assert declared == set(lib.EXPORTED_SYMBOLS), declared ^ set(lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(library, name), name
-    assert library.mosh2_version() == 100
+    assert library.mosh2_version() == 101
 
 
 def test_ctypes_struct_layout_matches_header(library):

@@ -10,7 +10,7 @@ from conftest import run_oracle
 from moshpp_b200 import lib
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
 def test_f64_device_source_equals_oracle(cases, emu, name):
     case = cases(name)
     out = run_oracle(case)
@@ -23,10 +23,14 @@ def test_f64_device_source_equals_oracle(cases, emu, name):
     assert np.abs(res.trans[fid] - out['trans']).max() < 1e-10
     if 'dmpls' in out:
         assert np.abs(res.dmpls[fid, :out['dmpls'].shape[1]] - out['dmpls']).max() < 1e-9
+    if 'expression' in out:                      # the expression coefficients are the tail of the linear block
+        pk = case['pack']
+        assert pk.n_expr > 0 and np.abs(out['expression'][:, :pk.n_expr]).max() > 1e-2
+        assert np.abs(res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl] - out['expression'][:, :pk.n_expr]).max() < 1e-9
     # identical dog-leg trajectories: same number of Jacobian builds and minimisations
     assert res.counters[fid, 2].sum() == dbg['oracle_stats']['j_evals']
     assert res.counters[fid, 3].sum() == dbg['oracle_stats']['minimizations']
-    for k, col in zip(lib.ERR_NAMES, range(6)):
+    for col, k in enumerate(lib.ERR_NAMES):
         if k in dbg['stageii_errs'] and k not in ('velo', 'extrap_dmpl'):
             assert np.allclose(res.errs[fid, col], dbg['stageii_errs'][k], rtol=1e-8, atol=1e-12)
     n_velo = int(((res.status[fid] & lib.ST_HAS_VELO) != 0).sum())

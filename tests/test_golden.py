@@ -13,7 +13,7 @@ def _load(name):
     return np.load(os.path.join(GOLD, f'stageii_{name}.npz'))
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
 def test_fixture_generation_is_reproducible(cases, name):
     g = _load(name)
     case = cases(name)
@@ -31,7 +31,7 @@ def test_oracle_reproduces_golden(cases, name):
     assert out['stageii_debug_details']['oracle_stats']['j_evals'] == int(g['j_evals'])
 
 
-@pytest.mark.parametrize('name', ['C2', 'C3'])
+@pytest.mark.parametrize('name', ['C2', 'C3', 'CF'])
 def test_device_source_reproduces_golden(cases, emu, name):
     g = _load(name)
     res = emu(cases(name))
@@ -39,10 +39,13 @@ def test_device_source_reproduces_golden(cases, emu, name):
     assert np.abs(res.fullpose[fid] - g['fullpose']).max() < 1e-9
     if 'dmpls' in g.files:
         assert np.abs(res.dmpls[fid, :g['dmpls'].shape[1]] - g['dmpls']).max() < 1e-9
+    if 'expression' in g.files:
+        pk = cases(name)['pack']
+        assert np.abs(res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl] - g['expression'][:, :pk.n_expr]).max() < 1e-9
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
 def test_cuda_reproduces_golden(cases, name):
     g = _load(name)
     fid = g['frame_ids']

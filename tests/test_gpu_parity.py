@@ -8,7 +8,7 @@ from moshpp_b200 import lib
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
 def test_f64_kernel_equals_oracle(cases, name):
     case = cases(name)
     out = run_oracle(case)
@@ -21,8 +21,11 @@ def test_f64_kernel_equals_oracle(cases, name):
     assert np.abs(res.trans[fid] - out['trans']).max() < 1e-9
     if 'dmpls' in out:
         assert np.abs(res.dmpls[fid, :out['dmpls'].shape[1]] - out['dmpls']).max() < 1e-8
+    if 'expression' in out:
+        pk = case['pack']
+        assert np.abs(res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl] - out['expression'][:, :pk.n_expr]).max() < 1e-8
     assert res.counters[fid, 2].sum() == dbg['oracle_stats']['j_evals']
-    for k, col in zip(lib.ERR_NAMES, range(6)):
+    for k, col in zip(lib.ERR_NAMES, range(len(lib.ERR_NAMES))):
         if k in dbg['stageii_errs'] and k not in ('velo', 'extrap_dmpl'):
             assert np.allclose(res.errs[fid, col], dbg['stageii_errs'][k], rtol=1e-7, atol=1e-10)
     mk = np.concatenate(dbg['markers_sim'])
@@ -30,7 +33,7 @@ def test_f64_kernel_equals_oracle(cases, name):
     assert np.abs(res.markers_sim[fid][vis[fid]] - mk).max() < 1e-9
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
 def test_f32_kernel_within_stated_tolerance(cases, name):
     """Tolerances of BASELINE.md section 4 for the fp32 path (sequential mode)."""
     case = cases(name)
@@ -123,6 +126,31 @@ def test_drop_in_callable_matches_reference_layout(cases):
     assert all(a.shape == b.shape for a, b in zip(dbg['markers_sim'], rdbg['markers_sim']))
     assert np.abs(np.concatenate(dbg['markers_obs']) - np.concatenate(rdbg['markers_obs'])).max() == 0
     assert np.abs(out['trans'] - ref['trans']).max() < 1e-4
+
+
+def test_drop_in_callable_with_face_expressions(cases):
+    """optimize_face: jaw + expression coefficients; return layout of chmosh.py:723-724,736 and the
+    AMASS writer's `expression` key."""
+    from moshpp_b200 import amass_io
+    from moshpp_b200.chmosh import mosh_stageii
+    case = cases('CF')
+    out = mosh_stageii(mocap_fname=case['mocap_fname'], cfg=case['cfg'], markers_latent=case['markers_latent'],
+                       latent_labels=case['latent_labels'], betas=case['betas'], marker_meta=case['marker_meta'],
+                       precision='f64', chunk_len=0)
+    ref = run_oracle(case)
+    assert 'dmpls' not in out and out['expression'].shape == ref['expression'].shape
+    assert np.abs(out['expression'] - ref['expression']).max() < 1e-8
+    assert np.abs(out['fullpose'] - ref['fullpose']).max() < 1e-8
+    dbg, rdbg = out['stageii_debug_details'], ref['stageii_debug_details']
+    assert set(dbg['stageii_errs'].keys()) == set(rdbg['stageii_errs'].keys()) >= {'poseF', 'expr'}
+    for k in ('poseF', 'expr'):
+        assert np.allclose(dbg['stageii_errs'][k], rdbg['stageii_errs'][k], rtol=1e-7, atol=1e-10)
+    assert np.abs(out['fullpose'][:, 66:69]).max() > 1e-3          # the jaw moved
+    merged = amass_io.merge_stageii(out, dict(betas=case['betas'], markers_latent=case['markers_latent'],
+                                              latent_labels=case['latent_labels']), case['cfg'], 0.0)
+    npz = amass_io.load_as_amass_npz(merged)
+    assert npz['expression'].shape == (len(out['fullpose']), case['cfg'].surface_model.num_expressions)
+    assert npz['pose_jaw'].shape == (len(out['fullpose']), 3)
 
 
 def test_library_is_the_cuda_build():
