@@ -250,7 +250,8 @@ void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) 
     // oversized case moves the big arrays to a per-CTA global workspace
     const int tries[3][2] = {{20, 0}, {10, 0}, {10, 1}};   // markers per tile (a warp owns ten), big
     const char *dev_tile = getenv("MOSH2_DEV_TILE");      // development aid: 10 = skip the 20-marker tile
-    for (int pass = (dev_tile && atoi(dev_tile) == 10) ? 1 : 0; pass < 3; ++pass) {
+    const bool dev_big = getenv("MOSH2_DEV_BIG") != nullptr;   // development aid: force the global-workspace layout
+    for (int pass = dev_big ? 2 : ((dev_tile && atoi(dev_tile) == 10) ? 1 : 0); pass < 3; ++pass) {
         m.tile_markers = tries[pass][0];
         m.dev_no_tc = getenv("MOSH2_DEV_NO_TC") ? 1 : 0;      // development aid: J^T J on the CUDA cores
         const bool in_global = tries[pass][1] != 0;

@@ -153,6 +153,25 @@ def test_drop_in_callable_with_face_expressions(cases):
     assert npz['pose_jaw'].shape == (len(out['fullpose']), 3)
 
 
+@pytest.mark.parametrize('name', ['C2', 'CF'])
+def test_f32_global_workspace_layout_matches_shared_memory_layout(cases, name, monkeypatch):
+    """Models whose normal equations do not fit the shared memory (e.g. SMPL-X with 80 expression coefficients) run
+    with A, its factor and the Jacobian tiles in a per-block global workspace and J^T J on the CUDA cores; the same
+    small case through both layouts must agree to f32 round-off and stay inside the f32 tolerances."""
+    case = cases(name)
+    a = gpu_solve(case, precision='f32')
+    monkeypatch.setenv('MOSH2_DEV_BIG', '1')
+    b = gpu_solve(case, precision='f32')
+    monkeypatch.delenv('MOSH2_DEV_BIG')
+    out = run_oracle(case)
+    fid = out['stageii_debug_details']['frame_ids']
+    bd = min(case['pack'].body_dof, 66)
+    assert np.array_equal(a.status, b.status)
+    assert np.abs(b.pose[fid] - out['_pose_reduced'])[:, :bd].max() < 1e-3
+    assert np.abs(b.trans[fid] - out['trans']).max() < 1e-4
+    assert np.abs(a.pose - b.pose)[:, :bd].max() < 1e-3 and np.abs(a.trans - b.trans).max() < 1e-4
+
+
 def test_library_is_the_cuda_build():
     from moshpp_b200 import lib
     L = lib.load_library()
