@@ -114,6 +114,7 @@ struct DevModel {
         if ((rc = up<int>(d.fk_order, nJ, &m.fk_order))) return rc;
         if ((rc = up<int>(d.level_ofs, size_t(d.n_levels) + 1, &m.level_ofs))) return rc;
         if ((rc = up<int>(d.w_joint, S * d.kw, &m.w_joint))) return rc;
+        // (the ancestor tables of the ABI are uploaded for completeness; the kernel derives a subtree mask itself)
         if ((rc = up<int>(d.anc_joint, S * d.na, &m.anc_joint))) return rc;
         if ((rc = up<int>(d.anc_mask, S * d.na, &m.anc_mask))) return rc;
         if ((rc = up<int8_t>(d.anc_pos, S * nJ, &m.anc_pos))) return rc;
@@ -244,10 +245,8 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
 
 template <class real>
 void plan_workspace(mosh2::Model<real> &m, size_t *smem, size_t *gws, int *big) {
-    // largest Jacobian tile that still fits the shared-memory budget; the f64 / oversized case moves the
-    // big arrays to a per-CTA global workspace
-    // preference order: table staging and 16-marker tiles while they fit the shared-memory budget; the f64 /
-    // oversized case moves the big arrays to a per-CTA global workspace
+    // preference order: 20-marker tiles, then 10-marker tiles, while the workspace fits the shared-memory budget; the
+    // f64 / oversized case moves A, its factor and the Jacobian tiles to a per-CTA global workspace
     const int tries[3][2] = {{20, 0}, {10, 0}, {10, 1}};   // markers per tile (a warp owns ten), big
     const char *dev_tile = getenv("MOSH2_DEV_TILE");      // development aid: 10 = skip the 20-marker tile
     const bool dev_big = getenv("MOSH2_DEV_BIG") != nullptr;   // development aid: force the global-workspace layout

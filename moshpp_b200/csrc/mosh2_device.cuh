@@ -14,8 +14,10 @@
 //   Jacobian  d v / d w_{a,k} = u_{a,k} x sum_{j in subtree(a)} w_j (p_j - tg_a)            (rigid part)
 //                              + Rskin Pd_j dvec(R_j)/dw_k                                    (pose blend)
 //             with u_{a,k} = Rg_par(a) vee(dR_{a,k} R_a^T); hand columns chained through C^T.
-//   normal eq A = J^T J and g = -J^T r are accumulated marker tile by marker tile; the prior, velocity,
-//             finger and DMPL terms have closed-form contributions (Q_k = .5 inv(cov_k), diagonals).
+//   normal eq A = J^T J and g = -J^T r are accumulated marker tile by marker tile (f32: J^T J on the tensor cores,
+//             tcgen05 with the accumulator in tensor memory); the prior, velocity, finger, face and DMPL / expression
+//             terms have closed-form contributions (Q_k = .5 inv(cov_k), diagonals).
+//   The workspace layout (struct Work) is computed on the host and arrives as a kernel parameter of shared-memory offsets.
 #pragma once
 #include <math.h>
 #include <stdint.h>
