@@ -3,7 +3,7 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
 reference`` legs may import this package; the product (``moshpp_b200``) never does.
 
-PARITY UNPINNED.  The reference (nghorbani/moshpp @ 6599a2d) ships no tests, golden vectors or
+PARITY UNPINNED (except rigid.py, see below).  The reference (nghorbani/moshpp @ 6599a2d) ships no tests, golden vectors or
 fixtures for this path, and its arithmetic lives in third-party modules that
 are neither vendored nor installable here:
 
@@ -20,6 +20,10 @@ What pins the oracle instead: analytic Jacobians == torch.autog
 independently written float64 forward; cv2.Rodrigues value + Jacobian; scipy least_squares optimum
 cross-check; ground-truth recovery on noise-free synthetic data; committed golden vectors emitted
 by this oracle (tests/golden/, generator script tests/golden/make_golden.py).
+
+Pinned by the reference itself: ``moshpp/rigid_transformations.py`` needs only numpy / scipy / cv2 and imports here;
+``rigid.py`` is checked against vectors produced by that unmodified module (tests/golden/ref_rigid.npz, generator
+tests/golden/make_reference_vectors.py, test tests/test_reference_vectors.py).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/src/moshpp unless noted).
