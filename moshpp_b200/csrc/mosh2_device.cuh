@@ -331,6 +331,7 @@ struct Work {
     SPtr<int> c_parents, c_fk_order, c_level_ofs, c_wj, c_free1, c_free2;
     SPtr<int> c_tin, c_tsz;   // pre-order index and subtree size of every joint: j in subtree(a) <=> tin[j]-tin[a] in [0, tsz[a])
     SPtr<real> c_wv, c_v0, c_coefs, c_j0, c_hmean, c_pmeans, c_pnlw;
+    SPtr<real> c_jd;          // joint-position directions of the per-frame linear coefficients (DMPL, expressions)
     SPtr<long long> prof;
     SPtr<uint8_t> vis;
     SPtr<uint32_t> c_chain;   // [joint][4 words]: the joint's ancestor chain, root first, one byte per joint id, 255-padded
@@ -510,6 +511,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ); w.c_amask.ofs = S.take<uint8_t>(size_t(d.S) * d.nJ);
     w.c_chain.ofs = S.take<uint32_t>(size_t(d.nJ) * (kMaxDepth / 4));
     w.c_pmeans.ofs = S.take<real>(d.K * d.D + 1); w.c_pnlw.ofs = S.take<real>(d.K + 1);
+    w.c_jd.ofs = S.take<real>(size_t(3) * d.nJ * d.nd + 1);
 }
 
 // configuration of one minimisation (one ch.minimize call of the reference)
@@ -660,7 +662,7 @@ struct Solver {
         }
         CTA_FOR(i, 3 * d.nJ) {
             real v = w.c_j0[i];
-            for (int q = 0; q < d.nd; ++q) v += m.jd[i * d.nd + q] * dl[q];
+            for (int q = 0; q < d.nd; ++q) v += w.c_jd[i * d.nd + q] * dl[q];
             w.Jp[i] = v;
         }
         M2_SYNC();
@@ -751,12 +753,24 @@ struct Solver {
         CTA_FOR(s, d.S) {
             real vpo[3];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                real a = w.c_v0[3 * s + q];
-                for (int e = 0; e < d.nd; ++e) a += m.sd[(3 * s + q) * d.nd + e] * dl[e];
-                for (int g = 0; g < nbg; ++g) a += w.Jt[(g * d.S + s) * 3 + q];
-                vpo[q] = a;
+            for (int q = 0; q < 3; ++q) vpo[q] = w.c_v0[3 * s + q];
+            // linear directions (DMPL, expressions): blocks of eight coefficients with a fixed trip count, so that the
+            // 24 (L2) loads of a block issue back to back
+            for (int e0 = 0; e0 < d.nd; e0 += 8) {
+                real sv[24];
+#pragma unroll
+                for (int u = 0; u < 24; ++u) {
+                    const int q = u >> 3, e = e0 + (u & 7);
+                    sv[u] = e < d.nd ? m.sd[(3 * s + q) * d.nd + e] : real(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 24; ++u) {
+                    const int e = e0 + (u & 7);
+                    vpo[u >> 3] += sv[u] * (e < d.nd ? dl[e] : real(0));
+                }
             }
+            for (int q = 0; q < 3; ++q)
+                for (int g = 0; g < nbg; ++g) vpo[q] += w.Jt[(g * d.S + s) * 3 + q];
             real v[3] = {0, 0, 0};
             real Rs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int i = 0; i < d.kw; ++i) {
@@ -1031,10 +1045,10 @@ struct Solver {
                 CTA_FOR(q, cnt * d.nd) {
                     const int j = w.c_fk_order[lo + q / d.nd], i = q % d.nd, a = w.c_parents[j];
                     real *o = w.dtg + 3 * (j * d.nd + i);
-                    if (a < 0) { for (int r = 0; r < 3; ++r) o[r] = m.jd[(3 * j + r) * d.nd + i]; }
+                    if (a < 0) { for (int r = 0; r < 3; ++r) o[r] = w.c_jd[(3 * j + r) * d.nd + i]; }
                     else {
                         real dj[3], t[3];
-                        for (int r = 0; r < 3; ++r) dj[r] = m.jd[(3 * j + r) * d.nd + i] - m.jd[(3 * a + r) * d.nd + i];
+                        for (int r = 0; r < 3; ++r) dj[r] = w.c_jd[(3 * j + r) * d.nd + i] - w.c_jd[(3 * a + r) * d.nd + i];
                         mat3_vec(w.Rg + 9 * a, dj, t);
                         for (int r = 0; r < 3; ++r) o[r] = w.dtg[3 * (a * d.nd + i) + r] + t[r];
                     }
@@ -1167,6 +1181,9 @@ struct Solver {
             CTA_FOR(it, tm * d.nd) {
                 const int ml = it / d.nd, i = it - ml * d.nd, mi = t0 + ml;
                 real val[3] = {0, 0, 0};
+                real sdv[9];                              // the nine (L2) loads of the item, issued together
+#pragma unroll
+                for (int u = 0; u < 9; ++u) sdv[u] = m.sd[(9 * mi + u) * d.nd + i];
                 for (int t = 0; t < 3; ++t) {
                     const int s = 3 * mi + t;
                     real dv[3] = {0, 0, 0};
@@ -1175,7 +1192,7 @@ struct Solver {
                         if (j < 0) continue;
                         const real wt = w.c_wv[s * d.kw + kk];
                         real df[3], o[3];
-                        for (int r = 0; r < 3; ++r) df[r] = m.sd[(3 * s + r) * d.nd + i] - m.jd[(3 * j + r) * d.nd + i];
+                        for (int r = 0; r < 3; ++r) df[r] = sdv[3 * t + r] - w.c_jd[(3 * j + r) * d.nd + i];
                         mat3_vec(w.Rg + 9 * j, df, o);
                         for (int r = 0; r < 3; ++r) dv[r] += wt * (o[r] + w.dtg[3 * (j * d.nd + i) + r]);
                     }
@@ -1993,6 +2010,7 @@ struct Solver {
         CTA_FOR(i, 3 * d.M) w.c_coefs[i] = m.coefs[i];
         CTA_FOR(i, 3 * d.nJ) w.c_j0[i] = m.j0[i];
         CTA_FOR(i, m.n_hand_full) w.c_hmean[i] = m.hands_mean[i];
+        CTA_FOR(i, 3 * d.nJ * d.nd) w.c_jd[i] = m.jd[i];
         CTA_FOR(i, d.K * d.D) w.c_pmeans[i] = m.prior_means[i];
         CTA_FOR(i, d.K) w.c_pnlw[i] = m.prior_nlw[i];
         CTA_FOR(i, 32) w.prof[i] = 0;
