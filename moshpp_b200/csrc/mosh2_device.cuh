@@ -1039,21 +1039,27 @@ struct Solver {
         if (!w.tc) CTA_FOR(i, n * ld) w.A[i] = 0;      // (tensor-core mode: A's storage holds the operand tiles for now)
         CTA_FOR(i, n) w.g[i] = 0;
         if (d.nd) {
-            // d tg_j / d delta_i = d tg_par + Rg_par (Jd_j - Jd_par)
-            for (int lv = 0; lv < m.n_levels; ++lv) {
-                const int lo = w.c_level_ofs[lv], cnt = w.c_level_ofs[lv + 1] - lo;
-                CTA_FOR(q, cnt * d.nd) {
-                    const int j = w.c_fk_order[lo + q / d.nd], i = q % d.nd, a = w.c_parents[j];
-                    real *o = w.dtg + 3 * (j * d.nd + i);
-                    if (a < 0) { for (int r = 0; r < 3; ++r) o[r] = w.c_jd[(3 * j + r) * d.nd + i]; }
-                    else {
-                        real dj[3], t[3];
-                        for (int r = 0; r < 3; ++r) dj[r] = w.c_jd[(3 * j + r) * d.nd + i] - w.c_jd[(3 * a + r) * d.nd + i];
-                        mat3_vec(w.Rg + 9 * a, dj, t);
-                        for (int r = 0; r < 3; ++r) o[r] = w.dtg[3 * (a * d.nd + i) + r] + t[r];
-                    }
+            // d tg_j / d delta_i = d tg_par + Rg_par (Jd_j - Jd_par): every (joint, coefficient) item sums down the joint's own
+            // ancestor chain (root first, the order of the level-wise recursion), so there is no barrier per tree level
+            CTA_FOR(q, d.nJ * d.nd) {
+                const int j = q / d.nd, i = q - j * d.nd;
+                uint32_t cw[kMaxDepth / 4];
+#pragma unroll
+                for (int u = 0; u < kMaxDepth / 4; ++u) cw[u] = w.c_chain[j * (kMaxDepth / 4) + u];
+                int prev = int(cw[0] & 255u);
+                real acc[3];
+                for (int r = 0; r < 3; ++r) acc[r] = w.c_jd[(3 * prev + r) * d.nd + i];
+                for (int k = 1; k < kMaxDepth; ++k) {
+                    const int cj = int((cw[k >> 2] >> (8 * (k & 3))) & 255u);
+                    if (cj == 255) break;
+                    real dj[3], t[3];
+                    for (int r = 0; r < 3; ++r) dj[r] = w.c_jd[(3 * cj + r) * d.nd + i] - w.c_jd[(3 * prev + r) * d.nd + i];
+                    mat3_vec(w.Rg + 9 * prev, dj, t);
+                    for (int r = 0; r < 3; ++r) acc[r] = acc[r] + t[r];
+                    prev = cj;
                 }
-                M2_SYNC();
+                real *o = w.dtg + 3 * (j * d.nd + i);
+                for (int r = 0; r < 3; ++r) o[r] = acc[r];
             }
         }
         M2_SYNC();
