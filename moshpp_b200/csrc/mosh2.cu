@@ -207,14 +207,16 @@ struct mosh2_job {
 namespace {
 
 template <class real, bool BIG>
-void launch_kernel(mosh2_job *j, const mosh2::Model<real> &m, const mosh2::Job<real> &job, int threads) {
+cudaError_t launch_kernel(mosh2_job *j, const mosh2::Model<real> &m, const mosh2::Job<real> &job, int threads) {
     const mosh2::Dims d = mosh2::make_dims(m);
     mosh2::Work<real, BIG> w{};
     mosh2::Arena S{mosh2::kSmemHeader}, G{0};
     mosh2::carve<real, BIG>(w, d, m, S, G);
     w.tc = (w.tc_ok && threads >= 128) ? 1 : 0;
-    cudaFuncSetAttribute(mosh2_stageii_kernel<real, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem));
+    const cudaError_t e = cudaFuncSetAttribute(mosh2_stageii_kernel<real, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem));
+    if (e != cudaSuccess) return e;
     mosh2_stageii_kernel<real, BIG><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job, w, d);
+    return cudaGetLastError();
 }
 
 template <class real>
@@ -236,8 +238,8 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
         if (t >= 128 && t <= threads && t % 32 == 0) threads = t;
     }
     CU(cudaEventRecord(j->ev0, j->stream));
-    if (j->big_in_global) launch_kernel<real, true>(j, m, job, threads);
-    else launch_kernel<real, false>(j, m, job, threads);
+    if (j->big_in_global) CU((launch_kernel<real, true>(j, m, job, threads)));
+    else CU((launch_kernel<real, false>(j, m, job, threads)));
     CU(cudaGetLastError());
     CU(cudaEventRecord(j->ev1, j->stream));
     return 0;
