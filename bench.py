@@ -4,14 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
 
-Workload at N=1: BASELINE.json configs[1] -- SMPL-H (V=6890, 52 joints), one 500-frame synthetic
-sequence, 53 markers, fingers on (111 free variables in Step 2).  A "step" is one pass of the hot path
-over that sequence: every frame solved by the reference's schedule (Procrustes + 3 dog-legs on the first
-frame of a chunk, Step 1 + Step 2 dog-legs on every frame).  At N>1 every rank solves its own sequence of
-the same shape (weak scaling, no data-path collective); NCCL is used for the barrier, the
-max-over-ranks of the device time and the result gather of the e2e leg.
+N = 1   workload = the configuration BASELINE.json's north star quotes its target on: ONE 4000-frame SMPL-H sequence
+        (V = 6890, 52 joints, 53 markers, fingers on: 111 free variables in Step 2).  A step = one pass of the hot path
+        over that sequence: every frame solved by the reference's schedule (Procrustes + 3 dog-legs on a cold start,
+        Step 1 + Step 2 dog-legs on every frame).  ``value`` = frames / device time of the kernel (CUDA events on the
+        launching stream, inputs resident, L2 flushed between steps).  ``e2e`` = the same through the reference-facing
+        plug-in call ``chmosh.mosh_stageii(mocap_fname, cfg, ...)`` by wall clock: file read, per-subject packing,
+        model upload, pinned H2D, kernel, D2H, result dictionary.  BASELINE configs[1] (500 frames) rides along as
+        ``secondary``, the 32-sequence configs[4] on one GPU as ``c5_one_gpu`` (the strong-scaling base of N > 1).
+N > 1   workload = BASELINE configs[4]: 32 SMPL-H sequences x 4000 frames, sharded over the N GPUs (strong scaling on
+        the fixed workload): rank 0 owns all observations, NCCL scatter (grouped send/recv), per-rank solves (device
+        pointers in and out of the C-ABI), NCCL gather of the result rows to rank 0.  ``value`` = 128000 frames / max
+        over ranks of the device time of the rank's solves; ``e2e`` = pinned host buffers on rank 0 -> host results on
+        rank 0 by wall clock, scatter and gather inside.
 
-JSON keys follow the driver contract; see DESIGN.md section 7 for how each number is obtained.
+JSON keys follow the driver contract; DESIGN.md section 7 says how each number is obtained.
 """
 from __future__ import annotations
 
@@ -31,7 +38,9 @@ if ROOT not in sys.path:
 
 METRIC = 'mocap frames solved/sec (Stage-II)'
 UNIT = 'frames/s'
-WORKLOAD = 'C2'
+NS_DESC = 'north-star target: one 4000-frame SMPL-H sequence, 53 markers, Stage II, 1 GPU'
+C5_DESC = 'BASELINE configs[4]: 32 SMPL-H sequences x 4000 frames, 53 markers, sharded over the GPUs (NCCL scatter / gather)'
+C5_SEQUENCES = 32
 
 
 def algorithmic_bytes(pk, has_velo=True, fingers=True):
@@ -50,7 +59,7 @@ class ClockSampler:
 
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+         'clocks_event_reasons.sw_power_cap,utilization.gpu')
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -78,37 +87,27 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        num = lambda s: s.replace('.', '').isdigit()
+        busy = [r for r in self.rows if len(r) > 7 and num(r[7]) and float(r[7]) > 0] or self.rows
+        sm = sorted(float(r[0]) for r in busy if num(r[0]))
         reasons = []
         for name, col in (('hw_slowdown', 3), ('hw_thermal_slowdown', 4), ('sw_thermal_slowdown', 5), ('sw_power_cap', 6)):
             if any(len(r) > col and r[col].lower().startswith('active') for r in self.rows):
                 reasons.append(name)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if self.rows[0][1].replace('.', '').isdigit() else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if num(self.rows[0][1]) else None,
+                'reasons': reasons, 'samples': len(self.rows), 'samples_under_load': len(busy)}
 
 
-def make_workload(rank: int, frames: int | None = None):
-    from moshpp_b200 import chmosh, synth
+def make_case(config: str, seq_idx: int, frames=None, tag=''):
+    from moshpp_b200 import synth
+    d = tempfile.mkdtemp(prefix=f'mosh_bench_{tag}')
+    return synth.make_case(d, config, frames=frames, seq_idx=seq_idx)
+
+
+def dense(case):
     from moshpp_b200.mocap_interface import MocapSession
-    d = tempfile.mkdtemp(prefix=f'mosh_bench_r{rank}_')
-    case = synth.make_case(d, WORKLOAD, frames=frames, seq_idx=rank)
-    pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'],
-                                             case['betas'], case['marker_meta'])
     mocap = MocapSession(case['mocap_fname'], case['cfg'].mocap.unit)
-    obs, vis = mocap.frames_for_labels(case['latent_labels'], range(len(mocap)))
-    return case, pk, opts, obs, vis
-
-
-def cpu_reference_fps(case, n_frames: int):
-    """The reference's CPU algorithm (float64 oracle in reference-cost mode: full mesh + dense 3V x P
-    Jacobian every evaluation, frame-serial) on the first n_frames frames of the workload."""
-    from oracle import stageii
-    t0 = time.time()
-    out = stageii.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'],
-                               case['betas'], case['marker_meta'], mode='reference_cost', max_frames=n_frames)
-    dt = time.time() - t0
-    st = out['stageii_debug_details']['oracle_stats']
-    return st['frames'] / st['elapsed'], st, dt
+    return mocap.frames_for_labels(case['latent_labels'], range(len(mocap)))
 
 
 def blas_threads():
@@ -119,10 +118,28 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path is not runnable here
-    (chumpy / psbody.smpl absent); the oracle port in reference-cost mode is timed on the
-    host cores, a bounded sample of the workload per step."""
+def cpu_reference_frames(case, n_frames: int):
+    """The reference's CPU algorithm (float64 oracle in reference-cost mode: full mesh + dense 3V x P Jacobian on every
+    evaluation, frame-serial, numpy / BLAS on all host cores) over the first n_frames frames of the workload.
+    Returns the wall-clock stamp after every solved frame (seconds from the start of the frame loop)."""
+    from oracle import stageii
+    stamps = []
+    t0 = [None]
+
+    def on_frame(fi):
+        stamps.append(time.perf_counter())
+
+    t_start = time.perf_counter()
+    stageii.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'],
+                         case['betas'], case['marker_meta'], mode='reference_cost', max_frames=n_frames, on_frame=on_frame)
+    return np.array(stamps), t_start
+
+
+def run_reference(args, rank):
+    """--impl reference: chumpy / psbody.smpl are absent, so the reference's own CPU implementation of
+    the path is the oracle port in reference-cost mode.  ONE frame-serial solve of the first (W + K) * n frames of the
+    same workload as the CUDA arm; step s = frames [s n, (s+1) n).  The cold-start frame (Procrustes + five
+    minimisations) therefore lies in the warm-up steps and the timed steps are steady-state frames."""
     if rank != 0:
         return
     try:        # torchrun pins OMP_NUM_THREADS=1; the reference arm may use every host core
@@ -130,28 +147,69 @@ def run_reference(args, rank, world):
         threadpool_limits(limits=os.cpu_count())
     except Exception:
         pass
-    case, pk, opts, obs, vis = make_workload(0)
-    n = args.cpu_frames
-    vals = []
-    for s in range(args.warmup + args.steps):
-        fps, st, dt = cpu_reference_fps(case, n)
-        if s >= args.warmup:
-            vals.append((fps, dt))
-    fps = float(np.mean([v[0] for v in vals]))
-    ms = float(np.mean([v[1] for v in vals])) * 1e3
+    n_steps = args.warmup + args.steps
+    per = max(1, int(round(args.cpu_frames / n_steps)))
+    case = make_case('C5', 0, tag='ref_')
+    stamps, t_start = cpu_reference_frames(case, n_steps * per)
+    edges = np.concatenate([[t_start], stamps])[::per]           # step boundaries
+    step_s = np.diff(edges)[args.warmup:args.warmup + args.steps]
+    fps = per * len(step_s) / float(step_s.sum())
+    cold = float(stamps[0] - t_start)
+    workload = NS_DESC if args.gpus == 1 else C5_DESC
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': args.warmup, 'ms_per_step': float(step_s.mean()) * 1e3, 'higher_is_better': True,
+        'scaling': 'weak' if args.gpus == 1 else 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic (seeded procedural SMPL-H model, markers, motion)',
-        'config': {'workload': 'BASELINE configs[1]: SMPL-H 500-frame sequence, 53 markers, Stage II', 'frames': 500,
-                   'markers': pk.n_markers, 'free_vars': len(pk.free_step2)},
+        'config': {'workload': workload, 'frames': 4000, 'markers': 53, 'free_vars': 111,
+                   'frames_per_step': per, 'frames_solved': int(n_steps * per)},
         'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
-                         'sample': f'first {n} frames of the 500-frame workload per step, frame-serial, reference-cost mode '
-                                   '(full 6890-vertex mesh and dense 20670x156 Jacobian per evaluation); restated reference, not chumpy'},
+                         'sample': f'frames {args.warmup * per}..{n_steps * per - 1} of the 4000-frame sequence (one frame-serial '
+                                   f'solve, {per} frames per step; the cold-start frame, {cold:.1f} s, lies in the warm-up steps), '
+                                   'reference-cost mode: full 6890-vertex mesh and dense 20670x156 Jacobian per evaluation; '
+                                   'restated reference, not chumpy',
+                         'cold_start_frame_s': cold},
         'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def load_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the Stage-II kernel from this round's
+    `ncu --set full` capture of the same workload (profiles/traffic.json), or None."""
+    tfile = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        t = json.load(open(tfile))
+        e = t.get(key)
+        if isinstance(e, dict):
+            return e.get('dram_bytes_per_launch'), e.get('source')
+    except Exception:
+        pass
+    return None, None
+
+
+def roofline(ab, builds, useful_builds, ms, traffic_key):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    per_unit = ab['B_K1'] + ab['B_K2']
+    achieved = per_unit * builds / (ms * 1e-3) / 1e9
+    useful = per_unit * useful_builds / (ms * 1e-3) / 1e9
+    traffic, src = load_traffic(traffic_key)
+    return {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+            'traffic': traffic, 'traffic_source': src,
+            'achieved_useful': useful, 'frac_useful': useful / peak,
+            'bytes_per_frame_iteration': per_unit, 'frame_iterations_per_launch': builds,
+            'useful_frame_iterations_per_launch': useful_builds,
+            'note': 'achieved = (B_K1+B_K2) x frame-iterations executed / kernel time (SURVEY 8(d) effective-bandwidth '
+                    'definition of the J-materialising formulation); *_useful counts only the iterations of the emitted '
+                    'frames (what the sequential solve needs), i.e. without the warm-up of the time-parallel chunks. The '
+                    'fused kernel keeps J on chip: its DRAM traffic is `traffic`. peak: '
+                    + ('measured copy bandwidth (MEASURED_PEAKS.json)' if peaks else 'fallback 6650 GB/s')}
 
 
 def main():
@@ -162,9 +220,13 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--chunk-len', type=int, default=None)
     ap.add_argument('--chunk-warmup', type=int, default=None)
+    ap.add_argument('--warmup-full', type=int, default=None)
     ap.add_argument('--precision', default='f32', choices=['f32', 'f64'])
-    ap.add_argument('--cpu-frames', type=int, default=5, help='frames of the CPU baseline sample')
+    ap.add_argument('--cpu-frames', type=int, default=50, help='frames of the reference arm (all steps together)')
+    ap.add_argument('--cpu-baseline-frames', type=int, default=10, help='frames of the cpu_baseline sample of the CUDA arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='N=1: skip the C2 and C5-on-one-GPU legs')
+    ap.add_argument('--sequences', type=int, default=C5_SEQUENCES, help='N>1: number of 4000-frame sequences')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -173,143 +235,340 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
 
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
-    import torch.distributed as dist
-    from moshpp_b200 import chmosh, lib
+    from moshpp_b200 import chmosh
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a B200: the Stage-II path has no CPU fallback')
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    case, pk, opts, obs, vis = make_workload(rank)
-    F = obs.shape[0]
-    chunk_len = args.chunk_len if args.chunk_len is not None else chmosh.auto_chunk_len(F)
     if args.chunk_warmup is None:
         args.chunk_warmup = chmosh.DEFAULT_WARMUP
+    if args.warmup_full is None:
+        args.warmup_full = chmosh.DEFAULT_WARMUP_FULL
+    if world > 1:
+        run_sharded(args, rank, local_rank, world)
+    else:
+        run_single(args)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N = 1
+# ------------------------------------------------------------------------------------------------------------------
+def time_job(model, pk, opts, obs, vis, args, chunk_len, flush, steps, warmup):
+    """Device time of `steps` launches of one resident job (CUDA events on the job's stream)."""
+    from moshpp_b200 import lib
     prec = {'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[args.precision]
-    model = lib.Model(pk, device=local_rank)
-    job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=args.chunk_warmup, precision=prec)
+    F = obs.shape[0]
+    job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full, precision=prec)
     job.upload(obs, vis)
     job.sync()
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f'cuda:{local_rank}')   # > 126 MB L2
+    for _ in range(warmup):
+        flush()
+        job.launch()
+        job.sync()
+    ms = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        flush()                         # outside the CUDA-event bracket of the step
+        job.launch()
+        job.sync()
+        ms.append(job.kernel_ms())
+    wall = time.perf_counter() - t0
+    totals = job.totals()
+    # C-ABI job-level end to end: pinned H2D + kernel + D2H of all result arrays
+    e2e = []
+    for i in range(2 + steps):
+        t1 = time.perf_counter()
+        job.upload(obs, vis)
+        job.launch()
+        res = job.download()
+        if i >= 2:
+            e2e.append(time.perf_counter() - t1)
+    solved = int(((res.status & lib.ST_SOLVED) != 0).sum())
+    out = dict(ms=float(np.mean(ms)), e2e_job_ms=float(np.mean(e2e)) * 1e3, totals=totals, chunks=job.num_chunks, solved=solved,
+               wall=wall, flags=int(np.bitwise_or.reduce(res.status)))
+    job.close()
+    return out
 
-    def flush_l2():
+
+def time_plugin(case, args, steps, warmup, chunk_len=None):
+    """Wall clock of the reference-facing call chmosh.mosh_stageii (what MoSh.mosh_stageii invokes), per call."""
+    from moshpp_b200 import chmosh
+    ts = []
+    out = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = chmosh.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'],
+                                  case['marker_meta'], chunk_len=chunk_len, chunk_warmup=args.chunk_warmup,
+                                  warmup_full=args.warmup_full, precision=args.precision)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)) * 1e3, out
+
+
+def run_single(args):
+    import torch
+    from moshpp_b200 import chmosh, lib, shard
+
+    dev = 0
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f'cuda:{dev}')   # > 126 MB L2
+
+    def flush():
+        flush_buf.add_(1)
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    esz = 4 if args.precision == 'f32' else 8
+
+    # ---- headline: one 4000-frame SMPL-H sequence
+    case = make_case('C5', 0, tag='ns_')
+    pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
+    obs, vis = dense(case)
+    F = obs.shape[0]
+    chunk_len = args.chunk_len if args.chunk_len is not None else chmosh.auto_chunk_len(F)
+    model = lib.Model(pk, device=dev)
+    ns = time_job(model, pk, opts, obs, vis, args, chunk_len, flush, args.steps, args.warmup)
+    e2e_ms, out = time_plugin(case, args, args.steps, 2, chunk_len=args.chunk_len)
+    b = out['stageii_debug_details']['b200']
+    h2d = obs.size * esz + vis.size
+    d2h = F * (pk.p_full + pk.p_red + 3 + pk.n_dmpl + 3 * pk.n_markers + 8) * esz + F * 5 * 4
+    ab = algorithmic_bytes(pk)
+    line = {
+        'metric': METRIC, 'value': F / (ns['ms'] * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ns['ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision,
+        'data': 'synthetic (seeded procedural SMPL-H model, markers, motion)',
+        'config': {'workload': NS_DESC, 'frames': F, 'markers': pk.n_markers, 'free_vars': ab['n'], 'residual_rows': ab['R'],
+                   'chunk_len': chunk_len, 'chunk_warmup': args.chunk_warmup, 'warmup_full': args.warmup_full,
+                   'chunks': ns['chunks'], 'l2': 'flushed between timed steps (256 MiB write)', 'frames_solved': ns['solved'],
+                   'frame_iterations_per_step': ns['totals']['builds'],
+                   'useful_frame_iterations': ns['totals']['emitted_builds'],
+                   'executed_over_useful': ns['totals']['builds'] / max(1, ns['totals']['emitted_builds']),
+                   'residual_evals_per_step': ns['totals']['evaluations'], 'status_flags_or': ns['flags']},
+        'roofline': roofline(ab, ns['totals']['builds'], ns['totals']['emitted_builds'], ns['ms'], 'NS'),
+        'e2e': {'value': F / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step': e2e_ms,
+                'what': 'wall clock of chmosh.mosh_stageii(mocap_fname, cfg, ...) per call: mocap file read, per-subject '
+                        'packing (prepare_stageii), model upload, job create, pinned H2D, kernel, D2H, result dictionary',
+                'kernel_ms_inside': b['kernel_ms'],
+                'c_abi_job_level': {'value': F / (ns['e2e_job_ms'] * 1e-3), 'ms_per_step': ns['e2e_job_ms'],
+                                    'what': 'mosh2_job_upload + launch + download with host buffers (resident model and job)'}},
+        'gpu_launches': args.steps,
+        'wall_s_timed_region': ns['wall'],
+    }
+    model.close()
+
+    if not args.no_secondary:
+        ksteps = min(args.steps, 5)
+        # ---- BASELINE configs[1]: 500 frames
+        c2 = make_case('C2', 0, tag='c2_')
+        pk2, opts2, _ = chmosh.prepare_stageii(c2['cfg'], c2['markers_latent'], c2['latent_labels'], c2['betas'], c2['marker_meta'])
+        o2, v2 = dense(c2)
+        m2 = lib.Model(pk2, device=dev)
+        r2 = time_job(m2, pk2, opts2, o2, v2, args, chmosh.auto_chunk_len(o2.shape[0]), flush, ksteps, 3)
+        m2.close()
+        e2, _ = time_plugin(c2, args, ksteps, 2)
+        line['secondary'] = {
+            'workload': 'BASELINE configs[1]: SMPL-H 500-frame sequence, 53 markers', 'value': o2.shape[0] / (r2['ms'] * 1e-3),
+            'ms_per_step': r2['ms'], 'e2e_value': o2.shape[0] / (e2 * 1e-3), 'e2e_ms_per_step': e2, 'chunks': r2['chunks'],
+            'frame_iterations_per_step': r2['totals']['builds'], 'useful_frame_iterations': r2['totals']['emitted_builds'],
+            'steps': ksteps}
+        # ---- BASELINE configs[4] on ONE GPU (the base of the strong-scaling run at N > 1)
+        line['c5_one_gpu'] = c5_local(args, dev, ksteps, flush)
+
+    sampler.stop()
+    line['clocks'] = sampler.summary()
+    if not args.no_cpu_baseline:
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
+        n = max(2, args.cpu_baseline_frames)
+        stamps, t_start = cpu_reference_frames(case, n)
+        steady = (n - 1) / float(stamps[-1] - stamps[0])
+        line['cpu_baseline'] = {
+            'value': steady, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+            'sample': f'frames 1..{n - 1} of the same 4000-frame workload (steady state; frame 0, the cold start with five '
+                      f'minimisations, took {stamps[0] - t_start:.1f} s and is reported apart), frame-serial float64 oracle in '
+                      'reference-cost mode (full mesh + dense Jacobian per evaluation); restated reference, not chumpy',
+            'value_incl_cold_start': n / float(stamps[-1] - t_start)}
+    print(json.dumps(line), flush=True)
+
+
+def c5_inputs(n_seq, pin=True):
+    """Observations of n_seq 4000-frame sequences (same subject, model and marker layout; different motion, noise and
+    drop-outs per sequence) as float32 / uint8 host tensors."""
+    import torch
+    from moshpp_b200 import chmosh, synth
+    d = tempfile.mkdtemp(prefix='mosh_bench_c5_')
+    first = synth.make_case(d, 'C5', seq_idx=0)
+    pk, opts, _ = chmosh.prepare_stageii(first['cfg'], first['markers_latent'], first['latent_labels'], first['betas'], first['marker_meta'])
+    obs_list, vis_list = [], []
+    F = first['obs'].shape[0]
+    for i in range(n_seq):
+        # one subject (betas, markers_latent) across all sequences: new motion / noise / drop-outs per sequence
+        pose, trans, dm = synth.make_motion(pk, F, seed=synth.SEED_MOTION + 4 + 1000 * i)
+        mk = synth.forward_markers(pk, pose, trans, None)
+        nrng = np.random.default_rng(synth.SEED_NOISE + i)
+        o = mk + nrng.normal(0.0, 1e-3, mk.shape)
+        drng = np.random.default_rng(synth.SEED_DROPOUT + i)
+        v = np.ones((F, pk.n_markers), dtype=bool)
+        for m in range(pk.n_markers):
+            missing = 0
+            while missing < 0.03 * F:
+                L = int(drng.integers(5, 51))
+                s = int(drng.integers(0, F - 1))
+                v[s:s + L, m] = False
+                missing += L
+        o[~v] = 0.0
+        ot, vt = torch.from_numpy(o.astype(np.float32)), torch.from_numpy(v.astype(np.uint8))
+        obs_list.append(ot.pin_memory() if pin else ot)
+        vis_list.append(vt.pin_memory() if pin else vt)
+    return pk, opts, obs_list, vis_list
+
+
+def c5_local(args, dev, steps, flush):
+    """All 32 sequences on one GPU (no scatter): the N = 1 point of the strong-scaling series."""
+    import torch
+    from moshpp_b200 import shard
+    pk, opts, obs_list, vis_list = c5_inputs(args.sequences)
+    F = [int(o.shape[0]) for o in obs_list]
+    solver = shard.GpuRankSolver({i: pk for i in range(len(F))}, opts, dict(enumerate(F)), dev,
+                                 chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full)
+    resident = {i: (obs_list[i].cuda(dev), vis_list[i].cuda(dev)) for i in range(len(F))}
+    torch.cuda.synchronize()
+    ms, e2e = [], []
+    for s in range(2 + steps):
+        flush()
+        solver(resident)
+        if s >= 2:
+            ms.append(solver.span_ms())
+    for s in range(1 + steps):
+        t0 = time.perf_counter()
+        mine = {i: (obs_list[i].cuda(dev, non_blocking=True), vis_list[i].cuda(dev, non_blocking=True)) for i in range(len(F))}
+        rows = solver(mine)
+        host = {i: r.cpu() for i, r in rows.items()}
+        if s >= 1:
+            e2e.append(time.perf_counter() - t0)
+    tot = solver.totals()
+    out = {'workload': C5_DESC + ' -- all on one GPU', 'value': sum(F) / (np.mean(ms) * 1e-3), 'ms_per_step': float(np.mean(ms)),
+           'e2e_value': sum(F) / float(np.mean(e2e)), 'e2e_ms_per_step': float(np.mean(e2e)) * 1e3,
+           'chunk_len': solver.jobs[0].schedule.chunk_len, 'frame_iterations_per_step': tot['builds'],
+           'useful_frame_iterations': tot['emitted_builds'], 'steps': steps, 'sequences': len(F)}
+    solver.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N > 1: BASELINE configs[4], strong scaling
+# ------------------------------------------------------------------------------------------------------------------
+def run_sharded(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from moshpp_b200 import shard
+
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dev = torch.device('cuda', local_rank)
+    dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        t = torch.tensor([float(x)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_seq = args.sequences
+    # every rank builds the (small) subject constants itself; only rank 0 owns observations
+    if rank == 0:
+        pk, opts, obs_list, vis_list = c5_inputs(n_seq)
+    else:
+        pk, opts, _, _ = c5_inputs(0)
+        obs_list = vis_list = None
+    F = [4000] * n_seq
+    assignment = shard.assign_sequences(F, world)
+    mine_ids = assignment[rank]
+    solver = shard.GpuRankSolver({i: pk for i in mine_ids}, opts, {i: F[i] for i in mine_ids}, local_rank,
+                                 chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full)
+    width = solver.jobs[mine_ids[0]].row_width
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush():
         flush_buf.add_(1)
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    shapes = [(f, pk.n_markers) for f in F]
+    # ---- device-timed leg: this rank's sequences resident on its GPU
+    resident = shard.scatter_observations(obs_list, vis_list, assignment, shapes)
     for _ in range(args.warmup):
-        flush_l2()
-        job.launch()
-        job.sync()
-
+        flush()
+        solver(resident)
     barrier()
     t_wall0 = time.perf_counter()
     dev_ms = []
     for _ in range(args.steps):
-        flush_l2()                      # outside the CUDA-event bracket of the step
-        job.launch()
-        job.sync()
-        dev_ms.append(job.kernel_ms())  # CUDA events on the launching stream
+        flush()
+        solver(resident)
+        dev_ms.append(solver.span_ms())      # CUDA events on the jobs' streams: first start -> last end on this rank
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    totals = job.totals()
-    res = job.download()
-    ms_step = float(np.mean(dev_ms))
-    if world > 1:
-        t = torch.tensor([ms_step], device=f'cuda:{local_rank}')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step_max = float(t.item())
-    else:
-        ms_step_max = ms_step
-
-    # ---- e2e: host buffers in, host results out, through the C-ABI job calls (H2D + kernel + D2H)
-    h2d = obs.size * (4 if prec == lib.MOSH2_F32 else 8) + vis.size
-    esz = 4 if prec == lib.MOSH2_F32 else 8
-    d2h = F * (pk.p_full + pk.p_red + 3 + pk.n_dmpl + 3 * pk.n_markers + 6) * esz + F * 5 * 4
-    for _ in range(2):
-        job.upload(obs, vis); job.launch(); job.download()
-    barrier()
-    e2e_t = []
-    for _ in range(args.steps):
+    ms_step = allmax(np.mean(dev_ms))
+    tot = solver.totals()
+    tt = torch.tensor([tot['builds'], tot['emitted_builds'], tot['evaluations']], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt)
+    # ---- e2e: pinned host buffers on rank 0 -> scatter -> solve -> gather -> host results on rank 0
+    e2e = []
+    for s in range(2 + args.steps):
+        barrier()
         t0 = time.perf_counter()
-        job.upload(obs, vis)
-        job.launch()
-        res = job.download()            # includes the stream sync
-        e2e_t.append(time.perf_counter() - t0)
-    barrier()
-    e2e_ms = float(np.mean(e2e_t)) * 1e3
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=f'cuda:{local_rank}')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        # result gather of the sharded job (NCCL): every rank's reduced poses to rank 0
-        mine = torch.from_numpy(res.pose.astype(np.float32)).to(f'cuda:{local_rank}')
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
+        out, _ = shard.solve_sharded(F, [pk.n_markers] * n_seq, [width] * n_seq, solver, obs_list, vis_list)
+        host = {i: r.cpu() for i, r in out.items()}          # rank 0: D2H of every sequence's rows
+        torch.cuda.synchronize()
+        dt = allmax(time.perf_counter() - t0)
+        if s >= 2:
+            e2e.append(dt)
     sampler.stop()
-
-    solved = int(((res.status & lib.ST_SOLVED) != 0).sum())
-    ab = algorithmic_bytes(pk)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    achieved = (ab['B_K1'] + ab['B_K2']) * totals['builds'] / (ms_step * 1e-3) / 1e9
-    traffic = None
-    tfile = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tfile):
-        try:
-            traffic = json.load(open(tfile)).get('dram_bytes_per_launch')
-        except Exception:
-            traffic = None
-
-    line = {
-        'metric': METRIC, 'value': world * F / (ms_step_max * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_step_max, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic (seeded procedural SMPL-H model, markers, motion)',
-        'config': {'workload': 'BASELINE configs[1]: SMPL-H 500-frame sequence, 53 markers, Stage II; one sequence per GPU',
-                   'frames': F, 'markers': pk.n_markers, 'free_vars': ab['n'], 'residual_rows': ab['R'],
-                   'chunk_len': chunk_len, 'chunk_warmup': args.chunk_warmup, 'chunks': job.num_chunks,
-                   'l2': 'flushed between timed steps (256 MiB write)', 'frames_solved': solved,
-                   'frame_iterations_per_step': totals['builds'], 'residual_evals_per_step': totals['evaluations']},
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic,
-                     'note': 'achieved = (B_K1+B_K2) x frame-iterations / kernel time, SURVEY 8(d) effective-bandwidth '
-                             'definition; the fused kernel keeps J on chip, so DRAM traffic is far below it. peak: '
-                             + ('measured (MEASURED_PEAKS.json)' if peaks else 'fallback 6650 GB/s')},
-        'e2e': {'value': world * F / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': e2e_ms},
-        'gpu_launches': args.steps,
-        'clocks': sampler.summary(),
-        'wall_s_timed_region': t_wall,
-    }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, st, dt = cpu_reference_fps(case, args.cpu_frames)
-        line['cpu_baseline'] = {
-            'value': fps, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
-            'sample': f'first {args.cpu_frames} frames of the same 500-frame workload, frame-serial float64 oracle in '
-                      f'reference-cost mode (full mesh + dense Jacobian per evaluation), {dt:.1f} s; restated reference, not chumpy'}
+    e2e_ms = float(np.mean(e2e)) * 1e3
+    total_frames = sum(F)
     if rank == 0:
+        solved = sum(int(((r[:, 3 * pk.n_joints + 3 + pk.n_dmpl + 8].numpy().astype(np.int64) & 1) != 0).sum()) for r in host.values())
+        ab = algorithmic_bytes(pk)
+        h2d = sum(int(o.numel()) * 4 + int(v.numel()) for o, v in zip(obs_list, vis_list))
+        d2h = total_frames * width * 4
+        builds, useful = int(tt[0].item()), int(tt[1].item())
+        line = {
+            'metric': METRIC, 'value': total_frames / (ms_step * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': args.precision, 'data': 'synthetic (seeded procedural SMPL-H model, markers, motion)',
+            'config': {'workload': C5_DESC, 'sequences': n_seq, 'frames': total_frames, 'markers': pk.n_markers,
+                       'free_vars': ab['n'], 'residual_rows': ab['R'], 'sequences_per_gpu': [len(a) for a in assignment],
+                       'chunk_len': solver.jobs[mine_ids[0]].schedule.chunk_len, 'chunk_warmup': args.chunk_warmup,
+                       'warmup_full': args.warmup_full, 'l2': 'flushed between timed steps (256 MiB write)',
+                       'frames_solved': solved, 'frame_iterations_per_step': builds, 'useful_frame_iterations': useful,
+                       'executed_over_useful': builds / max(1, useful),
+                       'collectives': 'grouped NCCL send/recv: scatter of observations from rank 0, gather of result rows to rank 0 '
+                                      '(inside e2e; the device-timed value has the observations resident)',
+                       'single_gpu_base': 'bench.py --gpus 1 reports the same 32-sequence workload on one GPU under c5_one_gpu'},
+            'roofline': roofline(ab, builds / world, useful / world, ms_step, 'C5'),
+            'e2e': {'value': total_frames / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': e2e_ms,
+                    'what': 'shard.solve_sharded: pinned host observations on rank 0 -> H2D -> NCCL scatter -> per-rank solves '
+                            '(device pointers through the C-ABI) -> NCCL gather -> D2H on rank 0; wall clock, max over ranks'},
+            'gpu_launches': args.steps * n_seq,
+            'clocks': sampler.summary(),
+            'wall_s_timed_region': t_wall,
+        }
         print(json.dumps(line), flush=True)
-    job.close()
-    model.close()
-    if world > 1:
-        dist.destroy_process_group()
+    solver.close()
+    dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOSH2_VERSION 101
+#define MOSH2_VERSION 102
 
 enum {
     MOSH2_OK = 0,
@@ -42,7 +42,10 @@ enum {
     MOSH2_ST_HAS_VELO = 4,     /* the velocity term was active (third processed frame on, chmosh.py:624) */
     MOSH2_ST_HAS_EXTRAP = 8,   /* the DMPL extrapolation term was active (chmosh.py:694-697)            */
     MOSH2_ST_GN_FALLBACK = 16, /* a Gauss-Newton system was not positive definite; Cauchy step used     */
-    MOSH2_ST_MAXITER = 32      /* a dog-leg hit maxiter                                                 */
+    MOSH2_ST_MAXITER = 32,     /* a dog-leg hit maxiter                                                 */
+    MOSH2_ST_SHORT_WARMUP = 64 /* chunked schedule: the chunk of this frame found fewer solved warm-up frames than
+                                  asked for (a long marker drop-out in front of it); rerun the range sequentially
+                                  if reference-exact continuity across the gap matters                          */
 };
 
 /* Constants of one (body model, betas, latent markers) triple, as laid out by
@@ -51,14 +54,9 @@ enum {
  * "slot" = 3*marker + t, t = 0..2 the three attachment vertices of a marker. */
 typedef struct mosh2_model_desc {
     int32_t n_joints, n_markers, body_dof, p_red, n_hand_red, n_hand_full, n_dmpl;
-    int32_t kw, na, n_levels; /* kw: skinning weights kept per slot, 1..8 (SMPL-family models: 4) */
-    const int32_t *parents;   /* [n_joints], -1 for the root                                 */
-    const int32_t *fk_order;  /* [n_joints] joints sorted by depth                           */
-    const int32_t *level_ofs; /* [n_levels+1] offsets into fk_order                          */
+    int32_t kw;               /* skinning weights kept per slot, 1..8 (SMPL-family models: 4) */
+    const int32_t *parents;   /* [n_joints], -1 for the root; the tree may be at most 16 levels deep */
     const int32_t *w_joint;   /* [3M*kw] skinning joint ids, -1 padded                       */
-    const int32_t *anc_joint; /* [3M*na] union of ancestors of the slot's joints, -1 padded  */
-    const int32_t *anc_mask;  /* [3M*na] bit i: w_joint[slot][i] lies in the ancestor's subtree */
-    const int8_t *anc_pos;    /* [3M*n_joints] index of a joint in anc_joint[slot], or -1    */
     const double *hand_comps; /* [n_hand_red * n_hand_full]  selected_components             */
     const double *hands_mean; /* [n_hand_full]                                               */
     const double *v0;         /* [3M*3]  shaped template rows                                */
@@ -118,28 +116,47 @@ void mosh2_default_options(mosh2_options *opt);
 int mosh2_model_create(const mosh2_model_desc *desc, int device, mosh2_model **out);
 void mosh2_model_destroy(mosh2_model *m);
 
-/* A job = device buffers for one sequence of n_frames frames.
- * chunk_len <= 0 solves the sequence exactly like the reference (one sequential pass);
- * chunk_len > 0 cuts it into chunks solved concurrently, each started chunk_warmup frames early. */
-int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, int32_t chunk_len,
-                     int32_t chunk_warmup, int32_t precision, mosh2_job **out);
+/* Parallel-in-time schedule of a job.  The reference solves the frames of a sequence one after
+ * the other (chmosh.py:584-724); chunk_len <= 0 does exactly that in one thread block.  chunk_len > 0 cuts the
+ * sequence into chunks solved concurrently; every chunk starts early enough to solve chunk_warmup frames (frames with
+ * at least one visible marker) before its first emitted frame, from the reference's own cold start.  The last
+ * warmup_full of those run the full per-frame schedule, the earlier ones a single linearisation of the Step-2 problem
+ * (warmup_full < 0 or >= chunk_warmup: all of them run the full schedule). */
+typedef struct mosh2_schedule {
+    int32_t chunk_len, chunk_warmup, warmup_full, reserved;
+} mosh2_schedule;
+
+/* A job = device buffers for one sequence of n_frames frames. */
+int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const mosh2_schedule *sched,
+                     int32_t precision, mosh2_job **out);
 /* obs [F*M*3] metres in latent-label order, vis [F*M] 0/1.  Async on the job's stream. */
 int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis);
+/* The same from DEVICE memory (e.g. the receive buffer of an NCCL scatter): d_obs [F*M*3] float32 (obs_f64 = 0) or
+ * float64 (obs_f64 = 1) on the job's device, d_vis [F*M]; converted to the job's precision on the device.  The
+ * copy is ordered after the work already queued on `producer_stream` (a cudaStream_t, may be NULL = legacy stream). */
+int mosh2_job_upload_device(mosh2_job *j, const void *d_obs, int32_t obs_f64, const uint8_t *d_vis, void *producer_stream);
 int mosh2_job_launch(mosh2_job *j);                 /* async */
 int mosh2_job_download(mosh2_job *j, const mosh2_result *res); /* async D2H + stream sync */
 int mosh2_job_sync(mosh2_job *j);
+/* Results as ONE packed float32 device row per frame, for device-side consumers (NCCL gather): row f =
+ * [fullpose 3*n_joints | trans 3 | dmpls n_dmpl | errs 8 | status 1 | jacobian builds 1] (status / builds stored as
+ * float values).  d_rows [F * mosh2_job_row_width()] on the job's device; async on the job's stream + stream sync. */
+int mosh2_job_row_width(mosh2_job *j);
+int mosh2_job_download_device(mosh2_job *j, float *d_rows);
 /* device time of the last launch (CUDA events on the job's stream), ms; valid after a sync */
 int mosh2_job_kernel_ms(mosh2_job *j, float *ms);
+/* device time from the start of `first`'s last launch to the end of `last`'s last launch (jobs of one device that were
+ * launched on their own streams at the same time: the span of the whole group is the maximum over all pairs), ms */
+int mosh2_job_span_ms(mosh2_job *first, mosh2_job *last, float *ms);
 int mosh2_job_num_chunks(mosh2_job *j);
-/* work done by the last launch over ALL processed frames (warm-up included):
- * out4 = {dog-leg iterations, residual evaluations, Jacobian/normal-equation builds, minimisations} */
-int mosh2_job_totals(mosh2_job *j, int32_t *out4);
+/* work done by the last launch: out8 = {dog-leg iterations, residual evaluations, Jacobian / normal-equation builds,
+ * minimisations} over ALL processed frames (warm-up included), then the same four over the EMITTED frames only */
+int mosh2_job_totals(mosh2_job *j, int32_t *out8);
 void mosh2_job_destroy(mosh2_job *j);
 
 /* upload + launch + download in one call (the call the Python wrapper makes). */
 int mosh2_solve(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const double *obs,
-                const uint8_t *vis, int32_t chunk_len, int32_t chunk_warmup, int32_t precision,
-                const mosh2_result *res);
+                const uint8_t *vis, const mosh2_schedule *sched, int32_t precision, const mosh2_result *res);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,8 @@ from .mocap_interface import MocapSession
 logger = logging.getLogger('moshpp_b200')
 
 NUM_SMS_B200 = 148
-DEFAULT_WARMUP = 48
+DEFAULT_WARMUP = 48          # solved frames every chunk is started early
+DEFAULT_WARMUP_FULL = 32     # the last 32 of them with the full per-frame schedule, the first 16 with one Step-2 iteration
 
 
 def _get(node, key, default=None):
@@ -74,6 +75,33 @@ def _read_vertices(fname: str) -> np.ndarray:
                     h.split()[1] == 'float' for h in header if h.startswith('property') and 'list' not in h):
                 return np.frombuffer(f.read(4 * nprops * n), dtype='<f4').reshape(n, nprops)[:, :3].astype(np.float64)
     raise NotImplementedError(f'cannot read v_template from {fname}')
+
+
+def plan_chunk_len(frame_counts, sm_budget: int = NUM_SMS_B200, warmup: int = DEFAULT_WARMUP,
+                   warmup_full: int = DEFAULT_WARMUP_FULL, min_len: int = 4) -> int:
+    """Chunk length for a set of sequences that are solved together on one GPU (one thread block per chunk, one block
+    per SM at a time).  The chunks run in waves of ``sm_budget``; a wave lasts as long as its longest chunk, i.e. about
+    chunk_len + warm-up frame solves.  Returns the length that minimises waves x (chunk_len + warm-up cost), where the
+    light warm-up frames cost about a quarter of a full one and the cold start about five."""
+    counts = [int(f) for f in frame_counts if f > 0]
+    if not counts:
+        return min_len
+    w_cost = warmup_full + 0.25 * max(0, warmup - warmup_full) + 5.0
+    best = None
+    for waves in range(1, 9):
+        lo, hi = min_len, max(max(counts), min_len)
+        while lo < hi:                                   # smallest L whose chunks fit `waves` waves
+            mid = (lo + hi) // 2
+            if sum(-(-f // mid) for f in counts) <= waves * sm_budget:
+                hi = mid
+            else:
+                lo = mid + 1
+        cost = waves * (lo + w_cost)
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, lo)
+        if lo == min_len:
+            break
+    return best[1]
 
 
 def auto_chunk_len(n_frames: int, sm_budget: int = NUM_SMS_B200) -> int:
@@ -183,13 +211,14 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
 
 def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_labels: list, betas: np.ndarray,
                  marker_meta: dict, v_template_fname=None, *, device: int = 0, chunk_len: Optional[int] = None,
-                 chunk_warmup: int = DEFAULT_WARMUP, precision: str = 'f32', sm_budget: int = NUM_SMS_B200,
-                 labels_map: Optional[dict] = None) -> dict:
+                 chunk_warmup: int = DEFAULT_WARMUP, warmup_full: int = DEFAULT_WARMUP_FULL, precision: str = 'f32',
+                 sm_budget: int = NUM_SMS_B200, labels_map='general') -> dict:
     """Stage II of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:458-459).
 
     Keyword-only extras: ``device``; ``chunk_len`` (None = automatic, 0 = the reference's single
-    sequential pass), ``chunk_warmup``; ``precision`` 'f32' | 'f64'; ``labels_map`` (the reference
-    passes its static synonym table general_labels_map, which is metadata outside this build).
+    sequential pass), ``chunk_warmup`` / ``warmup_full`` (mosh2_schedule, include/mosh2.h); ``precision`` 'f32' | 'f64';
+    ``labels_map``: 'general' (default) = the synonym table the reference always applies (chmosh.py:466), a dict, or
+    None for raw labels.
     """
     t0 = time.time()
     mocap = MocapSession(mocap_fname, mocap_unit=cfg.mocap.unit, mocap_rotate=cfg.mocap.rotate,
@@ -205,14 +234,14 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     if F == 0:
         raise ValueError('no frames selected')
     if chunk_len is None:
-        chunk_len = auto_chunk_len(F, sm_budget)
+        chunk_len = plan_chunk_len([F], sm_budget, chunk_warmup, warmup_full)
     if chunk_len >= F:
         chunk_len = 0
     prec = {'f32': _lib.MOSH2_F32, 'f64': _lib.MOSH2_F64}[precision]
 
     model = _lib.Model(pk, device=device)
     try:
-        job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, precision=prec)
+        job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec)
         try:
             job.upload(obs, vis)
             job.launch()
@@ -234,7 +263,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         'mocap_time_length': mocap.time_length(),
         'b200': {
             'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
-            'chunk_warmup': chunk_warmup, 'precision': precision, 'status': res.status.copy(),
+            'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'status': res.status.copy(),
             'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
             'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
         },

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -105,19 +106,20 @@ struct DevModel {
     int build(const mosh2_model_desc &d) {
         const size_t nJ = d.n_joints, S = size_t(3) * d.n_markers, nd = d.n_dmpl;
         m.nJ = d.n_joints; m.M = d.n_markers; m.body_dof = d.body_dof; m.p_red = d.p_red;
-        m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw; m.na = d.na;
-        m.n_levels = d.n_levels; m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
+        m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw;
+        m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
         m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
         int rc;
         if ((rc = up<int>(d.parents, nJ, &m.parents))) return rc;
-        if ((rc = up<int>(d.fk_order, nJ, &m.fk_order))) return rc;
-        if ((rc = up<int>(d.level_ofs, size_t(d.n_levels) + 1, &m.level_ofs))) return rc;
+        {   // joints sorted by depth (stable): parents before children
+            std::vector<int> depth(nJ, 0), order(nJ);
+            for (size_t j = 0; j < nJ; ++j) { int dj = 0; for (int a = d.parents[j]; a >= 0; a = d.parents[a]) ++dj; depth[j] = dj; }
+            for (size_t j = 0; j < nJ; ++j) order[j] = int(j);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return depth[a] < depth[b]; });
+            if ((rc = up<int>(order.data(), nJ, &m.fk_order))) return rc;
+        }
         if ((rc = up<int>(d.w_joint, S * d.kw, &m.w_joint))) return rc;
-        // (the ancestor tables of the ABI are uploaded for completeness; the kernel derives a subtree mask itself)
-        if ((rc = up<int>(d.anc_joint, S * d.na, &m.anc_joint))) return rc;
-        if ((rc = up<int>(d.anc_mask, S * d.na, &m.anc_mask))) return rc;
-        if ((rc = up<int8_t>(d.anc_pos, S * nJ, &m.anc_pos))) return rc;
         {   // dense blocks of the hand-PCA matrix (rows with the same non-zero column range), stored transposed
             std::vector<double> hct;
             mosh2::HandBlock blocks[mosh2::kMaxHandBlocks];
@@ -174,20 +176,87 @@ struct DevModel {
 
 }  // namespace
 
+template <class S, class D>
+__global__ void convert_kernel(const S *__restrict__ src, D *__restrict__ dst, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = D(src[i]);
+}
+
+// one packed float32 row per frame: [fullpose PF | trans 3 | dmpls nd | errs N_ERR | status | jacobian builds]
+template <class real>
+__global__ void pack_rows_kernel(const real *__restrict__ fullpose, const real *__restrict__ trans, const real *__restrict__ dmpls,
+                                 const real *__restrict__ errs, const int *__restrict__ status, const int *__restrict__ counters,
+                                 float *__restrict__ rows, int n_frames, int PF, int nd) {
+    const int width = PF + 3 + nd + mosh2::N_ERR + 2;
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= size_t(n_frames) * width) return;
+    const int f = int(i / width);
+    int c = int(i - size_t(f) * width);
+    float v;
+    if (c < PF) v = float(fullpose[size_t(f) * PF + c]);
+    else if ((c -= PF) < 3) v = float(trans[size_t(f) * 3 + c]);
+    else if ((c -= 3) < nd) v = float(dmpls[size_t(f) * nd + c]);
+    else if ((c -= nd) < mosh2::N_ERR) v = float(errs[size_t(f) * mosh2::N_ERR + c]);
+    else if ((c -= mosh2::N_ERR) == 0) v = float(status[f]);
+    else v = float(counters[4 * f + 2]);
+    rows[i] = v;
+}
+
+// Host copy of a model description: the caller's buffers need not outlive mosh2_model_create, and the device copy of a
+// precision is only built when the first job of that precision is created.
+struct HostDesc {
+    mosh2_model_desc d{};
+    std::vector<int32_t> parents, w_joint, free1, free2;
+    std::vector<double> hand_comps, hands_mean, v0, sd, pd, w_val, j0, jd, coefs, prior_means, prior_Q, prior_neglogw;
+    template <class T> static const T *keep(std::vector<T> &dst, const T *src, size_t n) {
+        dst.assign(src, src + n);
+        if (dst.empty()) dst.resize(1);
+        return dst.data();
+    }
+    void copy_from(const mosh2_model_desc &s) {
+        d = s;
+        const size_t nJ = s.n_joints, S = size_t(3) * s.n_markers, nd = s.n_dmpl, K = s.prior_k, D = s.prior_d;
+        d.parents = keep(parents, s.parents, nJ);
+        d.w_joint = keep(w_joint, s.w_joint, S * s.kw);
+        d.free1 = keep(free1, s.free1, s.n_free1);
+        d.free2 = keep(free2, s.free2, s.n_free2);
+        d.hand_comps = keep(hand_comps, s.hand_comps, size_t(s.n_hand_red) * s.n_hand_full);
+        d.hands_mean = keep(hands_mean, s.hands_mean, s.n_hand_full);
+        d.v0 = keep(v0, s.v0, S * 3);
+        d.sd = keep(sd, s.sd, S * 3 * nd);
+        d.pd = keep(pd, s.pd, (nJ - 1) * 3 * S * 9);
+        d.w_val = keep(w_val, s.w_val, S * s.kw);
+        d.j0 = keep(j0, s.j0, nJ * 3);
+        d.jd = keep(jd, s.jd, nJ * 3 * nd);
+        d.coefs = keep(coefs, s.coefs, size_t(s.n_markers) * 3);
+        d.prior_means = keep(prior_means, s.prior_means, K * D);
+        d.prior_Q = keep(prior_Q, s.prior_Q, K * D * D);
+        d.prior_neglogw = keep(prior_neglogw, s.prior_neglogw, K);
+    }
+};
+
 struct mosh2_model {
     int device = 0;
+    HostDesc host;
     DevModel<float> f32;
     DevModel<double> f64;
+    bool have_f32 = false, have_f64 = false;
     int n_joints = 0, n_markers = 0, p_red = 0, n_dmpl = 0;
+    int ensure(int precision) {
+        if (precision == MOSH2_F64) {
+            if (!have_f64) { const int rc = f64.build(host.d); if (rc) return rc; have_f64 = true; }
+        } else if (!have_f32) { const int rc = f32.build(host.d); if (rc) return rc; have_f32 = true; }
+        return 0;
+    }
 };
 
 struct mosh2_job {
     mosh2_model *model = nullptr;
     int precision = MOSH2_F32;
-    int n_frames = 0, chunk_len = 0, warmup = 0, n_chunks = 1;
+    int n_frames = 0, chunk_len = 0, warmup = 0, warm_full = 0, n_chunks = 1;
     mosh2::Options opt{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in = nullptr;
     size_t esz = 4;                 // element size of the compute type
     size_t smem = 0, gws_stride = 0;
     int big_in_global = 0;
@@ -223,6 +292,7 @@ template <class real>
 int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     mosh2::Job<real> job{};
     job.n_frames = j->n_frames; job.chunk_len = j->chunk_len; job.warmup = j->warmup; job.n_chunks = j->n_chunks;
+    job.warm_full = j->warm_full;
     job.obs = static_cast<const real *>(j->d_obs);
     job.vis = j->d_vis;
     real *out = static_cast<real *>(j->d_out);
@@ -298,9 +368,14 @@ int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out)
     if (d->n_expr < 0 || d->n_expr > d->n_dmpl || d->face_lo < 0 || d->face_hi < d->face_lo || d->face_hi > d->p_red)
         return fail(MOSH2_E_INVALID, "inconsistent face description: n_expr=%d of %d linear coefficients, jaw ids [%d, %d)", d->n_expr,
                     d->n_dmpl, d->face_lo, d->face_hi);
-    if (d->n_levels < 1 || d->n_levels > mosh2::kMaxDepth || d->n_joints > 254)
-        return fail(MOSH2_E_TOO_LARGE, "kinematic tree too deep or too large: %d levels (max %d), %d joints (max 254)", d->n_levels,
-                    mosh2::kMaxDepth, d->n_joints);
+    if (d->n_joints > 254) return fail(MOSH2_E_TOO_LARGE, "%d joints (max 254)", d->n_joints);
+    for (int j = 0; j < d->n_joints; ++j) {
+        int depth = 1;
+        for (int a = d->parents[j]; a >= 0; a = d->parents[a]) {
+            if (a >= d->n_joints || ++depth > d->n_joints) return fail(MOSH2_E_INVALID, "parents[] is not a forest (joint %d)", j);
+        }
+        if (depth > mosh2::kMaxDepth) return fail(MOSH2_E_TOO_LARGE, "kinematic chain of joint %d is %d levels deep (max %d)", j, depth, mosh2::kMaxDepth);
+    }
     if (d->body_dof + d->n_hand_full != 3 * d->n_joints || d->body_dof + d->n_hand_red != d->p_red)
         return fail(MOSH2_E_INVALID, "pose layout mismatch: body_dof=%d hand_full=%d hand_red=%d p_red=%d joints=%d",
                     d->body_dof, d->n_hand_full, d->n_hand_red, d->p_red, d->n_joints);
@@ -317,9 +392,7 @@ int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out)
     mosh2_model *m = new (std::nothrow) mosh2_model;
     if (!m) return fail(MOSH2_E_INVALID, "out of host memory");
     m->device = device; m->n_joints = d->n_joints; m->n_markers = d->n_markers; m->p_red = d->p_red; m->n_dmpl = d->n_dmpl;
-    int rc = m->f32.build(*d);
-    if (!rc) rc = m->f64.build(*d);
-    if (rc) { delete m; return rc; }
+    m->host.copy_from(*d);      // the device copy of a precision is built by the first job that asks for it
     *out = m;
     return 0;
 }
@@ -330,17 +403,20 @@ void mosh2_model_destroy(mosh2_model *m) {
     delete m;
 }
 
-int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, int32_t chunk_len,
-                     int32_t chunk_warmup, int32_t precision, mosh2_job **out) {
+int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const mosh2_schedule *sched,
+                     int32_t precision, mosh2_job **out) {
     if (!m || !opt || !out || n_frames < 1) return fail(MOSH2_E_INVALID, "bad argument");
     if (precision != MOSH2_F32 && precision != MOSH2_F64) return fail(MOSH2_E_INVALID, "precision must be MOSH2_F32 or MOSH2_F64");
     *out = nullptr;
     CU(cudaSetDevice(m->device));
+    if (const int rc = m->ensure(precision)) return rc;
     mosh2_job *j = new (std::nothrow) mosh2_job;
     if (!j) return fail(MOSH2_E_INVALID, "out of host memory");
     j->model = m; j->precision = precision; j->n_frames = n_frames;
+    const int chunk_len = sched ? sched->chunk_len : 0, chunk_warmup = sched ? sched->chunk_warmup : 0;
     j->chunk_len = chunk_len > 0 ? chunk_len : 0;
     j->warmup = chunk_warmup > 0 ? chunk_warmup : 0;
+    j->warm_full = (!sched || sched->warmup_full < 0 || sched->warmup_full > j->warmup) ? j->warmup : sched->warmup_full;
     j->n_chunks = j->chunk_len ? (n_frames + j->chunk_len - 1) / j->chunk_len : 1;
     j->esz = precision == MOSH2_F64 ? 8 : 4;
     mosh2::Options &o = j->opt;
@@ -375,12 +451,13 @@ int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames,
     chk(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
     chk(cudaEventCreate(&j->ev0));
     chk(cudaEventCreate(&j->ev1));
+    chk(cudaEventCreateWithFlags(&j->ev_in, cudaEventDisableTiming));
     chk(cudaMalloc(&j->d_obs, j->n_obs * j->esz));
     chk(cudaMalloc(&j->d_out, j->n_out * j->esz));
     chk(cudaMalloc(&j->d_vis, F * M));
     chk(cudaMalloc(&j->d_status, F * sizeof(int)));
     chk(cudaMalloc(&j->d_counters, F * 4 * sizeof(int)));
-    chk(cudaMalloc(&j->d_totals, 4 * sizeof(int)));
+    chk(cudaMalloc(&j->d_totals, 8 * sizeof(int)));
     chk(cudaMalloc(&j->d_prof, 32 * sizeof(long long)));
     if (j->gws_stride) chk(cudaMalloc(&j->d_gws, j->gws_stride * j->n_chunks));
     chk(cudaMallocHost(&j->h_obs, j->n_obs * j->esz));
@@ -417,7 +494,7 @@ int mosh2_job_launch(mosh2_job *j) {
     CU(cudaMemsetAsync(j->d_out, 0, j->n_out * j->esz, j->stream));
     CU(cudaMemsetAsync(j->d_status, 0, size_t(j->n_frames) * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_counters, 0, size_t(j->n_frames) * 4 * sizeof(int), j->stream));
-    CU(cudaMemsetAsync(j->d_totals, 0, 4 * sizeof(int), j->stream));
+    CU(cudaMemsetAsync(j->d_totals, 0, 8 * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_prof, 0, 32 * sizeof(long long), j->stream));
     if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
     return launch<float>(j, j->model->f32.m);
@@ -437,6 +514,14 @@ int mosh2_job_kernel_ms(mosh2_job *j, float *ms) {
     return 0;
 }
 
+int mosh2_job_span_ms(mosh2_job *first, mosh2_job *last, float *ms) {
+    if (!first || !last || !ms) return fail(MOSH2_E_INVALID, "null argument");
+    if (first->model->device != last->model->device) return fail(MOSH2_E_INVALID, "jobs live on different devices");
+    CU(cudaSetDevice(first->model->device));
+    CU(cudaEventElapsedTime(ms, first->ev0, last->ev1));
+    return 0;
+}
+
 int mosh2_job_num_chunks(mosh2_job *j) { return j ? j->n_chunks : 0; }
 
 // development builds (-DMOSH2_PROFILE) only: 32 phase clock sums of the last launch; not part of mosh2.h
@@ -448,11 +533,49 @@ int mosh2_dev_phase_clocks(mosh2_job *j, long long *out32) {
     return 0;
 }
 
-int mosh2_job_totals(mosh2_job *j, int32_t *out4) {
-    if (!j || !out4) return fail(MOSH2_E_INVALID, "null argument");
+int mosh2_job_totals(mosh2_job *j, int32_t *out8) {
+    if (!j || !out8) return fail(MOSH2_E_INVALID, "null argument");
     CU(cudaSetDevice(j->model->device));
     CU(cudaStreamSynchronize(j->stream));
-    CU(cudaMemcpy(out4, j->d_totals, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out8, j->d_totals, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mosh2_job_upload_device(mosh2_job *j, const void *d_obs, int32_t obs_f64, const uint8_t *d_vis, void *producer_stream) {
+    if (!j || !d_obs || !d_vis) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaEventRecord(j->ev_in, static_cast<cudaStream_t>(producer_stream)));
+    CU(cudaStreamWaitEvent(j->stream, j->ev_in, 0));
+    const size_t n = j->n_obs, nv = size_t(j->n_frames) * j->model->n_markers;
+    const bool dst64 = j->precision == MOSH2_F64;
+    if (dst64 == (obs_f64 != 0)) CU(cudaMemcpyAsync(j->d_obs, d_obs, n * j->esz, cudaMemcpyDeviceToDevice, j->stream));
+    else {
+        const int blocks = int((n + 255) / 256);
+        if (dst64) convert_kernel<float, double><<<blocks, 256, 0, j->stream>>>(static_cast<const float *>(d_obs), static_cast<double *>(j->d_obs), n);
+        else convert_kernel<double, float><<<blocks, 256, 0, j->stream>>>(static_cast<const double *>(d_obs), static_cast<float *>(j->d_obs), n);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(j->d_vis, d_vis, nv, cudaMemcpyDeviceToDevice, j->stream));
+    return 0;
+}
+
+int mosh2_job_row_width(mosh2_job *j) { return j ? 3 * j->model->n_joints + 3 + j->model->n_dmpl + mosh2::N_ERR + 2 : 0; }
+
+int mosh2_job_download_device(mosh2_job *j, float *d_rows) {
+    if (!j || !d_rows) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    const int PF = 3 * j->model->n_joints, nd = j->model->n_dmpl, width = mosh2_job_row_width(j);
+    const size_t total = size_t(j->n_frames) * width;
+    const int blocks = int((total + 255) / 256);
+    if (j->precision == MOSH2_F64) {
+        const double *o = static_cast<const double *>(j->d_out);
+        pack_rows_kernel<double><<<blocks, 256, 0, j->stream>>>(o + j->o_fullpose, o + j->o_trans, o + j->o_dmpls, o + j->o_errs, j->d_status, j->d_counters, d_rows, j->n_frames, PF, nd);
+    } else {
+        const float *o = static_cast<const float *>(j->d_out);
+        pack_rows_kernel<float><<<blocks, 256, 0, j->stream>>>(o + j->o_fullpose, o + j->o_trans, o + j->o_dmpls, o + j->o_errs, j->d_status, j->d_counters, d_rows, j->n_frames, PF, nd);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(j->stream));
     return 0;
 }
 
@@ -492,14 +615,15 @@ void mosh2_job_destroy(mosh2_job *j) {
     cudaFreeHost(j->h_obs); cudaFreeHost(j->h_out); cudaFreeHost(j->h_vis); cudaFreeHost(j->h_status); cudaFreeHost(j->h_counters);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
+    if (j->ev_in) cudaEventDestroy(j->ev_in);
     if (j->stream) cudaStreamDestroy(j->stream);
     delete j;
 }
 
 int mosh2_solve(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const double *obs, const uint8_t *vis,
-                int32_t chunk_len, int32_t chunk_warmup, int32_t precision, const mosh2_result *res) {
+                const mosh2_schedule *sched, int32_t precision, const mosh2_result *res) {
     mosh2_job *j = nullptr;
-    int rc = mosh2_job_create(m, opt, n_frames, chunk_len, chunk_warmup, precision, &j);
+    int rc = mosh2_job_create(m, opt, n_frames, sched, precision, &j);
     if (rc) return rc;
     rc = mosh2_job_upload(j, obs, vis);
     if (!rc) rc = mosh2_job_launch(j);

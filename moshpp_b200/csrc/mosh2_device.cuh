@@ -82,7 +82,7 @@ struct BPtr {                            // array in shared memory, or (BIG: f64
 
 namespace mosh2 {
 
-enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32 };
+enum { ST_SOLVED = 1, ST_SKIPPED = 2, ST_HAS_VELO = 4, ST_HAS_EXTRAP = 8, ST_GN_FALLBACK = 16, ST_MAXITER = 32, ST_SHORT_WARMUP = 64 };
 enum { ERR_DATA = 0, ERR_POSEB = 1, ERR_VELO = 2, ERR_POSEH = 3, ERR_DMPL = 4, ERR_EXTRAP = 5, ERR_POSEF = 6, ERR_EXPR = 7, N_ERR = 8 };
 
 constexpr int kBS = 4;            // register tile of the J^T J accumulation and of the Cholesky update
@@ -100,9 +100,9 @@ struct HandBlock {   // one dense block of the hand-PCA matrix: rows [r0,r1) of 
 
 template <class real>
 struct Model {
-    int nJ, M, body_dof, p_red, n_hand_red, n_hand_full, nd, kw, na, n_levels;
-    const int *parents, *fk_order, *level_ofs, *w_joint, *anc_joint, *anc_mask;
-    const int8_t *anc_pos;
+    int nJ, M, body_dof, p_red, n_hand_red, n_hand_full, nd, kw;
+    const int *parents, *w_joint;
+    const int *fk_order;        // joints sorted by depth (parents before children); derived from `parents` by the host library
     int hb_n, hct_size;
     HandBlock hb[kMaxHandBlocks];
     const real *hct;            // compact transposed hand-PCA blocks
@@ -131,11 +131,12 @@ struct Options {
 template <class real>
 struct Job {
     int n_frames, chunk_len, warmup, n_chunks;
+    int warm_full;          // the last warm_full warm-up frames run the full per-frame schedule, the earlier ones one linearisation
     const real *obs;        // F*M*3
     const uint8_t *vis;     // F*M
     real *fullpose, *pose, *trans, *dmpls, *markers_sim, *errs;
     int *status, *counters;
-    int *totals;            // [4] iterations, evaluations, builds, minimisations over ALL processed frames (incl. warm-up)
+    int *totals;            // [8] iterations, evaluations, builds, minimisations over ALL processed frames (incl. warm-up), then over the emitted frames
     long long *prof;        // [32] phase clock sums (MOSH2_PROFILE builds only, else unused)
     char *gws;              // optional per-CTA global workspace (f64 / large models)
     size_t gws_stride;
@@ -328,7 +329,7 @@ struct Work {
     SPtr<int> colmap, colsrc, jlist, isc;
     // small per-model tables staged in shared memory (a dependent global load costs several hundred cycles and the
     // kinematic-tree walk alone chains three of them per level)
-    SPtr<int> c_parents, c_fk_order, c_level_ofs, c_wj, c_free1, c_free2;
+    SPtr<int> c_parents, c_fk_order, c_wj, c_free1, c_free2;
     SPtr<int> c_tin, c_tsz;   // pre-order index and subtree size of every joint: j in subtree(a) <=> tin[j]-tin[a] in [0, tsz[a])
     SPtr<real> c_wv, c_v0, c_coefs, c_j0, c_hmean, c_pmeans, c_pnlw;
     SPtr<real> c_jd;          // joint-position directions of the per-frame linear coefficients (DMPL, expressions)
@@ -504,7 +505,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.vis.ofs = S.take<uint8_t>(d.M);
     // small per-model tables are always staged in shared memory (a dependent global load costs ~600 cycles and the
     // kinematic-tree walk chains three of them per level); the larger ones stay in global memory / L2
-    w.c_parents.ofs = S.take<int>(d.nJ); w.c_fk_order.ofs = S.take<int>(d.nJ); w.c_level_ofs.ofs = S.take<int>(m.n_levels + 1);
+    w.c_parents.ofs = S.take<int>(d.nJ); w.c_fk_order.ofs = S.take<int>(d.nJ);
     w.c_wj.ofs = S.take<int>(d.S * d.kw); w.c_free1.ofs = S.take<int>(d.n1); w.c_free2.ofs = S.take<int>(d.n2);
     w.c_wv.ofs = S.take<real>(d.S * d.kw); w.c_v0.ofs = S.take<real>(3 * d.S); w.c_coefs.ofs = S.take<real>(3 * d.M);
     w.c_j0.ofs = S.take<real>(3 * d.nJ); w.c_hmean.ofs = S.take<real>(m.n_hand_full + 1);
@@ -1747,12 +1748,16 @@ struct Solver {
     //      one loop around a single eval() / build() / gauss_newton() call site each (the 32 KB instruction cache
     //      makes code size a first-order cost).  The dog-leg control flow is chumpy's
     //      (SURVEY.md Appendix A.6): outer iterations, inner retries until a step improves, e_3 / e_2 / maxiter.
-    M2_D void solve_frame(int f, bool emit, bool first, bool fingers, bool dyn, bool face) {
+    //      `light` (warm-up frames of a chunk only, never an emitted frame): the frame is tracked with a single
+    //      linearisation of the Step-2 problem (one accepted dog-leg step) instead of the two minimisations -- enough to
+    //      carry the state along the sequential trajectory until the last, fully solved warm-up frames.
+    M2_D void solve_frame(int f, bool emit, bool first, bool fingers, bool dyn, bool face, bool light) {
         const Options &o = job.opt;
         const real e1 = real(1e-15), e2 = real(1e-15);
         enum { OP_PROCRUSTES, OP_BEGIN, OP_TRIAL, OP_OUTPUT };
         int op = first ? OP_PROCRUSTES : OP_BEGIN;
-        int stage = first ? 0 : 3;     // 0..2 first-frame annealing (chmosh.py:637-653), 3 Step 1 (665-671), 4 Step 2 (676-705)
+        int stage = first ? 0 : (light ? 4 : 3);   // 0..2 first-frame annealing (chmosh.py:637-653), 3 Step 1 (665-671), 4 Step 2 (676-705)
+        const int maxit = light ? 1 : o.maxiter;
         StepCfg<real> c;
         c.free = w.c_free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false; c.face = false;
         c.wp = 0; c.e3 = real(o.e3_first);
@@ -1811,7 +1816,7 @@ struct Solver {
                 if (delta <= e2 * npn) done = true;
                 if (done || improved) {
                     in_iter = false;
-                    if (!done && iter >= o.maxiter) { done = true; frame_flags |= ST_MAXITER; }
+                    if (!done && iter >= maxit) { done = true; if (!light) frame_flags |= ST_MAXITER; }
                 }
             }
             // ---------------- the one linearisation site
@@ -1900,8 +1905,13 @@ struct Solver {
 #if M2_GPU
             atomicAdd(job.totals + 0, n_iter); atomicAdd(job.totals + 1, n_eval);
             atomicAdd(job.totals + 2, n_build); atomicAdd(job.totals + 3, n_min);
+            if (emit) {
+                atomicAdd(job.totals + 4, n_iter); atomicAdd(job.totals + 5, n_eval);
+                atomicAdd(job.totals + 6, n_build); atomicAdd(job.totals + 7, n_min);
+            }
 #else
             job.totals[0] += n_iter; job.totals[1] += n_eval; job.totals[2] += n_build; job.totals[3] += n_min;
+            if (emit) { job.totals[4] += n_iter; job.totals[5] += n_eval; job.totals[6] += n_build; job.totals[7] += n_min; }
 #endif
         }
         if (emit) {
@@ -1998,17 +2008,52 @@ struct Solver {
     // ---- the chunk loop
     M2_D void run_chunk(int chunk) {
         const Options &o = job.opt;
-        int f_emit, f_begin, f_end;
-        if (job.chunk_len <= 0) { f_emit = 0; f_begin = 0; f_end = job.n_frames; }
+        int f_emit, f_begin, f_end, f_full;
+        bool short_warmup = false;
+        if (job.chunk_len <= 0) { f_emit = 0; f_begin = 0; f_end = job.n_frames; f_full = 0; }
         else {
             f_emit = chunk * job.chunk_len;
-            f_begin = f_emit - job.warmup; if (f_begin < 0) f_begin = 0;
             f_end = f_emit + job.chunk_len; if (f_end > job.n_frames) f_end = job.n_frames;
+            // The warm-up is counted in SOLVED frames (frames with at least one visible marker; the others are skipped,
+            // chmosh.py:586-588): walk back from the first emitted frame until `warmup` of them are found, so that a
+            // marker drop-out in front of a chunk does not shorten the history the chunk converges on.  The last
+            // `warm_full` solved warm-up frames run the full schedule.  A chunk that reaches frame 0 is the reference's
+            // own recursion from its own start: exact, never "short".
+            uint8_t *flag = reinterpret_cast<uint8_t *>(static_cast<real *>(w.red));      // >= 8*33*4 bytes of scratch
+            const int per = cta.nthr < 512 ? cta.nthr : 512;
+            const int max_back = 8 * (job.warmup > 0 ? job.warmup : 1) + 64;             // give up behind very long gaps
+            if (cta.tid == 0) { w.isc[4] = 0; w.isc[5] = f_emit; w.isc[6] = f_emit; w.isc[7] = 0; }
+            M2_SYNC();
+            for (int base = f_emit - 1; base >= 0; base -= per) {
+                if (cta.tid < per) {
+                    const int f = base - cta.tid;
+                    uint8_t any = 0;
+                    if (f >= 0) for (int i = 0; i < d.M; ++i) any |= job.vis[size_t(f) * d.M + i];
+                    flag[cta.tid] = any;
+                }
+                M2_SYNC();
+                if (cta.tid == 0) {
+                    int cnt = w.isc[4], fb = w.isc[5], ff = w.isc[6], stop = 0;
+                    for (int t = 0; t < per && !stop; ++t) {
+                        const int f = base - t;
+                        if (f < 0 || cnt >= job.warmup) { stop = 1; break; }
+                        if (f_emit - f > max_back) { stop = 2; break; }
+                        if (flag[t]) { ++cnt; fb = f; if (cnt <= job.warm_full) ff = f; }
+                    }
+                    if (cnt >= job.warmup) stop = 1;
+                    w.isc[4] = cnt; w.isc[5] = fb; w.isc[6] = ff; w.isc[7] = stop;
+                }
+                M2_SYNC();
+                if (w.isc[7]) break;
+            }
+            f_begin = w.isc[5]; f_full = w.isc[6];
+            // fewer solved warm-up frames than asked for, without having reached the start of the sequence
+            short_warmup = w.isc[4] < job.warmup && w.isc[7] == 2;
+            M2_SYNC();
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
         CTA_FOR(i, m.hct_size) w.hct[i] = m.hct[i];
         CTA_FOR(i, d.nJ) { w.c_parents[i] = m.parents[i]; w.c_fk_order[i] = m.fk_order[i]; }
-        CTA_FOR(i, m.n_levels + 1) w.c_level_ofs[i] = m.level_ofs[i];
         CTA_FOR(i, d.S * d.kw) { w.c_wj[i] = m.w_joint[i]; w.c_wv[i] = m.w_val[i]; }
         CTA_FOR(i, d.n1) w.c_free1[i] = m.free1[i];
         CTA_FOR(i, d.n2) w.c_free2[i] = m.free2[i];
@@ -2103,7 +2148,8 @@ struct Solver {
                 M2_SYNC();
             }
             has_extrap = dyn && have_dm_prev;
-            solve_frame(f, f >= f_emit, first, fingers, dyn, face);
+            if (short_warmup && f >= f_emit) frame_flags |= ST_SHORT_WARMUP;
+            solve_frame(f, f >= f_emit, first, fingers, dyn, face, /*light=*/!first && f < f_full);
             first = false;
         }
         M2_TACC(17);

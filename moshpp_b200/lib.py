@@ -13,12 +13,12 @@ import numpy as np
 
 from .pack import StageIIPack
 
+ABI_VERSION = 102          # MOSH2_VERSION of include/mosh2.h that the ctypes structs below encode
 MOSH2_F32, MOSH2_F64 = 0, 1
-ST_SOLVED, ST_SKIPPED, ST_HAS_VELO, ST_HAS_EXTRAP, ST_GN_FALLBACK, ST_MAXITER = 1, 2, 4, 8, 16, 32
+ST_SOLVED, ST_SKIPPED, ST_HAS_VELO, ST_HAS_EXTRAP, ST_GN_FALLBACK, ST_MAXITER, ST_SHORT_WARMUP = 1, 2, 4, 8, 16, 32, 64
 ERR_NAMES = ('data', 'poseB', 'velo', 'poseH', 'dmpl', 'extrap_dmpl', 'poseF', 'expr')   # column order of mosh2_result.errs
 
 _i32p = C.POINTER(C.c_int32)
-_i8p = C.POINTER(C.c_int8)
 _u8p = C.POINTER(C.c_uint8)
 _f64p = C.POINTER(C.c_double)
 
@@ -27,9 +27,8 @@ class ModelDesc(C.Structure):
     _fields_ = [
         ('n_joints', C.c_int32), ('n_markers', C.c_int32), ('body_dof', C.c_int32), ('p_red', C.c_int32),
         ('n_hand_red', C.c_int32), ('n_hand_full', C.c_int32), ('n_dmpl', C.c_int32),
-        ('kw', C.c_int32), ('na', C.c_int32), ('n_levels', C.c_int32),
-        ('parents', _i32p), ('fk_order', _i32p), ('level_ofs', _i32p), ('w_joint', _i32p),
-        ('anc_joint', _i32p), ('anc_mask', _i32p), ('anc_pos', _i8p),
+        ('kw', C.c_int32),
+        ('parents', _i32p), ('w_joint', _i32p),
         ('hand_comps', _f64p), ('hands_mean', _f64p), ('v0', _f64p), ('sd', _f64p), ('pd', _f64p),
         ('w_val', _f64p), ('j0', _f64p), ('jd', _f64p), ('coefs', _f64p),
         ('prior_k', C.c_int32), ('prior_d', C.c_int32), ('prior_off', C.c_int32),
@@ -48,6 +47,16 @@ class Options(C.Structure):
         ('maxiter', C.c_int32), ('optimize_fingers', C.c_int32), ('optimize_dynamics', C.c_int32),
         ('wt_poseF', C.c_double), ('wt_expr', C.c_double), ('optimize_face', C.c_int32),
     ]
+
+
+class Schedule(C.Structure):
+    """mosh2_schedule: chunk_len <= 0 = the reference's sequential pass; warmup_full < 0 = every warm-up frame runs
+    the full per-frame schedule."""
+    _fields_ = [('chunk_len', C.c_int32), ('chunk_warmup', C.c_int32), ('warmup_full', C.c_int32), ('reserved', C.c_int32)]
+
+
+def make_schedule(chunk_len: int = 0, chunk_warmup: int = 0, warmup_full: int = -1, reserved: int = 0) -> Schedule:
+    return Schedule(int(chunk_len), int(chunk_warmup), int(warmup_full), int(reserved))
 
 
 class Result(C.Structure):
@@ -81,6 +90,9 @@ def load_library(path: Optional[str] = None):
     lib = C.CDLL(p)
     vp = C.c_void_p
     lib.mosh2_version.restype = C.c_int
+    if lib.mosh2_version() != ABI_VERSION:
+        raise Mosh2Error(f'{p} implements ABI {lib.mosh2_version()}, this binding encodes {ABI_VERSION}: '
+                         'rebuild it with `python -m moshpp_b200.build --force`')
     lib.mosh2_last_error.restype = C.c_char_p
     lib.mosh2_device_count.restype = C.c_int
     lib.mosh2_default_options.argtypes = [C.POINTER(Options)]
@@ -88,17 +100,21 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(vp)]
     lib.mosh2_model_destroy.argtypes = [vp]
     lib.mosh2_model_destroy.restype = None
-    lib.mosh2_job_create.argtypes = [vp, C.POINTER(Options), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.mosh2_job_create.argtypes = [vp, C.POINTER(Options), C.c_int32, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
     lib.mosh2_job_upload.argtypes = [vp, _f64p, _u8p]
+    lib.mosh2_job_upload_device.argtypes = [vp, vp, C.c_int32, vp, vp]
+    lib.mosh2_job_row_width.argtypes = [vp]
+    lib.mosh2_job_download_device.argtypes = [vp, vp]
     lib.mosh2_job_launch.argtypes = [vp]
     lib.mosh2_job_download.argtypes = [vp, C.POINTER(Result)]
     lib.mosh2_job_sync.argtypes = [vp]
     lib.mosh2_job_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.mosh2_job_num_chunks.argtypes = [vp]
+    lib.mosh2_job_span_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     lib.mosh2_job_totals.argtypes = [vp, _i32p]
     lib.mosh2_job_destroy.argtypes = [vp]
     lib.mosh2_job_destroy.restype = None
-    lib.mosh2_solve.argtypes = [vp, C.POINTER(Options), C.c_int32, _f64p, _u8p, C.c_int32, C.c_int32, C.c_int32,
+    lib.mosh2_solve.argtypes = [vp, C.POINTER(Options), C.c_int32, _f64p, _u8p, C.POINTER(Schedule), C.c_int32,
                                 C.POINTER(Result)]
     if path is None:
         _LIB = lib
@@ -109,7 +125,7 @@ EXPORTED_SYMBOLS = (
     'mosh2_version', 'mosh2_last_error', 'mosh2_device_count', 'mosh2_default_options', 'mosh2_model_create',
     'mosh2_model_destroy', 'mosh2_job_create', 'mosh2_job_upload', 'mosh2_job_launch', 'mosh2_job_download',
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
-    'mosh2_solve')
+    'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -123,9 +139,7 @@ class DescHolder:
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         self.arrays = dict(
-            parents=i32(pk.parents), fk_order=i32(pk.fk_order), level_ofs=i32(pk.level_ofs), w_joint=i32(pk.w_joint),
-            anc_joint=i32(pk.anc_joint), anc_mask=i32(pk.anc_mask),
-            anc_pos=np.ascontiguousarray(pk.anc_pos, dtype=np.int8),
+            parents=i32(pk.parents), w_joint=i32(pk.w_joint),
             hand_comps=f64(pk.hand_comps), hands_mean=f64(pk.hands_mean), v0=f64(pk.v0), sd=f64(pk.sd), pd=f64(pk.pd),
             w_val=f64(pk.w_val), j0=f64(pk.j0), jd=f64(pk.jd), coefs=f64(pk.coefs),
             prior_means=f64(pk.prior_means), prior_Q=f64(pk.prior_Q), prior_neglogw=f64(pk.prior_neglogw),
@@ -134,10 +148,9 @@ class DescHolder:
         d = ModelDesc()
         d.n_joints, d.n_markers, d.body_dof, d.p_red = pk.n_joints, pk.n_markers, pk.body_dof, pk.p_red
         d.n_hand_red, d.n_hand_full, d.n_dmpl = pk.n_hand_red, pk.n_hand_full, pk.n_dmpl
-        d.kw, d.na, d.n_levels = pk.kw, pk.na, pk.n_levels
-        for k in ('parents', 'fk_order', 'level_ofs', 'w_joint', 'anc_joint', 'anc_mask', 'free1', 'free2'):
+        d.kw = pk.kw
+        for k in ('parents', 'w_joint', 'free1', 'free2'):
             setattr(d, k, _ptr(a[k], _i32p))
-        d.anc_pos = _ptr(a['anc_pos'], _i8p)
         for k in ('hand_comps', 'hands_mean', 'v0', 'sd', 'pd', 'w_val', 'j0', 'jd', 'coefs', 'prior_means',
                   'prior_Q', 'prior_neglogw'):
             setattr(d, k, _ptr(a[k], _f64p))
@@ -210,21 +223,22 @@ class Model:
             raise Mosh2Error(f'{what} failed ({rc}): {self.lib.mosh2_last_error().decode()}')
 
     def solve(self, obs: np.ndarray, vis: np.ndarray, options: Options, *, chunk_len: int = 0,
-              chunk_warmup: int = 0, precision: int = MOSH2_F32) -> ResultArrays:
+              chunk_warmup: int = 0, warmup_full: int = -1, precision: int = MOSH2_F32) -> ResultArrays:
         """One blocking call: H2D, kernel, D2H (mosh2_solve)."""
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
         F = obs.shape[0]
         assert obs.shape == (F, self.pk.n_markers, 3) and vis8.shape == (F, self.pk.n_markers)
         res = ResultArrays(F, pack_dims(self.pk))
+        sched = make_schedule(chunk_len, chunk_warmup, warmup_full)
         rc = self.lib.mosh2_solve(self.handle, C.byref(options), F, _ptr(obs, _f64p), _ptr(vis8, _u8p),
-                                  chunk_len, chunk_warmup, precision, C.byref(res.c))
+                                  C.byref(sched), precision, C.byref(res.c))
         self._check(rc, 'mosh2_solve')
         return res
 
     def job(self, n_frames: int, options: Options, *, chunk_len: int = 0, chunk_warmup: int = 0,
-            precision: int = MOSH2_F32) -> 'Job':
-        return Job(self, n_frames, options, chunk_len, chunk_warmup, precision)
+            warmup_full: int = -1, precision: int = MOSH2_F32) -> 'Job':
+        return Job(self, n_frames, options, make_schedule(chunk_len, chunk_warmup, warmup_full), precision)
 
     def close(self):
         if self.handle:
@@ -241,11 +255,12 @@ class Model:
 class Job:
     """Staged upload / launch / download on device-resident buffers (used by bench.py)."""
 
-    def __init__(self, model: Model, n_frames: int, options: Options, chunk_len: int, chunk_warmup: int, precision: int):
+    def __init__(self, model: Model, n_frames: int, options: Options, schedule: Schedule, precision: int):
         self.model, self.lib, self.n_frames = model, model.lib, n_frames
         self.handle = C.c_void_p()
         self.options = options
-        rc = self.lib.mosh2_job_create(model.handle, C.byref(options), n_frames, chunk_len, chunk_warmup, precision,
+        self.schedule = schedule
+        rc = self.lib.mosh2_job_create(model.handle, C.byref(options), n_frames, C.byref(schedule), precision,
                                        C.byref(self.handle))
         model._check(rc, 'mosh2_job_create')
         self.result = ResultArrays(n_frames, pack_dims(model.pk))
@@ -256,6 +271,21 @@ class Job:
         vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
         self._keep = (obs, vis8)
         self.model._check(self.lib.mosh2_job_upload(self.handle, _ptr(obs, _f64p), _ptr(vis8, _u8p)), 'mosh2_job_upload')
+
+    def upload_device(self, d_obs_ptr: int, obs_is_f64: bool, d_vis_ptr: int, producer_stream: int = 0):
+        """Observations already on this job's GPU (raw device pointers, e.g. ``tensor.data_ptr()`` of an NCCL receive
+        buffer; ``producer_stream`` = the cudaStream_t the producer was queued on)."""
+        self.model._check(self.lib.mosh2_job_upload_device(self.handle, C.c_void_p(d_obs_ptr), int(bool(obs_is_f64)),
+                                                           C.c_void_p(d_vis_ptr), C.c_void_p(producer_stream)),
+                          'mosh2_job_upload_device')
+
+    @property
+    def row_width(self) -> int:
+        return int(self.lib.mosh2_job_row_width(self.handle))
+
+    def download_device(self, d_rows_ptr: int):
+        """Packed float32 result rows into a device buffer of n_frames * row_width floats (include/mosh2.h)."""
+        self.model._check(self.lib.mosh2_job_download_device(self.handle, C.c_void_p(d_rows_ptr)), 'mosh2_job_download_device')
 
     def launch(self):
         self.model._check(self.lib.mosh2_job_launch(self.handle), 'mosh2_job_launch')
@@ -272,11 +302,19 @@ class Job:
         self.model._check(self.lib.mosh2_job_kernel_ms(self.handle, C.byref(ms)), 'mosh2_job_kernel_ms')
         return float(ms.value)
 
+    def span_ms(self, last: 'Job') -> float:
+        """Device time from the start of this job's last launch to the end of ``last``'s (same device)."""
+        ms = C.c_float()
+        self.model._check(self.lib.mosh2_job_span_ms(self.handle, last.handle, C.byref(ms)), 'mosh2_job_span_ms')
+        return float(ms.value)
+
     def totals(self) -> Dict[str, int]:
-        """Work of the last launch over all processed frames, warm-up included."""
-        t = np.zeros(4, dtype=np.int32)
+        """Work of the last launch over all processed frames (warm-up included) and over the emitted frames only."""
+        t = np.zeros(8, dtype=np.int32)
         self.model._check(self.lib.mosh2_job_totals(self.handle, _ptr(t, _i32p)), 'mosh2_job_totals')
-        return dict(iterations=int(t[0]), evaluations=int(t[1]), builds=int(t[2]), minimisations=int(t[3]))
+        return dict(iterations=int(t[0]), evaluations=int(t[1]), builds=int(t[2]), minimisations=int(t[3]),
+                    emitted_iterations=int(t[4]), emitted_evaluations=int(t[5]), emitted_builds=int(t[6]),
+                    emitted_minimisations=int(t[7]))
 
     @property
     def num_chunks(self) -> int:

@@ -1,17 +1,49 @@
-"""Mocap input adapter with the reference's label clean-up, units and visibility rule.
+"""Mocap input adapter: file -> dense ``(F x M x 3 observations, F x M visibility)`` in latent-label order.
 
-Restates tools/mocap_interface.py:87-162 (``read_mocap``) and :165-295 (``MocapSession``) for the
-formats that can be read here: .npz, .pkl, .mat (scipy) and .c3d (through ``c3d_io`` because ezc3d
-is not installable).  The dense ``frames_for_labels`` view replaces the per-frame dictionaries of
-``markers_asdict`` (:254-273) that the Stage-II loop consumes at chmosh.py:582-594.
+The Stage-II loop of the reference consumes one ``{label: xyz}`` dictionary per frame
+(tools/mocap_interface.py:254-273 ``markers_asdict``, stacked at chmosh.py:582-594).  The device wants the same
+information as two dense arrays, so this adapter is built around a column table instead of per-frame dictionaries:
+
+* ``load_markers``   one reader per container (.npz / .pkl / .mat / .c3d via ``c3d_io``), registered by extension;
+* ``ColumnTable``    what every input column means after the reference's label clean-up -- blanks removed, subject
+                     prefix dropped, synonyms resolved through the label map (chmosh.py:466 always passes
+                     ``general_labels_map``; shipped here as data/label_synonyms.tsv), ``*``-labels / excluded /
+                     non-selected columns dropped (tools/mocap_interface.py:194-215);
+* ``MocapSession``   the reference's attribute surface (``markers`` in metres with missing samples zeroed, ``labels``,
+                     ``frame_rate``, ``subject_names``, ``multi_subject``, ``time_length()``) plus
+                     ``frames_for_labels`` -- the dense view.  A sample is missing when a coordinate is NaN or all
+                     three are exactly zero (:277); of several columns with one label the LAST AVAILABLE one of a
+                     frame wins, which is what writing the per-frame dictionary in column order does (:262-271).
 """
 from __future__ import annotations
 
+import os
 import pickle
-from collections import OrderedDict
-from typing import Dict, List, Optional, Sequence
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
+
+UNIT_PER_METRE = {'mm': 1000.0, 'cm': 100.0, 'm': 1.0}
+_SYNONYM_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'label_synonyms.tsv')
+_synonyms: Optional[Dict[str, str]] = None
+
+
+def general_labels_map() -> Dict[str, str]:
+    """raw label -> canonical label (the reference's marker_layout/labels_map.py:34-231, stored grouped by canonical
+    label in data/label_synonyms.tsv)."""
+    global _synonyms
+    if _synonyms is None:
+        table: Dict[str, str] = {}
+        with open(_SYNONYM_FILE) as f:
+            for line in f:
+                if line.startswith('#') or not line.strip():
+                    continue
+                canon, raws = line.rstrip('\n').split('\t')
+                for raw in raws.split(' '):
+                    table[raw] = canon
+        _synonyms = table
+    return _synonyms
 
 
 def rotate_points_xyz(points: np.ndarray, rxyz_deg: Sequence[float]) -> np.ndarray:
@@ -20,161 +52,179 @@ def rotate_points_xyz(points: np.ndarray, rxyz_deg: Sequence[float]) -> np.ndarr
     rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
     ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
     rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
-    R = rz @ ry @ rx
-    return np.einsum('cd,fnd->fnc', R, points)
+    return np.einsum('cd,fnd->fnc', rz @ ry @ rx, points)
+
+
+# --------------------------------------------------------------------------------------
+# containers
+# --------------------------------------------------------------------------------------
+def _from_npz(fname):
+    z = np.load(fname, allow_pickle=True)
+    rate = None
+    if 'frame_rate' in z.files:
+        rate = float(z['frame_rate'])
+    elif 'required_parameters' in z.files:
+        rate = z['required_parameters'].item().get('frame_rate')
+    return z['markers'], (z['labels'].tolist() if 'labels' in z.files else None), rate
+
+
+def _from_pkl(fname):
+    with open(fname, 'rb') as f:
+        md = pickle.load(f, encoding='latin-1')
+    rate = md['required_parameters']['frame_rate'] if 'required_parameters' in md else md.get('frame_rate')
+    labels = md.get('labels', None)
+    if isinstance(labels, np.ndarray):
+        labels = labels.tolist()
+    if labels:   # unlabeled trajectories are stored as arrays: they become starred placeholders
+        labels = [f'*{i}' if isinstance(l, np.ndarray) else l for i, l in enumerate(labels)]
+    return md['markers'], labels or None, rate
+
+
+def _from_mat(fname):
+    import scipy.io
+    md = scipy.io.loadmat(fname)
+    keys = [k for k in ('MoCaps', 'Markers') if k in md]
+    if not keys:
+        raise ValueError("The .mat file do not have the expected field for marker data! "
+                         "Expected fields are ['MoCaps', 'Markers']")
+    labels = np.vstack(md['Labels'][0]).ravel().tolist() if 'Labels' in md else None
+    return md[keys[-1]], labels, None
+
+
+def _from_c3d(fname):
+    from .c3d_io import read_c3d
+    return read_c3d(fname)
+
+
+READERS: Dict[str, Callable] = {'.npz': _from_npz, '.pkl': _from_pkl, '.mat': _from_mat, '.c3d': _from_c3d}
+
+
+def load_markers(mocap_fname: str) -> Tuple[np.ndarray, List[str], Optional[float]]:
+    """(markers F x L x 3 float64 in file units, one label per column, frame rate or None).
+    Columns without a label get the placeholder ``*<index>`` (tools/mocap_interface.py:118-124,150-152)."""
+    fname = str(mocap_fname)
+    ext = os.path.splitext(fname)[1].lower()
+    if ext not in READERS:
+        raise ValueError(f"Error! Could not recognize file format for {fname}")
+    markers, labels, rate = READERS[ext](fname)
+    markers = np.array(markers, dtype=np.float64)
+    labels = [] if labels is None else [l.decode() if isinstance(l, bytes) else str(l) for l in labels]
+    labels += [f'*{i}' for i in range(len(labels), markers.shape[1])]
+    return markers, labels, rate
 
 
 def read_mocap(mocap_fname: str) -> Dict:
-    """tools/mocap_interface.py:87-162."""
-    labels = None
-    frame_rate = None
-    mocap_fname = str(mocap_fname)
-    if mocap_fname.endswith('.mat'):
-        import scipy.io
-        md = scipy.io.loadmat(mocap_fname)
-        markers = None
-        for key in ('MoCaps', 'Markers'):
-            if key in md:
-                markers = md[key]
-        if markers is None:
-            raise ValueError("The .mat file do not have the expected field for marker data! "
-                             "Expected fields are ['MoCaps', 'Markers']")
-        if 'Labels' in md:
-            labels = np.vstack(md['Labels'][0]).ravel().tolist()
-    elif mocap_fname.endswith('.pkl'):
-        with open(mocap_fname, 'rb') as f:
-            md = pickle.load(f, encoding='latin-1')
-        markers = md['markers']
-        if 'required_parameters' in md:
-            frame_rate = md['required_parameters']['frame_rate']
-        elif 'frame_rate' in md:
-            frame_rate = md['frame_rate']
-        labels = md.get('labels', False)
-        if isinstance(labels, np.ndarray):
-            labels = labels.tolist()
-        labels = [f'*{i}' if isinstance(l, np.ndarray) else l for i, l in enumerate(labels)] if labels else None
-    elif mocap_fname.endswith('.c3d'):
-        from .c3d_io import read_c3d
-        markers, labels, frame_rate = read_c3d(mocap_fname)
-        if len(labels) < markers.shape[1]:
-            labels = labels + [f'*{len(labels) + i:d}' for i in range(markers.shape[1] - len(labels))]
-    elif mocap_fname.endswith('.npz'):
-        md = np.load(mocap_fname, allow_pickle=True)
-        markers = md['markers']
-        if 'frame_rate' in md.files:
-            frame_rate = float(md['frame_rate'])
-        elif 'required_parameters' in md.files:
-            rp = md['required_parameters'].item()
-            if 'frame_rate' in rp:
-                frame_rate = rp['frame_rate']
-        labels = md['labels'].tolist() if 'labels' in md.files else None
-    else:
-        raise ValueError(f"Error! Could not recognize file format for {mocap_fname}")
+    """Dictionary form of ``load_markers`` with the per-subject column masks (tools/mocap_interface.py:87-162)."""
+    markers, labels, rate = load_markers(mocap_fname)
+    return {'markers': markers, 'labels': labels, 'frame_rate': rate, 'subject_mask': subject_masks(labels)}
 
-    markers = np.array(markers, dtype=np.float64)
-    if labels is None:
-        labels = [f'*{i}' for i in range(markers.shape[1])]
-    elif len(labels) < markers.shape[1]:
-        labels = list(labels) + [f'*{i}' for i in range(markers.shape[1] - len(labels))]
-    labels = [l.decode() if isinstance(l, bytes) else str(l) for l in labels]
 
-    subject_mask, subject_id_map = [], {}
-    for l in labels:
-        name = l.split(':')[0] if ':' in l else 'null'
-        if name not in subject_id_map:
-            subject_id_map[name] = len(subject_id_map)
-        subject_mask.append(subject_id_map[name])
-    subject_mask = {n: np.array([i == sid for i in subject_mask], dtype=bool) for n, sid in subject_id_map.items()}
-    return {'markers': markers, 'labels': labels, 'frame_rate': frame_rate, 'subject_mask': subject_mask}
+def subject_masks(raw_labels: Sequence[str]) -> Dict[str, np.ndarray]:
+    """Column mask per capture subject: the text before ':' of a raw label, 'null' without one."""
+    names = np.array([l.split(':')[0] if ':' in l else 'null' for l in raw_labels], dtype=object)
+    order = list(dict.fromkeys(names.tolist()))
+    return {n: names == n for n in order}
+
+
+# --------------------------------------------------------------------------------------
+# label clean-up
+# --------------------------------------------------------------------------------------
+@dataclass
+class ColumnTable:
+    labels: List[str]          # cleaned label of every KEPT column
+    keep: np.ndarray           # bool mask over the input columns
+
+    @classmethod
+    def build(cls, raw_labels: Sequence[str], *, labels_map: Optional[Dict[str, str]], only_markers, exclude_markers,
+              ignore_stared_labels: bool, remove_label_before_colon: bool) -> 'ColumnTable':
+        clean = [l.replace(' ', '') for l in raw_labels]
+        if remove_label_before_colon:
+            clean = [l.rsplit(':', 1)[-1] for l in clean]
+        if labels_map is not None:
+            clean = [labels_map.get(l, l) for l in clean]
+        if only_markers is not None:                     # a positive list overrides the two negative rules
+            wanted = set(only_markers)
+            keep = np.array([l in wanted for l in clean], dtype=bool)
+        else:
+            banned = set(exclude_markers or ())
+            keep = np.array([not (ignore_stared_labels and l.startswith('*')) and l not in banned for l in clean], dtype=bool)
+        return cls([l for l, k in zip(clean, keep) if k], keep)
 
 
 class MocapSession:
-    """tools/mocap_interface.py:165-295 (reader side)."""
+    """One capture file, cleaned up like the reference's ``MocapSession`` (tools/mocap_interface.py:165-252).
+
+    ``labels_map``: ``'general'`` (default) = the shipped synonym table the reference's Stage I / II always apply
+    (chmosh.py:124,466); a dict = custom table; ``None`` = raw labels."""
 
     def __init__(self, mocap_fname, mocap_unit: str, mocap_rotate=None, exclude_markers: List[str] = None,
-                 only_subjects: List[str] = None, only_markers: List[str] = None, labels_map: dict = None,
+                 only_subjects: List[str] = None, only_markers: List[str] = None, labels_map='general',
                  ignore_stared_labels: bool = True, remove_label_before_colon: bool = True):
-        scale = {'mm': 1000., 'cm': 100., 'm': 1.}[mocap_unit]
-        self.mocap_fname = mocap_fname
-        self.read_status = False
+        if mocap_unit not in UNIT_PER_METRE:
+            raise KeyError(mocap_unit)
         if only_subjects:
             assert isinstance(only_subjects, list), ValueError(
                 f'attribute only_subjects should be a list of strings as subject names: {only_subjects}')
-        rd = read_mocap(mocap_fname)
-        labels = [l.replace(' ', '') for l in rd['labels']]
-        if remove_label_before_colon:
-            labels = [l.split(':')[-1] for l in labels]
-        if labels_map is not None:
-            labels = [labels_map.get(l, l) for l in labels]
-        if only_markers is not None:
-            good = [l in only_markers for l in labels]
-        else:
-            good = [True] * len(labels)
-            if ignore_stared_labels:
-                good = [g and not l.startswith('*') for g, l in zip(good, labels)]
-            if exclude_markers is not None:
-                good = [g and l not in exclude_markers for g, l in zip(good, labels)]
-        good = np.asarray(good, dtype=bool)
-        labels = [l for l, g in zip(labels, good) if g]
-        subject_mask = {k: v[good] for k, v in rd['subject_mask'].items()}
-        subject_names = sorted(subject_mask.keys())
-        markers = rd['markers'][:, good].copy()
-        nan_mask = np.logical_not(MocapSession.marker_availability_mask(markers))
-        markers[nan_mask] = 0.
+        self.mocap_fname = mocap_fname
+        self.read_status = False
+        raw, raw_labels, rate = load_markers(mocap_fname)
+        if isinstance(labels_map, str):
+            if labels_map != 'general':
+                raise ValueError(f'unknown labels_map {labels_map!r}')
+            labels_map = general_labels_map()
+        table = ColumnTable.build(raw_labels, labels_map=labels_map, only_markers=only_markers,
+                                  exclude_markers=exclude_markers, ignore_stared_labels=ignore_stared_labels,
+                                  remove_label_before_colon=remove_label_before_colon)
+        subjects = {n: m[table.keep] for n, m in subject_masks(raw_labels).items()}
+        markers = raw[:, table.keep]
+        markers[~self.marker_availability_mask(markers)] = 0.0
         if mocap_rotate is not None:
             markers = rotate_points_xyz(markers, mocap_rotate).reshape(markers.shape)
+        labels = table.labels
         if only_subjects:
-            if not np.all([s in subject_names for s in only_subjects]):
+            missing = [s for s in only_subjects if s not in subjects]
+            if missing:      # the reference logs an error and leaves the session unread (read_status False)
                 return
-            selm = np.zeros(markers.shape[1], dtype=bool)
-            for s in only_subjects:
-                selm = np.logical_or(selm, subject_mask[s])
-            subject_mask = {k: v[selm] for k, v in subject_mask.items() if k in only_subjects}
-            subject_names = only_subjects
-            markers = markers[:, selm]
-            labels = (np.array(labels)[selm]).tolist()
-        self.markers = markers / scale
+            cols = np.logical_or.reduce([subjects[s] for s in only_subjects])
+            subjects = {s: subjects[s][cols] for s in only_subjects}
+            markers = markers[:, cols]
+            labels = [l for l, c in zip(labels, cols) if c]
+        self.markers = markers / UNIT_PER_METRE[mocap_unit]
         self.labels = labels
-        self.subject_mask = subject_mask
-        self.subject_names = subject_names
-        self.multi_subject = len([s for s in subject_names if s != 'null']) > 1
-        fr = rd.get('frame_rate', 120.)
-        self.frame_rate = 120. if fr is None else fr
+        self.subject_mask = subjects
+        self.subject_names = list(only_subjects) if only_subjects else sorted(subjects)
+        self.multi_subject = sum(1 for s in self.subject_names if s != 'null') > 1
+        self.frame_rate = 120. if rate is None else rate
         self.read_status = True
 
     @staticmethod
-    def marker_availability_mask(markers):
-        """A marker is missing if any coordinate is NaN or all three are exactly 0 (line 277)."""
-        return np.logical_and(np.isnan(markers).sum(-1) == 0, (markers == 0).sum(-1) != 3)
-
-    def markers_asdict(self) -> List[Dict[str, np.ndarray]]:
-        ok = MocapSession.marker_availability_mask(self.markers)
-        out = []
-        for t in range(self.markers.shape[0]):
-            m = OrderedDict()
-            for i, l in enumerate(self.labels):
-                if ok[t, i]:
-                    m[l] = self.markers[t, i, :]
-            out.append(m)
-        return out
+    def marker_availability_mask(markers: np.ndarray) -> np.ndarray:
+        """False where a sample is missing: a NaN coordinate, or all three exactly 0 (:277)."""
+        return ~np.isnan(markers).any(-1) & ~(markers == 0).all(-1)
 
     def frames_for_labels(self, latent_labels: Sequence[str], frame_ids: Sequence[int]):
-        """Dense view of what chmosh.py:582-594 builds frame by frame: observations F x M x 3 in
-        ``latent_labels`` order and the F x M visibility mask (label present and sample available)."""
-        lab_idx = {}
-        for i, l in enumerate(self.labels):
-            lab_idx[l] = i
-        cols = np.array([lab_idx.get(l, -1) for l in latent_labels], dtype=np.int64)
+        """Observations ``F x M x 3`` (metres) in ``latent_labels`` order and the ``F x M`` visibility mask -- label
+        present in the file and sample available in the frame.  What chmosh.py:582-594 stacks frame by frame."""
         frame_ids = np.asarray(list(frame_ids), dtype=np.int64)
         mk = self.markers[frame_ids]
-        ok = MocapSession.marker_availability_mask(mk)
-        have = cols >= 0
-        obs = np.zeros((len(frame_ids), len(cols), 3))
-        vis = np.zeros((len(frame_ids), len(cols)), dtype=bool)
-        obs[:, have] = mk[:, cols[have]]
-        vis[:, have] = ok[:, cols[have]]
-        obs[~vis] = 0.0
+        ok = self.marker_availability_mask(mk)
+        F, M = len(frame_ids), len(latent_labels)
+        obs = np.zeros((F, M, 3))
+        vis = np.zeros((F, M), dtype=bool)
+        columns: Dict[str, List[int]] = {}
+        for c, l in enumerate(self.labels):
+            columns.setdefault(l, []).append(c)
+        for m, l in enumerate(latent_labels):
+            for c in columns.get(l, ()):                 # later columns overwrite earlier ones where they are available
+                sel = ok[:, c]
+                obs[sel, m] = mk[sel, c]
+                vis[:, m] |= sel
         return obs, vis
+
+    def markers_asdict(self) -> List[Dict[str, np.ndarray]]:
+        """Per-frame ``{label: xyz}`` of the available samples (compatibility view; the solver uses the dense one)."""
+        ok = self.marker_availability_mask(self.markers)
+        return [{l: self.markers[t, c] for c, l in enumerate(self.labels) if ok[t, c]} for t in range(len(self))]
 
     def __len__(self):
         return self.markers.shape[0]

@@ -224,17 +224,10 @@ class StageIIPack:
     n_hand_full: int
     n_dmpl: int              # per-frame linear coefficients in all: DMPL first, then expressions
     kw: int                  # skinning weights kept per slot (ELL width)
-    na: int                  # ancestor-list width per slot
-    n_levels: int
     # ---- int arrays
     parents: np.ndarray      # nJ int32
-    fk_order: np.ndarray     # nJ int32, joints sorted by depth
-    level_ofs: np.ndarray    # n_levels+1 int32 offsets into fk_order
     slot_vid: np.ndarray     # 3M int32 (bookkeeping only)
     w_joint: np.ndarray      # 3M x kw int32 (-1 pad)
-    anc_joint: np.ndarray    # 3M x na int32 (-1 pad)
-    anc_mask: np.ndarray     # 3M x na int32 bit i set <=> w_joint[:, i] is in the subtree of anc
-    anc_pos: np.ndarray      # 3M x nJ int8  position of joint in anc_joint (-1 if absent)
     # ---- float64 arrays (converted to the compute type by the library)
     hand_comps: np.ndarray   # n_hand_red x n_hand_full
     hands_mean: np.ndarray   # n_hand_full
@@ -338,17 +331,6 @@ def pose_partitions(model_type: str, p_red: int, optimize_fingers: bool, optimiz
     return dict(root=root, body=body, face=face, finger=finger, step1=sorted(step1), step2=step2)
 
 
-def _subtree_matrix(parents: np.ndarray) -> np.ndarray:
-    nj = len(parents)
-    sub = np.eye(nj, dtype=bool)           # sub[a, j] <=> j in subtree(a)
-    for j in range(1, nj):
-        a = parents[j]
-        while a >= 0:
-            sub[a, j] = True
-            a = parents[a]
-    return sub
-
-
 def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarray, *,
                num_betas: int, prior: Optional[BodyPrior], dmpl_dirs: Optional[np.ndarray] = None,
                num_dmpls: int = 0, optimize_fingers: bool = False, optimize_toes: bool = False,
@@ -401,35 +383,8 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
         js = np.nonzero(wsel[s])[0]
         w_joint[s, :len(js)] = js
         w_val[s, :len(js)] = wsel[s, js]
-    if kw > 30:
-        raise ValueError(f'a marker vertex has {kw} non-zero skinning weights; the kernel packs the subtree mask in 31 bits')
-
-    sub = _subtree_matrix(model.parents)
-    anc_lists = []
-    for s in range(3 * M):
-        js = w_joint[s][w_joint[s] >= 0]
-        anc = np.nonzero(sub[:, js].any(1))[0]
-        anc_lists.append(anc)
-    na = int(max(len(a) for a in anc_lists))
-    anc_joint = -np.ones((3 * M, na), dtype=np.int32)
-    anc_mask = np.zeros((3 * M, na), dtype=np.int32)
-    anc_pos = -np.ones((3 * M, nj), dtype=np.int8)
-    for s, anc in enumerate(anc_lists):
-        anc_joint[s, :len(anc)] = anc
-        for ai, a in enumerate(anc):
-            anc_pos[s, a] = ai
-            m = 0
-            for i in range(kw):
-                if w_joint[s, i] >= 0 and sub[a, w_joint[s, i]]:
-                    m |= (1 << i)
-            anc_mask[s, ai] = m
-
-    depth = np.zeros(nj, dtype=np.int64)
-    for j in range(1, nj):
-        depth[j] = depth[model.parents[j]] + 1
-    fk_order = np.argsort(depth, kind='stable').astype(np.int32)
-    n_levels = int(depth.max()) + 1
-    level_ofs = np.searchsorted(depth[fk_order], np.arange(n_levels + 1)).astype(np.int32)
+    if kw > 8:
+        raise ValueError(f'a marker vertex has {kw} non-zero skinning weights; the kernel keeps at most 8 per vertex')
 
     parts = pose_partitions(model.model_type, model.p_red, optimize_fingers, optimize_face, optimize_toes)
     p_red = model.p_red
@@ -445,10 +400,9 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
     pack = StageIIPack(
         model_type=model.model_type, n_joints=nj, n_markers=M, body_dof=model.body_dof, p_red=p_red,
         p_full=model.p_full, n_hand_red=model.hand_comps.shape[0], n_hand_full=model.hands_mean.shape[0],
-        n_dmpl=nd, n_expr=n_expr, kw=kw, na=na, n_levels=n_levels,
-        parents=model.parents.astype(np.int32), fk_order=fk_order, level_ofs=level_ofs,
-        slot_vid=slot_vid.astype(np.int32), w_joint=w_joint, anc_joint=anc_joint, anc_mask=anc_mask,
-        anc_pos=anc_pos,
+        n_dmpl=nd, n_expr=n_expr, kw=kw,
+        parents=model.parents.astype(np.int32),
+        slot_vid=slot_vid.astype(np.int32), w_joint=w_joint,
         hand_comps=np.ascontiguousarray(model.hand_comps), hands_mean=np.ascontiguousarray(model.hands_mean),
         v0=np.ascontiguousarray(v_shaped[slot_vid]), sd=np.ascontiguousarray(sd), pd=pd,
         w_val=np.ascontiguousarray(w_val), j0=np.ascontiguousarray(j0), jd=np.ascontiguousarray(jd),

@@ -1,9 +1,11 @@
-"""Sequence sharding over the GPUs of one box.
+"""Sequence sharding over the GPUs of one box (BASELINE config 5).
 
-Sequences are independent (nothing is shared but the static model), so the path shards with no
-data-path collective: every rank solves its own sequences.  ``torch.distributed`` (NCCL on GPUs, gloo in
-the CPU tests) only carries the trivial scatter of observations from rank 0 and the gather of per-frame
-results back to it.  One process per GPU; launch with torchrun.
+Sequences are independent (nothing is shared but the static model), so the path shards with no data-path
+collective: rank 0 owns the observations of every sequence, scatters each one to the rank that will solve it,
+every rank solves its sequences on its own GPU, and the per-frame result rows travel back to rank 0.  The scatter
+and the gather are grouped point-to-point transfers of ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the
+CPU tests); on GPUs the received tensors never touch the host: the C-ABI takes and returns device pointers
+(``mosh2_job_upload_device`` / ``mosh2_job_download_device``).  One process per GPU; launch with torchrun.
 """
 from __future__ import annotations
 
@@ -33,76 +35,145 @@ def _device(dist):
     return torch.device('cpu')
 
 
-def scatter_observations(obs_list: Optional[List[np.ndarray]], vis_list: Optional[List[np.ndarray]],
-                         assignment: List[List[int]], shapes: List[tuple], src: int = 0):
-    """Rank ``src`` holds every sequence's (obs F x M x 3, vis F x M); each rank receives the ones assigned
-    to it.  ``shapes[i] = (F_i, M_i)`` must be known on every rank (it is derived from the job list)."""
+def _run_p2p(ops):
+    import torch.distributed as dist
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+
+
+def scatter_observations(obs_list, vis_list, assignment: List[List[int]], shapes: List[tuple], src: int = 0):
+    """Rank ``src`` holds every sequence's observations (``obs_list[i]``: F x M x 3 float32 tensor or array, host or
+    device; ``vis_list[i]``: F x M uint8); every rank gets {seq: (obs, vis)} tensors on its own device for the
+    sequences assigned to it.  ``shapes[i] = (F_i, M_i)`` is known on every rank (it is derived from the job list).
+    All transfers go out as one grouped batch."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = _device(dist)
+
+    def on_dev(a, dtype):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+
     mine: Dict[int, tuple] = {}
-    reqs = []
+    ops, keep = [], []
     if rank == src:
         for r in range(world):
             for i in assignment[r]:
-                o = torch.from_numpy(np.ascontiguousarray(obs_list[i], dtype=np.float32))
-                v = torch.from_numpy(np.ascontiguousarray(vis_list[i], dtype=np.uint8))
+                o, v = on_dev(obs_list[i], torch.float32), on_dev(vis_list[i], torch.uint8)
                 if r == src:
-                    mine[i] = (o.numpy().astype(np.float64), v.numpy().astype(bool))
+                    mine[i] = (o, v)
                 else:
-                    reqs.append(dist.isend(o.to(dev), dst=r))
-                    reqs.append(dist.isend(v.to(dev), dst=r))
+                    keep += [o, v]
+                    ops += [dist.P2POp(dist.isend, o, r), dist.P2POp(dist.isend, v, r)]
     else:
         for i in assignment[rank]:
             F, M = shapes[i]
             o = torch.empty((F, M, 3), dtype=torch.float32, device=dev)
             v = torch.empty((F, M), dtype=torch.uint8, device=dev)
-            dist.recv(o, src=src)
-            dist.recv(v, src=src)
-            mine[i] = (o.cpu().numpy().astype(np.float64), v.cpu().numpy().astype(bool))
-    for q in reqs:
-        q.wait()
+            mine[i] = (o, v)
+            ops += [dist.P2POp(dist.irecv, o, src), dist.P2POp(dist.irecv, v, src)]
+    _run_p2p(ops)
     return mine
 
 
-def gather_results(local: Dict[int, Dict[str, np.ndarray]], assignment: List[List[int]],
-                   row_widths: List[int], shapes: List[tuple], dst: int = 0):
-    """Gathers per-sequence result rows (one float32 matrix F_i x row_widths[i] per sequence, e.g.
-    [fullpose | trans | dmpls]) to rank ``dst``.  Returns {seq: matrix} on dst, {} elsewhere."""
+def gather_results(local: Dict[int, 'object'], assignment: List[List[int]], row_widths: List[int], shapes: List[tuple],
+                   dst: int = 0):
+    """Gathers per-sequence result rows (one float32 tensor F_i x row_widths[i] per sequence on the rank's device) to
+    rank ``dst``.  Returns {seq: tensor on dst's device} on dst, {} elsewhere."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = _device(dist)
-    out: Dict[int, np.ndarray] = {}
-    reqs = []
+    out: Dict[int, 'torch.Tensor'] = {}
+    ops = []
     if rank == dst:
         for r in range(world):
             for i in assignment[r]:
                 if r == dst:
-                    out[i] = np.asarray(local[i], dtype=np.float32)
+                    out[i] = local[i]
                 else:
-                    buf = torch.empty((shapes[i][0], row_widths[i]), dtype=torch.float32, device=dev)
-                    dist.recv(buf, src=r)
-                    out[i] = buf.cpu().numpy()
+                    out[i] = torch.empty((shapes[i][0], row_widths[i]), dtype=torch.float32, device=dev)
+                    ops.append(dist.P2POp(dist.irecv, out[i], r))
     else:
         for i in assignment[rank]:
-            t = torch.from_numpy(np.ascontiguousarray(local[i], dtype=np.float32)).to(dev)
-            reqs.append(dist.isend(t, dst=dst))
-    for q in reqs:
-        q.wait()
+            ops.append(dist.P2POp(dist.isend, local[i].contiguous(), dst))
+    _run_p2p(ops)
     return out
 
 
 def solve_sharded(frame_counts: Sequence[int], n_markers: Sequence[int], row_widths: Sequence[int],
-                  solve_fn: Callable[[int, np.ndarray, np.ndarray], np.ndarray],
-                  obs_list: Optional[List[np.ndarray]] = None, vis_list: Optional[List[np.ndarray]] = None):
-    """Scatter -> per-rank solves -> gather.  ``solve_fn(seq_index, obs, vis)`` returns the F x width
-    result matrix of one sequence (on a GPU box it wraps ``lib.Model.solve`` on the rank's device)."""
+                  solve_fn: Callable[[Dict[int, tuple]], Dict[int, 'object']], obs_list=None, vis_list=None):
+    """Scatter -> per-rank solves -> gather.  ``solve_fn({seq: (obs, vis)})`` gets this rank's sequences as tensors on
+    the rank's device and returns {seq: F x width float32 tensor on the same device}.  Returns
+    ({seq: rows} on rank 0 / {} elsewhere, assignment)."""
     import torch.distributed as dist
     world = dist.get_world_size()
     assignment = assign_sequences(list(frame_counts), world)
     shapes = [(int(f), int(m)) for f, m in zip(frame_counts, n_markers)]
     mine = scatter_observations(obs_list, vis_list, assignment, shapes)
-    local = {i: solve_fn(i, o, v) for i, (o, v) in mine.items()}
+    local = solve_fn(mine)
     return gather_results(local, assignment, list(row_widths), shapes), assignment
+
+
+class GpuRankSolver:
+    """This rank's share of a sharded run on its GPU: one model (all sequences of BASELINE config 5 share the body
+    model, shape and marker layout; pass ``packs`` per sequence otherwise), one resident job per local sequence, every
+    job on its own stream so that the chunks of all local sequences fill the GPU together.  The chunk length is planned
+    for all local sequences together (chmosh.plan_chunk_len: whole waves of one chunk per SM)."""
+
+    def __init__(self, packs: Dict[int, object], options, frame_counts: Dict[int, int], device: int, *,
+                 chunk_warmup: int, warmup_full: int, sm_budget: int = 148, precision=None):
+        from . import lib
+        self.lib = lib
+        self.device = device
+        prec = lib.MOSH2_F32 if precision is None else precision
+        self.models, self.jobs = {}, {}
+        from .chmosh import plan_chunk_len
+        common = plan_chunk_len(list(frame_counts.values()), sm_budget, chunk_warmup, warmup_full)
+        for i, F in frame_counts.items():
+            pk = packs[i]
+            key = id(pk)
+            if key not in self.models:
+                self.models[key] = lib.Model(pk, device=device)
+            chunk_len = 0 if common >= F else common
+            self.jobs[i] = self.models[key].job(F, options, chunk_len=chunk_len, chunk_warmup=chunk_warmup,
+                                                warmup_full=warmup_full, precision=prec)
+
+    def __call__(self, mine: Dict[int, tuple]) -> Dict[int, 'object']:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+        out = {}
+        for i, (o, v) in mine.items():                 # all uploads and launches are queued before the first wait
+            j = self.jobs[i]
+            j.upload_device(o.data_ptr(), False, v.data_ptr(), stream)
+            j.launch()
+        torch.cuda.current_stream().synchronize()      # the row buffers are written on the jobs' own streams
+        for i in mine:
+            j = self.jobs[i]
+            rows = torch.empty((j.n_frames, j.row_width), dtype=torch.float32, device=f'cuda:{self.device}')
+            j.download_device(rows.data_ptr())         # packs on the job's stream and waits for it
+            out[i] = rows
+        return out
+
+    def kernel_ms(self) -> Dict[int, float]:
+        return {i: j.kernel_ms() for i, j in self.jobs.items()}
+
+    def span_ms(self) -> float:
+        """Device time of the last round of launches of all local jobs (CUDA events on the jobs' streams)."""
+        js = list(self.jobs.values())
+        return max(a.span_ms(b) for a in js for b in js)
+
+    def totals(self) -> Dict[str, int]:
+        agg: Dict[str, int] = {}
+        for j in self.jobs.values():
+            for k, v in j.totals().items():
+                agg[k] = agg.get(k, 0) + v
+        return agg
+
+    def close(self):
+        for j in self.jobs.values():
+            j.close()
+        for m in self.models.values():
+            m.close()

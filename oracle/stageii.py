@@ -11,8 +11,9 @@ Modes
                       then selects rows, i.e. the reference's cost structure; used
                       as the CPU baseline.  Both modes give the same numbers (tests/test_oracle_*).
 
-``chunk=(L, W)`` emulates the device's parallel-in-time schedule: frames are cut into chunks of L,
-each solved like an independent sequence that starts W frames early (DESIGN.md "Chunked schedule").
+``chunk=(L, W[, W_full])`` emulates the device's parallel-in-time schedule: frames are cut into chunks of L,
+each solved like an independent sequence that starts W solved frames early, the last W_full of them with the
+full per-frame schedule and the earlier ones with one Step-2 iteration (DESIGN.md "Chunked schedule").
 ``chunk=None`` is the reference's single sequential pass.
 
 DMPL with SMPL-X is rejected by the reference (chmosh.py:508-509); BASELINE config 3 asks for it, so
@@ -297,8 +298,8 @@ class StageIISolver:
                 dm_beta += np.einsum('mcd,mdb->mcb', L, dv_beta[t[:, k]])
         return {'markers': mk, 'dm_pose': dm_pose, 'dm_beta': dm_beta}
 
-    def _minimize(self, objective, e_3):
-        x, st = minimize_dogleg(objective, objective.x0(), e_3=e_3, delta_0=0.5, maxiter=self.maxiter)
+    def _minimize(self, objective, e_3, maxiter=None):
+        x, st = minimize_dogleg(objective, objective.x0(), e_3=e_3, delta_0=0.5, maxiter=maxiter or self.maxiter)
         objective.assign(x)
         self.stats['r_evals'] += st.r_evals
         self.stats['j_evals'] += st.j_evals
@@ -312,9 +313,12 @@ class StageIISolver:
         if self.nd:
             self.betas[self.lin_ids] = 0.0
 
-    def solve_range(self, obs_frames: List[Optional[Tuple[np.ndarray, np.ndarray]]], emit_from: int = 0):
+    def solve_range(self, obs_frames: List[Optional[Tuple[np.ndarray, np.ndarray]]], emit_from: int = 0,
+                    light_until: int = 0, on_frame=None):
         """The frame loop chmosh.py:584-724 over ``obs_frames`` (each ``(vis_idx, obs m x 3)`` or None for a
-        frame without visible markers).  Frames before ``emit_from`` are solved but not reported."""
+        frame without visible markers).  Frames before ``emit_from`` are solved but not reported.  Device-schedule
+        emulation only (not reference behaviour): frames before ``light_until`` other than the first solved one are
+        tracked with a single dog-leg iteration of the Step-2 problem."""
         w = self.wts
         M = self.n_markers
         pose_prev = None
@@ -343,6 +347,7 @@ class StageIISolver:
             if pose_prev is not None:
                 terms.append(['velo', (wt_velo, self.pose + (self.pose - pose_prev))])           # line 626
 
+            was_first = first
             if first:
                 sim = self.evaluate(False)['markers'][vis]
                 rv, T = perform_rigid_adjustment(sim, obs)                                       # line 634
@@ -358,7 +363,9 @@ class StageIISolver:
                 if self.optimize_dynamics:
                     dmpl_prev = self.betas[self.dmpl_ids].copy()
 
-            self._minimize(_Objective(self, obs, vis, terms, self.step1_ids, False), 1e-2)        # Step 1
+            light = (not was_first) and fi < light_until
+            if not light:
+                self._minimize(_Objective(self, obs, vis, terms, self.step1_ids, False), 1e-2)    # Step 1
 
             if self.optimize_fingers:
                 terms.append(['poseH', wt_poseH])
@@ -371,8 +378,10 @@ class StageIISolver:
                     terms.append(['extrap_dmpl', (6.0, cur + (cur - dmpl_prev))])                # line 697 (App. B-1)
                 terms.append(['dmpl', wt_dmpl])
             obj2 = _Objective(self, obs, vis, terms, self.step2_ids, self.nd > 0)
-            self._minimize(obj2, 1e-2)                                                           # Step 2
+            self._minimize(obj2, 1e-2, maxiter=1 if light else None)                             # Step 2
 
+            if on_frame is not None:
+                on_frame(fi)                  # bench.py: wall-clock stamp after every solved frame
             if fi >= emit_from:
                 errs = obj2.term_sse()
                 mk = self.evaluate(False)['markers'][vis]
@@ -387,23 +396,30 @@ class StageIISolver:
 def frames_from_mocap(markers, labels, latent_labels):
     """``markers_asdict`` + the per-frame stacking of chmosh.py:582-594 on dense arrays.
     markers: F x L x 3 in metres with missing samples already zeroed (mocap_interface.py:223-225)."""
-    lab_idx = {}
+    cols = {}
     for i, l in enumerate(labels):
-        lab_idx[l] = i                       # later duplicates win, like dict assignment in markers_asdict
+        cols.setdefault(l, []).append(i)
     avail = np.logical_and(np.isnan(markers).sum(-1) == 0, (markers == 0).sum(-1) != 3)   # mocap_interface.py:277
     frames = []
     for t in range(markers.shape[0]):
-        vis = [li for li, l in enumerate(latent_labels) if l in lab_idx and avail[t, lab_idx[l]]]
+        # markers_asdict writes the frame's dictionary in column order and only for available samples
+        # (mocap_interface.py:262-271): of several columns with one label the last AVAILABLE one wins
+        pick = {}
+        for li, l in enumerate(latent_labels):
+            for c in cols.get(l, ()):
+                if avail[t, c]:
+                    pick[li] = c
+        vis = sorted(pick)
         if not vis:
             frames.append(None)
             continue
-        obs = np.vstack([markers[t, lab_idx[latent_labels[li]]] for li in vis])
+        obs = np.vstack([markers[t, pick[li]] for li in vis])
         frames.append((np.asarray(vis, dtype=np.int64), obs))
     return frames
 
 
 def mosh_stageii(mocap_fname, cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname=None,
-                 *, mode='lean', chunk=None, max_frames=None, allow_smplx_dmpl=True, mocap=None) -> dict:
+                 *, mode='lean', chunk=None, max_frames=None, allow_smplx_dmpl=True, mocap=None, on_frame=None) -> dict:
     """Same signature and return layout as the reference (chmosh.py:458-459, 726-741)."""
     if mocap is None:
         # host IO adapter (outside the oracle's scope, SURVEY.md 8(f-1)); shared with the product
@@ -419,14 +435,24 @@ def mosh_stageii(mocap_fname, cfg, markers_latent, latent_labels, betas, marker_
     frames = frames_from_mocap(mocap.markers[sel], mocap.labels, solver.latent_labels)
     t0 = time.time()
     if chunk is None:
-        per = solver.solve_range(frames)
+        per = solver.solve_range(frames, on_frame=on_frame)
     else:
-        L, W = chunk
+        L, W = chunk[:2]
+        W_full = chunk[2] if len(chunk) > 2 and 0 <= chunk[2] <= W else W
         per = []
         for s in range(0, len(frames), L):
-            lo = max(0, s - W)
+            # the warm-up is counted in solved frames (frames with a visible marker), walking back from the chunk
+            lo, full_from, cnt = s, s, 0
+            while lo > 0 and cnt < W:
+                lo -= 1
+                if frames[lo] is not None:
+                    cnt += 1
+                    if cnt <= W_full:
+                        full_from = lo
+            while lo < s and frames[lo] is None:
+                lo += 1
             solver.reset()
-            res = solver.solve_range(frames[lo:s + L], emit_from=s - lo)
+            res = solver.solve_range(frames[lo:s + L], emit_from=s - lo, light_until=full_from - lo)
             for r in res:
                 r['fidx'] += lo
             per += res

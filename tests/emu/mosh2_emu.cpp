@@ -8,6 +8,7 @@
 #include "../../moshpp_b200/csrc/mosh2_device.cuh"
 #include "../../moshpp_b200/csrc/mosh2_host.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -30,17 +31,19 @@ struct HostModel {
     void build(const mosh2_model_desc &d) {
         const size_t nJ = d.n_joints, S = size_t(3) * d.n_markers, nd = d.n_dmpl;
         m.nJ = d.n_joints; m.M = d.n_markers; m.body_dof = d.body_dof; m.p_red = d.p_red;
-        m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw; m.na = d.na;
-        m.n_levels = d.n_levels; m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
+        m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw;
+        m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
         m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
         m.parents = up<int>(d.parents, nJ);
-        m.fk_order = up<int>(d.fk_order, nJ);
-        m.level_ofs = up<int>(d.level_ofs, size_t(d.n_levels) + 1);
+        {
+            std::vector<int> depth(nJ, 0), order(nJ);
+            for (size_t j = 0; j < nJ; ++j) { int dj = 0; for (int a = d.parents[j]; a >= 0; a = d.parents[a]) ++dj; depth[j] = dj; }
+            for (size_t j = 0; j < nJ; ++j) order[j] = int(j);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return depth[a] < depth[b]; });
+            m.fk_order = up<int>(order.data(), nJ);
+        }
         m.w_joint = up<int>(d.w_joint, S * d.kw);
-        m.anc_joint = up<int>(d.anc_joint, S * d.na);
-        m.anc_mask = up<int>(d.anc_mask, S * d.na);
-        m.anc_pos = up<int8_t>(d.anc_pos, S * nJ);
         {
             std::vector<double> hct;
             mosh2::HandBlock blocks[mosh2::kMaxHandBlocks];
@@ -95,7 +98,8 @@ struct HostModel {
 
 template <class real>
 int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, const double *obs, const uint8_t *vis,
-        int chunk_len, int warmup, const mosh2_result *res) {
+        const mosh2_schedule *sched, const mosh2_result *res) {
+    const int chunk_len = sched ? sched->chunk_len : 0, warmup = sched ? sched->chunk_warmup : 0;
     HostModel<real> hm;
     hm.build(*desc);
     const size_t F = n_frames, M = desc->n_markers, PF = size_t(3) * desc->n_joints, PR = desc->p_red, nd = desc->n_dmpl;
@@ -106,13 +110,14 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     job.n_frames = n_frames;
     job.chunk_len = chunk_len > 0 ? chunk_len : 0;
     job.warmup = warmup > 0 ? warmup : 0;
+    job.warm_full = (!sched || sched->warmup_full < 0 || sched->warmup_full > job.warmup) ? job.warmup : sched->warmup_full;
     job.n_chunks = job.chunk_len ? (n_frames + job.chunk_len - 1) / job.chunk_len : 1;
     job.obs = o.data(); job.vis = vis;
     job.fullpose = fullpose.data(); job.pose = pose.data(); job.trans = trans.data();
     job.dmpls = nd ? dmpls.data() : nullptr; job.markers_sim = mk.data(); job.errs = errs.data();
     std::vector<int> status(F, 0), counters(F * 4, 0);
     job.status = status.data(); job.counters = counters.data();
-    int totals[4] = {0, 0, 0, 0};
+    int totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     job.totals = totals;
     job.prof = nullptr;
     job.gws = nullptr; job.gws_stride = 0;
@@ -170,8 +175,8 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
 }  // namespace
 
 extern "C" int mosh2_emu_solve(const mosh2_model_desc *desc, const mosh2_options *opt, int32_t n_frames,
-                               const double *obs, const uint8_t *vis, int32_t chunk_len, int32_t warmup,
+                               const double *obs, const uint8_t *vis, const mosh2_schedule *sched,
                                int32_t precision, const mosh2_result *res) {
-    if (precision == MOSH2_F64) return run<double>(desc, opt, n_frames, obs, vis, chunk_len, warmup, res);
-    return run<float>(desc, opt, n_frames, obs, vis, chunk_len, warmup, res);
+    if (precision == MOSH2_F64) return run<double>(desc, opt, n_frames, obs, vis, sched, res);
+    return run<float>(desc, opt, n_frames, obs, vis, sched, res);
 }

@@ -23,7 +23,8 @@ def test_header_symbols_are_exported(library):
     assert declared == set(lib.EXPORTED_SYMBOLS), declared ^ set(lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(library, name), name
-    assert library.mosh2_version() == 101
+    version = int(re.search(r'#define MOSH2_VERSION (\d+)', header).group(1))
+    assert library.mosh2_version() == version == lib.ABI_VERSION
 
 
 def test_ctypes_struct_layout_matches_header(library):
@@ -49,3 +50,10 @@ def test_product_does_not_import_oracle():
         if fn.endswith('.py'):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), fn
+
+
+def test_stale_library_is_rejected(library, tmp_path, monkeypatch):
+    """A library of another ABI version must not load silently (the ctypes structs would no longer match)."""
+    monkeypatch.setattr(lib, 'ABI_VERSION', lib.ABI_VERSION + 1)
+    with pytest.raises(lib.Mosh2Error, match='implements ABI'):
+        lib.load_library(lib.default_library_path())

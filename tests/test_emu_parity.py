@@ -85,3 +85,28 @@ def test_frames_without_markers_are_skipped(cases, emu):
     # velocity term needs two processed predecessors (chmosh.py:624-626,656-657)
     assert not (res.status[0] & lib.ST_HAS_VELO) and not (res.status[1] & lib.ST_HAS_VELO)
     assert res.status[2] & lib.ST_HAS_VELO and res.status[4] & lib.ST_HAS_VELO
+
+
+def test_light_warmup_schedule_matches_oracle_emulation(cases, emu):
+    """Chunks with a light warm-up (one Step-2 iteration per frame) followed by fully solved warm-up frames: the device
+    source against the oracle's independent emulation of the same schedule, incl. frames without markers inside the
+    warm-up window (the warm-up is counted in solved frames)."""
+    from conftest import dense_obs
+    case = cases('C2')
+    obs, vis = dense_obs(case)
+    vis = vis.copy()
+    vis[6] = False
+    vis[7] = False
+    from oracle import stageii
+    from moshpp_b200.mocap_interface import MocapSession
+    mocap = MocapSession(case['mocap_fname'], case['cfg'].mocap.unit)
+    mocap.markers[6:8] = 0.0
+    out = stageii.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'],
+                               case['betas'], case['marker_meta'], chunk=(4, 5, 2), mocap=mocap)
+    res = emu(case, chunk_len=4, warmup=5, warmup_full=2, obs_vis=(obs, vis))
+    fid = out['stageii_debug_details']['frame_ids']
+    assert 6 not in fid and res.status[6] == lib.ST_SKIPPED
+    assert np.abs(res.pose[fid] - out['_pose_reduced']).max() < 1e-9
+    # not the same numbers as with a fully solved warm-up
+    full = emu(case, chunk_len=4, warmup=5, obs_vis=(obs, vis))
+    assert np.abs(full.pose[fid] - res.pose[fid]).max() > 1e-6

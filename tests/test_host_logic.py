@@ -89,3 +89,50 @@ def test_amass_writer_round_trip(cases, emu, tmp_path):
     assert np.array_equal(back['trans'], merged['trans']) and back['num_markers'] == 67
     parts = amass_io.turn_fullpose_into_parts(np.zeros((2, 48)), 'mano')
     assert parts['pose_hand'].shape == (2, 45) and 'pose_body' not in parts
+
+
+def test_synonym_labels_are_resolved_like_the_reference(cases, tmp_path):
+    """The reference builds its Stage-II MocapSession with labels_map=general_labels_map (chmosh.py:466): a capture that
+    names markers HEAD_TOP / L_ANK / ... must yield the same dense observations as one with the canonical names."""
+    from moshpp_b200.mocap_interface import MocapSession, general_labels_map
+    table = general_labels_map()
+    assert table['HEAD_TOP'] == 'ARIEL' and table['L_ANK'] == 'LANK' and table['MIDBACK'] == 'T8' and len(table) >= 190
+    case = cases('C1')
+    z = np.load(case['mocap_fname'].replace('.c3d', '.npz')) if case['mocap_fname'].endswith('.npz') else None
+    ref = MocapSession(case['mocap_fname'], 'mm')
+    obs0, vis0 = ref.frames_for_labels(case['latent_labels'], range(len(ref)))
+    # rename every column that has a synonym to (one of) its raw spellings, with a subject prefix and a blank
+    inverse = {}
+    for raw, canon in table.items():
+        inverse.setdefault(canon, raw)
+    raw_labels = ['subj:' + inverse.get(l, l).replace('_', '_ ', 1) for l in ref.labels]
+    renamed = sum(1 for l in ref.labels if l in inverse)
+    assert renamed >= 10
+    fn = str(tmp_path / 'synonyms.npz')
+    np.savez(fn, markers=ref.markers * 1000.0, labels=np.array(raw_labels), frame_rate=120.0)
+    obs1, vis1 = MocapSession(fn, 'mm').frames_for_labels(case['latent_labels'], range(len(ref)))
+    assert np.array_equal(vis0, vis1) and np.allclose(obs0, obs1, atol=1e-12)
+    # opt-out: raw labels -> the renamed markers are invisible
+    _, vis2 = MocapSession(fn, 'mm', labels_map=None).frames_for_labels(case['latent_labels'], range(len(ref)))
+    assert vis2.sum() < vis1.sum()
+
+
+def test_duplicate_labels_take_the_last_available_sample(tmp_path):
+    """markers_asdict writes a frame's dictionary in column order and only for available samples
+    (tools/mocap_interface.py:262-271): of two columns with one label the last AVAILABLE one wins, per frame."""
+    from moshpp_b200.mocap_interface import MocapSession
+    from oracle.stageii import frames_from_mocap
+    mk = np.zeros((3, 3, 3))
+    mk[:, 0] = [[1, 1, 1], [2, 2, 2], [3, 3, 3]]                 # A, always there
+    mk[:, 1] = [[10, 10, 10], [np.nan, 0, 0], [0, 0, 0]]         # A again: present, NaN, all-zero
+    mk[:, 2] = [[7, 7, 7], [8, 8, 8], [9, 9, 9]]                 # B
+    fn = str(tmp_path / 'dup.npz')
+    np.savez(fn, markers=mk, labels=np.array(['A', 'A', 'B']), frame_rate=100.0)
+    s = MocapSession(fn, 'm')
+    obs, vis = s.frames_for_labels(['A', 'B', 'C'], range(3))
+    assert vis.tolist() == [[True, True, False]] * 3
+    assert obs[:, 0, 0].tolist() == [10.0, 2.0, 3.0] and obs[:, 1, 0].tolist() == [7.0, 8.0, 9.0]
+    d = s.markers_asdict()
+    assert [float(f['A'][0]) for f in d] == [10.0, 2.0, 3.0]
+    fr = frames_from_mocap(s.markers, s.labels, ['A', 'B', 'C'])      # the oracle's restatement of the same rule
+    assert [float(f[1][0, 0]) for f in fr] == [10.0, 2.0, 3.0]

@@ -36,16 +36,22 @@ def _worker(rank, world, port, case_dir, q):
     cases = [synth.make_case(rank_dir, 'C4', frames=F, seq_idx=i) for i in range(n_seq)]
     emu = C.CDLL(build.build_emu())
 
-    def solve(i, obs, vis):
+    def solve_one(i, obs, vis):
         pk, cfg = cases[i]['pack'], cases[i]['cfg']
         h = lib.DescHolder(pk)
         opt = lib.make_options(cfg.opt_settings.weights, optimize_fingers=True)
         res = lib.ResultArrays(F, lib.pack_dims(pk))
         o = np.ascontiguousarray(obs, dtype=np.float64)
         v = np.ascontiguousarray(vis, dtype=np.uint8)
-        emu.mosh2_emu_solve(C.byref(h.desc), C.byref(opt), F, o.ctypes.data_as(lib._f64p), v.ctypes.data_as(lib._u8p),
-                            0, 0, lib.MOSH2_F64, C.byref(res.c))
+        sched = lib.make_schedule(0, 0)
+        rc = emu.mosh2_emu_solve(C.byref(h.desc), C.byref(opt), F, o.ctypes.data_as(lib._f64p), v.ctypes.data_as(lib._u8p),
+                                 C.byref(sched), lib.MOSH2_F64, C.byref(res.c))
+        assert rc == 0
         return np.concatenate([res.fullpose, res.trans], axis=1)
+
+    def solve(mine):         # {seq: (obs, vis) tensors on this rank's device} -> {seq: rows tensor}
+        import torch
+        return {i: torch.from_numpy(solve_one(i, o.numpy(), v.numpy()).astype(np.float32)) for i, (o, v) in mine.items()}
 
     obs_list = vis_list = None
     if rank == 0:
@@ -58,8 +64,8 @@ def _worker(rank, world, port, case_dir, q):
     out, assignment = shard.solve_sharded([F] * n_seq, [20] * n_seq, [48 + 3] * n_seq, solve, obs_list, vis_list)
     if rank == 0:
         # every sequence solved locally on rank 0 must equal what came back through scatter + gather
-        ref = {i: solve(i, obs_list[i].astype(np.float32).astype(np.float64), vis_list[i]) for i in range(n_seq)}
-        err = max(float(np.abs(out[i] - ref[i].astype(np.float32)).max()) for i in range(n_seq))
+        ref = {i: solve_one(i, obs_list[i].astype(np.float32).astype(np.float64), vis_list[i]) for i in range(n_seq)}
+        err = max(float(np.abs(out[i].numpy() - ref[i].astype(np.float32)).max()) for i in range(n_seq))
         q.put((sorted(out.keys()), assignment, err))
     dist.barrier()
     dist.destroy_process_group()
@@ -75,7 +81,7 @@ def test_scatter_solve_gather_world2(tmp_path):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    keys, assignment, err = q.get(timeout=300)
+    keys, assignment, err = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
