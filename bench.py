@@ -457,7 +457,7 @@ def c5_local(args, dev, steps, flush):
     tot = solver.totals()
     out = {'workload': C5_DESC + ' -- all on one GPU', 'value': sum(F) / (np.mean(ms) * 1e-3), 'ms_per_step': float(np.mean(ms)),
            'e2e_value': sum(F) / float(np.mean(e2e)), 'e2e_ms_per_step': float(np.mean(e2e)) * 1e3,
-           'chunk_len': solver.jobs[0].schedule.chunk_len, 'frame_iterations_per_step': tot['builds'],
+           'chunk_len': solver.chunk_len, 'chunks': solver.num_chunks(), 'frame_iterations_per_step': tot['builds'],
            'useful_frame_iterations': tot['emitted_builds'], 'steps': steps, 'sequences': len(F)}
     solver.close()
     return out
@@ -496,7 +496,7 @@ def run_sharded(args, rank, local_rank, world):
     mine_ids = assignment[rank]
     solver = shard.GpuRankSolver({i: pk for i in mine_ids}, opts, {i: F[i] for i in mine_ids}, local_rank,
                                  chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full)
-    width = solver.jobs[mine_ids[0]].row_width
+    width = solver.row_width
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def flush():
@@ -550,7 +550,7 @@ def run_sharded(args, rank, local_rank, world):
             'dtype': args.precision, 'data': 'synthetic (seeded procedural SMPL-H model, markers, motion)',
             'config': {'workload': C5_DESC, 'sequences': n_seq, 'frames': total_frames, 'markers': pk.n_markers,
                        'free_vars': ab['n'], 'residual_rows': ab['R'], 'sequences_per_gpu': [len(a) for a in assignment],
-                       'chunk_len': solver.jobs[mine_ids[0]].schedule.chunk_len, 'chunk_warmup': args.chunk_warmup,
+                       'chunk_len': solver.chunk_len, 'chunks_per_gpu': solver.num_chunks(), 'chunk_warmup': args.chunk_warmup,
                        'warmup_full': args.warmup_full, 'l2': 'flushed between timed steps (256 MiB write)',
                        'frames_solved': solved, 'frame_iterations_per_step': builds, 'useful_frame_iterations': useful,
                        'executed_over_useful': builds / max(1, useful),

@@ -129,13 +129,31 @@ typedef struct mosh2_schedule {
 /* A job = device buffers for one sequence of n_frames frames. */
 int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const mosh2_schedule *sched,
                      int32_t precision, mosh2_job **out);
+/* The same for n_seq sequences of ONE subject (one model) solved by one launch: the job's frame axis holds the sequences
+ * back to back (n_frames = sum of frame_counts), chunks never straddle a sequence boundary and every sequence starts
+ * from its own cold start.  All per-frame buffers (obs, vis, results) are indexed by the concatenated frame axis. */
+int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_seq, const int32_t *frame_counts,
+                           const mosh2_schedule *sched, int32_t precision, mosh2_job **out);
 /* obs [F*M*3] metres in latent-label order, vis [F*M] 0/1.  Async on the job's stream. */
 int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis);
 /* The same from DEVICE memory (e.g. the receive buffer of an NCCL scatter): d_obs [F*M*3] float32 (obs_f64 = 0) or
  * float64 (obs_f64 = 1) on the job's device, d_vis [F*M]; converted to the job's precision on the device.  The
  * copy is ordered after the work already queued on `producer_stream` (a cudaStream_t, may be NULL = legacy stream). */
 int mosh2_job_upload_device(mosh2_job *j, const void *d_obs, int32_t obs_f64, const uint8_t *d_vis, void *producer_stream);
-int mosh2_job_launch(mosh2_job *j);                 /* async */
+/* ... for frames [frame0, frame0 + n) of the job's frame axis only (one sequence of a batch job) */
+int mosh2_job_upload_device_range(mosh2_job *j, int32_t frame0, int32_t n, const void *d_obs, int32_t obs_f64,
+                                  const uint8_t *d_vis, void *producer_stream);
+int mosh2_job_launch(mosh2_job *j);                 /* async; all chunks; clears the result buffers first */
+/* Boundary check of the chunked schedule.  Every chunk that does not start at the beginning of its sequence reports the
+ * state x = [trans | pose | dmpl] it reached on its LAST warm-up frame and that frame's index (or -1); the emitted result
+ * of the same frame was produced by an earlier chunk further along its own history.  Their difference measures what the
+ * warm-up left of the cold start, chunk by chunk.  x [n_chunks * (3 + p_red + n_dmpl)], frames [n_chunks]; syncs. */
+int mosh2_job_warm_states(mosh2_job *j, double *x, int32_t *frames);
+/* Re-solves the listed chunks only (e.g. those that failed the boundary check); the rows of all other frames keep the
+ * values of the previous launch.  chunk_warmup >= 0: with that warm-up, from a cold start.  chunk_warmup < 0: RESUME --
+ * no warm-up; the chunk continues the recursion from the rows the previous launch emitted for the last two solved frames
+ * in front of it, exactly as the previous chunk would have gone on (boundary repair).  async */
+int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids, int32_t chunk_warmup, int32_t warmup_full);
 int mosh2_job_download(mosh2_job *j, const mosh2_result *res); /* async D2H + stream sync */
 int mosh2_job_sync(mosh2_job *j);
 /* Results as ONE packed float32 device row per frame, for device-side consumers (NCCL gather): row f =

@@ -209,23 +209,105 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
     return data
 
 
+# Boundary tolerances of the chunked schedule: what a chunk's warm-up state may differ from the emitted result of the same
+# frame (root+body pose rad, other pose coefficients, translation m, dmpl / expression coefficients).  'fast' keeps the
+# chunk starts a factor of three inside BASELINE.md section 4's per-frame tolerances; 'exact' is the parity mode.
+BOUNDARY_TOL = {'fast': (3e-4, 3e-3, 3e-5, 3e-3), 'exact': (1e-6, 1e-5, 1e-7, 1e-5)}
+
+
+def default_schedule(model_type: str, mode: str = 'fast'):
+    """(chunk_warmup, warmup_full, precision) a sequence is solved with; ``solve_verified`` repairs the chunk boundaries
+    the warm-up left open.  The reference's frame recursion forgets its start geometrically, at a rate set by the
+    velocity term against the weakest other term on a pose coefficient: 0.86 per frame for the
+    body models, 0.93 for the hand-only MANO model (no body prior: only poseH holds the finger coefficients)."""
+    if mode == 'exact':
+        return 256, -1, 'f64'
+    if model_type == 'mano':      # 30 unknowns, no prior: float32 cold starts can take another branch; float64 costs little here
+        return 256, 224, 'f64'
+    return DEFAULT_WARMUP, DEFAULT_WARMUP_FULL, 'f32'
+
+
+def solve_verified(job, obs, vis, *, tol, max_rounds: int = 6):
+    """Upload + launch + download, then the boundary check of the chunked schedule and its repair.
+
+    Every chunk reports the state it reached on its last warm-up frame; the emitted result of that frame comes from the
+    previous chunk, which is further along its own history.  Where the two differ by more than ``tol`` (root+body pose,
+    other pose coefficients, translation, dmpl / expression coefficients) the chunk is solved again in RESUME mode: it
+    continues the recursion from the rows the previous chunk emitted, exactly as that chunk would have gone on
+    (mosh2_job_relaunch_chunks, chunk_warmup < 0).  A repair round costs one chunk length, not a warm-up.  Neighbouring
+    failing chunks are repaired in consecutive rounds (a chunk must not read rows that are being rewritten).  Chunks that
+    still fail after ``max_rounds`` keep MOSH2_ST_SHORT_WARMUP on their frames.  Returns (ResultArrays, report)."""
+    job.upload(obs, vis)
+    job.launch()
+    res = job.download()
+    kernel_ms = [job.kernel_ms()]
+    report = {'rounds': 0, 'repaired_chunks': [], 'boundary_delta_first': None, 'boundary_delta_max': None, 'unverified_chunks': 0}
+    if job.schedule.chunk_len <= 0 or tol is None:
+        report['kernel_ms'] = kernel_ms
+        return res, report
+    tol = np.asarray(tol, dtype=np.float64)
+    bad = np.zeros(0, dtype=np.int64)
+    for rnd in range(max_rounds + 1):
+        d = job.boundary_deltas(res)
+        bad = np.nonzero((d > tol[None]).any(1))[0]
+        if rnd == 0:
+            report['boundary_delta_first'] = d.max(0).tolist()
+            report['chunks_over_tol_first'] = int(len(bad))
+        report['boundary_delta_max'] = d.max(0).tolist()
+        if not len(bad) or rnd == max_rounds:
+            break
+        # of a run of consecutive failing chunks only every other one per round, starting with the first
+        take, last = [], -2
+        for c in bad:
+            if c - 1 != last:
+                take.append(int(c))
+                last = int(c)
+        job.relaunch_chunks(take, -1)
+        res = job.download()
+        kernel_ms.append(job.kernel_ms())
+        report['rounds'] += 1
+        report['repaired_chunks'].append(len(take))
+    if len(bad):
+        report['unverified_chunks'] = int(len(bad))
+        L = job.schedule.chunk_len
+        for c in bad:          # (single-sequence jobs: chunk c emits frames [c L, (c+1) L))
+            sl = slice(int(c) * L, (int(c) + 1) * L)
+            res.status[sl] |= np.where((res.status[sl] & _lib.ST_SOLVED) != 0, _lib.ST_SHORT_WARMUP, 0).astype(res.status.dtype)
+        logger.warning('%d chunks did not pass the boundary check after %d repair rounds (max delta %s); their frames carry '
+                       'MOSH2_ST_SHORT_WARMUP', len(bad), report['rounds'], report['boundary_delta_max'])
+    report['kernel_ms'] = kernel_ms
+    return res, report
+
+
 def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_labels: list, betas: np.ndarray,
-                 marker_meta: dict, v_template_fname=None, *, device: int = 0, chunk_len: Optional[int] = None,
-                 chunk_warmup: int = DEFAULT_WARMUP, warmup_full: int = DEFAULT_WARMUP_FULL, precision: str = 'f32',
+                 marker_meta: dict, v_template_fname=None, *, device: int = 0, mode: str = 'fast',
+                 chunk_len: Optional[int] = None, chunk_warmup: Optional[int] = None, warmup_full: Optional[int] = None,
+                 precision: Optional[str] = None, verify: bool = True, boundary_tol=None,
                  sm_budget: int = NUM_SMS_B200, labels_map='general') -> dict:
     """Stage II of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:458-459).
 
-    Keyword-only extras: ``device``; ``chunk_len`` (None = automatic, 0 = the reference's single
-    sequential pass), ``chunk_warmup`` / ``warmup_full`` (mosh2_schedule, include/mosh2.h); ``precision`` 'f32' | 'f64';
-    ``labels_map``: 'general' (default) = the synonym table the reference always applies (chmosh.py:466), a dict, or
-    None for raw labels.
+    Keyword-only extras.  ``mode``: 'fast' (default) = float32, chunked in time with a verified warm-up -- within
+    BASELINE.md section 4's tolerances of the reference's sequential float64 result except on the few frames where that
+    result is itself ill-conditioned; 'exact' = the parity mode: float64, long fully solved
+    warm-up, tight boundary check.  ``chunk_len`` (None = planned, 0 = the reference's single sequential pass in one
+    thread block), ``chunk_warmup`` / ``warmup_full`` (mosh2_schedule, include/mosh2.h), ``precision`` 'f32' | 'f64',
+    ``verify`` / ``boundary_tol`` override the mode's presets.  ``labels_map``: 'general' (default) = the synonym table
+    the reference always applies (chmosh.py:466), a dict, or None for raw labels.
     """
     t0 = time.time()
+    if mode not in BOUNDARY_TOL:
+        raise ValueError(f"mode must be 'fast' or 'exact', not {mode!r}")
     mocap = MocapSession(mocap_fname, mocap_unit=cfg.mocap.unit, mocap_rotate=cfg.mocap.rotate,
                          labels_map=labels_map,
                          only_subjects=[cfg.mocap.subject_name] if cfg.mocap.multi_subject else None)
     pk, opts, flags = prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname)
     dyn = bool(opts.optimize_dynamics)
+    w_def, wf_def, prec_def = default_schedule(pk.model_type, mode)
+    chunk_warmup = w_def if chunk_warmup is None else int(chunk_warmup)
+    warmup_full = (wf_def if chunk_warmup == w_def else -1) if warmup_full is None else int(warmup_full)
+    precision = precision or prec_def
+    if boundary_tol is None:
+        boundary_tol = BOUNDARY_TOL[mode]
 
     end = len(mocap) if cfg.mocap.end_fidx == -1 else cfg.mocap.end_fidx
     selected_frames = range(cfg.mocap.start_fidx, end, cfg.mocap.ds_rate)                         # chmosh.py:539-540
@@ -234,7 +316,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     if F == 0:
         raise ValueError('no frames selected')
     if chunk_len is None:
-        chunk_len = plan_chunk_len([F], sm_budget, chunk_warmup, warmup_full)
+        chunk_len = plan_chunk_len([F], sm_budget, chunk_warmup, warmup_full if warmup_full >= 0 else chunk_warmup)
     if chunk_len >= F:
         chunk_len = 0
     prec = {'f32': _lib.MOSH2_F32, 'f64': _lib.MOSH2_F64}[precision]
@@ -243,11 +325,10 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     try:
         job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec)
         try:
-            job.upload(obs, vis)
-            job.launch()
-            res = job.download()
-            kernel_ms = job.kernel_ms()
+            res, report = solve_verified(job, obs, vis, tol=boundary_tol if verify else None)
+            kernel_ms = float(sum(report['kernel_ms']))
             n_chunks = job.num_chunks
+            totals = job.totals()
         finally:
             job.close()
     finally:
@@ -263,7 +344,8 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         'mocap_time_length': mocap.time_length(),
         'b200': {
             'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
-            'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'status': res.status.copy(),
+            'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'mode': mode,
+            'boundary_check': report, 'totals': totals, 'status': res.status.copy(),
             'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
             'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
         },

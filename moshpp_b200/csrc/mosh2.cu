@@ -52,7 +52,7 @@ mosh2_stageii_kernel(const __grid_constant__ mosh2::Model<real> m, const __grid_
     // is shared-memory base + a parameter word.  BIG = true (f64 / oversized models): A, its factor and the Jacobian
     // tiles live in a per-CTA global workspace whose base is parked in the shared-memory header.
     if (BIG) {
-        if (threadIdx.x == 0) *reinterpret_cast<char **>(mosh2::m2_smem()) = job.gws + size_t(blockIdx.x) * job.gws_stride;
+        if (threadIdx.x == 0) *reinterpret_cast<char **>(mosh2::m2_smem()) = job.gws + size_t(blockIdx.x) * job.gws_stride;   // (per block, not per chunk)
         __syncthreads();
     }
     mosh2::Cta c{int(threadIdx.x), int(blockDim.x)};
@@ -68,7 +68,7 @@ mosh2_stageii_kernel(const __grid_constant__ mosh2::Model<real> m, const __grid_
         s.tc_tmem = *w.tmem_slot;
         s.tc_kt = 4 * d.tmk;
     }
-    s.run_chunk(blockIdx.x);
+    s.run_chunk(job.chunk_ids ? job.chunk_ids[blockIdx.x] : int(blockIdx.x));
     if (w.tc) {
         mosh2::tc::fence_before();
         __syncthreads();
@@ -254,6 +254,11 @@ struct mosh2_job {
     mosh2_model *model = nullptr;
     int precision = MOSH2_F32;
     int n_frames = 0, chunk_len = 0, warmup = 0, warm_full = 0, n_chunks = 1;
+    int *d_chunk_tab = nullptr, *d_chunk_ids = nullptr, *d_warm_f = nullptr;
+    void *d_warm_x = nullptr;
+    std::vector<int> tab;             // host copy of the chunk table
+    int launch_blocks = 0;            // blocks of the next launch (all chunks, or the subset in d_chunk_ids)
+    bool subset = false;
     mosh2::Options opt{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in = nullptr;
@@ -284,15 +289,16 @@ cudaError_t launch_kernel(mosh2_job *j, const mosh2::Model<real> &m, const mosh2
     w.tc = (w.tc_ok && threads >= 128) ? 1 : 0;
     const cudaError_t e = cudaFuncSetAttribute(mosh2_stageii_kernel<real, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(j->smem));
     if (e != cudaSuccess) return e;
-    mosh2_stageii_kernel<real, BIG><<<j->n_chunks, threads, j->smem, j->stream>>>(m, job, w, d);
+    mosh2_stageii_kernel<real, BIG><<<j->launch_blocks, threads, j->smem, j->stream>>>(m, job, w, d);
     return cudaGetLastError();
 }
 
 template <class real>
 int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     mosh2::Job<real> job{};
-    job.n_frames = j->n_frames; job.chunk_len = j->chunk_len; job.warmup = j->warmup; job.n_chunks = j->n_chunks;
-    job.warm_full = j->warm_full;
+    job.n_frames = j->n_frames; job.n_chunks = j->n_chunks;
+    job.chunk_tab = j->d_chunk_tab; job.chunk_ids = j->subset ? j->d_chunk_ids : nullptr;
+    job.warm_x = static_cast<real *>(j->d_warm_x); job.warm_f = j->d_warm_f;
     job.obs = static_cast<const real *>(j->d_obs);
     job.vis = j->d_vis;
     real *out = static_cast<real *>(j->d_out);
@@ -405,7 +411,19 @@ void mosh2_model_destroy(mosh2_model *m) {
 
 int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const mosh2_schedule *sched,
                      int32_t precision, mosh2_job **out) {
-    if (!m || !opt || !out || n_frames < 1) return fail(MOSH2_E_INVALID, "bad argument");
+    return mosh2_job_create_batch(m, opt, 1, &n_frames, sched, precision, out);
+}
+
+int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_seq, const int32_t *frame_counts,
+                           const mosh2_schedule *sched, int32_t precision, mosh2_job **out) {
+    if (!m || !opt || !out || n_seq < 1 || !frame_counts) return fail(MOSH2_E_INVALID, "bad argument");
+    long long total = 0;
+    for (int q = 0; q < n_seq; ++q) {
+        if (frame_counts[q] < 1) return fail(MOSH2_E_INVALID, "sequence %d has %d frames", q, frame_counts[q]);
+        total += frame_counts[q];
+    }
+    if (total > 0x3fffffff) return fail(MOSH2_E_TOO_LARGE, "%lld frames in one job", total);
+    const int32_t n_frames = int32_t(total);
     if (precision != MOSH2_F32 && precision != MOSH2_F64) return fail(MOSH2_E_INVALID, "precision must be MOSH2_F32 or MOSH2_F64");
     *out = nullptr;
     CU(cudaSetDevice(m->device));
@@ -417,7 +435,10 @@ int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames,
     j->chunk_len = chunk_len > 0 ? chunk_len : 0;
     j->warmup = chunk_warmup > 0 ? chunk_warmup : 0;
     j->warm_full = (!sched || sched->warmup_full < 0 || sched->warmup_full > j->warmup) ? j->warmup : sched->warmup_full;
-    j->n_chunks = j->chunk_len ? (n_frames + j->chunk_len - 1) / j->chunk_len : 1;
+    j->tab = mosh2_host::chunk_table(frame_counts, n_seq, j->chunk_len, j->warmup, j->warm_full);
+    const std::vector<int> &tab = j->tab;
+    j->n_chunks = int(tab.size() / mosh2::kChunkRec);
+    j->launch_blocks = j->n_chunks;
     j->esz = precision == MOSH2_F64 ? 8 : 4;
     mosh2::Options &o = j->opt;
     o.wt_data = opt->wt_data; o.wt_poseB = opt->wt_poseB; o.wt_poseH = opt->wt_poseH; o.wt_velo = opt->wt_velo;
@@ -458,6 +479,11 @@ int mosh2_job_create(mosh2_model *m, const mosh2_options *opt, int32_t n_frames,
     chk(cudaMalloc(&j->d_status, F * sizeof(int)));
     chk(cudaMalloc(&j->d_counters, F * 4 * sizeof(int)));
     chk(cudaMalloc(&j->d_totals, 8 * sizeof(int)));
+    chk(cudaMalloc(&j->d_chunk_tab, tab.size() * sizeof(int)));
+    chk(cudaMalloc(&j->d_chunk_ids, size_t(j->n_chunks) * sizeof(int)));
+    chk(cudaMalloc(&j->d_warm_f, size_t(j->n_chunks) * sizeof(int)));
+    chk(cudaMalloc(&j->d_warm_x, size_t(j->n_chunks) * (3 + m->p_red + m->n_dmpl) * j->esz));
+    if (e == cudaSuccess) chk(cudaMemcpy(j->d_chunk_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     chk(cudaMalloc(&j->d_prof, 32 * sizeof(long long)));
     if (j->gws_stride) chk(cudaMalloc(&j->d_gws, j->gws_stride * j->n_chunks));
     chk(cudaMallocHost(&j->h_obs, j->n_obs * j->esz));
@@ -496,8 +522,45 @@ int mosh2_job_launch(mosh2_job *j) {
     CU(cudaMemsetAsync(j->d_counters, 0, size_t(j->n_frames) * 4 * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_totals, 0, 8 * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_prof, 0, 32 * sizeof(long long), j->stream));
+    j->subset = false;
+    j->launch_blocks = j->n_chunks;
     if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
     return launch<float>(j, j->model->f32.m);
+}
+
+int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids, int32_t chunk_warmup, int32_t warmup_full) {
+    if (!j || n < 1 || !chunk_ids) return fail(MOSH2_E_INVALID, "bad argument");
+    CU(cudaSetDevice(j->model->device));
+    const int wf = chunk_warmup < 0 ? 0 : ((warmup_full < 0 || warmup_full > chunk_warmup) ? chunk_warmup : warmup_full);
+    for (int k = 0; k < n; ++k) {
+        const int c = chunk_ids[k];
+        if (c < 0 || c >= j->n_chunks) return fail(MOSH2_E_INVALID, "chunk %d out of range (%d chunks)", c, j->n_chunks);
+        j->tab[size_t(c) * mosh2::kChunkRec + 3] = chunk_warmup;
+        j->tab[size_t(c) * mosh2::kChunkRec + 4] = wf;
+    }
+    CU(cudaStreamSynchronize(j->stream));
+    CU(cudaMemcpy(j->d_chunk_tab, j->tab.data(), j->tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(j->d_chunk_ids, chunk_ids, size_t(n) * sizeof(int), cudaMemcpyHostToDevice));
+    // the rows of the frames these chunks emit are rewritten by the kernel; everything else of the last launch stays
+    j->subset = true;
+    j->launch_blocks = n;
+    if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
+    return launch<float>(j, j->model->f32.m);
+}
+
+int mosh2_job_warm_states(mosh2_job *j, double *x, int32_t *frames) {
+    if (!j || !x || !frames) return fail(MOSH2_E_INVALID, "null argument");
+    CU(cudaSetDevice(j->model->device));
+    CU(cudaStreamSynchronize(j->stream));
+    const size_t nx = size_t(3) + j->model->p_red + j->model->n_dmpl, n = size_t(j->n_chunks) * nx;
+    CU(cudaMemcpy(frames, j->d_warm_f, size_t(j->n_chunks) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (j->precision == MOSH2_F64) CU(cudaMemcpy(x, j->d_warm_x, n * sizeof(double), cudaMemcpyDeviceToHost));
+    else {
+        std::vector<float> tmp(n);
+        CU(cudaMemcpy(tmp.data(), j->d_warm_x, n * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) x[i] = double(tmp[i]);
+    }
+    return 0;
 }
 
 int mosh2_job_sync(mosh2_job *j) {
@@ -542,20 +605,28 @@ int mosh2_job_totals(mosh2_job *j, int32_t *out8) {
 }
 
 int mosh2_job_upload_device(mosh2_job *j, const void *d_obs, int32_t obs_f64, const uint8_t *d_vis, void *producer_stream) {
+    if (!j) return fail(MOSH2_E_INVALID, "null argument");
+    return mosh2_job_upload_device_range(j, 0, j->n_frames, d_obs, obs_f64, d_vis, producer_stream);
+}
+
+int mosh2_job_upload_device_range(mosh2_job *j, int32_t frame0, int32_t nfr, const void *d_obs, int32_t obs_f64,
+                                  const uint8_t *d_vis, void *producer_stream) {
     if (!j || !d_obs || !d_vis) return fail(MOSH2_E_INVALID, "null argument");
+    if (frame0 < 0 || nfr < 1 || frame0 + nfr > j->n_frames) return fail(MOSH2_E_INVALID, "frame range [%d, %d) outside the job's %d frames", frame0, frame0 + nfr, j->n_frames);
     CU(cudaSetDevice(j->model->device));
     CU(cudaEventRecord(j->ev_in, static_cast<cudaStream_t>(producer_stream)));
     CU(cudaStreamWaitEvent(j->stream, j->ev_in, 0));
-    const size_t n = j->n_obs, nv = size_t(j->n_frames) * j->model->n_markers;
+    const size_t M = j->model->n_markers, n = size_t(nfr) * M * 3, nv = size_t(nfr) * M, o0 = size_t(frame0) * M * 3;
     const bool dst64 = j->precision == MOSH2_F64;
-    if (dst64 == (obs_f64 != 0)) CU(cudaMemcpyAsync(j->d_obs, d_obs, n * j->esz, cudaMemcpyDeviceToDevice, j->stream));
+    char *dst = static_cast<char *>(j->d_obs) + o0 * j->esz;
+    if (dst64 == (obs_f64 != 0)) CU(cudaMemcpyAsync(dst, d_obs, n * j->esz, cudaMemcpyDeviceToDevice, j->stream));
     else {
         const int blocks = int((n + 255) / 256);
-        if (dst64) convert_kernel<float, double><<<blocks, 256, 0, j->stream>>>(static_cast<const float *>(d_obs), static_cast<double *>(j->d_obs), n);
-        else convert_kernel<double, float><<<blocks, 256, 0, j->stream>>>(static_cast<const double *>(d_obs), static_cast<float *>(j->d_obs), n);
+        if (dst64) convert_kernel<float, double><<<blocks, 256, 0, j->stream>>>(static_cast<const float *>(d_obs), reinterpret_cast<double *>(dst), n);
+        else convert_kernel<double, float><<<blocks, 256, 0, j->stream>>>(static_cast<const double *>(d_obs), reinterpret_cast<float *>(dst), n);
         CU(cudaGetLastError());
     }
-    CU(cudaMemcpyAsync(j->d_vis, d_vis, nv, cudaMemcpyDeviceToDevice, j->stream));
+    CU(cudaMemcpyAsync(j->d_vis + size_t(frame0) * M, d_vis, nv, cudaMemcpyDeviceToDevice, j->stream));
     return 0;
 }
 
@@ -611,7 +682,7 @@ void mosh2_job_destroy(mosh2_job *j) {
     if (!j) return;
     cudaSetDevice(j->model->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
-    cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_prof); cudaFree(j->d_gws);
+    cudaFree(j->d_chunk_tab); cudaFree(j->d_chunk_ids); cudaFree(j->d_warm_f); cudaFree(j->d_warm_x); cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_prof); cudaFree(j->d_gws);
     cudaFreeHost(j->h_obs); cudaFreeHost(j->h_out); cudaFreeHost(j->h_vis); cudaFreeHost(j->h_status); cudaFreeHost(j->h_counters);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);

@@ -89,6 +89,7 @@ constexpr int kBS = 4;            // register tile of the J^T J accumulation and
 constexpr int kBlendGroups = 4;   // upper bound of the joint groups of the pose-blend partial sums (run time: 1..3, one round of threads)
 constexpr int kCholNB = 8;        // block column width of the Cholesky factorisation
 constexpr int kMaxHandBlocks = 4;
+constexpr int kChunkRec = 5;      // ints per chunk-table record
 
 struct Cta {
     int tid, nthr;
@@ -130,8 +131,12 @@ struct Options {
 
 template <class real>
 struct Job {
-    int n_frames, chunk_len, warmup, n_chunks;
-    int warm_full;          // the last warm_full warm-up frames run the full per-frame schedule, the earlier ones one linearisation
+    int n_frames, n_chunks;
+    const int *chunk_tab;   // [n_chunks][kChunkRec]: first emitted frame, end of the emitted range, first frame of the chunk's
+                            // sequence, warm-up (solved frames), how many of them (the last ones) run the full per-frame schedule
+    const int *chunk_ids;   // launch of a subset of the chunks: blockIdx.x -> chunk, or null (all chunks)
+    real *warm_x;           // [n_chunks][NX] state after the chunk's last warm-up frame (boundary check against the emitted
+    int *warm_f;            // [n_chunks]     result of that frame, which an earlier chunk produced), and that frame's index or -1
     const real *obs;        // F*M*3
     const uint8_t *vis;     // F*M
     real *fullpose, *pose, *trans, *dmpls, *markers_sim, *errs;
@@ -2008,27 +2013,29 @@ struct Solver {
     // ---- the chunk loop
     M2_D void run_chunk(int chunk) {
         const Options &o = job.opt;
-        int f_emit, f_begin, f_end, f_full;
+        // chunk table (host-built, mosh2_host::chunk_table): the chunk emits frames [f_emit, f_end) of the sequence that
+        // starts at frame s0 of the job's frame axis (a job may hold several sequences of one subject back to back)
+        const int *rec = job.chunk_tab + kChunkRec * chunk;
+        const int f_emit = rec[0], f_end = rec[1], s0 = rec[2], warmup = rec[3], warm_full = rec[4];
+        int f_begin = f_emit, f_full = f_emit;
         bool short_warmup = false;
-        if (job.chunk_len <= 0) { f_emit = 0; f_begin = 0; f_end = job.n_frames; f_full = 0; }
-        else {
-            f_emit = chunk * job.chunk_len;
-            f_end = f_emit + job.chunk_len; if (f_end > job.n_frames) f_end = job.n_frames;
+        if (cta.tid == 0 && job.warm_f) job.warm_f[chunk] = -1;
+        if (f_emit > s0 && warmup > 0) {   // (warmup < 0: resume, see below)
             // The warm-up is counted in SOLVED frames (frames with at least one visible marker; the others are skipped,
             // chmosh.py:586-588): walk back from the first emitted frame until `warmup` of them are found, so that a
             // marker drop-out in front of a chunk does not shorten the history the chunk converges on.  The last
-            // `warm_full` solved warm-up frames run the full schedule.  A chunk that reaches frame 0 is the reference's
-            // own recursion from its own start: exact, never "short".
+            // `warm_full` solved warm-up frames run the full schedule.  A chunk that reaches the first frame of its
+            // sequence is the reference's own recursion from its own start: exact, never "short".
             uint8_t *flag = reinterpret_cast<uint8_t *>(static_cast<real *>(w.red));      // >= 8*33*4 bytes of scratch
             const int per = cta.nthr < 512 ? cta.nthr : 512;
-            const int max_back = 8 * (job.warmup > 0 ? job.warmup : 1) + 64;             // give up behind very long gaps
+            const int max_back = 8 * warmup + 64;             // give up behind very long gaps
             if (cta.tid == 0) { w.isc[4] = 0; w.isc[5] = f_emit; w.isc[6] = f_emit; w.isc[7] = 0; }
             M2_SYNC();
-            for (int base = f_emit - 1; base >= 0; base -= per) {
+            for (int base = f_emit - 1; base >= s0; base -= per) {
                 if (cta.tid < per) {
                     const int f = base - cta.tid;
                     uint8_t any = 0;
-                    if (f >= 0) for (int i = 0; i < d.M; ++i) any |= job.vis[size_t(f) * d.M + i];
+                    if (f >= s0) for (int i = 0; i < d.M; ++i) any |= job.vis[size_t(f) * d.M + i];
                     flag[cta.tid] = any;
                 }
                 M2_SYNC();
@@ -2036,11 +2043,11 @@ struct Solver {
                     int cnt = w.isc[4], fb = w.isc[5], ff = w.isc[6], stop = 0;
                     for (int t = 0; t < per && !stop; ++t) {
                         const int f = base - t;
-                        if (f < 0 || cnt >= job.warmup) { stop = 1; break; }
+                        if (f < s0 || cnt >= warmup) { stop = 1; break; }
                         if (f_emit - f > max_back) { stop = 2; break; }
-                        if (flag[t]) { ++cnt; fb = f; if (cnt <= job.warm_full) ff = f; }
+                        if (flag[t]) { ++cnt; fb = f; if (cnt <= warm_full) ff = f; }
                     }
-                    if (cnt >= job.warmup) stop = 1;
+                    if (cnt >= warmup) stop = 1;
                     w.isc[4] = cnt; w.isc[5] = fb; w.isc[6] = ff; w.isc[7] = stop;
                 }
                 M2_SYNC();
@@ -2048,7 +2055,7 @@ struct Solver {
             }
             f_begin = w.isc[5]; f_full = w.isc[6];
             // fewer solved warm-up frames than asked for, without having reached the start of the sequence
-            short_warmup = w.isc[4] < job.warmup && w.isc[7] == 2;
+            short_warmup = w.isc[4] < warmup && w.isc[7] == 2;
             M2_SYNC();
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
@@ -2106,6 +2113,29 @@ struct Solver {
         M2_SYNC();
         M2_T0();
         bool first = true, have_prev = false, have_dm_prev = false;
+        if (warmup < 0 && f_emit > s0) {
+            // Resume (boundary repair, mosh2_job_relaunch_chunks with chunk_warmup < 0): no warm-up of its own -- the chunk
+            // continues the recursion from the rows the previous launch EMITTED for the last two solved frames in front of
+            // it (the end of the previous chunk's trajectory, stored in the compute precision), i.e. exactly as that
+            // chunk would have gone on.
+            if (cta.tid == 0) {
+                int f1 = -1, f2 = -1;
+                for (int f = f_emit - 1; f >= s0 && f2 < 0; --f)
+                    if (job.status[f] & ST_SOLVED) { if (f1 < 0) f1 = f; else f2 = f; }
+                w.isc[4] = f1; w.isc[5] = f2;
+            }
+            M2_SYNC();
+            const int f1 = w.isc[4], f2 = w.isc[5];
+            if (f1 >= 0) {
+                CTA_FOR(i, 3) w.x[i] = job.trans[size_t(f1) * 3 + i];
+                CTA_FOR(i, d.PR) w.x[3 + i] = job.pose[size_t(f1) * d.PR + i];
+                if (job.dmpls) CTA_FOR(i, d.nd) w.x[3 + d.PR + i] = job.dmpls[size_t(f1) * d.nd + i];
+                if (f2 >= 0) CTA_FOR(i, d.PR) w.pose_prev[i] = job.pose[size_t(f2) * d.PR + i];
+                first = false;
+                have_prev = f2 >= 0;
+            }
+            M2_SYNC();
+        }
         wv = real(o.wt_velo); wdm = real(o.wt_dmpl); wex = real(o.wt_extrap);
         wxp = real(o.wt_expr);
         const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd - m.n_expr > 0;
@@ -2150,6 +2180,10 @@ struct Solver {
             has_extrap = dyn && have_dm_prev;
             if (short_warmup && f >= f_emit) frame_flags |= ST_SHORT_WARMUP;
             solve_frame(f, f >= f_emit, first, fingers, dyn, face, /*light=*/!first && f < f_full);
+            if (f < f_emit && job.warm_x) {      // (overwritten until the last warm-up frame: its state is what counts)
+                CTA_FOR(i, d.NX) job.warm_x[size_t(chunk) * d.NX + i] = w.x[i];
+                if (cta.tid == 0) job.warm_f[chunk] = f;
+            }
             first = false;
         }
         M2_TACC(17);

@@ -101,11 +101,15 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_model_destroy.argtypes = [vp]
     lib.mosh2_model_destroy.restype = None
     lib.mosh2_job_create.argtypes = [vp, C.POINTER(Options), C.c_int32, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
+    lib.mosh2_job_create_batch.argtypes = [vp, C.POINTER(Options), C.c_int32, _i32p, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
     lib.mosh2_job_upload.argtypes = [vp, _f64p, _u8p]
+    lib.mosh2_job_upload_device_range.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp]
     lib.mosh2_job_upload_device.argtypes = [vp, vp, C.c_int32, vp, vp]
     lib.mosh2_job_row_width.argtypes = [vp]
     lib.mosh2_job_download_device.argtypes = [vp, vp]
     lib.mosh2_job_launch.argtypes = [vp]
+    lib.mosh2_job_warm_states.argtypes = [vp, _f64p, _i32p]
+    lib.mosh2_job_relaunch_chunks.argtypes = [vp, C.c_int32, _i32p, C.c_int32, C.c_int32]
     lib.mosh2_job_download.argtypes = [vp, C.POINTER(Result)]
     lib.mosh2_job_sync.argtypes = [vp]
     lib.mosh2_job_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -125,7 +129,8 @@ EXPORTED_SYMBOLS = (
     'mosh2_version', 'mosh2_last_error', 'mosh2_device_count', 'mosh2_default_options', 'mosh2_model_create',
     'mosh2_model_destroy', 'mosh2_job_create', 'mosh2_job_upload', 'mosh2_job_launch', 'mosh2_job_download',
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
-    'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms')
+    'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
+    'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -238,6 +243,8 @@ class Model:
 
     def job(self, n_frames: int, options: Options, *, chunk_len: int = 0, chunk_warmup: int = 0,
             warmup_full: int = -1, precision: int = MOSH2_F32) -> 'Job':
+        """``n_frames``: frames of one sequence, or a list of frame counts = several sequences of this subject solved by
+        one launch (mosh2_job_create_batch); the job's frame axis then holds them back to back."""
         return Job(self, n_frames, options, make_schedule(chunk_len, chunk_warmup, warmup_full), precision)
 
     def close(self):
@@ -255,13 +262,17 @@ class Model:
 class Job:
     """Staged upload / launch / download on device-resident buffers (used by bench.py)."""
 
-    def __init__(self, model: Model, n_frames: int, options: Options, schedule: Schedule, precision: int):
+    def __init__(self, model: Model, n_frames, options: Options, schedule: Schedule, precision: int):
+        counts = np.ascontiguousarray(np.atleast_1d(n_frames), dtype=np.int32)
+        self.frame_counts = counts
+        self.seq_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        n_frames = int(counts.sum())
         self.model, self.lib, self.n_frames = model, model.lib, n_frames
         self.handle = C.c_void_p()
         self.options = options
         self.schedule = schedule
-        rc = self.lib.mosh2_job_create(model.handle, C.byref(options), n_frames, C.byref(schedule), precision,
-                                       C.byref(self.handle))
+        rc = self.lib.mosh2_job_create_batch(model.handle, C.byref(options), len(counts), _ptr(counts, _i32p), C.byref(schedule),
+                                             precision, C.byref(self.handle))
         model._check(rc, 'mosh2_job_create')
         self.result = ResultArrays(n_frames, pack_dims(model.pk))
         self._keep = None
@@ -279,6 +290,12 @@ class Job:
                                                            C.c_void_p(d_vis_ptr), C.c_void_p(producer_stream)),
                           'mosh2_job_upload_device')
 
+    def upload_device_range(self, frame0: int, n: int, d_obs_ptr: int, obs_is_f64: bool, d_vis_ptr: int, producer_stream: int = 0):
+        """... for frames [frame0, frame0 + n) of the job's frame axis (one sequence of a batch job)."""
+        self.model._check(self.lib.mosh2_job_upload_device_range(self.handle, int(frame0), int(n), C.c_void_p(d_obs_ptr),
+                                                                 int(bool(obs_is_f64)), C.c_void_p(d_vis_ptr),
+                                                                 C.c_void_p(producer_stream)), 'mosh2_job_upload_device_range')
+
     @property
     def row_width(self) -> int:
         return int(self.lib.mosh2_job_row_width(self.handle))
@@ -292,6 +309,38 @@ class Job:
 
     def sync(self):
         self.model._check(self.lib.mosh2_job_sync(self.handle), 'mosh2_job_sync')
+
+    def warm_states(self):
+        """(x [n_chunks, 3 + p_red + n_dmpl], frame [n_chunks]): the state every chunk reached on its last warm-up frame and
+        that frame's index (-1: the chunk starts its sequence).  See mosh2_job_warm_states."""
+        pk = self.model.pk
+        n = self.num_chunks
+        x = np.zeros((n, 3 + pk.p_red + pk.n_dmpl))
+        fr = np.zeros(n, dtype=np.int32)
+        self.model._check(self.lib.mosh2_job_warm_states(self.handle, _ptr(x, _f64p), _ptr(fr, _i32p)), 'mosh2_job_warm_states')
+        return x, fr
+
+    def boundary_deltas(self, res: 'ResultArrays'):
+        """Per chunk: max |warm-up state - emitted result| on the chunk's last warm-up frame, split into
+        (root + body pose [rad], remaining pose coefficients, translation [m], dmpl / expression coefficients)."""
+        pk = self.model.pk
+        x, fr = self.warm_states()
+        bd = min(pk.body_dof, 66)
+        out = np.zeros((len(fr), 4))
+        ok = fr >= 0
+        f = fr[ok]
+        dp = np.abs(x[ok, 3:3 + pk.p_red] - res.pose[f])
+        out[ok, 0] = dp[:, :bd].max(1)
+        out[ok, 1] = dp[:, bd:].max(1) if pk.p_red > bd else 0.0
+        out[ok, 2] = np.abs(x[ok, :3] - res.trans[f]).max(1)
+        if pk.n_dmpl:
+            out[ok, 3] = np.abs(x[ok, 3 + pk.p_red:] - res.dmpls[f, :pk.n_dmpl]).max(1)
+        return out
+
+    def relaunch_chunks(self, chunk_ids, chunk_warmup: int, warmup_full: int = -1):
+        ids = np.ascontiguousarray(chunk_ids, dtype=np.int32)
+        self.model._check(self.lib.mosh2_job_relaunch_chunks(self.handle, len(ids), _ptr(ids, _i32p), int(chunk_warmup),
+                                                             int(warmup_full)), 'mosh2_job_relaunch_chunks')
 
     def download(self) -> ResultArrays:
         self.model._check(self.lib.mosh2_job_download(self.handle, C.byref(self.result.c)), 'mosh2_job_download')

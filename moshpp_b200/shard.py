@@ -118,62 +118,68 @@ def solve_sharded(frame_counts: Sequence[int], n_markers: Sequence[int], row_wid
 
 
 class GpuRankSolver:
-    """This rank's share of a sharded run on its GPU: one model (all sequences of BASELINE config 5 share the body
-    model, shape and marker layout; pass ``packs`` per sequence otherwise), one resident job per local sequence, every
-    job on its own stream so that the chunks of all local sequences fill the GPU together.  The chunk length is planned
-    for all local sequences together (chmosh.plan_chunk_len: whole waves of one chunk per SM)."""
+    """This rank's share of a sharded run on its GPU.  Sequences that share a pack (one subject: body model, shape and
+    marker layout, as in BASELINE config 5) are solved by ONE launch: a batch job holds them back to back on its frame
+    axis, its chunks are planned for all of them together (chmosh.plan_chunk_len: whole waves of one chunk per SM) and
+    never straddle a sequence.  Different subjects get a job each, on their own streams."""
 
     def __init__(self, packs: Dict[int, object], options, frame_counts: Dict[int, int], device: int, *,
                  chunk_warmup: int, warmup_full: int, sm_budget: int = 148, precision=None):
         from . import lib
-        self.lib = lib
+        from .chmosh import plan_chunk_len
         self.device = device
         prec = lib.MOSH2_F32 if precision is None else precision
-        self.models, self.jobs = {}, {}
-        from .chmosh import plan_chunk_len
         common = plan_chunk_len(list(frame_counts.values()), sm_budget, chunk_warmup, warmup_full)
-        for i, F in frame_counts.items():
-            pk = packs[i]
-            key = id(pk)
-            if key not in self.models:
-                self.models[key] = lib.Model(pk, device=device)
-            chunk_len = 0 if common >= F else common
-            self.jobs[i] = self.models[key].job(F, options, chunk_len=chunk_len, chunk_warmup=chunk_warmup,
-                                                warmup_full=warmup_full, precision=prec)
+        groups: Dict[int, List[int]] = {}
+        for i in frame_counts:
+            groups.setdefault(id(packs[i]), []).append(i)
+        self.models, self.jobs, self.where = [], [], {}
+        for ids in groups.values():
+            model = lib.Model(packs[ids[0]], device=device)
+            counts = [int(frame_counts[i]) for i in ids]
+            job = model.job(counts, options, chunk_len=common if common < max(counts) else 0, chunk_warmup=chunk_warmup,
+                            warmup_full=warmup_full, precision=prec)
+            self.models.append(model)
+            self.jobs.append(job)
+            for k, i in enumerate(ids):
+                self.where[i] = (job, int(job.seq_offsets[k]), counts[k])
+        self.chunk_len = common
+        self.row_width = self.jobs[0].row_width
 
     def __call__(self, mine: Dict[int, tuple]) -> Dict[int, 'object']:
         import torch
         stream = torch.cuda.current_stream().cuda_stream
+        for i, (o, v) in mine.items():                 # device-to-device, ordered after the producer (NCCL) stream
+            job, f0, n = self.where[i]
+            job.upload_device_range(f0, n, o.data_ptr(), False, v.data_ptr(), stream)
+        for job in self.jobs:
+            job.launch()
+        torch.cuda.current_stream().synchronize()      # the row buffers below are written on the jobs' own streams
         out = {}
-        for i, (o, v) in mine.items():                 # all uploads and launches are queued before the first wait
-            j = self.jobs[i]
-            j.upload_device(o.data_ptr(), False, v.data_ptr(), stream)
-            j.launch()
-        torch.cuda.current_stream().synchronize()      # the row buffers are written on the jobs' own streams
-        for i in mine:
-            j = self.jobs[i]
-            rows = torch.empty((j.n_frames, j.row_width), dtype=torch.float32, device=f'cuda:{self.device}')
-            j.download_device(rows.data_ptr())         # packs on the job's stream and waits for it
-            out[i] = rows
+        for job in self.jobs:
+            rows = torch.empty((job.n_frames, job.row_width), dtype=torch.float32, device=f'cuda:{self.device}')
+            job.download_device(rows.data_ptr())       # packs on the job's stream and waits for it
+            for i, (jb, f0, n) in self.where.items():
+                if jb is job and i in mine:
+                    out[i] = rows[f0:f0 + n]
         return out
 
-    def kernel_ms(self) -> Dict[int, float]:
-        return {i: j.kernel_ms() for i, j in self.jobs.items()}
-
     def span_ms(self) -> float:
-        """Device time of the last round of launches of all local jobs (CUDA events on the jobs' streams)."""
-        js = list(self.jobs.values())
-        return max(a.span_ms(b) for a in js for b in js)
+        """Device time of the last round of launches (CUDA events on the jobs' streams: first start -> last end)."""
+        return max(a.span_ms(b) for a in self.jobs for b in self.jobs)
+
+    def num_chunks(self) -> int:
+        return sum(j.num_chunks for j in self.jobs)
 
     def totals(self) -> Dict[str, int]:
         agg: Dict[str, int] = {}
-        for j in self.jobs.values():
+        for j in self.jobs:
             for k, v in j.totals().items():
                 agg[k] = agg.get(k, 0) + v
         return agg
 
     def close(self):
-        for j in self.jobs.values():
+        for j in self.jobs:
             j.close()
-        for m in self.models.values():
+        for m in self.models:
             m.close()

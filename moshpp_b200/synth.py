@@ -567,7 +567,8 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
     data = np.full((F, pk.n_markers + 2, 3), np.nan)
     data[:, :pk.n_markers] = np.where(vis[:, perm, None], obs[:, perm], np.nan) * 1000.0
     data[:, -1] = 1000.0 * (trans + 0.3)
-    mocap_fname = os.path.join(out_dir, f'mocap_{config}_{seq_idx:02d}_{F}.{c["mocap_ext"]}')
+    side = f'_{hand_side}' if mt == 'mano' else ''
+    mocap_fname = os.path.join(out_dir, f'mocap_{config}{side}_{seq_idx:02d}_{F}.{c["mocap_ext"]}')
     if write_mocap:
         if c['mocap_ext'] == 'npz':
             np.savez(mocap_fname, markers=data, labels=np.array(file_labels), frame_rate=120.0)

@@ -98,8 +98,9 @@ struct HostModel {
 
 template <class real>
 int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, const double *obs, const uint8_t *vis,
-        const mosh2_schedule *sched, const mosh2_result *res) {
+        const mosh2_schedule *sched, const mosh2_result *res, int n_seq = 1, const int *seq_counts = nullptr, bool resume_all = false) {
     const int chunk_len = sched ? sched->chunk_len : 0, warmup = sched ? sched->chunk_warmup : 0;
+    if (!seq_counts) seq_counts = &n_frames;
     HostModel<real> hm;
     hm.build(*desc);
     const size_t F = n_frames, M = desc->n_markers, PF = size_t(3) * desc->n_joints, PR = desc->p_red, nd = desc->n_dmpl;
@@ -108,10 +109,12 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     std::vector<real> fullpose(F * PF), pose(F * PR), trans(F * 3), dmpls(F * nd + 1), mk(F * M * 3), errs(F * mosh2::N_ERR);
     mosh2::Job<real> job{};
     job.n_frames = n_frames;
-    job.chunk_len = chunk_len > 0 ? chunk_len : 0;
-    job.warmup = warmup > 0 ? warmup : 0;
-    job.warm_full = (!sched || sched->warmup_full < 0 || sched->warmup_full > job.warmup) ? job.warmup : sched->warmup_full;
-    job.n_chunks = job.chunk_len ? (n_frames + job.chunk_len - 1) / job.chunk_len : 1;
+    const int wu = warmup > 0 ? warmup : 0;
+    const int wf = (!sched || sched->warmup_full < 0 || sched->warmup_full > wu) ? wu : sched->warmup_full;
+    std::vector<int> tab = mosh2_host::chunk_table(seq_counts, n_seq, chunk_len, wu, wf);
+    job.n_chunks = int(tab.size() / mosh2::kChunkRec);
+    job.chunk_tab = tab.data();
+    job.chunk_ids = nullptr; job.warm_x = nullptr; job.warm_f = nullptr;
     job.obs = o.data(); job.vis = vis;
     job.fullpose = fullpose.data(); job.pose = pose.data(); job.trans = trans.data();
     job.dmpls = nd ? dmpls.data() : nullptr; job.markers_sim = mk.data(); job.errs = errs.data();
@@ -158,6 +161,15 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
         mosh2::Solver<real, false> s(hm.m, job, w, d, cta);
         s.run_chunk(c);
     }
+    if (resume_all) {       // boundary repair of every chunk, in order: chunk c continues from the rows chunk c-1 emitted
+        for (int c = 1; c < job.n_chunks; ++c) {
+            tab[size_t(c) * mosh2::kChunkRec + 3] = -1;
+            std::memset(smem_base, 0, S0.off + 64);
+            mosh2::Cta cta{0, 1};
+            mosh2::Solver<real, false> s(hm.m, job, w, d, cta);
+            s.run_chunk(c);
+        }
+    }
     auto conv = [](double *dst, const std::vector<real> &src, size_t n) {
         if (dst) for (size_t i = 0; i < n; ++i) dst[i] = double(src[i]);
     };
@@ -179,4 +191,22 @@ extern "C" int mosh2_emu_solve(const mosh2_model_desc *desc, const mosh2_options
                                int32_t precision, const mosh2_result *res) {
     if (precision == MOSH2_F64) return run<double>(desc, opt, n_frames, obs, vis, sched, res);
     return run<float>(desc, opt, n_frames, obs, vis, sched, res);
+}
+
+// several sequences of one subject back to back on the frame axis (mosh2_job_create_batch)
+extern "C" int mosh2_emu_solve_batch(const mosh2_model_desc *desc, const mosh2_options *opt, int32_t n_seq, const int32_t *frame_counts,
+                                     const double *obs, const uint8_t *vis, const mosh2_schedule *sched,
+                                     int32_t precision, const mosh2_result *res) {
+    int total = 0;
+    for (int q = 0; q < n_seq; ++q) total += frame_counts[q];
+    if (precision == MOSH2_F64) return run<double>(desc, opt, total, obs, vis, sched, res, n_seq, frame_counts);
+    return run<float>(desc, opt, total, obs, vis, sched, res, n_seq, frame_counts);
+}
+
+// chunked solve followed by a resume (mosh2_job_relaunch_chunks with chunk_warmup < 0) of every chunk in order
+extern "C" int mosh2_emu_solve_resumed(const mosh2_model_desc *desc, const mosh2_options *opt, int32_t n_frames,
+                                       const double *obs, const uint8_t *vis, const mosh2_schedule *sched,
+                                       int32_t precision, const mosh2_result *res) {
+    if (precision == MOSH2_F64) return run<double>(desc, opt, n_frames, obs, vis, sched, res, 1, nullptr, true);
+    return run<float>(desc, opt, n_frames, obs, vis, sched, res, 1, nullptr, true);
 }

@@ -110,3 +110,67 @@ def test_light_warmup_schedule_matches_oracle_emulation(cases, emu):
     # not the same numbers as with a fully solved warm-up
     full = emu(case, chunk_len=4, warmup=5, obs_vis=(obs, vis))
     assert np.abs(full.pose[fid] - res.pose[fid]).max() > 1e-6
+
+
+def test_batch_job_equals_separate_sequences(cases, emu):
+    """mosh2_job_create_batch: several sequences of one subject back to back on the job's frame axis.  Every sequence
+    starts from its own cold start, chunks and their warm-up never reach across a sequence boundary: the rows of each
+    sequence equal those of the sequence solved on its own, in the sequential and in the chunked schedule."""
+    import ctypes as C
+    from conftest import dense_obs
+    from moshpp_b200 import build
+    case = cases('C2')
+    obs, vis = dense_obs(case)
+    counts = np.array([7, 9], dtype=np.int32)                     # 16 frames cut into two "sequences"
+    handle = C.CDLL(build.build_emu())
+    pk, cfg = case['pack'], case['cfg']
+    h = lib.DescHolder(pk)
+    opt = lib.make_options(cfg.opt_settings.weights, optimize_fingers=True)
+    o = np.ascontiguousarray(obs, dtype=np.float64)
+    v8 = np.ascontiguousarray(vis, dtype=np.uint8)
+    for L, W, WF in ((0, 0, -1), (3, 4, 2)):
+        sched = lib.make_schedule(L, W, WF)
+        res = lib.ResultArrays(16, lib.pack_dims(pk))
+        rc = handle.mosh2_emu_solve_batch(C.byref(h.desc), C.byref(opt), 2, counts.ctypes.data_as(lib._i32p),
+                                          o.ctypes.data_as(lib._f64p), v8.ctypes.data_as(lib._u8p), C.byref(sched),
+                                          lib.MOSH2_F64, C.byref(res.c))
+        assert rc == 0
+        a = emu(case, chunk_len=L, warmup=W, warmup_full=WF, obs_vis=(obs[:7], vis[:7]))
+        b = emu(case, chunk_len=L, warmup=W, warmup_full=WF, obs_vis=(obs[7:], vis[7:]))
+        assert np.array_equal(res.pose[:7], a.pose) and np.array_equal(res.pose[7:], b.pose)
+        assert np.array_equal(res.status[:7], a.status) and np.array_equal(res.status[7:], b.status)
+        assert not (res.status[7] & lib.ST_HAS_VELO)              # the second sequence starts cold
+
+
+@pytest.mark.parametrize('name', ['C2', 'C3'])
+def test_resumed_chunks_continue_the_sequential_recursion(cases, emu, name):
+    """Boundary repair (mosh2_job_relaunch_chunks, chunk_warmup < 0): a chunk that resumes from the rows the previous
+    chunk emitted goes on exactly as that chunk would have.  Cold-started chunks without any warm-up, then every chunk
+    resumed in order, therefore reproduce the single sequential pass bit for bit -- pose, velocity term, DMPL terms."""
+    import ctypes as C
+    from conftest import dense_obs
+    from moshpp_b200 import build
+    case = cases(name)
+    obs, vis = dense_obs(case)
+    vis = vis.copy()
+    vis[5] = False                               # a skipped frame right before a chunk boundary
+    seq = emu(case, obs_vis=(obs, vis))
+    cold = emu(case, chunk_len=3, warmup=0, obs_vis=(obs, vis))
+    assert np.abs(cold.pose - seq.pose).max() > 1e-4
+    handle = C.CDLL(build.build_emu())
+    pk, cfg = case['pack'], case['cfg']
+    h = lib.DescHolder(pk)
+    opt = lib.make_options(cfg.opt_settings.weights, optimize_fingers=cfg.moshpp.optimize_fingers and pk.finger_hi > pk.finger_lo,
+                           optimize_dynamics=cfg.moshpp.optimize_dynamics)
+    F = obs.shape[0]
+    res = lib.ResultArrays(F, lib.pack_dims(pk))
+    o = np.ascontiguousarray(obs, dtype=np.float64)
+    v8 = np.ascontiguousarray(vis, dtype=np.uint8)
+    sched = lib.make_schedule(3, 0, -1)
+    rc = handle.mosh2_emu_solve_resumed(C.byref(h.desc), C.byref(opt), F, o.ctypes.data_as(lib._f64p), v8.ctypes.data_as(lib._u8p),
+                                        C.byref(sched), lib.MOSH2_F64, C.byref(res.c))
+    assert rc == 0
+    assert np.array_equal(res.status, seq.status)
+    assert np.array_equal(res.pose, seq.pose) and np.array_equal(res.trans, seq.trans) and np.array_equal(res.errs, seq.errs)
+    if pk.n_dmpl:
+        assert np.array_equal(res.dmpls, seq.dmpls)
