@@ -258,38 +258,39 @@ def main():
 # N = 1
 # ------------------------------------------------------------------------------------------------------------------
 def time_job(model, pk, opts, obs, vis, args, chunk_len, flush, steps, warmup):
-    """Device time of `steps` launches of one resident job (CUDA events on the job's stream)."""
-    from moshpp_b200 import lib
+    """Device time of `steps` passes of the product's solve on one resident job: the launch over all chunks, the boundary
+    check and the repair launches (chmosh.launch_verified), each launch bracketed by CUDA events on the job's stream."""
+    from moshpp_b200 import chmosh, lib
     prec = {'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[args.precision]
+    tol = chmosh.BOUNDARY_TOL['fast']
     F = obs.shape[0]
     job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full, precision=prec)
     job.upload(obs, vis)
     job.sync()
     for _ in range(warmup):
         flush()
-        job.launch()
-        job.sync()
-    ms = []
+        chmosh.launch_verified(job, tol)
+    ms, first_ms, launches = [], [], 0
     t0 = time.perf_counter()
     for _ in range(steps):
-        flush()                         # outside the CUDA-event bracket of the step
-        job.launch()
-        job.sync()
-        ms.append(job.kernel_ms())
+        flush()                         # outside the CUDA-event brackets of the step
+        bad, rep = chmosh.launch_verified(job, tol)
+        ms.append(sum(rep['kernel_ms']))
+        first_ms.append(rep['kernel_ms'][0])
+        launches += len(rep['kernel_ms'])
     wall = time.perf_counter() - t0
     totals = job.totals()
-    # C-ABI job-level end to end: pinned H2D + kernel + D2H of all result arrays
+    # C-ABI job-level end to end: pinned H2D + launches + D2H of all result arrays
     e2e = []
     for i in range(2 + steps):
         t1 = time.perf_counter()
-        job.upload(obs, vis)
-        job.launch()
-        res = job.download()
+        res, _ = chmosh.solve_verified(job, obs, vis, tol=tol)
         if i >= 2:
             e2e.append(time.perf_counter() - t1)
     solved = int(((res.status & lib.ST_SOLVED) != 0).sum())
-    out = dict(ms=float(np.mean(ms)), e2e_job_ms=float(np.mean(e2e)) * 1e3, totals=totals, chunks=job.num_chunks, solved=solved,
-               wall=wall, flags=int(np.bitwise_or.reduce(res.status)))
+    out = dict(ms=float(np.mean(ms)), first_launch_ms=float(np.mean(first_ms)), e2e_job_ms=float(np.mean(e2e)) * 1e3, totals=totals,
+               chunks=job.num_chunks, solved=solved, wall=wall, flags=int(np.bitwise_or.reduce(res.status)), launches=launches,
+               boundary=rep)
     job.close()
     return out
 
@@ -347,16 +348,21 @@ def run_single(args):
                    'frame_iterations_per_step': ns['totals']['builds'],
                    'useful_frame_iterations': ns['totals']['emitted_builds'],
                    'executed_over_useful': ns['totals']['builds'] / max(1, ns['totals']['emitted_builds']),
-                   'residual_evals_per_step': ns['totals']['evaluations'], 'status_flags_or': ns['flags']},
+                   'residual_evals_per_step': ns['totals']['evaluations'], 'status_flags_or': ns['flags'],
+                   'launches_per_step': ns['launches'] / args.steps, 'first_launch_ms': ns['first_launch_ms'],
+                   'boundary_check': {k: ns['boundary'][k] for k in ('rounds', 'repaired_chunks', 'chunks_over_tol_first',
+                                                                     'boundary_delta_first', 'boundary_delta_max', 'unverified_chunks')},
+                   'schedule': 'time-parallel chunks, verified: launch over all chunks + boundary check + resume-mode repair '
+                               'launches of the chunks whose warm-up left more than the tolerance (all inside ms_per_step)'},
         'roofline': roofline(ab, ns['totals']['builds'], ns['totals']['emitted_builds'], ns['ms'], 'NS'),
         'e2e': {'value': F / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_ms,
                 'what': 'wall clock of chmosh.mosh_stageii(mocap_fname, cfg, ...) per call: mocap file read, per-subject '
                         'packing (prepare_stageii), model upload, job create, pinned H2D, kernel, D2H, result dictionary',
-                'kernel_ms_inside': b['kernel_ms'],
+                'kernel_ms_inside': b['kernel_ms'], 'host_ms_last_call': b['host_ms'],
                 'c_abi_job_level': {'value': F / (ns['e2e_job_ms'] * 1e-3), 'ms_per_step': ns['e2e_job_ms'],
-                                    'what': 'mosh2_job_upload + launch + download with host buffers (resident model and job)'}},
-        'gpu_launches': args.steps,
+                                    'what': 'mosh2_job_upload + verified launches + download with host buffers (resident model and job)'}},
+        'gpu_launches': ns['launches'],
         'wall_s_timed_region': ns['wall'],
     }
     model.close()
@@ -404,6 +410,11 @@ def c5_inputs(n_seq, pin=True):
     drop-outs per sequence) as float32 / uint8 host tensors."""
     import torch
     from moshpp_b200 import chmosh, synth
+    try:        # torchrun pins OMP_NUM_THREADS=1; synthesising the observations is set-up work, let it use the host cores
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))))
+    except Exception:
+        pass
     d = tempfile.mkdtemp(prefix='mosh_bench_c5_')
     first = synth.make_case(d, 'C5', seq_idx=0)
     pk, opts, _ = chmosh.prepare_stageii(first['cfg'], first['markers_latent'], first['latent_labels'], first['betas'], first['marker_meta'])

@@ -149,6 +149,10 @@ int mosh2_job_launch(mosh2_job *j);                 /* async; all chunks; clears
  * of the same frame was produced by an earlier chunk further along its own history.  Their difference measures what the
  * warm-up left of the cold start, chunk by chunk.  x [n_chunks * (3 + p_red + n_dmpl)], frames [n_chunks]; syncs. */
 int mosh2_job_warm_states(mosh2_job *j, double *x, int32_t *frames);
+/* The same comparison done on the device: out [n_chunks * 4] = per chunk max |warm-up state - emitted row| over the pose
+ * coefficients [0, body_ids), the remaining pose coefficients, the translation, the dmpl / expression coefficients
+ * (zeros for chunks that start their sequence).  Queued behind the last launch on the job's stream; syncs. */
+int mosh2_job_boundary_deltas(mosh2_job *j, int32_t body_ids, float *out);
 /* Re-solves the listed chunks only (e.g. those that failed the boundary check); the rows of all other frames keep the
  * values of the previous launch.  chunk_warmup >= 0: with that warm-up, from a cold start.  chunk_warmup < 0: RESUME --
  * no warm-up; the chunk continues the recursion from the rows the previous launch emitted for the last two solved frames

@@ -36,8 +36,8 @@ from .mocap_interface import MocapSession
 logger = logging.getLogger('moshpp_b200')
 
 NUM_SMS_B200 = 148
-DEFAULT_WARMUP = 48          # solved frames every chunk is started early
-DEFAULT_WARMUP_FULL = 32     # the last 32 of them with the full per-frame schedule, the first 16 with one Step-2 iteration
+DEFAULT_WARMUP = 64          # solved frames every chunk is started early
+DEFAULT_WARMUP_FULL = 48     # the last 48 of them with the full per-frame schedule, the first 16 with one Step-2 iteration
 
 
 def _get(node, key, default=None):
@@ -200,11 +200,25 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         expr = np.zeros((len(fid), tail))
         expr[:, :pk.n_expr] = res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl]
         data['expression'] = expr
+    # per-frame lists over the visible markers (chmosh.py:716-718): one gather per array, cut into per-frame views; the
+    # label lists are built once per visibility pattern (drop-outs come in runs) and copied
+    vf = vis[fid]
+    ends = np.cumsum(vf.sum(1))
+    starts = ends - vf.sum(1)
+    sim_cat, obs_cat = res.markers_sim[fid][vf], obs[fid][vf]
+    by_pattern: dict = {}
+    labels_obs = []
+    for row in vf:
+        key = row.tobytes()
+        names = by_pattern.get(key)
+        if names is None:
+            names = by_pattern[key] = labels[row].tolist()
+        labels_obs.append(list(names))
     data['stageii_debug_details'] = {
         'stageii_errs': errs,
-        'markers_sim': [res.markers_sim[f][vis[f]] for f in fid],
-        'markers_obs': [obs[f][vis[f]] for f in fid],
-        'labels_obs': [labels[vis[f]].tolist() for f in fid],
+        'markers_sim': [sim_cat[a:b] for a, b in zip(starts, ends)],
+        'markers_obs': [obs_cat[a:b] for a, b in zip(starts, ends)],
+        'labels_obs': labels_obs,
     }
     return data
 
@@ -227,28 +241,22 @@ def default_schedule(model_type: str, mode: str = 'fast'):
     return DEFAULT_WARMUP, DEFAULT_WARMUP_FULL, 'f32'
 
 
-def solve_verified(job, obs, vis, *, tol, max_rounds: int = 6):
-    """Upload + launch + download, then the boundary check of the chunked schedule and its repair.
-
-    Every chunk reports the state it reached on its last warm-up frame; the emitted result of that frame comes from the
-    previous chunk, which is further along its own history.  Where the two differ by more than ``tol`` (root+body pose,
-    other pose coefficients, translation, dmpl / expression coefficients) the chunk is solved again in RESUME mode: it
-    continues the recursion from the rows the previous chunk emitted, exactly as that chunk would have gone on
-    (mosh2_job_relaunch_chunks, chunk_warmup < 0).  A repair round costs one chunk length, not a warm-up.  Neighbouring
-    failing chunks are repaired in consecutive rounds (a chunk must not read rows that are being rewritten).  Chunks that
-    still fail after ``max_rounds`` keep MOSH2_ST_SHORT_WARMUP on their frames.  Returns (ResultArrays, report)."""
-    job.upload(obs, vis)
+def launch_verified(job, tol, max_rounds: int = 6):
+    """Launch + boundary check + repair rounds on the observations the job already holds (device work only; see
+    ``solve_verified``).  Returns (chunk ids still over tolerance, report); report['kernel_ms'] lists the device time of
+    every launch (CUDA events on the job's stream)."""
     job.launch()
-    res = job.download()
-    kernel_ms = [job.kernel_ms()]
     report = {'rounds': 0, 'repaired_chunks': [], 'boundary_delta_first': None, 'boundary_delta_max': None, 'unverified_chunks': 0}
-    if job.schedule.chunk_len <= 0 or tol is None:
-        report['kernel_ms'] = kernel_ms
-        return res, report
-    tol = np.asarray(tol, dtype=np.float64)
+    kernel_ms = []
     bad = np.zeros(0, dtype=np.int64)
+    if job.schedule.chunk_len <= 0 or tol is None:
+        job.sync()
+        report['kernel_ms'] = [job.kernel_ms()]
+        return bad, report
+    tol = np.asarray(tol, dtype=np.float64)
     for rnd in range(max_rounds + 1):
-        d = job.boundary_deltas(res)
+        d = job.boundary_deltas()                # on the device, behind the launch; 16 bytes per chunk come back
+        kernel_ms.append(job.kernel_ms())
         bad = np.nonzero((d > tol[None]).any(1))[0]
         if rnd == 0:
             report['boundary_delta_first'] = d.max(0).tolist()
@@ -263,10 +271,25 @@ def solve_verified(job, obs, vis, *, tol, max_rounds: int = 6):
                 take.append(int(c))
                 last = int(c)
         job.relaunch_chunks(take, -1)
-        res = job.download()
-        kernel_ms.append(job.kernel_ms())
         report['rounds'] += 1
         report['repaired_chunks'].append(len(take))
+    report['kernel_ms'] = kernel_ms
+    return bad, report
+
+
+def solve_verified(job, obs, vis, *, tol, max_rounds: int = 6):
+    """Upload + launch + download, then the boundary check of the chunked schedule and its repair.
+
+    Every chunk reports the state it reached on its last warm-up frame; the emitted result of that frame comes from the
+    previous chunk, which is further along its own history.  Where the two differ by more than ``tol`` (root+body pose,
+    other pose coefficients, translation, dmpl / expression coefficients) the chunk is solved again in RESUME mode: it
+    continues the recursion from the rows the previous chunk emitted, exactly as that chunk would have gone on
+    (mosh2_job_relaunch_chunks, chunk_warmup < 0).  A repair round costs one chunk length, not a warm-up.  Neighbouring
+    failing chunks are repaired in consecutive rounds (a chunk must not read rows that are being rewritten).  Chunks that
+    still fail after ``max_rounds`` keep MOSH2_ST_SHORT_WARMUP on their frames.  Returns (ResultArrays, report)."""
+    job.upload(obs, vis)
+    bad, report = launch_verified(job, tol, max_rounds)
+    res = job.download()
     if len(bad):
         report['unverified_chunks'] = int(len(bad))
         L = job.schedule.chunk_len
@@ -275,7 +298,6 @@ def solve_verified(job, obs, vis, *, tol, max_rounds: int = 6):
             res.status[sl] |= np.where((res.status[sl] & _lib.ST_SOLVED) != 0, _lib.ST_SHORT_WARMUP, 0).astype(res.status.dtype)
         logger.warning('%d chunks did not pass the boundary check after %d repair rounds (max delta %s); their frames carry '
                        'MOSH2_ST_SHORT_WARMUP', len(bad), report['rounds'], report['boundary_delta_max'])
-    report['kernel_ms'] = kernel_ms
     return res, report
 
 
@@ -295,12 +317,22 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     the reference always applies (chmosh.py:466), a dict, or None for raw labels.
     """
     t0 = time.time()
+    lap = {}
+    tl = [time.perf_counter()]
+
+    def mark(name):
+        now = time.perf_counter()
+        lap[name] = lap.get(name, 0.0) + (now - tl[0]) * 1e3
+        tl[0] = now
+
     if mode not in BOUNDARY_TOL:
         raise ValueError(f"mode must be 'fast' or 'exact', not {mode!r}")
     mocap = MocapSession(mocap_fname, mocap_unit=cfg.mocap.unit, mocap_rotate=cfg.mocap.rotate,
                          labels_map=labels_map,
                          only_subjects=[cfg.mocap.subject_name] if cfg.mocap.multi_subject else None)
+    mark('read_mocap_ms')
     pk, opts, flags = prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname)
+    mark('prepare_ms')
     dyn = bool(opts.optimize_dynamics)
     w_def, wf_def, prec_def = default_schedule(pk.model_type, mode)
     chunk_warmup = w_def if chunk_warmup is None else int(chunk_warmup)
@@ -320,12 +352,16 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     if chunk_len >= F:
         chunk_len = 0
     prec = {'f32': _lib.MOSH2_F32, 'f64': _lib.MOSH2_F64}[precision]
+    mark('dense_view_ms')
 
     model = _lib.Model(pk, device=device)
+    mark('model_create_ms')
     try:
         job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec)
+        mark('job_create_ms')
         try:
             res, report = solve_verified(job, obs, vis, tol=boundary_tol if verify else None)
+            mark('solve_ms')
             kernel_ms = float(sum(report['kernel_ms']))
             n_chunks = job.num_chunks
             totals = job.totals()
@@ -334,7 +370,9 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     finally:
         model.close()
 
+    mark('close_ms')
     data = assemble_stageii_data(res, obs, vis, latent_labels, pk, flags, dyn)
+    mark('assemble_ms')
     dbg = data['stageii_debug_details']
     dbg.update({
         'markers_orig': mocap.markers[selected_frames],
@@ -345,7 +383,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         'b200': {
             'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
             'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'mode': mode,
-            'boundary_check': report, 'totals': totals, 'status': res.status.copy(),
+            'boundary_check': report, 'totals': totals, 'host_ms': lap, 'status': res.status.copy(),
             'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
             'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
         },

@@ -202,6 +202,31 @@ __global__ void pack_rows_kernel(const real *__restrict__ fullpose, const real *
     rows[i] = v;
 }
 
+// boundary check on the device: per chunk max |state on the last warm-up frame - emitted row of that frame| over
+// (root+body pose, other pose coefficients, translation, linear coefficients); one warp per chunk
+template <class real>
+__global__ void boundary_delta_kernel(const real *__restrict__ warm_x, const int *__restrict__ warm_f, const real *__restrict__ pose,
+                                      const real *__restrict__ trans, const real *__restrict__ dmpls, float *__restrict__ out,
+                                      int n_chunks, int PR, int nd, int body) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= n_chunks) return;
+    const int f = warm_f[c];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (f >= 0) {
+        const real *x = warm_x + size_t(c) * (3 + PR + nd);
+        for (int i = lane; i < PR; i += 32) {
+            const float d = fabsf(float(x[3 + i] - pose[size_t(f) * PR + i]));
+            if (i < body) v[0] = fmaxf(v[0], d); else v[1] = fmaxf(v[1], d);
+        }
+        if (lane < 3) v[2] = fabsf(float(x[lane] - trans[size_t(f) * 3 + lane]));
+        for (int i = lane; i < nd; i += 32) v[3] = fmaxf(v[3], fabsf(float(x[3 + PR + i] - dmpls[size_t(f) * nd + i])));
+    }
+    for (int q = 0; q < 4; ++q) {
+        for (int o = 16; o > 0; o >>= 1) v[q] = fmaxf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+        if (lane == 0) out[4 * c + q] = v[q];
+    }
+}
+
 // Host copy of a model description: the caller's buffers need not outlive mosh2_model_create, and the device copy of a
 // precision is only built when the first job of that precision is created.
 struct HostDesc {
@@ -256,7 +281,9 @@ struct mosh2_job {
     int n_frames = 0, chunk_len = 0, warmup = 0, warm_full = 0, n_chunks = 1;
     int *d_chunk_tab = nullptr, *d_chunk_ids = nullptr, *d_warm_f = nullptr;
     void *d_warm_x = nullptr;
-    std::vector<int> tab;             // host copy of the chunk table
+    float *d_delta = nullptr;
+    std::vector<int> tab, tab0;       // host copy of the chunk table (tab0: as created; repairs edit tab)
+    bool tab_dirty = false;
     int launch_blocks = 0;            // blocks of the next launch (all chunks, or the subset in d_chunk_ids)
     bool subset = false;
     mosh2::Options opt{};
@@ -436,6 +463,7 @@ int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_s
     j->warmup = chunk_warmup > 0 ? chunk_warmup : 0;
     j->warm_full = (!sched || sched->warmup_full < 0 || sched->warmup_full > j->warmup) ? j->warmup : sched->warmup_full;
     j->tab = mosh2_host::chunk_table(frame_counts, n_seq, j->chunk_len, j->warmup, j->warm_full);
+    j->tab0 = j->tab;
     const std::vector<int> &tab = j->tab;
     j->n_chunks = int(tab.size() / mosh2::kChunkRec);
     j->launch_blocks = j->n_chunks;
@@ -482,6 +510,7 @@ int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_s
     chk(cudaMalloc(&j->d_chunk_tab, tab.size() * sizeof(int)));
     chk(cudaMalloc(&j->d_chunk_ids, size_t(j->n_chunks) * sizeof(int)));
     chk(cudaMalloc(&j->d_warm_f, size_t(j->n_chunks) * sizeof(int)));
+    chk(cudaMalloc(&j->d_delta, size_t(j->n_chunks) * 4 * sizeof(float)));
     chk(cudaMalloc(&j->d_warm_x, size_t(j->n_chunks) * (3 + m->p_red + m->n_dmpl) * j->esz));
     if (e == cudaSuccess) chk(cudaMemcpy(j->d_chunk_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     chk(cudaMalloc(&j->d_prof, 32 * sizeof(long long)));
@@ -522,6 +551,11 @@ int mosh2_job_launch(mosh2_job *j) {
     CU(cudaMemsetAsync(j->d_counters, 0, size_t(j->n_frames) * 4 * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_totals, 0, 8 * sizeof(int), j->stream));
     CU(cudaMemsetAsync(j->d_prof, 0, 32 * sizeof(long long), j->stream));
+    if (j->tab_dirty) {               // a full launch runs the schedule the job was created with
+        j->tab = j->tab0;
+        CU(cudaMemcpyAsync(j->d_chunk_tab, j->tab.data(), j->tab.size() * sizeof(int), cudaMemcpyHostToDevice, j->stream));
+        j->tab_dirty = false;
+    }
     j->subset = false;
     j->launch_blocks = j->n_chunks;
     if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
@@ -538,6 +572,7 @@ int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids,
         j->tab[size_t(c) * mosh2::kChunkRec + 3] = chunk_warmup;
         j->tab[size_t(c) * mosh2::kChunkRec + 4] = wf;
     }
+    j->tab_dirty = true;
     CU(cudaStreamSynchronize(j->stream));
     CU(cudaMemcpy(j->d_chunk_tab, j->tab.data(), j->tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(j->d_chunk_ids, chunk_ids, size_t(n) * sizeof(int), cudaMemcpyHostToDevice));
@@ -546,6 +581,23 @@ int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids,
     j->launch_blocks = n;
     if (j->precision == MOSH2_F64) return launch<double>(j, j->model->f64.m);
     return launch<float>(j, j->model->f32.m);
+}
+
+int mosh2_job_boundary_deltas(mosh2_job *j, int32_t body_ids, float *out) {
+    if (!j || !out || body_ids < 0) return fail(MOSH2_E_INVALID, "bad argument");
+    CU(cudaSetDevice(j->model->device));
+    const int PR = j->model->p_red, nd = j->model->n_dmpl, blocks = (j->n_chunks + 3) / 4;
+    if (j->precision == MOSH2_F64) {
+        const double *o = static_cast<const double *>(j->d_out);
+        boundary_delta_kernel<double><<<blocks, 128, 0, j->stream>>>(static_cast<const double *>(j->d_warm_x), j->d_warm_f, o + j->o_pose, o + j->o_trans, o + j->o_dmpls, j->d_delta, j->n_chunks, PR, nd, body_ids);
+    } else {
+        const float *o = static_cast<const float *>(j->d_out);
+        boundary_delta_kernel<float><<<blocks, 128, 0, j->stream>>>(static_cast<const float *>(j->d_warm_x), j->d_warm_f, o + j->o_pose, o + j->o_trans, o + j->o_dmpls, j->d_delta, j->n_chunks, PR, nd, body_ids);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, j->d_delta, size_t(j->n_chunks) * 4 * sizeof(float), cudaMemcpyDeviceToHost, j->stream));
+    CU(cudaStreamSynchronize(j->stream));
+    return 0;
 }
 
 int mosh2_job_warm_states(mosh2_job *j, double *x, int32_t *frames) {
@@ -682,7 +734,7 @@ void mosh2_job_destroy(mosh2_job *j) {
     if (!j) return;
     cudaSetDevice(j->model->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
-    cudaFree(j->d_chunk_tab); cudaFree(j->d_chunk_ids); cudaFree(j->d_warm_f); cudaFree(j->d_warm_x); cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_prof); cudaFree(j->d_gws);
+    cudaFree(j->d_chunk_tab); cudaFree(j->d_chunk_ids); cudaFree(j->d_warm_f); cudaFree(j->d_warm_x); cudaFree(j->d_delta); cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_prof); cudaFree(j->d_gws);
     cudaFreeHost(j->h_obs); cudaFreeHost(j->h_out); cudaFreeHost(j->h_vis); cudaFreeHost(j->h_status); cudaFreeHost(j->h_counters);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);

@@ -198,6 +198,11 @@ template <class real> M2_HD real accept_slack();
 template <> M2_HD float accept_slack<float>() { return 1e-5f; }
 template <> M2_HD double accept_slack<double>() { return 0.0; }
 
+// boundary repair: a re-solved frame "coincides" with the row it replaces below this (rad; translation in 0.1 m)
+template <class real> M2_HD real merge_tol();
+template <> M2_HD float merge_tol<float>() { return 2e-5f; }
+template <> M2_HD double merge_tol<double>() { return 1e-10; }
+
 template <class real> struct alignas(16) Vec4 { real x, y, z, w; };
 template <class real> M2_HD Vec4<real> ld4(const real *p) { return *reinterpret_cast<const Vec4<real> *>(p); }
 template <class real>
@@ -548,6 +553,8 @@ struct Solver {
     // counters of the current frame
     int n_iter, n_eval, n_build, n_min, frame_flags;
     int prof_base = 0;        // development builds: offset of the phase-timer slots
+    bool resuming = false;    // boundary repair: the chunk continues from emitted rows (run_chunk)
+    real resume_diff = 0;     // ... and how far the frame just solved is from the row it replaces
     unsigned int tc_tmem = 0, tc_phase = 0;   // tensor-memory base address, parity of the MMA completion barrier
     int tc_kt = 0;            // rows per Jacobian tile (K extent of one tile's MMAs)
 
@@ -555,6 +562,24 @@ struct Solver {
         : m(m_), job(j_), w(w_), cta(c_), d(d_) {}
 
 #define CTA_FOR(i, n) _Pragma("unroll 1") for (int i = cta.tid; i < (n); i += cta.nthr)
+
+    // ---- CTA-wide maximum of one per-thread value, broadcast (rare path: boundary repair)
+    M2_D void cta_max(real *v) {
+#if M2_GPU
+        real x = v[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const real y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x ? y : x; }
+        const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = (cta.nthr + 31) >> 5;
+        if (lane == 0) w.red[warp] = x;
+        __syncthreads();
+        if (cta.tid == 0) { real mx = w.red[0]; for (int q = 1; q < nwarp; ++q) mx = w.red[q] > mx ? w.red[q] : mx; w.red[32] = mx; }
+        __syncthreads();
+        v[0] = w.red[32];
+        __syncthreads();
+#else
+        (void)v;
+#endif
+    }
 
     // ---- FK, executed by `nl` lanes (one warp on the GPU) starting at lane id `l`.  Every lane multiplies down the
     //      ancestor chain of its own joint (root first), which it reads as four words: no level-by-level hand-over
@@ -1919,6 +1944,18 @@ struct Solver {
             if (emit) { job.totals[4] += n_iter; job.totals[5] += n_eval; job.totals[6] += n_build; job.totals[7] += n_min; }
 #endif
         }
+        if (emit && resuming) {
+            // how far is the re-solved frame from the row it replaces?  (run_chunk stops the repair once the two
+            // trajectories have merged: the remaining rows of the chunk are then still valid)
+            real dm[1] = {0};
+            if (job.status[f] & ST_SOLVED) {
+                CTA_FOR(i, d.PR) { const real e = r_abs(w.x[3 + i] - job.pose[size_t(f) * d.PR + i]); if (e > dm[0]) dm[0] = e; }
+                CTA_FOR(i, 3) { const real e = real(10) * r_abs(w.x[i] - job.trans[size_t(f) * 3 + i]); if (e > dm[0]) dm[0] = e; }
+            } else dm[0] = real(1);
+            // (max via the sum reduction of a one-hot power is overkill: reduce the maximum over threads with shuffles)
+            cta_max(dm);
+            resume_diff = dm[0];
+        }
         if (emit) {
             CTA_FOR(i, d.PF) job.fullpose[size_t(f) * d.PF + i] = w.fullpose[i];
             CTA_FOR(i, d.PR) job.pose[size_t(f) * d.PR + i] = w.x[3 + i];
@@ -2133,9 +2170,11 @@ struct Solver {
                 if (f2 >= 0) CTA_FOR(i, d.PR) w.pose_prev[i] = job.pose[size_t(f2) * d.PR + i];
                 first = false;
                 have_prev = f2 >= 0;
+                resuming = true;
             }
             M2_SYNC();
         }
+        int calm = 0;                              // consecutive re-solved frames that coincide with the rows they replace
         wv = real(o.wt_velo); wdm = real(o.wt_dmpl); wex = real(o.wt_extrap);
         wxp = real(o.wt_expr);
         const bool fingers = o.optimize_fingers != 0, dyn = o.optimize_dynamics != 0 && d.nd - m.n_expr > 0;
@@ -2180,6 +2219,12 @@ struct Solver {
             has_extrap = dyn && have_dm_prev;
             if (short_warmup && f >= f_emit) frame_flags |= ST_SHORT_WARMUP;
             solve_frame(f, f >= f_emit, first, fingers, dyn, face, /*light=*/!first && f < f_full);
+            if (resuming) {
+                // merged with the old trajectory (two frames in a row within round-off of the rows they replace: the state
+                // the recursion carries, pose_t and pose_{t-1}, is the old one): the rest of the chunk stands as it is
+                calm = resume_diff <= merge_tol<real>() ? calm + 1 : 0;
+                if (calm >= 2) break;
+            }
             if (f < f_emit && job.warm_x) {      // (overwritten until the last warm-up frame: its state is what counts)
                 CTA_FOR(i, d.NX) job.warm_x[size_t(chunk) * d.NX + i] = w.x[i];
                 if (cta.tid == 0) job.warm_f[chunk] = f;

@@ -109,6 +109,7 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_job_download_device.argtypes = [vp, vp]
     lib.mosh2_job_launch.argtypes = [vp]
     lib.mosh2_job_warm_states.argtypes = [vp, _f64p, _i32p]
+    lib.mosh2_job_boundary_deltas.argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
     lib.mosh2_job_relaunch_chunks.argtypes = [vp, C.c_int32, _i32p, C.c_int32, C.c_int32]
     lib.mosh2_job_download.argtypes = [vp, C.POINTER(Result)]
     lib.mosh2_job_sync.argtypes = [vp]
@@ -130,7 +131,8 @@ EXPORTED_SYMBOLS = (
     'mosh2_model_destroy', 'mosh2_job_create', 'mosh2_job_upload', 'mosh2_job_launch', 'mosh2_job_download',
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
     'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
-    'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks')
+    'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks',
+    'mosh2_job_boundary_deltas')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -320,22 +322,15 @@ class Job:
         self.model._check(self.lib.mosh2_job_warm_states(self.handle, _ptr(x, _f64p), _ptr(fr, _i32p)), 'mosh2_job_warm_states')
         return x, fr
 
-    def boundary_deltas(self, res: 'ResultArrays'):
+    def boundary_deltas(self):
         """Per chunk: max |warm-up state - emitted result| on the chunk's last warm-up frame, split into
-        (root + body pose [rad], remaining pose coefficients, translation [m], dmpl / expression coefficients)."""
+        (root + body pose [rad], remaining pose coefficients, translation [m], dmpl / expression coefficients);
+        computed on the device from the last launch (mosh2_job_boundary_deltas)."""
         pk = self.model.pk
-        x, fr = self.warm_states()
-        bd = min(pk.body_dof, 66)
-        out = np.zeros((len(fr), 4))
-        ok = fr >= 0
-        f = fr[ok]
-        dp = np.abs(x[ok, 3:3 + pk.p_red] - res.pose[f])
-        out[ok, 0] = dp[:, :bd].max(1)
-        out[ok, 1] = dp[:, bd:].max(1) if pk.p_red > bd else 0.0
-        out[ok, 2] = np.abs(x[ok, :3] - res.trans[f]).max(1)
-        if pk.n_dmpl:
-            out[ok, 3] = np.abs(x[ok, 3 + pk.p_red:] - res.dmpls[f, :pk.n_dmpl]).max(1)
-        return out
+        out = np.zeros((self.num_chunks, 4), dtype=np.float32)
+        self.model._check(self.lib.mosh2_job_boundary_deltas(self.handle, min(pk.body_dof, 66), out.ctypes.data_as(C.POINTER(C.c_float))),
+                          'mosh2_job_boundary_deltas')
+        return out.astype(np.float64)
 
     def relaunch_chunks(self, chunk_ids, chunk_warmup: int, warmup_full: int = -1):
         ids = np.ascontiguousarray(chunk_ids, dtype=np.int32)

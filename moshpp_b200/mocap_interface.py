@@ -205,20 +205,31 @@ class MocapSession:
     def frames_for_labels(self, latent_labels: Sequence[str], frame_ids: Sequence[int]):
         """Observations ``F x M x 3`` (metres) in ``latent_labels`` order and the ``F x M`` visibility mask -- label
         present in the file and sample available in the frame.  What chmosh.py:582-594 stacks frame by frame."""
-        frame_ids = np.asarray(list(frame_ids), dtype=np.int64)
-        mk = self.markers[frame_ids]
-        ok = self.marker_availability_mask(mk)
-        F, M = len(frame_ids), len(latent_labels)
+        if isinstance(frame_ids, range) and len(frame_ids):       # a view, no copy
+            mk = self.markers[frame_ids.start:frame_ids.stop:frame_ids.step]
+        else:
+            mk = self.markers[np.asarray(list(frame_ids), dtype=np.int64)]
+        ok = (mk != 0).any(-1)        # missing samples were zeroed at load time (NaN included), so this is the :277 rule
+        F, M = mk.shape[0], len(latent_labels)
         obs = np.zeros((F, M, 3))
         vis = np.zeros((F, M), dtype=bool)
         columns: Dict[str, List[int]] = {}
         for c, l in enumerate(self.labels):
             columns.setdefault(l, []).append(c)
+        # one gather for the labels that own exactly one column (the normal case) ...
+        single = [(m, columns[l][0]) for m, l in enumerate(latent_labels) if len(columns.get(l, ())) == 1]
+        if single:
+            ms, cs = (np.array(x) for x in zip(*single))
+            vis[:, ms] = ok[:, cs]
+            obs[:, ms] = np.where(ok[:, cs, None], mk[:, cs], 0.0)
+        # ... duplicates: later columns overwrite earlier ones where they are available
         for m, l in enumerate(latent_labels):
-            for c in columns.get(l, ()):                 # later columns overwrite earlier ones where they are available
-                sel = ok[:, c]
-                obs[sel, m] = mk[sel, c]
-                vis[:, m] |= sel
+            cols = columns.get(l, ())
+            if len(cols) > 1:
+                for c in cols:
+                    sel = ok[:, c]
+                    obs[sel, m] = mk[sel, c]
+                    vis[:, m] |= sel
         return obs, vis
 
     def markers_asdict(self) -> List[Dict[str, np.ndarray]]:

@@ -14,7 +14,9 @@ Reference behaviour restated here (file:line under /root/reference/src/moshpp):
 """
 from __future__ import annotations
 
+import os
 import pickle
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -69,6 +71,31 @@ def _dense_regressor(jreg) -> np.ndarray:
     return np.asarray(jreg, dtype=np.float64)
 
 
+_MODEL_FILE_CACHE: 'OrderedDict[tuple, dict]' = OrderedDict()
+
+
+def _read_model_pickle(fname: str) -> dict:
+    """The unpickled body-model file, kept for the (path, mtime, size) it was read from: a subject's sequences (and all
+    subjects of one model family) share the 80-300 MB file, and unpickling it costs more than solving a sequence.  The
+    entry is dropped as soon as the file changes; at most two models are kept.  The arrays are never written to."""
+    st = os.stat(fname)
+    key = (os.path.realpath(fname), st.st_mtime_ns, st.st_size)
+    dd = _MODEL_FILE_CACHE.get(key)
+    if dd is None:
+        with open(fname, 'rb') as f:
+            dd = pickle.load(f, encoding='latin-1')
+        _MODEL_FILE_CACHE[key] = dd
+        while len(_MODEL_FILE_CACHE) > 2:
+            _MODEL_FILE_CACHE.popitem(last=False)
+    else:
+        _MODEL_FILE_CACHE.move_to_end(key)
+    return dd
+
+
+def clear_file_cache():
+    _MODEL_FILE_CACHE.clear()
+
+
 def load_surface_model(surface_model_fname: str,
                        pose_hand_prior_fname: Optional[str] = None,
                        use_hands_mean: bool = False,
@@ -78,8 +105,7 @@ def load_surface_model(surface_model_fname: str,
     """Same inputs and model-type rules as the reference loader (smpl_fast_derivatives.py:52-145)."""
     if not str(surface_model_fname).endswith('.pkl'):
         raise ValueError('surface_model_fname could only be a pkl file.')
-    with open(surface_model_fname, 'rb') as f:
-        dd = pickle.load(f, encoding='latin-1')
+    dd = _read_model_pickle(str(surface_model_fname))
 
     posedirs = np.asarray(dd['posedirs'], dtype=np.float64)
     njoint_parms = posedirs.shape[2] // 3

@@ -144,6 +144,7 @@ class GpuRankSolver:
             for k, i in enumerate(ids):
                 self.where[i] = (job, int(job.seq_offsets[k]), counts[k])
         self.chunk_len = common
+        self.reports = []
         self.row_width = self.jobs[0].row_width
 
     def __call__(self, mine: Dict[int, tuple]) -> Dict[int, 'object']:
@@ -152,8 +153,8 @@ class GpuRankSolver:
         for i, (o, v) in mine.items():                 # device-to-device, ordered after the producer (NCCL) stream
             job, f0, n = self.where[i]
             job.upload_device_range(f0, n, o.data_ptr(), False, v.data_ptr(), stream)
-        for job in self.jobs:
-            job.launch()
+        from .chmosh import BOUNDARY_TOL, launch_verified
+        self.reports = [launch_verified(job, BOUNDARY_TOL['fast'])[1] for job in self.jobs]   # launch + boundary check + repair
         torch.cuda.current_stream().synchronize()      # the row buffers below are written on the jobs' own streams
         out = {}
         for job in self.jobs:
@@ -165,8 +166,10 @@ class GpuRankSolver:
         return out
 
     def span_ms(self) -> float:
-        """Device time of the last round of launches (CUDA events on the jobs' streams: first start -> last end)."""
-        return max(a.span_ms(b) for a in self.jobs for b in self.jobs)
+        """Device time of the last solve: per job the sum over its launches (first launch over all chunks + repair
+        launches, CUDA events on the job's stream); jobs of different subjects run concurrently on their own streams, so
+        the rank's time is the maximum over its jobs."""
+        return max(float(sum(r['kernel_ms'])) for r in self.reports)
 
     def num_chunks(self) -> int:
         return sum(j.num_chunks for j in self.jobs)
