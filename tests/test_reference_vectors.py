@@ -41,3 +41,74 @@ def test_c3d_writer_output_is_what_the_reference_parser_read(tmp_path):
     pts, lab, rate = c3d_io.read_c3d(fn)
     assert lab == labels and rate == 120.0
     assert np.allclose(pts, g['data'], rtol=0, atol=1e-3, equal_nan=True)                   # float32 millimetres
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# rows a5, a6, a7: vectors emitted by the UNMODIFIED prior/gmm_prior_ch.py and transformed_lm.py running over the
+# forward-only chumpy stand-in tests/golden/ref_shim (make_reference_vectors.py: prior_and_marker_vectors)
+# --------------------------------------------------------------------------------------------------------------------
+def _prior_file(tmp_path, g):
+    import pickle
+    fn = str(tmp_path / 'prior.pkl')
+    with open(fn, 'wb') as f:
+        pickle.dump(dict(covars=g['covars'], means=g['means'], weights=g['weights']), f)
+    return fn
+
+
+def test_oracle_prior_equals_reference(tmp_path):
+    """create_gmm_body_prior (gmm_prior_ch.py:107-134) and MaxMixtureComplete (42-72): normalised weights, Cholesky
+    factors, arg-min component and the D+1 residual on probe poses that select every component."""
+    from oracle import prior as oprior
+    g = np.load(os.path.join(GOLD, 'ref_prior.npz'))
+    fn = _prior_file(tmp_path, g)
+    for tag, excl in (('63', True), ('69', False)):
+        mm = oprior.create_gmm_body_prior(fn, exclude_hands=excl)
+        assert np.abs(mm.precs - g[f'chols_{tag}']).max() < 1e-10 * np.abs(g[f'chols_{tag}']).max()
+        assert np.allclose(mm.weights, g[f'weights_{tag}'].ravel(), rtol=1e-12, atol=0)
+        assert np.array_equal(mm.means, g[f'means_{tag}'])
+        for x, r_ref, k_ref in zip(g[f'x_{tag}'], g[f'r_{tag}'], g[f'k_{tag}']):
+            k, _ = mm.select(x)
+            assert k == int(k_ref)
+            assert np.abs(mm.r(x) - r_ref).max() < 1e-9 * max(1.0, np.abs(r_ref).max())
+        assert len(set(g[f'k_{tag}'].tolist())) == len(mm.weights)          # every component was exercised
+
+
+def test_device_prior_constants_equal_reference(tmp_path):
+    """What the device consumes (pack.create_gmm_body_prior: Q = .5 inv(cov), -log w) reproduces the reference's residual:
+    sum r[:-1]^2 = (x - mu_k)^T Q_k (x - mu_k), r[-1]^2 = -log w_k, and the same arg-min component."""
+    from moshpp_b200 import pack
+    g = np.load(os.path.join(GOLD, 'ref_prior.npz'))
+    fn = _prior_file(tmp_path, g)
+    for tag, excl in (('63', True), ('69', False)):
+        bp = pack.create_gmm_body_prior(fn, exclude_hands=excl)
+        L = g[f'chols_{tag}']
+        assert np.abs(bp.Q - 0.5 * L @ np.transpose(L, (0, 2, 1))).max() < 1e-9 * np.abs(bp.Q).max()
+        for x, r_ref, k_ref in zip(g[f'x_{tag}'], g[f'r_{tag}'], g[f'k_{tag}']):
+            dx = x[None] - bp.means
+            q = np.einsum('ki,kij,kj->k', dx, bp.Q, dx) + bp.neglogw            # what the kernel minimises over k
+            k = int(np.argmin(q))
+            assert k == int(k_ref)
+            assert abs(q[k] - (r_ref ** 2).sum()) < 1e-9 * max(1.0, (r_ref ** 2).sum())
+            assert abs(bp.neglogw[k] - r_ref[-1] ** 2) < 1e-10 * max(1.0, r_ref[-1] ** 2)
+
+
+def test_marker_attachment_equals_reference():
+    """TransformedCoeffs (transformed_lm.py:59-113) incl. the SMPL-X eyeball exclusion and the collinear-neighbour
+    fallback, TransformedLms (130-159): the oracle's restatement and the product's host pack against the reference."""
+    from moshpp_b200 import pack
+    from oracle import markers as omk
+    g = np.load(os.path.join(GOLD, 'ref_lms.npz'))
+    for tag in ('smplh', 'smplx', 'line'):
+        can, mk = g[f'can_{tag}'], g[f'markers_latent_{tag}']
+        ref_closest, ref_coefs = g[f'closest_{tag}'][:, :3], g[f'coefs_{tag}']
+        tc = omk.TransformedCoeffs(can, mk)
+        assert np.array_equal(tc.closest[:, :3], ref_closest)
+        assert np.abs(tc.coefs - ref_coefs).max() < 1e-12
+        closest, coefs = pack.attach_markers(can, mk)                           # brute-force 8-NN of the product
+        assert np.array_equal(closest, ref_closest)
+        assert np.abs(coefs - ref_coefs).max() < 1e-12
+        posed = g[f'posed_{tag}']
+        sim = omk.transformed_lms(tc, posed[ref_closest[:, 0]], posed[ref_closest[:, 1]], posed[ref_closest[:, 2]])
+        assert np.abs(sim - g[f'markers_{tag}']).max() < 1e-12
+    assert (g['closest_smplx'] < 9383).all()                                    # eyeball vertices were never chosen
+    assert g['closest_line'][0, 2] != 2                                         # the collinear third neighbour was swapped
