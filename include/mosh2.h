@@ -112,6 +112,9 @@ int mosh2_device_count(void);
 
 void mosh2_default_options(mosh2_options *opt);
 
+/* Job buffers (device and pinned host memory) are recycled between jobs; this returns the cached blocks to the driver. */
+void mosh2_release_cached_memory(void);
+
 /* Uploads the constants to `device` (both f32 and f64 copies). */
 int mosh2_model_create(const mosh2_model_desc *desc, int device, mosh2_model **out);
 void mosh2_model_destroy(mosh2_model *m);

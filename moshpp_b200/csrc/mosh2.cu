@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -37,6 +39,72 @@ int fail(int code, const char *fmt, ...) {
         cudaError_t e_ = (expr);                                                                   \
         if (e_ != cudaSuccess) return fail(MOSH2_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Caching allocator for job buffers.  A Stage-II call creates a job, runs it and destroys it; cudaMallocHost / cudaMalloc /
+// cudaFree(Host) of its few tens of megabytes cost more wall clock than the solve itself and vary by 10x between calls.
+// Freed blocks are therefore kept (per device, pinned host memory apart) and handed to the next job that fits; the cache
+// is bounded and mosh2_release_cached_memory() empties it.
+// ---------------------------------------------------------------------------------------------------------------------
+class BlockCache {
+  public:
+    // dev >= 0: device memory of that device; dev == -1: pinned host memory
+    cudaError_t get(int dev, size_t bytes, void **out) {
+        const size_t need = round_up(bytes);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto &pool = pools_[dev];
+            auto it = pool.lower_bound(need);
+            if (it != pool.end() && it->first <= 2 * need + (1u << 20)) {
+                *out = it->second;
+                sizes_[*out] = it->first;
+                cached_ -= it->first;
+                pool.erase(it);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = dev < 0 ? cudaMallocHost(out, need) : cudaMalloc(out, need);
+        if (e != cudaSuccess) {             // make room and try once more
+            release_all();
+            cudaGetLastError();
+            e = dev < 0 ? cudaMallocHost(out, need) : cudaMalloc(out, need);
+        }
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> lock(mu_); sizes_[*out] = need; }
+        return e;
+    }
+    void put(int dev, void *p) {
+        if (!p) return;
+        size_t bytes = 0;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = sizes_.find(p);
+            if (it == sizes_.end()) { lock_free(dev, p); return; }
+            bytes = it->second;
+            sizes_.erase(it);
+            if (cached_ + bytes <= kLimit) { pools_[dev].emplace(bytes, p); cached_ += bytes; return; }
+        }
+        lock_free(dev, p);
+    }
+    void release_all() {
+        std::map<int, std::multimap<size_t, void *>> pools;
+        { std::lock_guard<std::mutex> lock(mu_); pools.swap(pools_); cached_ = 0; }
+        for (auto &dp : pools)
+            for (auto &b : dp.second) lock_free(dp.first, b.second);
+    }
+
+  private:
+    static constexpr size_t kLimit = size_t(1) << 30;      // cached bytes, all pools together
+    static size_t round_up(size_t b) { const size_t g = b < (1u << 20) ? 4096 : (1u << 18); return (b + g - 1) / g * g; }
+    static void lock_free(int dev, void *p) {
+        if (dev < 0) cudaFreeHost(p);
+        else { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(dev); cudaFree(p); cudaSetDevice(cur); }
+    }
+    std::mutex mu_;
+    std::map<int, std::multimap<size_t, void *>> pools_;
+    std::map<void *, size_t> sizes_;
+    size_t cached_ = 0;
+};
+BlockCache g_blocks;
 
 constexpr size_t kMaxSmem = 227 * 1024;
 #ifndef MOSH2_F32_THREADS
@@ -81,15 +149,16 @@ template <class real>
 struct DevModel {
     mosh2::Model<real> m{};
     std::vector<void *> owned;
+    int device = 0;
     ~DevModel() {
-        for (void *p : owned) cudaFree(p);
+        for (void *p : owned) g_blocks.put(device, p);
     }
     template <class T, class U>
     int up(const U *src, size_t n, const T **dst) {
         *dst = nullptr;
         if (n == 0) {       // keep a valid pointer so kernels can form addresses
             void *p = nullptr;
-            CU(cudaMalloc(&p, 16));
+            CU(g_blocks.get(device, 16, &p));
             owned.push_back(p);
             *dst = static_cast<const T *>(p);
             return 0;
@@ -97,7 +166,7 @@ struct DevModel {
         std::vector<T> tmp(n);
         for (size_t i = 0; i < n; ++i) tmp[i] = static_cast<T>(src[i]);
         void *p = nullptr;
-        CU(cudaMalloc(&p, n * sizeof(T)));
+        CU(g_blocks.get(device, n * sizeof(T), &p));
         owned.push_back(p);
         CU(cudaMemcpy(p, tmp.data(), n * sizeof(T), cudaMemcpyHostToDevice));
         *dst = static_cast<const T *>(p);
@@ -269,8 +338,8 @@ struct mosh2_model {
     int n_joints = 0, n_markers = 0, p_red = 0, n_dmpl = 0;
     int ensure(int precision) {
         if (precision == MOSH2_F64) {
-            if (!have_f64) { const int rc = f64.build(host.d); if (rc) return rc; have_f64 = true; }
-        } else if (!have_f32) { const int rc = f32.build(host.d); if (rc) return rc; have_f32 = true; }
+            if (!have_f64) { f64.device = device; const int rc = f64.build(host.d); if (rc) return rc; have_f64 = true; }
+        } else if (!have_f32) { f32.device = device; const int rc = f32.build(host.d); if (rc) return rc; have_f32 = true; }
         return 0;
     }
 };
@@ -501,25 +570,25 @@ int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_s
     chk(cudaEventCreate(&j->ev0));
     chk(cudaEventCreate(&j->ev1));
     chk(cudaEventCreateWithFlags(&j->ev_in, cudaEventDisableTiming));
-    chk(cudaMalloc(&j->d_obs, j->n_obs * j->esz));
-    chk(cudaMalloc(&j->d_out, j->n_out * j->esz));
-    chk(cudaMalloc(&j->d_vis, F * M));
-    chk(cudaMalloc(&j->d_status, F * sizeof(int)));
-    chk(cudaMalloc(&j->d_counters, F * 4 * sizeof(int)));
-    chk(cudaMalloc(&j->d_totals, 8 * sizeof(int)));
-    chk(cudaMalloc(&j->d_chunk_tab, tab.size() * sizeof(int)));
-    chk(cudaMalloc(&j->d_chunk_ids, size_t(j->n_chunks) * sizeof(int)));
-    chk(cudaMalloc(&j->d_warm_f, size_t(j->n_chunks) * sizeof(int)));
-    chk(cudaMalloc(&j->d_delta, size_t(j->n_chunks) * 4 * sizeof(float)));
-    chk(cudaMalloc(&j->d_warm_x, size_t(j->n_chunks) * (3 + m->p_red + m->n_dmpl) * j->esz));
+    chk(g_blocks.get(m->device, j->n_obs * j->esz, reinterpret_cast<void **>(&j->d_obs)));
+    chk(g_blocks.get(m->device, j->n_out * j->esz, reinterpret_cast<void **>(&j->d_out)));
+    chk(g_blocks.get(m->device, F * M, reinterpret_cast<void **>(&j->d_vis)));
+    chk(g_blocks.get(m->device, F * sizeof(int), reinterpret_cast<void **>(&j->d_status)));
+    chk(g_blocks.get(m->device, F * 4 * sizeof(int), reinterpret_cast<void **>(&j->d_counters)));
+    chk(g_blocks.get(m->device, 8 * sizeof(int), reinterpret_cast<void **>(&j->d_totals)));
+    chk(g_blocks.get(m->device, tab.size() * sizeof(int), reinterpret_cast<void **>(&j->d_chunk_tab)));
+    chk(g_blocks.get(m->device, size_t(j->n_chunks) * sizeof(int), reinterpret_cast<void **>(&j->d_chunk_ids)));
+    chk(g_blocks.get(m->device, size_t(j->n_chunks) * sizeof(int), reinterpret_cast<void **>(&j->d_warm_f)));
+    chk(g_blocks.get(m->device, size_t(j->n_chunks) * 4 * sizeof(float), reinterpret_cast<void **>(&j->d_delta)));
+    chk(g_blocks.get(m->device, size_t(j->n_chunks) * (3 + m->p_red + m->n_dmpl) * j->esz, reinterpret_cast<void **>(&j->d_warm_x)));
     if (e == cudaSuccess) chk(cudaMemcpy(j->d_chunk_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
-    chk(cudaMalloc(&j->d_prof, 32 * sizeof(long long)));
-    if (j->gws_stride) chk(cudaMalloc(&j->d_gws, j->gws_stride * j->n_chunks));
-    chk(cudaMallocHost(&j->h_obs, j->n_obs * j->esz));
-    chk(cudaMallocHost(&j->h_out, j->n_out * j->esz));
-    chk(cudaMallocHost(&j->h_vis, F * M));
-    chk(cudaMallocHost(&j->h_status, F * sizeof(int)));
-    chk(cudaMallocHost(&j->h_counters, F * 4 * sizeof(int)));
+    chk(g_blocks.get(m->device, 32 * sizeof(long long), reinterpret_cast<void **>(&j->d_prof)));
+    if (j->gws_stride) chk(g_blocks.get(m->device, j->gws_stride * j->n_chunks, reinterpret_cast<void **>(&j->d_gws)));
+    chk(g_blocks.get(-1, j->n_obs * j->esz, reinterpret_cast<void **>(&j->h_obs)));
+    chk(g_blocks.get(-1, j->n_out * j->esz, reinterpret_cast<void **>(&j->h_out)));
+    chk(g_blocks.get(-1, F * M, reinterpret_cast<void **>(&j->h_vis)));
+    chk(g_blocks.get(-1, F * sizeof(int), reinterpret_cast<void **>(&j->h_status)));
+    chk(g_blocks.get(-1, F * 4 * sizeof(int), reinterpret_cast<void **>(&j->h_counters)));
     if (e != cudaSuccess) {
         mosh2_job_destroy(j);
         return fail(MOSH2_E_CUDA, "job allocation failed: %s", cudaGetErrorString(e));
@@ -629,6 +698,8 @@ int mosh2_job_kernel_ms(mosh2_job *j, float *ms) {
     return 0;
 }
 
+void mosh2_release_cached_memory(void) { g_blocks.release_all(); }
+
 int mosh2_job_span_ms(mosh2_job *first, mosh2_job *last, float *ms) {
     if (!first || !last || !ms) return fail(MOSH2_E_INVALID, "null argument");
     if (first->model->device != last->model->device) return fail(MOSH2_E_INVALID, "jobs live on different devices");
@@ -734,8 +805,13 @@ void mosh2_job_destroy(mosh2_job *j) {
     if (!j) return;
     cudaSetDevice(j->model->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
-    cudaFree(j->d_chunk_tab); cudaFree(j->d_chunk_ids); cudaFree(j->d_warm_f); cudaFree(j->d_warm_x); cudaFree(j->d_delta); cudaFree(j->d_obs); cudaFree(j->d_out); cudaFree(j->d_vis); cudaFree(j->d_status); cudaFree(j->d_counters); cudaFree(j->d_totals); cudaFree(j->d_prof); cudaFree(j->d_gws);
-    cudaFreeHost(j->h_obs); cudaFreeHost(j->h_out); cudaFreeHost(j->h_vis); cudaFreeHost(j->h_status); cudaFreeHost(j->h_counters);
+    const int dv = j->model->device;
+    for (void *p : {static_cast<void *>(j->d_chunk_tab), static_cast<void *>(j->d_chunk_ids), static_cast<void *>(j->d_warm_f), j->d_warm_x,
+                    static_cast<void *>(j->d_delta), j->d_obs, j->d_out, static_cast<void *>(j->d_vis), static_cast<void *>(j->d_status),
+                    static_cast<void *>(j->d_counters), static_cast<void *>(j->d_totals), static_cast<void *>(j->d_prof), j->d_gws})
+        g_blocks.put(dv, p);
+    for (void *p : {j->h_obs, j->h_out, static_cast<void *>(j->h_vis), static_cast<void *>(j->h_status), static_cast<void *>(j->h_counters)})
+        g_blocks.put(-1, p);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
     if (j->ev_in) cudaEventDestroy(j->ev_in);

@@ -553,6 +553,8 @@ struct Solver {
     // counters of the current frame
     int n_iter, n_eval, n_build, n_min, frame_flags;
     int prof_base = 0;        // development builds: offset of the phase-timer slots
+    bool fwd_at_x = false;    // the forward scratch of the latest evaluation belongs to the current state w.x ...
+    bool fwd_has_prior = false;   // ... including the prior products
     bool resuming = false;    // boundary repair: the chunk continues from emitted rows (run_chunk)
     real resume_diff = 0;     // ... and how far the frame just solved is from the row it replaces
     unsigned int tc_tmem = 0, tc_phase = 0;   // tensor-memory base address, parity of the MMA completion barrier
@@ -669,11 +671,15 @@ struct Solver {
     }
 
     // ---- forward evaluation at state xs; leaves SSE terms in w.sc[0..6], argmin component in w.isc[0]
-    M2_D void eval(const real *xs, const StepCfg<real> &c) {
+    //      `reuse`: the forward scratch of the previous evaluation already belongs to this state (the last trial step was
+    //      accepted, so x = that trial point): only the terms that depend on the frame's observations, weights and targets
+    //      are computed again -- same numbers as a full evaluation, since the forward depends on the state alone.
+    M2_D void eval(const real *xs, const StepCfg<real> &c, bool reuse = false) {
         ++n_eval;
         M2_T0();
         const real *th = xs + 3;
         const real *dl = xs + 3 + d.PR;
+        if (!reuse) {
         CTA_FOR(i, d.PF) {
             real v;
             if (i < m.body_dof) {
@@ -823,7 +829,14 @@ struct Solver {
         }
         M2_SYNC();
         M2_TACC(3);
+        }   // !reuse
         // simulated markers and data residual (transformed_lm.py:130-159); the prior products share the phase
+        if (reuse) {
+            CTA_FOR(mi, d.M) {
+                const bool vis = w.vis[mi] != 0;
+                for (int q = 0; q < 3; ++q) w.rm[3 * mi + q] = vis ? (w.mk[3 * mi + q] - w.obs[3 * mi + q]) * wd : real(0);
+            }
+        } else
         CTA_FOR(mi, d.M) {
             const real *v0 = w.vp + 9 * mi, *v1 = v0 + 3, *v2 = v0 + 6;
             real e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
@@ -1813,12 +1826,17 @@ struct Solver {
             }
             const int n = c.n;
             // ---------------- the one evaluation site
-            eval(op == OP_TRIAL ? w.xt : w.x, c);
-#if defined(MOSH2_EXP_WARM)
-            prof_base = 20; eval(op == OP_TRIAL ? w.xt : w.x, c); --n_eval; prof_base = 0;   // experiment: the same code again, now warm
-#endif
+            {
+                // A stage that starts where the last accepted trial step ended (Step 2 after Step 1, Step 1 of the next
+                // frame, the output evaluation) finds the forward pass of that state still in shared memory.
+                const bool reuse = op != OP_TRIAL && fwd_at_x && (fwd_has_prior || !(c.wp > real(0)));
+                eval(op == OP_TRIAL ? w.xt : w.x, c, reuse);
+                if (!reuse) fwd_has_prior = c.wp > real(0);
+                fwd_at_x = op != OP_TRIAL;                     // (a trial point becomes the state only if it is accepted)
+            }
             if (op == OP_PROCRUSTES) {                         // chmosh.py:634
                 procrustes();
+                fwd_at_x = false;
                 op = OP_BEGIN;
                 need_setup = true;
                 continue;
@@ -1837,6 +1855,7 @@ struct Solver {
                 if (rho > real(0)) rho = rho / (real(2) * gd - dAd);
                 if (improved) {
                     CTA_FOR(i, d.NX) w.x[i] = w.xt[i];
+                    fwd_at_x = true;
                     M2_SYNC();
                     if (c.e3 > real(0) && (sse0 - sse1) / sse0 < c.e3) done = true;
                     else { do_build = true; sse0 = sse1; }
@@ -2150,6 +2169,7 @@ struct Solver {
         M2_SYNC();
         M2_T0();
         bool first = true, have_prev = false, have_dm_prev = false;
+        fwd_at_x = false;
         if (warmup < 0 && f_emit > s0) {
             // Resume (boundary repair, mosh2_job_relaunch_chunks with chunk_warmup < 0): no warm-up of its own -- the chunk
             // continues the recursion from the rows the previous launch EMITTED for the last two solved frames in front of

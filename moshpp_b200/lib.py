@@ -97,6 +97,8 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_device_count.restype = C.c_int
     lib.mosh2_default_options.argtypes = [C.POINTER(Options)]
     lib.mosh2_default_options.restype = None
+    lib.mosh2_release_cached_memory.argtypes = []
+    lib.mosh2_release_cached_memory.restype = None
     lib.mosh2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(vp)]
     lib.mosh2_model_destroy.argtypes = [vp]
     lib.mosh2_model_destroy.restype = None
@@ -132,7 +134,7 @@ EXPORTED_SYMBOLS = (
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
     'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
     'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks',
-    'mosh2_job_boundary_deltas')
+    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -329,7 +331,7 @@ class Job:
         pk = self.model.pk
         out = np.zeros((self.num_chunks, 4), dtype=np.float32)
         self.model._check(self.lib.mosh2_job_boundary_deltas(self.handle, min(pk.body_dof, 66), out.ctypes.data_as(C.POINTER(C.c_float))),
-                          'mosh2_job_boundary_deltas')
+                          'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory')
         return out.astype(np.float64)
 
     def relaunch_chunks(self, chunk_ids, chunk_warmup: int, warmup_full: int = -1):
