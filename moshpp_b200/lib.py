@@ -331,7 +331,7 @@ class Job:
         pk = self.model.pk
         out = np.zeros((self.num_chunks, 4), dtype=np.float32)
         self.model._check(self.lib.mosh2_job_boundary_deltas(self.handle, min(pk.body_dof, 66), out.ctypes.data_as(C.POINTER(C.c_float))),
-                          'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory')
+                          'mosh2_job_boundary_deltas')
         return out.astype(np.float64)
 
     def relaunch_chunks(self, chunk_ids, chunk_warmup: int, warmup_full: int = -1):
