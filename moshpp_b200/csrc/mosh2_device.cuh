@@ -2191,6 +2191,13 @@ struct Solver {
                 first = false;
                 have_prev = f2 >= 0;
                 resuming = true;
+                M2_SYNC();
+                // the boundary check of a resumed chunk: the state it started from against the row of that frame as it
+                // is when the check runs (it differs if the previous chunk was itself repaired afterwards)
+                if (job.warm_x) {
+                    CTA_FOR(i, d.NX) job.warm_x[size_t(chunk) * d.NX + i] = w.x[i];
+                    if (cta.tid == 0) job.warm_f[chunk] = f1;
+                }
             }
             M2_SYNC();
         }
