@@ -183,6 +183,26 @@ void mosh2_job_destroy(mosh2_job *j);
 int mosh2_solve(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, const double *obs,
                 const uint8_t *vis, const mosh2_schedule *sched, int32_t precision, const mosh2_result *res);
 
+/* ---- Stage-I surface term --------------------------------------------------------------------------
+ * Distance of samples to a triangle mesh with derivatives -- replaces the reference's only native code,
+ *   scan2mesh/mesh_distance/sample2meshdist.h:67-207 (plane / edge / vertex distance and gradients under the three
+ *   robustifiers), sample2meshdist.pyx:55-103 (`somedistance`: the loop over samples) and the nearest (triangle, part) query
+ *   of psbody.mesh's AABB tree (mesh_distance_main.py:346-376).
+ * kind: 0 distance, 1 squared distance, 2 Geman-McClure(sigma) of the squared distance.  part: 0 the triangle's plane
+ * (signed distance), 1..3 its edges ab / bc / ca, 4..6 its vertices a / b / c.  nearest_tri / nearest_part: both NULL =
+ * searched on the device (brute force over all triangles, float32), or both given (what `somedistance` takes).
+ * Output arrays may be NULL.  d_tri holds d value / d (a, b, c) of the sample's triangle, 9 numbers per sample. */
+typedef struct mosh2_mesh_distance_out {
+    double *value;     /* [S]     f(distance)                  */
+    int32_t *tri;      /* [S]     nearest triangle             */
+    int32_t *part;     /* [S]     nearest part of that triangle */
+    double *d_sample;  /* [S * 3] d value / d sample           */
+    double *d_tri;     /* [S * 9] d value / d (a, b, c)        */
+} mosh2_mesh_distance_out;
+int mosh2_mesh_distance(int32_t device, int32_t kind, double sigma, int32_t n_samples, const double *samples, int32_t n_verts,
+                        const double *verts, int32_t n_tris, const int32_t *tris, const int32_t *nearest_tri,
+                        const int32_t *nearest_part, const mosh2_mesh_distance_out *out, float *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ def _nvcc() -> str:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, "mosh2.cu"), os.path.join(CSRC, "mosh2_device.cuh"), os.path.join(CSRC, "mosh2_host.h"),
-            os.path.join(ROOT, 'include', 'mosh2.h')]
+            os.path.join(CSRC, "mesh_distance.cuh"), os.path.join(ROOT, 'include', 'mosh2.h')]
     if force or _stale(LIB, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, srcs[0]]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "mesh_distance.cuh"
 #include "mosh2_device.cuh"
 #include "mosh2_host.h"
 
@@ -829,6 +830,82 @@ int mosh2_solve(mosh2_model *m, const mosh2_options *opt, int32_t n_frames, cons
     if (!rc) rc = mosh2_job_download(j, res);
     mosh2_job_destroy(j);
     return rc;
+}
+
+// ---- Stage-I surface term: point-to-triangle-mesh distance with derivatives (mesh_distance.cuh) ----------------------------
+int mosh2_mesh_distance(int32_t device, int32_t kind, double sigma, int32_t n_samples, const double *samples, int32_t n_verts,
+                        const double *verts, int32_t n_tris, const int32_t *tris, const int32_t *nearest_tri,
+                        const int32_t *nearest_part, const mosh2_mesh_distance_out *out, float *kernel_ms) {
+    if (!samples || !verts || !tris || !out || n_samples < 1 || n_verts < 1 || n_tris < 1 || kind < 0 || kind > 2)
+        return fail(MOSH2_E_INVALID, "bad argument");
+    if ((nearest_tri == nullptr) != (nearest_part == nullptr)) return fail(MOSH2_E_INVALID, "nearest_tri and nearest_part go together");
+    if (n_tris >= (1 << 28)) return fail(MOSH2_E_TOO_LARGE, "%d triangles (the search packs the index into 29 bits)", n_tris);
+    for (int64_t i = 0; i < int64_t(3) * n_tris; ++i)
+        if (tris[i] < 0 || tris[i] >= n_verts) return fail(MOSH2_E_INVALID, "triangle %lld refers to vertex %d of %d", (long long)(i / 3), tris[i], n_verts);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(MOSH2_E_NO_DEVICE, "no CUDA device: libmosh2 has no CPU path"); }
+    if (device < 0 || device >= ndev) return fail(MOSH2_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    const size_t S = n_samples, V = n_verts, T = n_tris;
+    struct Buf { int dev; void *p = nullptr; ~Buf() { g_blocks.put(dev, p); } };
+    Buf d_s{device}, d_sf{device}, d_v{device}, d_f{device}, d_soup{device}, d_best{device}, d_tri{device}, d_part{device}, d_val{device}, d_ds{device}, d_dt{device};
+    CU(g_blocks.get(device, S * 3 * sizeof(double), &d_s.p));
+    CU(g_blocks.get(device, S * 3 * sizeof(float), &d_sf.p));
+    CU(g_blocks.get(device, V * 3 * sizeof(double), &d_v.p));
+    CU(g_blocks.get(device, T * 3 * sizeof(int), &d_f.p));
+    CU(g_blocks.get(device, T * mosh2_md::kSoupFloats * sizeof(float), &d_soup.p));
+    CU(g_blocks.get(device, S * sizeof(unsigned long long), &d_best.p));
+    CU(g_blocks.get(device, S * sizeof(int), &d_tri.p));
+    CU(g_blocks.get(device, S * sizeof(int), &d_part.p));
+    CU(g_blocks.get(device, S * sizeof(double), &d_val.p));
+    CU(g_blocks.get(device, S * 3 * sizeof(double), &d_ds.p));
+    CU(g_blocks.get(device, S * 9 * sizeof(double), &d_dt.p));
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    auto cleanup = [&]() { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st); };
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    chk(cudaMemcpyAsync(d_s.p, samples, S * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    chk(cudaMemcpyAsync(d_v.p, verts, V * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    chk(cudaMemcpyAsync(d_f.p, tris, T * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+    chk(cudaEventRecord(e0, st));
+    if (nearest_tri) {
+        chk(cudaMemcpyAsync(d_tri.p, nearest_tri, S * sizeof(int), cudaMemcpyHostToDevice, st));
+        chk(cudaMemcpyAsync(d_part.p, nearest_part, S * sizeof(int), cudaMemcpyHostToDevice, st));
+    } else {
+        convert_kernel<double, float><<<int((S * 3 + 255) / 256), 256, 0, st>>>(static_cast<const double *>(d_s.p), static_cast<float *>(d_sf.p), S * 3);
+        mosh2_md::soup_kernel<<<int((T + 255) / 256), 256, 0, st>>>(static_cast<const double *>(d_v.p), static_cast<const int *>(d_f.p), int(T), static_cast<float *>(d_soup.p));
+        chk(cudaMemsetAsync(d_best.p, 0xff, S * sizeof(unsigned long long), st));
+        // triangle ranges: enough blocks to fill the GPU (148 SMs, several blocks each), whole tiles per block
+        const int sblocks = int((S + mosh2_md::kSamplesPerBlock - 1) / mosh2_md::kSamplesPerBlock);
+        int splits = (4 * 148 + sblocks - 1) / sblocks;
+        const int tiles = int((T + mosh2_md::kTileTris - 1) / mosh2_md::kTileTris);
+        if (splits > tiles) splits = tiles;
+        if (splits < 1) splits = 1;
+        const int per = ((tiles + splits - 1) / splits) * mosh2_md::kTileTris;
+        splits = int((T + per - 1) / per);
+        mosh2_md::nearest_kernel<<<dim3(sblocks, splits), mosh2_md::kSamplesPerBlock, 0, st>>>(
+            static_cast<const float *>(d_sf.p), int(S), static_cast<const float *>(d_soup.p), int(T), per, static_cast<unsigned long long *>(d_best.p));
+        mosh2_md::unpack_kernel<<<int((S + 255) / 256), 256, 0, st>>>(static_cast<const unsigned long long *>(d_best.p), int(S), static_cast<int *>(d_tri.p), static_cast<int *>(d_part.p));
+    }
+    mosh2_md::evaluate_kernel<<<int((S + 127) / 128), 128, 0, st>>>(kind, sigma, static_cast<const double *>(d_s.p), int(S), static_cast<const double *>(d_v.p),
+                                                                   static_cast<const int *>(d_f.p), static_cast<const int *>(d_tri.p), static_cast<const int *>(d_part.p),
+                                                                   static_cast<double *>(d_val.p), static_cast<double *>(d_ds.p), static_cast<double *>(d_dt.p));
+    chk(cudaGetLastError());
+    chk(cudaEventRecord(e1, st));
+    if (out->value) chk(cudaMemcpyAsync(out->value, d_val.p, S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out->tri) chk(cudaMemcpyAsync(out->tri, d_tri.p, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (out->part) chk(cudaMemcpyAsync(out->part, d_part.p, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (out->d_sample) chk(cudaMemcpyAsync(out->d_sample, d_ds.p, S * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out->d_tri) chk(cudaMemcpyAsync(out->d_tri, d_dt.p, S * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    chk(cudaStreamSynchronize(st));
+    if (e == cudaSuccess && kernel_ms) chk(cudaEventElapsedTime(kernel_ms, e0, e1));
+    cleanup();
+    if (e != cudaSuccess) return fail(MOSH2_E_CUDA, "mosh2_mesh_distance: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 }  // extern "C"

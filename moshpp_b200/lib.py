@@ -66,6 +66,10 @@ class Result(C.Structure):
     ]
 
 
+class MeshDistanceOut(C.Structure):
+    _fields_ = [('value', _f64p), ('tri', _i32p), ('part', _i32p), ('d_sample', _f64p), ('d_tri', _f64p)]
+
+
 class Mosh2Error(RuntimeError):
     pass
 
@@ -98,6 +102,8 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_default_options.argtypes = [C.POINTER(Options)]
     lib.mosh2_default_options.restype = None
     lib.mosh2_release_cached_memory.argtypes = []
+    lib.mosh2_mesh_distance.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, _f64p, C.c_int32, _f64p, C.c_int32, _i32p, _i32p,
+                                        _i32p, C.POINTER(MeshDistanceOut), C.POINTER(C.c_float)]
     lib.mosh2_release_cached_memory.restype = None
     lib.mosh2_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(vp)]
     lib.mosh2_model_destroy.argtypes = [vp]
@@ -134,7 +140,7 @@ EXPORTED_SYMBOLS = (
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
     'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
     'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks',
-    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory')
+    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance')
 
 
 def _ptr(a: np.ndarray, typ):
