@@ -192,7 +192,8 @@ def test_tcgen05_jtj_building_block():
 
 @pytest.mark.parametrize('precision', ['f64', 'f32'])
 def test_boundary_repair_cascades_to_the_sequential_result(cases, precision):
-    """Chunks without any warm-up (cold starts: far off), then the boundary check with zero tolerance: every round
+    """Chunks with a single warm-up frame (a cold start right in front of the chunk: far off), then the boundary check with
+    zero tolerance: every round
     resumes the failing chunks from the rows their predecessors emitted; a resumed chunk whose predecessor is repaired
     later fails the next check (it reports the state it started from).  After at most one round per chunk the result
     is the single sequential pass, bit for bit -- the repair is exact, not an approximation."""
@@ -204,8 +205,8 @@ def test_boundary_repair_cascades_to_the_sequential_result(cases, precision):
     model = lib.Model(pk, device=0)
     try:
         seq = model.solve(obs, vis, opts, precision=prec)
-        job = model.job(obs.shape[0], opts, chunk_len=3, chunk_warmup=0, precision=prec)
-        cold = model.solve(obs, vis, opts, chunk_len=3, chunk_warmup=0, precision=prec)
+        job = model.job(obs.shape[0], opts, chunk_len=3, chunk_warmup=1, precision=prec)
+        cold = model.solve(obs, vis, opts, chunk_len=3, chunk_warmup=1, precision=prec)
         assert np.abs(cold.pose - seq.pose).max() > 1e-3
         res, rep = chmosh.solve_verified(job, obs, vis, tol=(0.0, 0.0, 0.0, 0.0), max_rounds=job.num_chunks + 1)
         assert rep['unverified_chunks'] == 0 and 1 <= rep['rounds'] <= job.num_chunks
