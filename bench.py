@@ -525,16 +525,19 @@ def run_sharded(args, rank, local_rank, world):
     barrier()
     t_wall0 = time.perf_counter()
     dev_ms = []
+    launches = 0
     for _ in range(args.steps):
         flush()
         solver(resident)
-        dev_ms.append(solver.span_ms())      # CUDA events on the jobs' streams: first start -> last end on this rank
+        dev_ms.append(solver.span_ms())      # CUDA events on the jobs' streams, summed over the launches of the solve
+        launches += sum(len(r['kernel_ms']) for r in solver.reports)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms_step = allmax(np.mean(dev_ms))
     tot = solver.totals()
-    tt = torch.tensor([tot['builds'], tot['emitted_builds'], tot['evaluations']], dtype=torch.float64, device=dev)
+    tt = torch.tensor([tot['builds'], tot['emitted_builds'], tot['evaluations'], launches], dtype=torch.float64, device=dev)
     dist.all_reduce(tt)
+    launches_total = tt[3].item()
     # ---- e2e: pinned host buffers on rank 0 -> scatter -> solve -> gather -> host results on rank 0
     e2e = []
     for s in range(2 + args.steps):
@@ -573,7 +576,7 @@ def run_sharded(args, rank, local_rank, world):
                     'ms_per_step': e2e_ms,
                     'what': 'shard.solve_sharded: pinned host observations on rank 0 -> H2D -> NCCL scatter -> per-rank solves '
                             '(device pointers through the C-ABI) -> NCCL gather -> D2H on rank 0; wall clock, max over ranks'},
-            'gpu_launches': args.steps * n_seq,
+            'gpu_launches': int(launches_total),
             'clocks': sampler.summary(),
             'wall_s_timed_region': t_wall,
         }

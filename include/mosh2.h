@@ -66,7 +66,8 @@ typedef struct mosh2_model_desc {
     const double *j0;         /* [n_joints*3]                                                */
     const double *jd;         /* [n_joints*3*n_dmpl]                                         */
     const double *coefs;      /* [M*3] marker attachment coefficients                        */
-    int32_t prior_k, prior_d, prior_off; /* max-mixture prior on pose[prior_off : prior_off+prior_d] */
+    int32_t prior_k, prior_d, prior_off; /* max-mixture prior on pose[prior_off : prior_off+prior_d] ...          */
+    const int32_t *prior_ids;            /* ... or, if not NULL, on pose[prior_ids[0..prior_d)] (animal models)      */
     const double *prior_means;   /* [K*D]                                                    */
     const double *prior_Q;       /* [K*D*D]  0.5 * inv(cov_k)                                */
     const double *prior_neglogw; /* [K]                                                      */

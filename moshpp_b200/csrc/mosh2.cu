@@ -177,7 +177,7 @@ struct DevModel {
         const size_t nJ = d.n_joints, S = size_t(3) * d.n_markers, nd = d.n_dmpl;
         m.nJ = d.n_joints; m.M = d.n_markers; m.body_dof = d.body_dof; m.p_red = d.p_red;
         m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw;
-        m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
+        m.prior_k = d.prior_k; m.prior_d = d.prior_d;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
         m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
         int rc;
@@ -238,6 +238,11 @@ struct DevModel {
             if ((rc = up<real>(qt.data(), qt.size(), &m.prior_Qt))) return rc;
         }
         if ((rc = up<real>(d.prior_neglogw, d.prior_k, &m.prior_nlw))) return rc;
+        {
+            std::vector<int> ids(d.prior_d);
+            for (int i = 0; i < d.prior_d; ++i) ids[i] = d.prior_ids ? d.prior_ids[i] : d.prior_off + i;
+            if ((rc = up<int>(ids.data(), ids.size(), &m.prior_ids))) return rc;
+        }
         if ((rc = up<int>(d.free1, d.n_free1, &m.free1))) return rc;
         if ((rc = up<int>(d.free2, d.n_free2, &m.free2))) return rc;
         return 0;
@@ -301,7 +306,7 @@ __global__ void boundary_delta_kernel(const real *__restrict__ warm_x, const int
 // precision is only built when the first job of that precision is created.
 struct HostDesc {
     mosh2_model_desc d{};
-    std::vector<int32_t> parents, w_joint, free1, free2;
+    std::vector<int32_t> parents, w_joint, free1, free2, prior_ids;
     std::vector<double> hand_comps, hands_mean, v0, sd, pd, w_val, j0, jd, coefs, prior_means, prior_Q, prior_neglogw;
     template <class T> static const T *keep(std::vector<T> &dst, const T *src, size_t n) {
         dst.assign(src, src + n);
@@ -315,6 +320,7 @@ struct HostDesc {
         d.w_joint = keep(w_joint, s.w_joint, S * s.kw);
         d.free1 = keep(free1, s.free1, s.n_free1);
         d.free2 = keep(free2, s.free2, s.n_free2);
+        if (s.prior_ids) d.prior_ids = keep(prior_ids, s.prior_ids, D);
         d.hand_comps = keep(hand_comps, s.hand_comps, size_t(s.n_hand_red) * s.n_hand_full);
         d.hands_mean = keep(hands_mean, s.hands_mean, s.n_hand_full);
         d.v0 = keep(v0, s.v0, S * 3);
@@ -472,6 +478,10 @@ int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out)
         return fail(MOSH2_E_INVALID, "inconsistent face description: n_expr=%d of %d linear coefficients, jaw ids [%d, %d)", d->n_expr,
                     d->n_dmpl, d->face_lo, d->face_hi);
     if (d->n_joints > 254) return fail(MOSH2_E_TOO_LARGE, "%d joints (max 254)", d->n_joints);
+    for (int i = 0; i < d->prior_d; ++i) {
+        const int id = d->prior_ids ? d->prior_ids[i] : d->prior_off + i;
+        if (id < 0 || id >= d->p_red) return fail(MOSH2_E_INVALID, "prior dimension %d refers to pose id %d of %d", i, id, d->p_red);
+    }
     for (int j = 0; j < d->n_joints; ++j) {
         int depth = 1;
         for (int a = d->parents[j]; a >= 0; a = d->parents[a]) {

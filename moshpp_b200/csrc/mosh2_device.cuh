@@ -110,7 +110,9 @@ struct Model {
     const real *hands_mean, *v0, *sd, *w_val, *j0, *jd, *coefs;
     const real *pdc;            // pose-blend table [(nJ-1)][9 e][3 c][Sp], Sp = 3M rounded up to 4: no padding; eval() reads four slots per 16-byte load
     const real *pd4;            // the same table as [(nJ-1)][9 e][3M slots][x y z -]: build() reads one slot (all three coordinates) per 16-byte load
-    int prior_k, prior_d, prior_off, prior_d4;
+    int prior_k, prior_d, prior_d4;
+    const int *prior_ids;       // [D] reduced-pose ids the prior sees, in the order of its dimensions (SMPL family: a contiguous run; the
+                                // animal models pick a subset of the joints, prior/dog_body_prior.py:51-53)
     const real *prior_means, *prior_Q4, *prior_nlw;   // Q4: [K][D][D4]
     const real *prior_Qt;       // Q transposed per component, [K][D l][D4 i]: threads over rows i read consecutive words
     int n1, n2;
@@ -331,7 +333,7 @@ struct Work {
     // state
     SPtr<real> x, xt, pose_prev, velo_tgt, dm_tgt;
     // forward scratch of the latest evaluation
-    SPtr<real> fullpose, Rl, dRl, Jp, Rg, tg, vp, pj, Rsk, mk, rm, obs, py, pq;
+    SPtr<real> fullpose, Rl, dRl, Jp, Rg, tg, vp, pj, Rsk, mk, rm, obs, py, pq, pxg;
     // Jacobian / normal equations
     SPtr<real> Loc, MtR, u, dtg, Linv, Pn, g, Ag, dgn, d, tmp, ds;
     BPtr<real, BIG> Jt, Jf, A, Lm;
@@ -339,7 +341,7 @@ struct Work {
     SPtr<int> colmap, colsrc, jlist, isc;
     // small per-model tables staged in shared memory (a dependent global load costs several hundred cycles and the
     // kinematic-tree walk alone chains three of them per level)
-    SPtr<int> c_parents, c_fk_order, c_wj, c_free1, c_free2;
+    SPtr<int> c_parents, c_fk_order, c_wj, c_free1, c_free2, c_pids;
     SPtr<int> c_tin, c_tsz;   // pre-order index and subtree size of every joint: j in subtree(a) <=> tin[j]-tin[a] in [0, tsz[a])
     SPtr<real> c_wv, c_v0, c_coefs, c_j0, c_hmean, c_pmeans, c_pnlw;
     SPtr<real> c_jd;          // joint-position directions of the per-frame linear coefficients (DMPL, expressions)
@@ -468,7 +470,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.Jp.ofs = S.take<real>(3 * d.nJ); w.Rg.ofs = S.take<real>(9 * d.nJ); w.tg.ofs = S.take<real>(3 * d.nJ);
     w.vp.ofs = S.take<real>(3 * d.S); w.pj.ofs = S.take<real>(3 * d.S * d.kw); w.Rsk.ofs = S.take<real>(9 * d.S);
     w.mk.ofs = S.take<real>(3 * d.M); w.rm.ofs = S.take<real>(3 * d.M); w.obs.ofs = S.take<real>(3 * d.M);
-    w.py.ofs = S.take<real>(d.K * d.D + 1); w.pq.ofs = S.take<real>(d.K + 1);
+    w.py.ofs = S.take<real>(d.K * d.D + 1); w.pq.ofs = S.take<real>(d.K + 1); w.pxg.ofs = S.take<real>(d.D + 1);
     // The Cholesky factor is alive only inside gauss_newton(); the Jacobian tiles and the other scratch of build()
     // (and the pose-blend partial sums of eval(), which live in Jt) are dead there, so they share its storage.
     // A and the Cholesky factor Lm are adjacent.  The factor is alive only inside gauss_newton(); the scratch of
@@ -517,6 +519,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     // kinematic-tree walk chains three of them per level); the larger ones stay in global memory / L2
     w.c_parents.ofs = S.take<int>(d.nJ); w.c_fk_order.ofs = S.take<int>(d.nJ);
     w.c_wj.ofs = S.take<int>(d.S * d.kw); w.c_free1.ofs = S.take<int>(d.n1); w.c_free2.ofs = S.take<int>(d.n2);
+    w.c_pids.ofs = S.take<int>(d.D + 1);
     w.c_wv.ofs = S.take<real>(d.S * d.kw); w.c_v0.ofs = S.take<real>(3 * d.S); w.c_coefs.ofs = S.take<real>(3 * d.M);
     w.c_j0.ofs = S.take<real>(3 * d.nJ); w.c_hmean.ofs = S.take<real>(m.n_hand_full + 1);
     w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ); w.c_amask.ofs = S.take<uint8_t>(size_t(d.S) * d.nJ);
@@ -702,6 +705,7 @@ struct Solver {
             for (int q = 0; q < d.nd; ++q) v += w.c_jd[i * d.nd + q] * dl[q];
             w.Jp[i] = v;
         }
+        CTA_FOR(i, d.D) w.pxg[i] = th[w.c_pids[i]];          // the pose coefficients the prior sees, in its own order
         M2_SYNC();
         M2_TACC(0);
         CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + kDR * j);
@@ -732,7 +736,7 @@ struct Solver {
         // product is bound by load latency, not by bytes); four adjacent lanes then add their quarters by shuffles.
         if (c.wp > real(0)) {
             const int D = d.D, D4 = d.D4;
-            const real *xb = th + m.prior_off;
+            const real *xb = w.pxg;
 #if M2_GPU
             const int nq = D4 >> 2, lchunk = (D + 3) >> 2;          // row quads per component, columns per quarter
             const int nitem = d.K * nq * 4, nround = (nitem + cta.nthr - 1) / cta.nthr;
@@ -865,7 +869,7 @@ struct Solver {
             for (int k = warp; k < d.K; k += nwarp) {
                 const real *mu = w.c_pmeans + k * d.D;
                 real sacc = 0;
-                for (int i = lane; i < d.D; i += 32) sacc += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
+                for (int i = lane; i < d.D; i += 32) sacc += (w.pxg[i] - mu[i]) * w.py[k * d.D + i];
                 sacc = warp_sum(sacc);
                 if (lane == 0) w.pq[k] = sacc + w.c_pnlw[k];
             }
@@ -873,7 +877,7 @@ struct Solver {
             for (int k = 0; k < d.K; ++k) {
                 const real *mu = w.c_pmeans + k * d.D;
                 real sacc = w.c_pnlw[k];
-                for (int i = 0; i < d.D; ++i) sacc += (th[m.prior_off + i] - mu[i]) * w.py[k * d.D + i];
+                for (int i = 0; i < d.D; ++i) sacc += (w.pxg[i] - mu[i]) * w.py[k * d.D + i];
                 w.pq[k] = sacc;
             }
 #endif
@@ -1430,7 +1434,7 @@ struct Solver {
                     qv[u] = 0;
                     if (idx < D * D) {
                         const int i = idx / D, l = idx - i * D;
-                        const int ci = w.colmap[3 + m.prior_off + i], cl = w.colmap[3 + m.prior_off + l];
+                        const int ci = w.colmap[3 + w.c_pids[i]], cl = w.colmap[3 + w.c_pids[l]];
                         if (ci >= 0 && cl >= 0) { dst[u] = ci * ld + cl; qv[u] = Q[i * d.D4 + l]; }
                     }
                 }
@@ -1438,7 +1442,7 @@ struct Solver {
                 for (int u = 0; u < 8; ++u) if (dst[u] >= 0) w.A[dst[u]] += w2 * qv[u];
             }
             CTA_FOR(i, D) {
-                const int ci = w.colmap[3 + m.prior_off + i];
+                const int ci = w.colmap[3 + w.c_pids[i]];
                 if (ci >= 0) w.g[ci] -= w2 * w.py[ks * D + i];
             }
             M2_SYNC();
@@ -2119,6 +2123,7 @@ struct Solver {
         CTA_FOR(i, d.nJ) { w.c_parents[i] = m.parents[i]; w.c_fk_order[i] = m.fk_order[i]; }
         CTA_FOR(i, d.S * d.kw) { w.c_wj[i] = m.w_joint[i]; w.c_wv[i] = m.w_val[i]; }
         CTA_FOR(i, d.n1) w.c_free1[i] = m.free1[i];
+        CTA_FOR(i, d.D) w.c_pids[i] = m.prior_ids[i];
         CTA_FOR(i, d.n2) w.c_free2[i] = m.free2[i];
         CTA_FOR(i, 3 * d.S) w.c_v0[i] = m.v0[i];
         CTA_FOR(i, 3 * d.M) w.c_coefs[i] = m.coefs[i];

@@ -31,7 +31,7 @@ class ModelDesc(C.Structure):
         ('parents', _i32p), ('w_joint', _i32p),
         ('hand_comps', _f64p), ('hands_mean', _f64p), ('v0', _f64p), ('sd', _f64p), ('pd', _f64p),
         ('w_val', _f64p), ('j0', _f64p), ('jd', _f64p), ('coefs', _f64p),
-        ('prior_k', C.c_int32), ('prior_d', C.c_int32), ('prior_off', C.c_int32),
+        ('prior_k', C.c_int32), ('prior_d', C.c_int32), ('prior_off', C.c_int32), ('prior_ids', _i32p),
         ('prior_means', _f64p), ('prior_Q', _f64p), ('prior_neglogw', _f64p),
         ('n_free1', C.c_int32), ('n_free2', C.c_int32), ('free1', _i32p), ('free2', _i32p),
         ('finger_lo', C.c_int32), ('finger_hi', C.c_int32),
@@ -170,6 +170,9 @@ class DescHolder:
                   'prior_Q', 'prior_neglogw'):
             setattr(d, k, _ptr(a[k], _f64p))
         d.prior_k, d.prior_d, d.prior_off = pk.prior_k, pk.prior_d, pk.prior_off
+        if getattr(pk, 'prior_ids', None) is not None and len(pk.prior_ids):
+            self.arrays['prior_ids'] = i32(pk.prior_ids)
+            d.prior_ids = _ptr(self.arrays['prior_ids'], _i32p)
         d.n_free1, d.n_free2 = len(pk.free_step1), len(pk.free_step2)
         d.finger_lo, d.finger_hi = pk.finger_lo, pk.finger_hi
         d.n_expr, d.face_lo, d.face_hi = pk.n_expr, pk.face_lo, pk.face_hi

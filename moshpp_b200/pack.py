@@ -268,6 +268,7 @@ class StageIIPack:
     prior_k: int = 0
     prior_d: int = 0
     prior_off: int = 3
+    prior_ids: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # non-contiguous prior dimensions (animal models)
     prior_means: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
     prior_Q: np.ndarray = field(default_factory=lambda: np.zeros((0, 0, 0)))
     prior_neglogw: np.ndarray = field(default_factory=lambda: np.zeros(0))

@@ -32,7 +32,7 @@ struct HostModel {
         const size_t nJ = d.n_joints, S = size_t(3) * d.n_markers, nd = d.n_dmpl;
         m.nJ = d.n_joints; m.M = d.n_markers; m.body_dof = d.body_dof; m.p_red = d.p_red;
         m.n_hand_red = d.n_hand_red; m.n_hand_full = d.n_hand_full; m.nd = d.n_dmpl; m.kw = d.kw;
-        m.prior_k = d.prior_k; m.prior_d = d.prior_d; m.prior_off = d.prior_off;
+        m.prior_k = d.prior_k; m.prior_d = d.prior_d;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
         m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
         m.parents = up<int>(d.parents, nJ);
@@ -91,6 +91,11 @@ struct HostModel {
             m.prior_Qt = up<real>(qt.data(), qt.size());
         }
         m.prior_nlw = up<real>(d.prior_neglogw, d.prior_k);
+        {
+            std::vector<int> ids(d.prior_d);
+            for (int i = 0; i < d.prior_d; ++i) ids[i] = d.prior_ids ? d.prior_ids[i] : d.prior_off + i;
+            m.prior_ids = up<int>(ids.data(), ids.size());
+        }
         m.free1 = up<int>(d.free1, d.n_free1);
         m.free2 = up<int>(d.free2, d.n_free2);
     }

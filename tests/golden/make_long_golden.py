@@ -26,6 +26,7 @@ LONG = {
     'C2': ('C2', dict(frames=500)),                                  # BASELINE configs[1]
     'NS': ('C5', dict(frames=4000, seq_idx=0)),                      # north-star target: 4000-frame SMPL-H sequence
     'C3': ('C3', dict(frames=640)),                                  # a window of configs[2], solved with its 4000-frame chunking
+    'C3F': ('C3', dict(frames=4000)),                                # configs[2] in full: SMPL-X + DMPL, 4000 frames
     'C4L': ('C4', dict(frames=2000, hand_side='left')),              # configs[3]
     'C4R': ('C4', dict(frames=2000, hand_side='right')),
     'C5a': ('C5', dict(frames=320, seq_idx=0)),                      # configs[4] shape: several sequences, one model family

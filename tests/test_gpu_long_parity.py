@@ -78,7 +78,8 @@ def _excursions(over):
 @pytest.mark.parametrize('key,kw,tol_body,max_over', [
     ('C2', {}, TOL_BODY, 0.0),                       # BASELINE configs[1]: 500 frames -> chunks of 4
     ('NS', {}, TOL_BODY, 0.01),                      # north-star target: 4000-frame SMPL-H -> chunks of 28
-    ('C3', dict(chunk_len=28), TOL_BODY, 0.03),      # 640-frame window of configs[2], cut with the chunk length of 4000 frames
+    ('C3', dict(chunk_len=28), 1e-4, 0.0),           # 640-frame window of configs[2], cut with the chunk length of 4000 frames
+    ('C3F', {}, 1e-4, 0.0),                          # configs[2] in full: SMPL-X + DMPL, 4000 frames (default: the exact preset)
     ('C4L', {}, 5e-3, 0.01),                         # configs[3]: hand-only model, the wrist is weakly observed
     ('C4R', {}, 5e-3, 0.01),
 ])
@@ -87,9 +88,9 @@ def test_default_product_path_vs_sequential_oracle(cases, key, kw, tol_body, max
     gold = np.load(os.path.join(GOLD, f'long_{key}.npz'))
     assert np.allclose(gold['obs_checksum'], [np.nansum(case['obs']), case['vis'].sum()], rtol=1e-12)   # same inputs
     out, b = _run_drop_in(case, **kw)
-    # the product path: float32 for the body models; float64 for the hand-only MANO model (30 unknowns, no prior: a
-    # float32 cold start can take another branch of the dog-leg, and float64 costs little at that size)
-    assert b['precision'] == ('f64' if key.startswith('C4') else 'f32') and b['mode'] == 'fast' and b['chunk_len'] > 0 and b['chunks'] > 1
+    # the product path: float32 for the body models without per-frame linear coefficients; float64 with DMPL (BASELINE
+    # config 3: float32 left the tolerance on 7 % of its frames) and for the hand-only MANO model (chmosh.default_schedule)
+    assert b['precision'] == ('f64' if key.startswith(('C4', 'C3')) else 'f32') and b['mode'] == 'fast' and b['chunk_len'] > 0 and b['chunks'] > 1
     assert np.array_equal(b['frame_ids'], gold['frame_ids'])
     bc = b['boundary_check']
     print(f'\n[{key}] boundary check: rounds {bc["rounds"]}, chunks over tolerance at first {bc.get("chunks_over_tol_first")}, repaired per round {bc["repaired_chunks"]}, first delta {bc["boundary_delta_first"]}, max delta {bc["boundary_delta_max"]}, '
@@ -111,7 +112,7 @@ def test_default_product_path_vs_sequential_oracle(cases, key, kw, tol_body, max
         over = rep[name] > tol
         runs = _excursions(over)
         assert over.sum() <= max_over * n, (name, int(over.sum()), n)
-        assert np.sqrt((rep[name] ** 2).mean()) <= (tol if max_over < 0.02 else 2 * tol), name   # typical frame: inside (C3: one event in a 640-frame window)
+        assert np.sqrt((rep[name] ** 2).mean()) <= tol, name                       # typical frame: well inside
         assert not runs or max(runs) <= 40, (name, runs)                            # excursions are short: they decay
     assert rep['body'].max() < 0.05 and rep['trans'].max() < 2e-3                    # and bounded
     if 'markers_sim' in gold.files and max_over == 0.0:
