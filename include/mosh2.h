@@ -78,6 +78,12 @@ typedef struct mosh2_model_desc {
      * expression coefficients (sd / jd hold their directions after the DMPL ones); [face_lo, face_hi) are the
      * reduced-pose ids of the jaw, penalised by poseF in Step 2 */
     int32_t n_expr, face_lo, face_hi;
+    /* animal_horse (chmosh.py:572-573,615-617; prior/horse_body_prior.py:56-71): besides the pose prior (here: prior_k = 1,
+     * Q = P P^T, -log w = 0) a joint-angle term r_i = 2 wt_pose exp(2 s_i pose[jangles_ids[i]]); its SSE is reported in
+     * the poseH column of mosh2_result.errs (animal models have no finger term).  n_jangles <= 16. */
+    int32_t n_jangles;
+    const int32_t *jangles_ids;
+    const double *jangles_signs;
 } mosh2_model_desc;
 
 /* Stage-II weights and dog-leg options (support_data/conf/moshpp_conf.yaml:95-125,

@@ -140,7 +140,9 @@ def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_te
         raise ValueError(f'{model.model_type} != {sm.type}')                                       # bodymodel_loader.py:108
     prior = None
     prior_fname = _get(mp, 'pose_body_prior_fname')
-    if prior_fname and model.model_type != 'mano':
+    if prior_fname and model.model_type == 'animal_horse':
+        prior = _pack.create_horse_body_prior(prior_fname)                                         # bodymodel_loader.py:121-125
+    elif prior_fname and model.model_type != 'mano':
         prior = _pack.create_gmm_body_prior(prior_fname, exclude_hands=model.model_type in ('smplh', 'smplx'))
     dyn = bool(_get(mp, 'optimize_dynamics', False))
     dmpl_dirs = None
@@ -175,6 +177,8 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
     errs = {'data': res.errs[fid, 0]}
     if pk.prior_k:
         errs['poseB'] = res.errs[fid, 1]
+    if len(getattr(pk, 'jangles_ids', ())):
+        errs['poseB_jangles'] = res.errs[fid, 3]       # (animal_horse: the finger column carries the joint-angle term)
     if flags['optimize_fingers'] and pk.finger_hi > pk.finger_lo:
         errs['poseH'] = res.errs[fid, 3]
     face = bool(flags.get('optimize_face')) and pk.n_expr > 0
@@ -185,7 +189,7 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         errs['dmpl'] = res.errs[fid, 4]
         errs['extrap_dmpl'] = res.errs[fid, 5][(st & _lib.ST_HAS_EXTRAP) != 0]
     errs['velo'] = res.errs[fid, 2][(st & _lib.ST_HAS_VELO) != 0]
-    errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseH', 'dmpl', 'poseF', 'expr') or len(v)}
+    errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseB_jangles', 'poseH', 'dmpl', 'poseF', 'expr') or len(v)}
     labels = np.asarray(latent_labels, dtype=object)
     data = {
         'fullpose': res.fullpose[fid].copy(),

@@ -180,6 +180,8 @@ struct DevModel {
         m.prior_k = d.prior_k; m.prior_d = d.prior_d;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
         m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
+        m.n_jang = d.n_jangles;
+        for (int i = 0; i < d.n_jangles && i < mosh2::kMaxJangles; ++i) { m.jang_id[i] = d.jangles_ids[i]; m.jang_sign[i] = real(d.jangles_signs[i]); }
         int rc;
         if ((rc = up<int>(d.parents, nJ, &m.parents))) return rc;
         {   // joints sorted by depth (stable): parents before children
@@ -306,7 +308,8 @@ __global__ void boundary_delta_kernel(const real *__restrict__ warm_x, const int
 // precision is only built when the first job of that precision is created.
 struct HostDesc {
     mosh2_model_desc d{};
-    std::vector<int32_t> parents, w_joint, free1, free2, prior_ids;
+    std::vector<int32_t> parents, w_joint, free1, free2, prior_ids, jangles_ids;
+    std::vector<double> jangles_signs;
     std::vector<double> hand_comps, hands_mean, v0, sd, pd, w_val, j0, jd, coefs, prior_means, prior_Q, prior_neglogw;
     template <class T> static const T *keep(std::vector<T> &dst, const T *src, size_t n) {
         dst.assign(src, src + n);
@@ -321,6 +324,7 @@ struct HostDesc {
         d.free1 = keep(free1, s.free1, s.n_free1);
         d.free2 = keep(free2, s.free2, s.n_free2);
         if (s.prior_ids) d.prior_ids = keep(prior_ids, s.prior_ids, D);
+        if (s.n_jangles > 0) { d.jangles_ids = keep(jangles_ids, s.jangles_ids, s.n_jangles); d.jangles_signs = keep(jangles_signs, s.jangles_signs, s.n_jangles); }
         d.hand_comps = keep(hand_comps, s.hand_comps, size_t(s.n_hand_red) * s.n_hand_full);
         d.hands_mean = keep(hands_mean, s.hands_mean, s.n_hand_full);
         d.v0 = keep(v0, s.v0, S * 3);
@@ -478,6 +482,10 @@ int mosh2_model_create(const mosh2_model_desc *d, int device, mosh2_model **out)
         return fail(MOSH2_E_INVALID, "inconsistent face description: n_expr=%d of %d linear coefficients, jaw ids [%d, %d)", d->n_expr,
                     d->n_dmpl, d->face_lo, d->face_hi);
     if (d->n_joints > 254) return fail(MOSH2_E_TOO_LARGE, "%d joints (max 254)", d->n_joints);
+    if (d->n_jangles < 0 || d->n_jangles > mosh2::kMaxJangles || (d->n_jangles > 0 && (!d->jangles_ids || !d->jangles_signs)))
+        return fail(MOSH2_E_INVALID, "joint-angle term: %d entries (max %d)", d->n_jangles, mosh2::kMaxJangles);
+    for (int i = 0; i < d->n_jangles; ++i)
+        if (d->jangles_ids[i] < 0 || d->jangles_ids[i] >= d->p_red) return fail(MOSH2_E_INVALID, "joint-angle entry %d refers to pose id %d of %d", i, d->jangles_ids[i], d->p_red);
     for (int i = 0; i < d->prior_d; ++i) {
         const int id = d->prior_ids ? d->prior_ids[i] : d->prior_off + i;
         if (id < 0 || id >= d->p_red) return fail(MOSH2_E_INVALID, "prior dimension %d refers to pose id %d of %d", i, id, d->p_red);

@@ -90,6 +90,7 @@ constexpr int kBlendGroups = 4;   // upper bound of the joint groups of the pose
 constexpr int kCholNB = 8;        // block column width of the Cholesky factorisation
 constexpr int kMaxHandBlocks = 4;
 constexpr int kChunkRec = 5;      // ints per chunk-table record
+constexpr int kMaxJangles = 16;   // joint-angle prior entries (the horse model has 12)
 
 struct Cta {
     int tid, nthr;
@@ -119,6 +120,9 @@ struct Model {
     const int *free1, *free2;
     int finger_lo, finger_hi;
     int n_expr, face_lo, face_hi;   // optimize_face: the last n_expr linear coefficients are expressions; jaw pose ids
+    int n_jang;                     // animal_horse: joint-angle term exp(2 s x)^2 on these reduced-pose ids (prior/horse_body_prior.py:56-71)
+    int jang_id[kMaxJangles];
+    real jang_sign[kMaxJangles];
     int tile_markers;           // markers per Jacobian tile (20 or 10: a warp owns ten), chosen by the host from the shared-memory budget
     int dev_no_tc;              // development switch (host): 1 = J^T J stays on the CUDA cores
 };
@@ -165,6 +169,8 @@ M2_HD float r_rsqrt(float x) {
 #endif
 }
 M2_HD double r_rsqrt(double x) { return 1.0 / sqrt(x); }
+M2_HD float r_exp(float x) { return expf(x); }
+M2_HD double r_exp(double x) { return exp(x); }
 M2_HD float r_abs(float x) { return fabsf(x); }
 M2_HD double r_abs(double x) { return fabs(x); }
 M2_HD void r_sincos(float x, float *s, float *c) {
@@ -887,6 +893,9 @@ struct Solver {
         CTA_FOR(i, 3 * d.M) part[ERR_DATA] += w.rm[i] * w.rm[i];
         if (c.velo) CTA_FOR(i, d.PR) { const real e = (th[i] - w.velo_tgt[i]) * wv; part[ERR_VELO] += e * e; }
         if (c.poseH) CTA_FOR(i, m.finger_hi - m.finger_lo) { const real e = th[m.finger_lo + i] * wH; part[ERR_POSEH] += e * e; }
+        // joint-angle term of the horse model: r_i = 2 wp exp(2 s_i x_i) (chmosh.py:615-617: power(exp(.), 2) * wt_pose * 2);
+        // animal models have no finger term, its column carries this one
+        if (c.wp > real(0)) CTA_FOR(i, m.n_jang) { const real e = real(2) * c.wp * r_exp(real(2) * m.jang_sign[i] * th[m.jang_id[i]]); part[ERR_POSEH] += e * e; }
         if (c.face) {
             CTA_FOR(i, m.face_hi - m.face_lo) { const real e = th[m.face_lo + i] * wF; part[ERR_POSEF] += e * e; }
             CTA_FOR(i, m.n_expr) { const real e = dl[nd_dm + i] * wxp; part[ERR_EXPR] += e * e; }
@@ -1467,6 +1476,18 @@ struct Solver {
             }
             w.A[cc * ld + cc] += da;
             w.g[cc] -= dg;
+        }
+        if (c.wp > real(0) && m.n_jang) {
+            M2_SYNC();
+            CTA_FOR(i, m.n_jang) {                 // J_ii = d r_i / d x_i = 4 wp s exp(2 s x);  A += J^2,  g -= J r
+                const int ci = w.colmap[3 + m.jang_id[i]];
+                if (ci >= 0) {
+                    const real sg = m.jang_sign[i], ex = r_exp(real(2) * sg * th[m.jang_id[i]]);
+                    const real Jd = real(4) * c.wp * sg * ex, rr = real(2) * c.wp * ex;
+                    w.A[ci * ld + ci] += Jd * Jd;
+                    w.g[ci] -= Jd * rr;
+                }
+            }
         }
         M2_SYNC();
         M2_TACC(10);

@@ -36,6 +36,7 @@ class ModelDesc(C.Structure):
         ('n_free1', C.c_int32), ('n_free2', C.c_int32), ('free1', _i32p), ('free2', _i32p),
         ('finger_lo', C.c_int32), ('finger_hi', C.c_int32),
         ('n_expr', C.c_int32), ('face_lo', C.c_int32), ('face_hi', C.c_int32),
+        ('n_jangles', C.c_int32), ('jangles_ids', _i32p), ('jangles_signs', _f64p),
     ]
 
 
@@ -176,6 +177,11 @@ class DescHolder:
         d.n_free1, d.n_free2 = len(pk.free_step1), len(pk.free_step2)
         d.finger_lo, d.finger_hi = pk.finger_lo, pk.finger_hi
         d.n_expr, d.face_lo, d.face_hi = pk.n_expr, pk.face_lo, pk.face_hi
+        jid = getattr(pk, 'jangles_ids', None)
+        if jid is not None and len(jid):
+            self.arrays['jangles_ids'], self.arrays['jangles_signs'] = i32(jid), f64(pk.jangles_signs)
+            d.n_jangles = len(jid)
+            d.jangles_ids, d.jangles_signs = _ptr(self.arrays['jangles_ids'], _i32p), _ptr(self.arrays['jangles_signs'], _f64p)
         self.desc = d
 
 

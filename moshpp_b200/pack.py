@@ -215,6 +215,21 @@ class BodyPrior:
     neglogw: np.ndarray    # K,  -log(w_k) with the reference's normalisation
 
 
+# joint-angle term of the horse model (prior/horse_body_prior.py:56-71): pose ids of the four legs' bend angles, all signs +1
+HORSE_JANGLES_IDS = np.array([6, 7, 8, 11, 12, 13, 20, 21, 22, 25, 26, 27], dtype=np.int32)
+HORSE_JANGLES_SIGNS = np.ones(12)
+
+
+def create_horse_body_prior(pose_body_prior_fname: str) -> BodyPrior:
+    """smal_horse_prior (prior/horse_body_prior.py:40-53, tail / mouth / ears disabled): r = (pose[3:84] - mean) . pic, i.e.
+    one component with Q = pic pic^T and no weight constant."""
+    with open(pose_body_prior_fname, 'rb') as f:
+        res = pickle.load(f, encoding='latin-1')
+    P = np.asarray(res['pic'], dtype=np.float64)[:81, :81]
+    mu = np.asarray(res['mean_pose'], dtype=np.float64)[:81]
+    return BodyPrior(means=np.ascontiguousarray(mu[None]), Q=np.ascontiguousarray((P @ P.T)[None]), neglogw=np.zeros(1))
+
+
 def create_gmm_body_prior(pose_body_prior_fname: str, exclude_hands: bool = False) -> BodyPrior:
     with open(pose_body_prior_fname, 'rb') as f:
         gmm = pickle.load(f, encoding='latin-1')
@@ -280,6 +295,8 @@ class StageIIPack:
     face_lo: int = 0         # reduced-pose ids [lo, hi) penalised by poseF in step 2 (the jaw)
     face_hi: int = 0
     n_expr: int = 0          # how many of the n_dmpl linear coefficients (the last ones) are expression coefficients
+    jangles_ids: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))    # animal_horse joint-angle term: reduced-pose ids
+    jangles_signs: np.ndarray = field(default_factory=lambda: np.zeros(0))            # ... and signs
     # ---- host-only bookkeeping
     closest: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.int64))
     can_verts_sel: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
@@ -349,7 +366,12 @@ def pose_partitions(model_type: str, p_red: int, optimize_fingers: bool, optimiz
             finger = all_ids[75:]
     elif model_type == 'mano':
         finger = all_ids[3:]
+    elif model_type == 'animal_horse':
+        body = all_ids[3:84]                                 # tail, mouth and ears stay at rest (chmosh.py:572-573)
     else:
+        # animal_dog and object are listed by the reference but cannot run its Stage II: MaxMixtureDog asserts that a
+        # covariance determinant IS zero (prior/dog_body_prior.py:73-74) and RigidObjectModel has no `fullpose`
+        # (chmosh.py:719); they are not built here
         raise NotImplementedError(f'surface model type {model_type!r} is outside the Stage-II hot path of this build')
     step1 = root + body
     if len(body) and not optimize_toes:
@@ -450,4 +472,6 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
         pack.prior_means = prior.means
         pack.prior_Q = prior.Q
         pack.prior_neglogw = prior.neglogw
+    if model.model_type == 'animal_horse':
+        pack.jangles_ids, pack.jangles_signs = HORSE_JANGLES_IDS.copy(), HORSE_JANGLES_SIGNS.copy()
     return pack

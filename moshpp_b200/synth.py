@@ -102,10 +102,29 @@ def skeleton(model_type: str):
         par = [-1] + [0 if p < 0 else 1 + p for p in hpar]
         rad = [0.03] + [0.009] * 15
         return pos, np.array(par), np.array(rad)
+    if model_type == 'animal_horse':
+        return _HORSE35, np.array(_HORSE35_PARENTS), np.array(_HORSE35_RADII)
     raise ValueError(model_type)
 
 
-NUM_VERTS = {'smpl': 6890, 'smplh': 6890, 'smplx': 10475, 'mano': 778}
+# a quadruped with 35 joints: 28 body joints (pose ids 0..83 are optimised), then tail (3), mouth, ears (2), forelock
+_HORSE35 = np.array([
+    [-0.50, 1.10, 0.0], [-0.25, 1.15, 0.0], [0.00, 1.15, 0.0], [0.25, 1.15, 0.0], [0.50, 1.15, 0.0],
+    [0.70, 1.35, 0.0], [0.85, 1.55, 0.0], [1.00, 1.65, 0.0],
+    [0.50, 0.95, 0.15], [0.50, 0.65, 0.15], [0.50, 0.35, 0.15], [0.50, 0.10, 0.15],
+    [0.50, 0.95, -0.15], [0.50, 0.65, -0.15], [0.50, 0.35, -0.15], [0.50, 0.10, -0.15],
+    [-0.50, 0.90, 0.15], [-0.50, 0.60, 0.15], [-0.55, 0.30, 0.15], [-0.50, 0.08, 0.15],
+    [-0.50, 0.90, -0.15], [-0.50, 0.60, -0.15], [-0.55, 0.30, -0.15], [-0.50, 0.08, -0.15],
+    [0.10, 1.00, 0.0], [-0.20, 1.00, 0.0], [0.62, 1.25, 0.0], [-0.62, 1.20, 0.0],
+    [-0.65, 1.10, 0.0], [-0.80, 1.00, 0.0], [-0.90, 0.85, 0.0], [1.12, 1.60, 0.0], [0.98, 1.78, 0.05], [0.98, 1.78, -0.05],
+    [1.05, 1.70, 0.0]])
+_HORSE35_PARENTS = [-1, 0, 1, 2, 3, 4, 5, 6, 4, 8, 9, 10, 4, 12, 13, 14, 0, 16, 17, 18, 0, 20, 21, 22, 2, 1, 4, 0,
+                    0, 28, 29, 7, 7, 7, 7]
+_HORSE35_RADII = [0.20, 0.20, 0.21, 0.20, 0.18, 0.11, 0.09, 0.08, 0.07, 0.06, 0.045, 0.04, 0.07, 0.06, 0.045, 0.04,
+                  0.08, 0.065, 0.045, 0.04, 0.08, 0.065, 0.045, 0.04, 0.12, 0.12, 0.10, 0.10, 0.04, 0.03, 0.025, 0.04,
+                  0.02, 0.02, 0.03]
+
+NUM_VERTS = {'smpl': 6890, 'smplh': 6890, 'smplx': 10475, 'mano': 778, 'animal_horse': 3889}
 
 
 def _bone_segments(pos, par, rad):
@@ -186,7 +205,7 @@ def make_body_model(model_type: str, n_verts: Optional[int] = None, n_betas: int
         segs_body = [s for s in segs if s[0] not in (23, 24)]
     else:
         segs_body = segs
-    torso = (0, 3, 6, 9) if model_type != 'mano' else ()
+    torso = {'mano': (), 'animal_horse': (0, 1, 2, 3, 4)}.get(model_type, (0, 3, 6, 9))
     verts = _sample_capsules(segs_body, V - n_eye, rng, torso_joints=torso)
     verts = verts[rng.permutation(len(verts))]
     if n_eye:
@@ -257,6 +276,15 @@ def make_body_prior(seed: int = SEED_MODEL + 2, n_comp: int = 8, dim: int = 69) 
         covars[k] = (q * lam) @ q.T
     weights = rng.dirichlet(np.ones(n_comp))
     return {'covars': covars, 'means': means, 'weights': weights}
+
+
+def make_horse_prior(seed: int = SEED_MODEL + 4, dim: int = 105) -> Dict[str, np.ndarray]:
+    """The horse pose prior's file layout (prior/horse_body_prior.py:41-47): 'pic' (a square root of the precision) and
+    'mean_pose' over the pose without the root."""
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((dim, dim)))
+    lam = np.exp(rng.uniform(np.log(1.0 / 0.6), np.log(1.0 / 0.08), dim))
+    return {'pic': (q * lam) @ q.T, 'mean_pose': 0.1 * rng.standard_normal(dim)}
 
 
 def make_dmpl(verts: np.ndarray, seed: int = SEED_MODEL + 3, n_dmpl: int = 8) -> Dict[str, np.ndarray]:
@@ -394,8 +422,11 @@ def make_motion(p: _pack.StageIIPack, n_frames: int, seed: int, fps: float = 120
         f = rng.uniform(0.2, 2.0, 3)
         ph = rng.uniform(0, 2 * np.pi, 3)
         pose[:, i] = (a[None] * np.sin(2 * np.pi * f[None] * t[:, None] + ph[None])).sum(1) + rng.normal(0, 0.05 * amp)
-    if p.model_type in ('smpl', 'smplh', 'smplx'):
+    if p.model_type in ('smpl', 'smplh', 'smplx', 'animal_horse'):
         pose[:, 30:36] *= 0.0            # toes are frozen in Stage II unless optimize_toes
+    if p.model_type == 'animal_horse':
+        pose[:, 84:] = 0.0               # tail, mouth and ears are never optimised (chmosh.py:572-573)
+        pose[:, 3:84] *= 0.6
     if p.model_type == 'smplx':
         if p.face_hi > p.face_lo:
             pose[:, 69:75] = 0.0         # eyes are never optimised; the jaw is, with optimize_face
@@ -476,6 +507,9 @@ CONFIGS = {
     # widening row: SMPL-X with face markers, jaw + expression coefficients free in Step 2
     'CF': dict(model_type='smplx', frames=200, n_body=41, n_finger=6, n_face=12, optimize_fingers=True, optimize_dynamics=False,
                optimize_face=True, mocap_ext='npz'),
+    # (new configurations go last: the motion seed depends on the position)
+    # the one animal variant whose Stage II runs in the reference
+    'CH': dict(model_type='animal_horse', frames=60, n_body=36, n_finger=0, optimize_fingers=False, optimize_dynamics=False, mocap_ext='npz'),
 }
 
 
@@ -505,7 +539,12 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
             pickle.dump(model, f, protocol=pickle.HIGHEST_PROTOCOL)
     if not os.path.exists(hand_prior_fname):
         np.savez(hand_prior_fname, **make_hand_prior())
-    if not os.path.exists(body_prior_fname):
+    if mt == 'animal_horse':
+        body_prior_fname = os.path.join(out_dir, 'pose_body_prior_horse.pkl')
+        if not os.path.exists(body_prior_fname):
+            with open(body_prior_fname, 'wb') as f:
+                pickle.dump(make_horse_prior(), f, protocol=pickle.HIGHEST_PROTOCOL)
+    elif not os.path.exists(body_prior_fname):
         with open(body_prior_fname, 'wb') as f:
             pickle.dump(make_body_prior(), f, protocol=pickle.HIGHEST_PROTOCOL)
     if c['optimize_dynamics'] and not os.path.exists(dmpl_fname):
@@ -534,7 +573,9 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
                                   use_hands_mean=cfg.surface_model.use_hands_mean,
                                   dof_per_hand=cfg.surface_model.dof_per_hand, surface_model_type=mt)
     prior = None
-    if mt != 'mano':
+    if mt == 'animal_horse':
+        prior = _pack.create_horse_body_prior(body_prior_fname)
+    elif mt != 'mano':
         prior = _pack.create_gmm_body_prior(body_prior_fname, exclude_hands=mt in ('smplh', 'smplx'))
     dm_dirs = None
     if c['optimize_dynamics']:

@@ -49,3 +49,29 @@ def create_gmm_body_prior(pose_body_prior_fname, exclude_hands=False) -> MaxMixt
     const = (2 * np.pi) ** (npose / 2.)
     weights = weights / (const * (sqrdets / sqrdets.min()))
     return MaxMixtureComplete(means=means, precs=chols, weights=weights)
+
+
+class HorsePosePrior:
+    """smal_horse_prior (prior/horse_body_prior.py:40-53, disable_tail_mouth_ear): r(x) = (x - mean_pose[:81]) . pic[:81, :81]."""
+
+    def __init__(self, prior_pklpath):
+        with open(prior_pklpath, 'rb') as f:
+            res = pickle.load(f, encoding='latin-1')
+        self.precs = np.asarray(res['pic'], dtype=np.float64)[:81, :81]
+        self.means = np.asarray(res['mean_pose'], dtype=np.float64)[:81]
+
+    def r(self, x):
+        return (x - self.means).dot(self.precs)
+
+    def dr_wrt_x(self, x):
+        return self.precs.T
+
+
+# smal_horse_joint_angle_prior (prior/horse_body_prior.py:56-71): entries of pose[3:84], i.e. pose ids 6, 7, 8, ... ; signs +1
+HORSE_JANGLES_IDS = np.array([6, 7, 8, 11, 12, 13, 20, 21, 22, 25, 26, 27]) - 3
+HORSE_JANGLES_SIGNS = np.ones(12)
+
+
+def horse_joint_angles(body_pose):
+    """power(exp(pose[idx] * sign), 2)"""
+    return np.exp(body_pose[HORSE_JANGLES_IDS] * HORSE_JANGLES_SIGNS) ** 2

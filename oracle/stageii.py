@@ -31,7 +31,7 @@ import numpy as np
 from .dogleg import minimize_dogleg
 from .lbs import LBS, OracleModel
 from .markers import TransformedCoeffs, transformed_lms
-from .prior import create_gmm_body_prior
+from .prior import HORSE_JANGLES_IDS, HORSE_JANGLES_SIGNS, HorsePosePrior, create_gmm_body_prior, horse_joint_angles
 from .rigid import perform_rigid_adjustment
 
 NUM_TRAIN_MARKERS = 46   # chmosh.py:460
@@ -91,6 +91,17 @@ class _Objective:
                     for bi, pid in enumerate(s.body_ids):
                         if pid in col:
                             J[:, 3 + col[pid]] = Jp[:, bi]
+            elif name == 'poseB_jangles':                                                          # chmosh.py:615-617
+                wt = payload
+                xb = s.pose[s.body_ids]
+                r = horse_joint_angles(xb) * wt
+                if want_jac:
+                    J = np.zeros((r.size, self.n))
+                    col = {pid: c for c, pid in enumerate(self.pose_ids)}
+                    for ri, (bi, sg) in enumerate(zip(HORSE_JANGLES_IDS, HORSE_JANGLES_SIGNS)):
+                        pid = s.body_ids[bi]
+                        if pid in col:
+                            J[ri, 3 + col[pid]] = 2.0 * sg * r[ri]
             elif name == 'velo':
                 wt, target = payload
                 r = (s.pose - target) * wt
@@ -155,6 +166,8 @@ class _Objective:
                 out[name] = float((((ev['markers'][self.vis] - self.obs) * payload) ** 2).sum())
             elif name == 'poseB':
                 out[name] = float(((s.prior.r(s.pose[s.body_ids]) * payload) ** 2).sum())
+            elif name == 'poseB_jangles':
+                out[name] = float(((horse_joint_angles(s.pose[s.body_ids]) * payload) ** 2).sum())
             elif name == 'velo':
                 out[name] = float((((s.pose - payload[1]) * payload[0]) ** 2).sum())
             elif name == 'poseH':
@@ -198,7 +211,9 @@ class StageIISolver:
         m = self.model
         assert m.model_type == sm.type
         self.prior = None
-        if mp.pose_body_prior_fname and m.model_type != 'mano':
+        if mp.pose_body_prior_fname and m.model_type == 'animal_horse':
+            self.prior = HorsePosePrior(mp.pose_body_prior_fname)                                 # bodymodel_loader.py:121-125
+        elif mp.pose_body_prior_fname and m.model_type != 'mano':
             self.prior = create_gmm_body_prior(mp.pose_body_prior_fname,
                                                exclude_hands=m.model_type in ('smplh', 'smplx'))  # bodymodel_loader.py:126-129
         self.betas = np.zeros(m.n_betas_model)
@@ -264,6 +279,8 @@ class StageIISolver:
                 self.finger_ids = all_ids[75:]
         elif sm.type == 'mano':
             self.finger_ids = all_ids[3:]
+        elif sm.type == 'animal_horse':
+            self.body_ids = all_ids[3:84]                                                       # line 572-573
         else:
             raise NotImplementedError(sm.type)
         ids = self.root_ids + self.body_ids
@@ -344,6 +361,8 @@ class StageIISolver:
             terms = [['data', wt_data]]
             if len(self.body_ids):
                 terms.append(['poseB', wt_pose])
+                if self.model.model_type == 'animal_horse':
+                    terms.append(['poseB_jangles', wt_pose * 2.])                                # lines 615-617
             if pose_prev is not None:
                 terms.append(['velo', (wt_velo, self.pose + (self.pose - pose_prev))])           # line 626
 
@@ -356,6 +375,8 @@ class StageIISolver:
                 for wt_first in [10. * wt_pose, 5. * wt_pose, wt_pose]:
                     if len(self.body_ids):
                         terms[1][1] = wt_first
+                        if self.model.model_type == 'animal_horse':
+                            terms[2][1] = wt_first * 2.                                          # lines 640-643
                     self._minimize(_Objective(self, obs, vis, terms, self.step1_ids, False), 1e-3)
                 first = False
             else:

@@ -22,6 +22,7 @@ SMALL = {
     'C3': dict(frames=10, n_verts=2000),
     'C4': dict(frames=12, n_verts=None),
     'CF': dict(frames=8, n_verts=2000),       # SMPL-X with face markers: jaw + expressions
+    'CH': dict(frames=10, n_verts=1500),      # animal_horse: single-Gaussian pose prior + joint-angle term
 }
 
 

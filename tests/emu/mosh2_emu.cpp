@@ -35,6 +35,8 @@ struct HostModel {
         m.prior_k = d.prior_k; m.prior_d = d.prior_d;
         m.n1 = d.n_free1; m.n2 = d.n_free2; m.finger_lo = d.finger_lo; m.finger_hi = d.finger_hi;
         m.n_expr = d.n_expr; m.face_lo = d.face_lo; m.face_hi = d.face_hi;
+        m.n_jang = d.n_jangles;
+        for (int i = 0; i < d.n_jangles && i < mosh2::kMaxJangles; ++i) { m.jang_id[i] = d.jangles_ids[i]; m.jang_sign[i] = real(d.jangles_signs[i]); }
         m.parents = up<int>(d.parents, nJ);
         {
             std::vector<int> depth(nJ, 0), order(nJ);

@@ -10,7 +10,7 @@ from conftest import run_oracle
 from moshpp_b200 import lib
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF', 'CH'])
 def test_f64_device_source_equals_oracle(cases, emu, name):
     case = cases(name)
     out = run_oracle(case)
@@ -33,6 +33,9 @@ def test_f64_device_source_equals_oracle(cases, emu, name):
     for col, k in enumerate(lib.ERR_NAMES):
         if k in dbg['stageii_errs'] and k not in ('velo', 'extrap_dmpl'):
             assert np.allclose(res.errs[fid, col], dbg['stageii_errs'][k], rtol=1e-8, atol=1e-12)
+    if 'poseB_jangles' in dbg['stageii_errs']:          # animal_horse: the joint-angle term is reported in the poseH column
+        assert np.allclose(res.errs[fid, lib.ERR_NAMES.index('poseH')], dbg['stageii_errs']['poseB_jangles'], rtol=1e-8, atol=1e-12)
+        assert dbg['stageii_errs']['poseB_jangles'].min() > 0
     n_velo = int(((res.status[fid] & lib.ST_HAS_VELO) != 0).sum())
     assert n_velo == len(dbg['stageii_errs'].get('velo', []))
 

@@ -13,7 +13,7 @@ def _load(name):
     return np.load(os.path.join(GOLD, f'stageii_{name}.npz'))
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF', 'CH'])
 def test_fixture_generation_is_reproducible(cases, name):
     g = _load(name)
     case = cases(name)
@@ -31,7 +31,7 @@ def test_oracle_reproduces_golden(cases, name):
     assert out['stageii_debug_details']['oracle_stats']['j_evals'] == int(g['j_evals'])
 
 
-@pytest.mark.parametrize('name', ['C2', 'C3', 'CF'])
+@pytest.mark.parametrize('name', ['C2', 'C3', 'CF', 'CH'])
 def test_device_source_reproduces_golden(cases, emu, name):
     g = _load(name)
     res = emu(cases(name))
@@ -45,7 +45,7 @@ def test_device_source_reproduces_golden(cases, emu, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF', 'CH'])
 def test_cuda_reproduces_golden(cases, name):
     g = _load(name)
     fid = g['frame_ids']

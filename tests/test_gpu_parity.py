@@ -8,7 +8,7 @@ from moshpp_b200 import lib
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF', 'CH'])
 def test_f64_kernel_equals_oracle(cases, name):
     case = cases(name)
     out = run_oracle(case)
@@ -33,7 +33,7 @@ def test_f64_kernel_equals_oracle(cases, name):
     assert np.abs(res.markers_sim[fid][vis[fid]] - mk).max() < 1e-9
 
 
-@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF'])
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4', 'CF', 'CH'])
 def test_f32_kernel_within_stated_tolerance(cases, name):
     """Tolerances of BASELINE.md section 4 for the fp32 path (sequential mode)."""
     case = cases(name)
@@ -215,3 +215,20 @@ def test_boundary_repair_cascades_to_the_sequential_result(cases, precision):
         job.close()
     finally:
         model.close()
+
+
+def test_drop_in_callable_with_the_horse_model(cases):
+    """animal_horse (chmosh.py:572-573,615-617): single-Gaussian pose prior + joint-angle term; the return
+    dictionary names the term like the reference does."""
+    from moshpp_b200.chmosh import mosh_stageii
+    case = cases('CH')
+    out = mosh_stageii(mocap_fname=case['mocap_fname'], cfg=case['cfg'], markers_latent=case['markers_latent'],
+                       latent_labels=case['latent_labels'], betas=case['betas'], marker_meta=case['marker_meta'],
+                       precision='f64', chunk_len=0)
+    ref = run_oracle(case)
+    assert np.abs(out['fullpose'] - ref['fullpose']).max() < 1e-8 and np.abs(out['trans'] - ref['trans']).max() < 1e-9
+    e, r = out['stageii_debug_details']['stageii_errs'], ref['stageii_debug_details']['stageii_errs']
+    assert set(e.keys()) == set(r.keys()) == {'data', 'poseB', 'poseB_jangles', 'velo'}
+    for k in ('data', 'poseB', 'poseB_jangles'):
+        assert np.allclose(e[k], r[k], rtol=1e-7, atol=1e-10)
+    assert np.abs(out['fullpose'][:, 84:]).max() == 0          # tail, mouth and ears stay at rest
