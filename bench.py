@@ -307,7 +307,7 @@ def time_plugin(case, args, steps, warmup, chunk_len=None):
                                   warmup_full=args.warmup_full, precision=args.precision)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
-    return float(np.mean(ts)) * 1e3, out
+    return float(np.mean(ts)) * 1e3, out, [round(t * 1e3, 1) for t in ts]
 
 
 def run_single(args):
@@ -333,7 +333,7 @@ def run_single(args):
     chunk_len = args.chunk_len if args.chunk_len is not None else chmosh.auto_chunk_len(F)
     model = lib.Model(pk, device=dev)
     ns = time_job(model, pk, opts, obs, vis, args, chunk_len, flush, args.steps, args.warmup)
-    e2e_ms, out = time_plugin(case, args, args.steps, 2, chunk_len=args.chunk_len)
+    e2e_ms, out, e2e_each = time_plugin(case, args, args.steps, 2, chunk_len=args.chunk_len)
     b = out['stageii_debug_details']['b200']
     h2d = obs.size * esz + vis.size
     d2h = F * (pk.p_full + pk.p_red + 3 + pk.n_dmpl + 3 * pk.n_markers + 8) * esz + F * 5 * 4
@@ -359,7 +359,7 @@ def run_single(args):
                 'ms_per_step': e2e_ms,
                 'what': 'wall clock of chmosh.mosh_stageii(mocap_fname, cfg, ...) per call: mocap file read, per-subject '
                         'packing (prepare_stageii), model upload, job create, pinned H2D, kernel, D2H, result dictionary',
-                'kernel_ms_inside': b['kernel_ms'], 'host_ms_last_call': b['host_ms'],
+                'kernel_ms_inside': b['kernel_ms'], 'host_ms_last_call': b['host_ms'], 'ms_each_call': e2e_each,
                 'c_abi_job_level': {'value': F / (ns['e2e_job_ms'] * 1e-3), 'ms_per_step': ns['e2e_job_ms'],
                                     'what': 'mosh2_job_upload + verified launches + download with host buffers (resident model and job)'}},
         'gpu_launches': ns['launches'],
@@ -376,7 +376,7 @@ def run_single(args):
         m2 = lib.Model(pk2, device=dev)
         r2 = time_job(m2, pk2, opts2, o2, v2, args, chmosh.auto_chunk_len(o2.shape[0]), flush, ksteps, 3)
         m2.close()
-        e2, _ = time_plugin(c2, args, ksteps, 2)
+        e2, _, _ = time_plugin(c2, args, ksteps, 2)
         line['secondary'] = {
             'workload': 'BASELINE configs[1]: SMPL-H 500-frame sequence, 53 markers', 'value': o2.shape[0] / (r2['ms'] * 1e-3),
             'ms_per_step': r2['ms'], 'e2e_value': o2.shape[0] / (e2 * 1e-3), 'e2e_ms_per_step': e2, 'chunks': r2['chunks'],

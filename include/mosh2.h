@@ -166,8 +166,11 @@ int mosh2_job_boundary_deltas(mosh2_job *j, int32_t body_ids, float *out);
 /* Re-solves the listed chunks only (e.g. those that failed the boundary check); the rows of all other frames keep the
  * values of the previous launch.  chunk_warmup >= 0: with that warm-up, from a cold start.  chunk_warmup < 0: RESUME --
  * no warm-up; the chunk continues the recursion from the rows the previous launch emitted for the last two solved frames
- * in front of it, exactly as the previous chunk would have gone on (boundary repair).  async */
-int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids, int32_t chunk_warmup, int32_t warmup_full);
+ * in front of it, exactly as the previous chunk would have gone on (boundary repair); the repair of a chunk stops early once
+ * two consecutive re-solved frames lie within merge_tol (rad; translation in 0.1 m) of the rows they replace -- the two
+ * trajectories have merged and the remaining rows of the chunk stand (merge_tol = 0: re-solve the whole chunk).  async */
+int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids, int32_t chunk_warmup, int32_t warmup_full,
+                              double merge_tol);
 int mosh2_job_download(mosh2_job *j, const mosh2_result *res); /* async D2H + stream sync */
 int mosh2_job_sync(mosh2_job *j);
 /* Results as ONE packed float32 device row per frame, for device-side consumers (NCCL gather): row f =

@@ -283,7 +283,7 @@ def launch_verified(job, tol, max_rounds: int = 12):
             if c - 1 != last:
                 take.append(int(c))
                 last = int(c)
-        job.relaunch_chunks(take, -1)
+        job.relaunch_chunks(take, -1, merge_tol=float(tol[0]) / 3.0)     # merged = a third of the boundary tolerance
         report['rounds'] += 1
         report['repaired_chunks'].append(len(take))
     report['kernel_ms'] = kernel_ms

@@ -364,6 +364,7 @@ struct mosh2_job {
     float *d_delta = nullptr;
     std::vector<int> tab, tab0;       // host copy of the chunk table (tab0: as created; repairs edit tab)
     bool tab_dirty = false;
+    double merge_tol = 0;
     int launch_blocks = 0;            // blocks of the next launch (all chunks, or the subset in d_chunk_ids)
     bool subset = false;
     mosh2::Options opt{};
@@ -405,7 +406,7 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     mosh2::Job<real> job{};
     job.n_frames = j->n_frames; job.n_chunks = j->n_chunks;
     job.chunk_tab = j->d_chunk_tab; job.chunk_ids = j->subset ? j->d_chunk_ids : nullptr;
-    job.warm_x = static_cast<real *>(j->d_warm_x); job.warm_f = j->d_warm_f;
+    job.warm_x = static_cast<real *>(j->d_warm_x); job.warm_f = j->d_warm_f; job.merge_tol = j->merge_tol;
     job.obs = static_cast<const real *>(j->d_obs);
     job.vis = j->d_vis;
     real *out = static_cast<real *>(j->d_out);
@@ -650,8 +651,9 @@ int mosh2_job_launch(mosh2_job *j) {
     return launch<float>(j, j->model->f32.m);
 }
 
-int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids, int32_t chunk_warmup, int32_t warmup_full) {
-    if (!j || n < 1 || !chunk_ids) return fail(MOSH2_E_INVALID, "bad argument");
+int mosh2_job_relaunch_chunks(mosh2_job *j, int32_t n, const int32_t *chunk_ids, int32_t chunk_warmup, int32_t warmup_full, double merge_tol) {
+    if (!j || n < 1 || !chunk_ids || !(merge_tol >= 0)) return fail(MOSH2_E_INVALID, "bad argument");
+    j->merge_tol = merge_tol;
     CU(cudaSetDevice(j->model->device));
     const int wf = chunk_warmup < 0 ? 0 : ((warmup_full < 0 || warmup_full > chunk_warmup) ? chunk_warmup : warmup_full);
     for (int k = 0; k < n; ++k) {

@@ -141,6 +141,7 @@ struct Job {
     const int *chunk_tab;   // [n_chunks][kChunkRec]: first emitted frame, end of the emitted range, first frame of the chunk's
                             // sequence, warm-up (solved frames), how many of them (the last ones) run the full per-frame schedule
     const int *chunk_ids;   // launch of a subset of the chunks: blockIdx.x -> chunk, or null (all chunks)
+    double merge_tol;       // resume mode: a re-solved frame within this of the row it replaces counts as merged (rad; 0.1 m)
     real *warm_x;           // [n_chunks][NX] state after the chunk's last warm-up frame (boundary check against the emitted
     int *warm_f;            // [n_chunks]     result of that frame, which an earlier chunk produced), and that frame's index or -1
     const real *obs;        // F*M*3
@@ -205,11 +206,6 @@ template <> M2_HD double pivot_eps<double>() { return 1e-13; }
 template <class real> M2_HD real accept_slack();
 template <> M2_HD float accept_slack<float>() { return 1e-5f; }
 template <> M2_HD double accept_slack<double>() { return 0.0; }
-
-// boundary repair: a re-solved frame "coincides" with the row it replaces below this (rad; translation in 0.1 m)
-template <class real> M2_HD real merge_tol();
-template <> M2_HD float merge_tol<float>() { return 2e-5f; }
-template <> M2_HD double merge_tol<double>() { return 1e-10; }
 
 template <class real> struct alignas(16) Vec4 { real x, y, z, w; };
 template <class real> M2_HD Vec4<real> ld4(const real *p) { return *reinterpret_cast<const Vec4<real> *>(p); }
@@ -2275,7 +2271,7 @@ struct Solver {
             if (resuming) {
                 // merged with the old trajectory (two frames in a row within round-off of the rows they replace: the state
                 // the recursion carries, pose_t and pose_{t-1}, is the old one): the rest of the chunk stands as it is
-                calm = resume_diff <= merge_tol<real>() ? calm + 1 : 0;
+                calm = resume_diff <= real(job.merge_tol) ? calm + 1 : 0;
                 if (calm >= 2) break;
             }
             if (f < f_emit && job.warm_x) {      // (overwritten until the last warm-up frame: its state is what counts)

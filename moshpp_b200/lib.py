@@ -119,7 +119,7 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_job_launch.argtypes = [vp]
     lib.mosh2_job_warm_states.argtypes = [vp, _f64p, _i32p]
     lib.mosh2_job_boundary_deltas.argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
-    lib.mosh2_job_relaunch_chunks.argtypes = [vp, C.c_int32, _i32p, C.c_int32, C.c_int32]
+    lib.mosh2_job_relaunch_chunks.argtypes = [vp, C.c_int32, _i32p, C.c_int32, C.c_int32, C.c_double]
     lib.mosh2_job_download.argtypes = [vp, C.POINTER(Result)]
     lib.mosh2_job_sync.argtypes = [vp]
     lib.mosh2_job_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -349,10 +349,11 @@ class Job:
                           'mosh2_job_boundary_deltas')
         return out.astype(np.float64)
 
-    def relaunch_chunks(self, chunk_ids, chunk_warmup: int, warmup_full: int = -1):
+    def relaunch_chunks(self, chunk_ids, chunk_warmup: int, warmup_full: int = -1, merge_tol: float = 0.0):
+        """Re-solves the listed chunks; ``chunk_warmup < 0`` = resume from the emitted rows (mosh2_job_relaunch_chunks)."""
         ids = np.ascontiguousarray(chunk_ids, dtype=np.int32)
         self.model._check(self.lib.mosh2_job_relaunch_chunks(self.handle, len(ids), _ptr(ids, _i32p), int(chunk_warmup),
-                                                             int(warmup_full)), 'mosh2_job_relaunch_chunks')
+                                                             int(warmup_full), float(merge_tol)), 'mosh2_job_relaunch_chunks')
 
     def download(self) -> ResultArrays:
         self.model._check(self.lib.mosh2_job_download(self.handle, C.byref(self.result.c)), 'mosh2_job_download')

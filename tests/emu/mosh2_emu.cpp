@@ -121,7 +121,7 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     std::vector<int> tab = mosh2_host::chunk_table(seq_counts, n_seq, chunk_len, wu, wf);
     job.n_chunks = int(tab.size() / mosh2::kChunkRec);
     job.chunk_tab = tab.data();
-    job.chunk_ids = nullptr; job.warm_x = nullptr; job.warm_f = nullptr;
+    job.chunk_ids = nullptr; job.warm_x = nullptr; job.warm_f = nullptr; job.merge_tol = 0;
     job.obs = o.data(); job.vis = vis;
     job.fullpose = fullpose.data(); job.pose = pose.data(); job.trans = trans.data();
     job.dmpls = nd ? dmpls.data() : nullptr; job.markers_sim = mk.data(); job.errs = errs.data();
