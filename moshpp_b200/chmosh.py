@@ -21,10 +21,13 @@ result converges geometrically in the warm-up length to the sequential one (meas
 """
 from __future__ import annotations
 
+import hashlib
 import logging
 import math
+import os
 import pickle
 import time
+from collections import OrderedDict
 from typing import Optional
 
 import numpy as np
@@ -107,6 +110,74 @@ def plan_chunk_len(frame_counts, sm_budget: int = NUM_SMS_B200, warmup: int = DE
 def auto_chunk_len(n_frames: int, sm_budget: int = NUM_SMS_B200) -> int:
     """Shortest chunks that still give about one chunk per available SM (latency = chunk_len + warm-up)."""
     return max(4, int(math.ceil(n_frames / max(1, sm_budget))))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Subject cache.  Everything ``prepare_stageii`` computes -- and the device copy of it -- depends on the subject (body
+# model file, shape, latent markers, layout, options), not on the sequence; a subject usually comes with many sequences
+# (the reference re-does this work per call).  The packed constants and their device model are kept for the last few
+# subjects, keyed by the CONTENT of every input (file identity = path + mtime + size).  Nothing sequence-dependent is cached.
+# ---------------------------------------------------------------------------------------------------------------------
+_SUBJECT_CACHE: 'OrderedDict[tuple, dict]' = OrderedDict()
+SUBJECT_CACHE_SIZE = 4
+
+
+def _file_id(fname):
+    if not fname:
+        return None
+    try:
+        st = os.stat(str(fname))
+        return (os.path.realpath(str(fname)), st.st_mtime_ns, st.st_size)
+    except OSError:
+        return (str(fname), None, None)
+
+
+def _subject_key(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname, device):
+    sm, mp = cfg.surface_model, cfg.moshpp
+    h = hashlib.blake2b(digest_size=16)
+    h.update(np.ascontiguousarray(betas, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(markers_latent, dtype=np.float64).tobytes())
+    w = cfg.opt_settings.weights
+    scalars = (
+        _file_id(sm.fname), _file_id(_get(mp, 'pose_hand_prior_fname')), _file_id(_get(mp, 'pose_body_prior_fname')),
+        _file_id(_get(sm, 'dmpl_fname')) if _get(mp, 'optimize_dynamics', False) else None, _file_id(v_template_fname),
+        str(sm.type), int(sm.num_betas), int(_get(sm, 'num_dmpls', 0) or 0), bool(sm.use_hands_mean), int(sm.dof_per_hand),
+        int(_get(sm, 'betas_expr_start_id', 0) or 0), int(_get(sm, 'num_expressions', 0) or 0),
+        bool(_get(mp, 'optimize_fingers', False)), bool(_get(mp, 'optimize_face', False)), bool(_get(mp, 'optimize_dynamics', False)),
+        bool(_get(mp, 'optimize_toes', False)), int(cfg.opt_settings.maxiter),
+        tuple(sorted((str(k), float(w[k])) for k in w.keys() if str(k).startswith('stageii_'))),
+        tuple(latent_labels), tuple(marker_meta['marker_type_mask'].keys()), tuple(marker_meta['marker_type'].items()), int(device))
+    h.update(repr(scalars).encode())
+    return h.hexdigest()
+
+
+def clear_subject_cache():
+    while _SUBJECT_CACHE:
+        _, e = _SUBJECT_CACHE.popitem(last=False)
+        e['model'].close()
+
+
+def subject_for(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname=None, device: int = 0):
+    """(StageIIPack, options, flags, lib.Model on ``device``) of a subject, from the cache or freshly prepared."""
+    key = _subject_key(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname, device)
+    e = _SUBJECT_CACHE.get(key)
+    if e is None:
+        pk, opts, flags = prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname)
+        e = dict(pk=pk, opts=opts, flags=flags, model=_lib.Model(pk, device=device), hit=False)
+        _SUBJECT_CACHE[key] = e
+        while len(_SUBJECT_CACHE) > SUBJECT_CACHE_SIZE:
+            _, old = _SUBJECT_CACHE.popitem(last=False)
+            old['model'].close()
+    else:
+        _SUBJECT_CACHE.move_to_end(key)
+        e['hit'] = True
+        for k in ('optimize_fingers', 'optimize_face'):          # the gating side effect of prepare_stageii (chmosh.py:475-486)
+            if not e['flags'][k] and bool(_get(cfg.moshpp, k, False)):
+                try:
+                    cfg.moshpp[k] = False
+                except Exception:
+                    pass
+    return e['pk'], e['opts'], dict(e['flags']), e['model'], e['hit']
 
 
 def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname=None):
@@ -318,7 +389,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
                  marker_meta: dict, v_template_fname=None, *, device: int = 0, mode: str = 'fast',
                  chunk_len: Optional[int] = None, chunk_warmup: Optional[int] = None, warmup_full: Optional[int] = None,
                  precision: Optional[str] = None, verify: bool = True, boundary_tol=None,
-                 sm_budget: int = NUM_SMS_B200, labels_map='general') -> dict:
+                 sm_budget: int = NUM_SMS_B200, labels_map='general', subject_cache: bool = True) -> dict:
     """Stage II of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:458-459).
 
     Keyword-only extras.  ``mode``: 'fast' (default) = float32, chunked in time with a verified warm-up -- within
@@ -327,7 +398,9 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     warm-up, tight boundary check.  ``chunk_len`` (None = planned, 0 = the reference's single sequential pass in one
     thread block), ``chunk_warmup`` / ``warmup_full`` (mosh2_schedule, include/mosh2.h), ``precision`` 'f32' | 'f64',
     ``verify`` / ``boundary_tol`` override the mode's presets.  ``labels_map``: 'general' (default) = the synonym table
-    the reference always applies (chmosh.py:466), a dict, or None for raw labels.
+    the reference always applies (chmosh.py:466), a dict, or None for raw labels.  ``subject_cache``: keep the packed
+    per-subject constants and their device copy for the next sequences of the same subject (keyed by the content of every
+    input; nothing sequence-dependent is cached).
     """
     t0 = time.time()
     lap = {}
@@ -344,7 +417,11 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
                          labels_map=labels_map,
                          only_subjects=[cfg.mocap.subject_name] if cfg.mocap.multi_subject else None)
     mark('read_mocap_ms')
-    pk, opts, flags = prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname)
+    if subject_cache:
+        pk, opts, flags, model, cache_hit = subject_for(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname, device)
+    else:
+        pk, opts, flags = prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_template_fname)
+        model, cache_hit = None, False
     mark('prepare_ms')
     dyn = bool(opts.optimize_dynamics)
     w_def, wf_def, prec_def, tol_def = default_schedule(pk.model_type, mode, pk.n_dmpl)
@@ -367,7 +444,9 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     prec = {'f32': _lib.MOSH2_F32, 'f64': _lib.MOSH2_F64}[precision]
     mark('dense_view_ms')
 
-    model = _lib.Model(pk, device=device)
+    own_model = model is None
+    if own_model:
+        model = _lib.Model(pk, device=device)
     mark('model_create_ms')
     try:
         job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec)
@@ -381,7 +460,8 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         finally:
             job.close()
     finally:
-        model.close()
+        if own_model:
+            model.close()
 
     mark('close_ms')
     data = assemble_stageii_data(res, obs, vis, latent_labels, pk, flags, dyn)
@@ -396,7 +476,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         'b200': {
             'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
             'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'mode': mode,
-            'boundary_check': report, 'totals': totals, 'host_ms': lap, 'status': res.status.copy(),
+            'boundary_check': report, 'totals': totals, 'host_ms': lap, 'subject_cache_hit': cache_hit, 'status': res.status.copy(),
             'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
             'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
         },
