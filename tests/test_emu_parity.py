@@ -177,3 +177,33 @@ def test_resumed_chunks_continue_the_sequential_recursion(cases, emu, name):
     assert np.array_equal(res.pose, seq.pose) and np.array_equal(res.trans, seq.trans) and np.array_equal(res.errs, seq.errs)
     if pk.n_dmpl:
         assert np.array_equal(res.dmpls, seq.dmpls)
+
+
+def test_rank_deficient_frames_are_flagged_and_recovered(cases, emu):
+    """A first frame seen through one marker (and a second through two) leaves the root orientation unobserved: the
+    Gauss-Newton system is numerically singular.  chumpy solves such a system with LU / lstsq (an arbitrary null-space
+    component, clipped by the trust region: there is no result to be faithful to); the kernel's Cholesky declares it
+    not positive definite, takes the Cauchy step and says so (MOSH2_ST_GN_FALLBACK).  Both stay finite, and once the
+    markers are back the recursion pulls the two solutions together again."""
+    from conftest import dense_obs
+    from moshpp_b200.mocap_interface import MocapSession
+    from oracle import stageii
+    case = cases('C1')
+    obs, vis = dense_obs(case)
+    vis = vis.copy()
+    vis[0, 1:] = False
+    vis[1, 2:] = False
+    res = emu(case, obs_vis=(obs, vis))
+    assert (res.status[:2] & lib.ST_GN_FALLBACK).all() and not (res.status[2:] & lib.ST_GN_FALLBACK).any()
+    assert (res.status & lib.ST_SOLVED).all() and np.isfinite(res.pose).all() and np.isfinite(res.errs).all()
+    mocap = MocapSession(case['mocap_fname'], case['cfg'].mocap.unit)
+    col = {l: i for i, l in enumerate(mocap.labels)}
+    for f, keep in ((0, 1), (1, 2)):
+        for l in case['latent_labels'][keep:]:
+            mocap.markers[f, col[l]] = 0.0
+    ref = stageii.mosh_stageii(case['mocap_fname'], case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'],
+                               case['marker_meta'], mocap=mocap)
+    d = np.abs(res.pose - ref['_pose_reduced']).max(1)
+    sse = ref['stageii_debug_details']['stageii_errs']['data']
+    assert d[-1] < 0.1 * d[2] or d[-1] < 1e-2                  # the difference decays once all markers are seen
+    assert np.abs(res.errs[-3:, 0] / sse[-3:] - 1).max() < 0.05
