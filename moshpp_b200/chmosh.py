@@ -239,11 +239,37 @@ def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_te
     return pk, opts, flags
 
 
+def observation_lists(obs: np.ndarray, vis: np.ndarray, latent_labels) -> dict:
+    """The result-independent half of chmosh.py:712-718: per-frame lists of the observed markers and their labels over the
+    frames with at least one visible marker (the frames the reference solves, chmosh.py:586-588).  Computed on the host
+    while the device solves (``mosh_stageii``); ``assemble_stageii_data`` builds it itself when it is not handed over."""
+    fid = np.nonzero(vis.any(1))[0]
+    vf = vis[fid]
+    cnt = vf.sum(1)
+    ends = np.cumsum(cnt)
+    starts = ends - cnt
+    obs_cat = obs[fid][vf]
+    labels = np.asarray(latent_labels, dtype=object)
+    # the label lists are built once per visibility pattern (drop-outs come in runs) and copied
+    by_pattern: dict = {}
+    labels_obs = []
+    for row in vf:
+        key = row.tobytes()
+        names = by_pattern.get(key)
+        if names is None:
+            names = by_pattern[key] = labels[row].tolist()
+        labels_obs.append(list(names))
+    return {'fid': fid, 'vf': vf, 'starts': starts, 'ends': ends, 'labels_obs': labels_obs,
+            'markers_obs': [obs_cat[a:b] for a, b in zip(starts, ends)]}
+
+
 def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.ndarray, latent_labels, pk,
-                          flags, dyn: bool) -> dict:
+                          flags, dyn: bool, lists: Optional[dict] = None) -> dict:
     """chmosh.py:712-741: per-frame lists over the frames that had at least one visible marker."""
     solved = (res.status & _lib.ST_SOLVED) != 0
     fid = np.nonzero(solved)[0]
+    if lists is None or not np.array_equal(lists['fid'], fid):
+        lists = observation_lists(obs, np.logical_and(vis, solved[:, None]), latent_labels)
     st = res.status[fid]
     errs = {'data': res.errs[fid, 0]}
     if pk.prior_k:
@@ -261,7 +287,6 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         errs['extrap_dmpl'] = res.errs[fid, 5][(st & _lib.ST_HAS_EXTRAP) != 0]
     errs['velo'] = res.errs[fid, 2][(st & _lib.ST_HAS_VELO) != 0]
     errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseB_jangles', 'poseH', 'dmpl', 'poseF', 'expr') or len(v)}
-    labels = np.asarray(latent_labels, dtype=object)
     data = {
         'fullpose': res.fullpose[fid].copy(),
         'trans': res.trans[fid].copy(),
@@ -275,25 +300,13 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         expr = np.zeros((len(fid), tail))
         expr[:, :pk.n_expr] = res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl]
         data['expression'] = expr
-    # per-frame lists over the visible markers (chmosh.py:716-718): one gather per array, cut into per-frame views; the
-    # label lists are built once per visibility pattern (drop-outs come in runs) and copied
-    vf = vis[fid]
-    ends = np.cumsum(vf.sum(1))
-    starts = ends - vf.sum(1)
-    sim_cat, obs_cat = res.markers_sim[fid][vf], obs[fid][vf]
-    by_pattern: dict = {}
-    labels_obs = []
-    for row in vf:
-        key = row.tobytes()
-        names = by_pattern.get(key)
-        if names is None:
-            names = by_pattern[key] = labels[row].tolist()
-        labels_obs.append(list(names))
+    # per-frame lists over the visible markers (chmosh.py:716-718): one gather, cut into per-frame views
+    sim_cat = res.markers_sim[fid][lists['vf']]
     data['stageii_debug_details'] = {
         'stageii_errs': errs,
-        'markers_sim': [sim_cat[a:b] for a, b in zip(starts, ends)],
-        'markers_obs': [obs_cat[a:b] for a, b in zip(starts, ends)],
-        'labels_obs': labels_obs,
+        'markers_sim': [sim_cat[a:b] for a, b in zip(lists['starts'], lists['ends'])],
+        'markers_obs': lists['markers_obs'],
+        'labels_obs': lists['labels_obs'],
     }
     return data
 
@@ -325,11 +338,14 @@ def default_schedule(model_type: str, mode: str = 'fast', n_linear: int = 0):
     return DEFAULT_WARMUP, DEFAULT_WARMUP_FULL, 'f32', BOUNDARY_TOL['fast']
 
 
-def launch_verified(job, tol, max_rounds: int = 12):
+def launch_verified(job, tol, max_rounds: int = 12, while_running=None):
     """Launch + boundary check + repair rounds on the observations the job already holds (device work only; see
     ``solve_verified``).  Returns (chunk ids still over tolerance, report); report['kernel_ms'] lists the device time of
-    every launch (CUDA events on the job's stream)."""
+    every launch (CUDA events on the job's stream).  ``while_running``: host work to do behind the (asynchronous) first
+    launch, before the first wait on the device."""
     job.launch()
+    if while_running is not None:
+        while_running()
     report = {'rounds': 0, 'repaired_chunks': [], 'boundary_delta_first': None, 'boundary_delta_max': None, 'unverified_chunks': 0}
     kernel_ms = []
     bad = np.zeros(0, dtype=np.int64)
@@ -361,7 +377,7 @@ def launch_verified(job, tol, max_rounds: int = 12):
     return bad, report
 
 
-def solve_verified(job, obs, vis, *, tol, max_rounds: int = 12):
+def solve_verified(job, obs, vis, *, tol, max_rounds: int = 12, while_running=None):
     """Upload + launch + download, then the boundary check of the chunked schedule and its repair.
 
     Every chunk reports the state it reached on its last warm-up frame; the emitted result of that frame comes from the
@@ -372,7 +388,7 @@ def solve_verified(job, obs, vis, *, tol, max_rounds: int = 12):
     failing chunks are repaired in consecutive rounds (a chunk must not read rows that are being rewritten).  Chunks that
     still fail after ``max_rounds`` keep MOSH2_ST_SHORT_WARMUP on their frames.  Returns (ResultArrays, report)."""
     job.upload(obs, vis)
-    bad, report = launch_verified(job, tol, max_rounds)
+    bad, report = launch_verified(job, tol, max_rounds, while_running)
     res = job.download()
     if len(bad):
         report['unverified_chunks'] = int(len(bad))
@@ -452,8 +468,19 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec)
         mark('job_create_ms')
         try:
-            res, report = solve_verified(job, obs, vis, tol=boundary_tol if verify else None)
+            # the result-independent half of the output (per-frame observation / label lists, the copy of the original
+            # markers) is put together on the host while the device solves
+            side = {}
+
+            def host_side():
+                t_side = time.perf_counter()
+                side['lists'] = observation_lists(obs, vis, latent_labels)
+                side['markers_orig'] = mocap.markers[selected_frames]
+                side['ms'] = (time.perf_counter() - t_side) * 1e3
+
+            res, report = solve_verified(job, obs, vis, tol=boundary_tol if verify else None, while_running=host_side)
             mark('solve_ms')
+            lap['overlapped_host_ms'] = side.get('ms', 0.0)
             kernel_ms = float(sum(report['kernel_ms']))
             n_chunks = job.num_chunks
             totals = job.totals()
@@ -464,11 +491,11 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
             model.close()
 
     mark('close_ms')
-    data = assemble_stageii_data(res, obs, vis, latent_labels, pk, flags, dyn)
+    data = assemble_stageii_data(res, obs, vis, latent_labels, pk, flags, dyn, side.get('lists'))
     mark('assemble_ms')
     dbg = data['stageii_debug_details']
     dbg.update({
-        'markers_orig': mocap.markers[selected_frames],
+        'markers_orig': side['markers_orig'] if 'markers_orig' in side else mocap.markers[selected_frames],
         'labels_orig': mocap.labels,
         'mocap_fname': mocap_fname,
         'mocap_frame_rate': mocap.frame_rate,

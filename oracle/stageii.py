@@ -472,6 +472,8 @@ def mosh_stageii(mocap_fname, cfg, markers_latent, latent_labels, betas, marker_
                         full_from = lo
             while lo < s and frames[lo] is None:
                 lo += 1
+            if cnt < W and cnt <= W_full + (W - W_full) // 4:
+                full_from = lo      # the walk-back reached the first frame: the chunk is the sequential recursion itself
             solver.reset()
             res = solver.solve_range(frames[lo:s + L], emit_from=s - lo, light_until=full_from - lo)
             for r in res:

@@ -207,3 +207,16 @@ def test_rank_deficient_frames_are_flagged_and_recovered(cases, emu):
     sse = ref['stageii_debug_details']['stageii_errs']['data']
     assert d[-1] < 0.1 * d[2] or d[-1] < 1e-2                  # the difference decays once all markers are seen
     assert np.abs(res.errs[-3:, 0] / sse[-3:] - 1).max() < 0.05
+
+
+def test_chunks_that_reach_the_sequence_start_are_exact(cases, emu):
+    """A chunk whose warm-up walk-back runs into the first frame of the sequence solves those frames fully (as long as that
+    costs no more than a regular warm-up): it is the reference's own recursion from its own start, so its rows equal the
+    single sequential pass bit for bit.  The first chunk with a complete warm-up window keeps its light frames."""
+    case = cases('C2')
+    seq = emu(case)
+    res = emu(case, chunk_len=4, warmup=12, warmup_full=8)
+    assert np.array_equal(res.pose[:12], seq.pose[:12]) and np.array_equal(res.trans[:12], seq.trans[:12])
+    assert np.array_equal(res.errs[:12], seq.errs[:12])
+    d = np.abs(res.pose[12:] - seq.pose[12:]).max()
+    assert 0 < d < 1e-1
