@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOSH2_VERSION 102
+#define MOSH2_VERSION 103
 
 enum {
     MOSH2_OK = 0,
@@ -146,6 +146,16 @@ int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_s
                            const mosh2_schedule *sched, int32_t precision, mosh2_job **out);
 /* obs [F*M*3] metres in latent-label order, vis [F*M] 0/1.  Async on the job's stream. */
 int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis);
+/* Mocap input adapter on the device -- what the reference does per frame in Python between the capture file and the frame
+ * loop (tools/mocap_interface.py:186,223-225,254-279 MocapSession / markers_asdict; chmosh.py:582-594).  `markers`: the raw
+ * marker table of the file, host memory, [n_file_frames][n_cols][3] float64 in file units; `col_of_marker` [M]: the file
+ * column that carries latent marker i's label after the label clean-up (-1: the file has no such label); job frame f is
+ * file frame frame_start + f * frame_step; `unit_per_metre` 1000 / 100 / 1 (mocap.unit); `rot3x3`: optional row-major
+ * rotation applied before the unit conversion (mocap.rotate), NULL for none.  A sample is missing when a coordinate is NaN
+ * or all three are exactly zero.  The table goes through pinned staging to the device, one kernel writes the job's
+ * observations (metres, compute precision) and visibility.  Async on the job's stream; replaces mosh2_job_upload. */
+int mosh2_job_upload_markers(mosh2_job *j, const double *markers, int32_t n_file_frames, int32_t n_cols, const int32_t *col_of_marker,
+                             int32_t frame_start, int32_t frame_step, double unit_per_metre, const double *rot3x3);
 /* The same from DEVICE memory (e.g. the receive buffer of an NCCL scatter): d_obs [F*M*3] float32 (obs_f64 = 0) or
  * float64 (obs_f64 = 1) on the job's device, d_vis [F*M]; converted to the job's precision on the device.  The
  * copy is ordered after the work already queued on `producer_stream` (a cudaStream_t, may be NULL = legacy stream). */

@@ -34,7 +34,7 @@ import numpy as np
 
 from . import lib as _lib
 from . import pack as _pack
-from .mocap_interface import MocapSession
+from .mocap_interface import MocapSession, rotation_xyz as _rotation_xyz
 
 logger = logging.getLogger('moshpp_b200')
 
@@ -387,7 +387,8 @@ def solve_verified(job, obs, vis, *, tol, max_rounds: int = 12, while_running=No
     (mosh2_job_relaunch_chunks, chunk_warmup < 0).  A repair round costs one chunk length, not a warm-up.  Neighbouring
     failing chunks are repaired in consecutive rounds (a chunk must not read rows that are being rewritten).  Chunks that
     still fail after ``max_rounds`` keep MOSH2_ST_SHORT_WARMUP on their frames.  Returns (ResultArrays, report)."""
-    job.upload(obs, vis)
+    if obs is not None:          # (None: the caller has uploaded already, e.g. through Job.upload_markers)
+        job.upload(obs, vis)
     bad, report = launch_verified(job, tol, max_rounds, while_running)
     res = job.download()
     if len(bad):
@@ -405,7 +406,8 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
                  marker_meta: dict, v_template_fname=None, *, device: int = 0, mode: str = 'fast',
                  chunk_len: Optional[int] = None, chunk_warmup: Optional[int] = None, warmup_full: Optional[int] = None,
                  precision: Optional[str] = None, verify: bool = True, boundary_tol=None,
-                 sm_budget: int = NUM_SMS_B200, labels_map='general', subject_cache: bool = True) -> dict:
+                 sm_budget: int = NUM_SMS_B200, labels_map='general', subject_cache: bool = True,
+                 device_adapter: bool = True) -> dict:
     """Stage II of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:458-459).
 
     Keyword-only extras.  ``mode``: 'fast' (default) = float32, chunked in time with a verified warm-up -- within
@@ -416,7 +418,8 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     ``verify`` / ``boundary_tol`` override the mode's presets.  ``labels_map``: 'general' (default) = the synonym table
     the reference always applies (chmosh.py:466), a dict, or None for raw labels.  ``subject_cache``: keep the packed
     per-subject constants and their device copy for the next sequences of the same subject (keyed by the content of every
-    input; nothing sequence-dependent is cached).
+    input; nothing sequence-dependent is cached).  ``device_adapter``: the mocap input adapter (missing-sample rule, label
+    order, units) runs on the GPU from the raw marker table of the file; False = on the host in front of the solve.
     """
     t0 = time.time()
     lap = {}
@@ -449,8 +452,20 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
 
     end = len(mocap) if cfg.mocap.end_fidx == -1 else cfg.mocap.end_fidx
     selected_frames = range(cfg.mocap.start_fidx, end, cfg.mocap.ds_rate)                         # chmosh.py:539-540
-    obs, vis = mocap.frames_for_labels(list(latent_labels), selected_frames)
-    F = obs.shape[0]
+    # Input adapter.  Normally on the device: the raw marker table of the file goes up as it is and one kernel produces the
+    # observations and the visibility mask (mosh2_job_upload_markers); the host copy of the same clean-up -- needed for the
+    # output dictionary only -- is made behind the solve.  Labels that own several columns, and frame selections that are
+    # not a forward range inside the file, take the host path (``frames_for_labels``) in front of the solve.
+    raw_cols = mocap.raw_columns_for_labels(list(latent_labels)) if device_adapter else None
+    if raw_cols is not None and not (len(selected_frames) and selected_frames.step > 0 and selected_frames.start >= 0
+                                     and selected_frames[-1] < len(mocap)):
+        raw_cols = None
+    if raw_cols is None:
+        obs, vis = mocap.frames_for_labels(list(latent_labels), selected_frames)
+        F = obs.shape[0]
+    else:
+        obs = vis = None
+        F = len(selected_frames)
     if F == 0:
         raise ValueError('no frames selected')
     if chunk_len is None:
@@ -474,11 +489,18 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
 
             def host_side():
                 t_side = time.perf_counter()
-                side['lists'] = observation_lists(obs, vis, latent_labels)
+                if raw_cols is not None:
+                    side['obs'], side['vis'] = mocap.frames_for_labels(list(latent_labels), selected_frames)
+                side['lists'] = observation_lists(side.get('obs', obs), side.get('vis', vis), latent_labels)
                 side['markers_orig'] = mocap.markers[selected_frames]
                 side['ms'] = (time.perf_counter() - t_side) * 1e3
 
+            if raw_cols is not None:
+                rot = None if cfg.mocap.rotate is None else _rotation_xyz(cfg.mocap.rotate)
+                job.upload_markers(mocap.raw, raw_cols, selected_frames.start, selected_frames.step, mocap.unit_per_metre, rot)
             res, report = solve_verified(job, obs, vis, tol=boundary_tol if verify else None, while_running=host_side)
+            if raw_cols is not None:
+                obs, vis = side['obs'], side['vis']
             mark('solve_ms')
             lap['overlapped_host_ms'] = side.get('ms', 0.0)
             kernel_ms = float(sum(report['kernel_ms']))
@@ -503,7 +525,11 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         'b200': {
             'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
             'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'mode': mode,
-            'boundary_check': report, 'totals': totals, 'host_ms': lap, 'subject_cache_hit': cache_hit, 'status': res.status.copy(),
+            'boundary_check': report, 'totals': totals, 'host_ms': lap, 'subject_cache_hit': cache_hit,
+            'device_adapter': raw_cols is not None,
+            'h2d_bytes': int(((F - 1) * selected_frames.step + 1) * mocap.raw.shape[1] * 24 + 4 * len(latent_labels)) if raw_cols is not None
+            else int(obs.size * (4 if precision == 'f32' else 8) + vis.size),
+            'status': res.status.copy(),
             'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
             'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
         },

@@ -184,8 +184,10 @@ struct DevModel {
         for (int i = 0; i < d.n_jangles && i < mosh2::kMaxJangles; ++i) { m.jang_id[i] = d.jangles_ids[i]; m.jang_sign[i] = real(d.jangles_signs[i]); }
         int rc;
         if ((rc = up<int>(d.parents, nJ, &m.parents))) return rc;
+        std::vector<int> order(nJ), ids(d.prior_d);
+        std::vector<double> hct;
         {   // joints sorted by depth (stable): parents before children
-            std::vector<int> depth(nJ, 0), order(nJ);
+            std::vector<int> depth(nJ, 0);
             for (size_t j = 0; j < nJ; ++j) { int dj = 0; for (int a = d.parents[j]; a >= 0; a = d.parents[a]) ++dj; depth[j] = dj; }
             for (size_t j = 0; j < nJ; ++j) order[j] = int(j);
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return depth[a] < depth[b]; });
@@ -193,7 +195,6 @@ struct DevModel {
         }
         if ((rc = up<int>(d.w_joint, S * d.kw, &m.w_joint))) return rc;
         {   // dense blocks of the hand-PCA matrix (rows with the same non-zero column range), stored transposed
-            std::vector<double> hct;
             mosh2::HandBlock blocks[mosh2::kMaxHandBlocks];
             const int nb = mosh2_host::hand_blocks(d.hand_comps, d.n_hand_red, d.n_hand_full, blocks, hct);
             m.hb_n = nb;
@@ -241,12 +242,27 @@ struct DevModel {
         }
         if ((rc = up<real>(d.prior_neglogw, d.prior_k, &m.prior_nlw))) return rc;
         {
-            std::vector<int> ids(d.prior_d);
             for (int i = 0; i < d.prior_d; ++i) ids[i] = d.prior_ids ? d.prior_ids[i] : d.prior_off + i;
             if ((rc = up<int>(ids.data(), ids.size(), &m.prior_ids))) return rc;
         }
         if ((rc = up<int>(d.free1, d.n_free1, &m.free1))) return rc;
         if ((rc = up<int>(d.free2, d.n_free2, &m.free2))) return rc;
+        {   // image of the staged shared-memory tables (mosh2::carve / stage_image): what a chunk fetches with one bulk copy
+            const mosh2::Dims dd = mosh2::make_dims(m);
+            mosh2::Work<real, false> w{};
+            mosh2::Arena S{mosh2::kSmemHeader}, G{0};
+            mosh2::carve<real, false>(w, dd, m, S, G);
+            std::vector<unsigned char> img(w.stage_bytes, 0);
+            const int *isrc[6] = {d.parents, order.data(), d.w_joint, d.free1, d.free2, ids.data()};
+            const double *rsrc[9] = {d.w_val, d.v0, d.coefs, d.j0, d.hands_mean, d.prior_means, d.prior_neglogw, d.jd, hct.data()};
+            mosh2::stage_image(w, dd, m.hct_size, m.n_hand_full, [&](uint32_t ofs, int id, size_t n) {
+                if (id < 6) { int *o = reinterpret_cast<int *>(img.data() + ofs); for (size_t i = 0; i < n; ++i) o[i] = isrc[id][i]; }
+                else { real *o = reinterpret_cast<real *>(img.data() + ofs); for (size_t i = 0; i < n; ++i) o[i] = real(rsrc[id - 6][i]); }
+            });
+            const unsigned char *blob = nullptr;
+            if ((rc = up<unsigned char>(img.data(), img.size(), &blob))) return rc;
+            m.stage_blob = blob;
+        }
         return 0;
     }
 };
@@ -302,6 +318,36 @@ __global__ void boundary_delta_kernel(const real *__restrict__ warm_x, const int
         for (int o = 16; o > 0; o >>= 1) v[q] = fmaxf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
         if (lane == 0) out[4 * c + q] = v[q];
     }
+}
+
+// Mocap input adapter on the device (tools/mocap_interface.py:186,223-225,254-279; chmosh.py:582-594): from the raw marker
+// table of a capture file [file frame][file column][xyz] (file units, float64) to the job's observations [frame][marker][xyz]
+// (metres, compute precision) and visibility.  A sample is missing when a coordinate is NaN or all three are exactly zero
+// (:277); such samples -- and markers whose label the file does not have (col < 0) -- are invisible and stored as zero.
+template <class real>
+__global__ void gather_markers_kernel(const double *__restrict__ raw, int n_cols, const int *__restrict__ col_of_marker, int M,
+                                      int n_frames, int frame_step, double unit_per_metre, const double *__restrict__ rot,
+                                      real *__restrict__ obs, uint8_t *__restrict__ vis) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= size_t(n_frames) * M) return;
+    const int f = int(i / M), mk = int(i - size_t(f) * M), col = col_of_marker[mk];
+    double x = 0, y = 0, z = 0;
+    bool ok = false;
+    if (col >= 0) {
+        const double *p = raw + (size_t(f) * frame_step * n_cols + col) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+        ok = !(isnan(x) || isnan(y) || isnan(z)) && !(x == 0.0 && y == 0.0 && z == 0.0);
+    }
+    if (!ok) { x = y = z = 0; }
+    else {
+        if (rot) {      // mocap.rotate: the points turned by Rz Ry Rx before the unit conversion (mocap_interface.py:218-221)
+            const double rx = rot[0] * x + rot[1] * y + rot[2] * z, ry = rot[3] * x + rot[4] * y + rot[5] * z, rz = rot[6] * x + rot[7] * y + rot[8] * z;
+            x = rx; y = ry; z = rz;
+        }
+        x = x / unit_per_metre; y = y / unit_per_metre; z = z / unit_per_metre;
+    }
+    obs[3 * i] = real(x); obs[3 * i + 1] = real(y); obs[3 * i + 2] = real(z);
+    vis[i] = ok ? 1 : 0;
 }
 
 // Host copy of a model description: the caller's buffers need not outlive mosh2_model_create, and the device copy of a
@@ -381,6 +427,9 @@ struct mosh2_job {
     // pinned staging
     void *h_obs = nullptr, *h_out = nullptr;
     uint8_t *h_vis = nullptr;
+    void *h_raw = nullptr, *d_raw = nullptr;     // raw marker table of mosh2_job_upload_markers (pinned staging, device copy)
+    int *d_cols = nullptr;
+    size_t raw_bytes = 0;
     int *h_status = nullptr, *h_counters = nullptr;
     size_t n_obs = 0, n_out = 0;
     size_t o_fullpose = 0, o_pose = 0, o_trans = 0, o_dmpls = 0, o_mk = 0, o_errs = 0;   // element offsets in d_out
@@ -632,6 +681,45 @@ int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis) {
     return 0;
 }
 
+int mosh2_job_upload_markers(mosh2_job *j, const double *markers, int32_t n_file_frames, int32_t n_cols, const int32_t *col_of_marker,
+                             int32_t frame_start, int32_t frame_step, double unit_per_metre, const double *rot3x3) {
+    if (!j || !markers || !col_of_marker) return fail(MOSH2_E_INVALID, "null argument");
+    const int F = j->n_frames, M = j->model->n_markers;
+    if (n_cols < 1 || frame_step < 1 || frame_start < 0 || !(unit_per_metre > 0) ||
+        size_t(frame_start) + size_t(F - 1) * frame_step >= size_t(n_file_frames))
+        return fail(MOSH2_E_INVALID, "frames %d + k*%d (k < %d) do not fit a file of %d frames", frame_start, frame_step, F, n_file_frames);
+    for (int i = 0; i < M; ++i)
+        if (col_of_marker[i] >= n_cols) return fail(MOSH2_E_INVALID, "marker %d: column %d of %d", i, col_of_marker[i], n_cols);
+    CU(cudaSetDevice(j->model->device));
+    const int dv = j->model->device;
+    // the rows [frame_start, last used frame] of the table, whole (all columns), through pinned staging
+    const size_t rows = size_t(F - 1) * frame_step + 1, bytes = rows * n_cols * 3 * sizeof(double), extra = 16 * sizeof(double);
+    if (bytes + extra > j->raw_bytes) {
+        g_blocks.put(-1, j->h_raw); g_blocks.put(dv, j->d_raw);
+        j->h_raw = j->d_raw = nullptr; j->raw_bytes = 0;
+        CU(g_blocks.get(-1, bytes + extra, &j->h_raw));
+        CU(g_blocks.get(dv, bytes + extra, &j->d_raw));
+        j->raw_bytes = bytes + extra;
+    }
+    if (!j->d_cols) CU(g_blocks.get(dv, size_t(M) * sizeof(int), reinterpret_cast<void **>(&j->d_cols)));
+    CU(cudaStreamSynchronize(j->stream));          // (the staging buffers may still feed an earlier upload)
+    char *h = static_cast<char *>(j->h_raw);
+    memcpy(h, markers + size_t(frame_start) * n_cols * 3, bytes);
+    if (rot3x3) memcpy(h + bytes, rot3x3, 9 * sizeof(double));
+    CU(cudaMemcpyAsync(j->d_raw, h, bytes + (rot3x3 ? 9 * sizeof(double) : 0), cudaMemcpyHostToDevice, j->stream));
+    CU(cudaMemcpyAsync(j->d_cols, col_of_marker, size_t(M) * sizeof(int), cudaMemcpyHostToDevice, j->stream));
+    const size_t n = size_t(F) * M;
+    const int blocks = int((n + 255) / 256);
+    const double *d_raw = static_cast<const double *>(j->d_raw);
+    const double *d_rot = rot3x3 ? reinterpret_cast<const double *>(static_cast<const char *>(j->d_raw) + bytes) : nullptr;
+    if (j->precision == MOSH2_F64)
+        gather_markers_kernel<double><<<blocks, 256, 0, j->stream>>>(d_raw, n_cols, j->d_cols, M, F, frame_step, unit_per_metre, d_rot, static_cast<double *>(j->d_obs), j->d_vis);
+    else
+        gather_markers_kernel<float><<<blocks, 256, 0, j->stream>>>(d_raw, n_cols, j->d_cols, M, F, frame_step, unit_per_metre, d_rot, static_cast<float *>(j->d_obs), j->d_vis);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int mosh2_job_launch(mosh2_job *j) {
     if (!j) return fail(MOSH2_E_INVALID, "null job");
     CU(cudaSetDevice(j->model->device));
@@ -831,7 +919,9 @@ void mosh2_job_destroy(mosh2_job *j) {
                     static_cast<void *>(j->d_delta), j->d_obs, j->d_out, static_cast<void *>(j->d_vis), static_cast<void *>(j->d_status),
                     static_cast<void *>(j->d_counters), static_cast<void *>(j->d_totals), static_cast<void *>(j->d_prof), j->d_gws})
         g_blocks.put(dv, p);
-    for (void *p : {j->h_obs, j->h_out, static_cast<void *>(j->h_vis), static_cast<void *>(j->h_status), static_cast<void *>(j->h_counters)})
+    g_blocks.put(dv, j->d_raw);
+    g_blocks.put(dv, j->d_cols);
+    for (void *p : {j->h_obs, j->h_out, static_cast<void *>(j->h_vis), static_cast<void *>(j->h_status), static_cast<void *>(j->h_counters), j->h_raw})
         g_blocks.put(-1, p);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);

@@ -125,6 +125,8 @@ struct Model {
     real jang_sign[kMaxJangles];
     int tile_markers;           // markers per Jacobian tile (20 or 10: a warp owns ten), chosen by the host from the shared-memory budget
     int dev_no_tc;              // development switch (host): 1 = J^T J stays on the CUDA cores
+    const unsigned char *stage_blob;   // the small per-model tables laid out exactly like the staged region of the shared-memory
+                                       // workspace (carve(): Work::stage_ofs / stage_bytes); one bulk asynchronous copy per chunk
 };
 
 struct Options {
@@ -356,6 +358,7 @@ struct Work {
     SPtr<float> Xhi, Xlo;
     SPtr<unsigned long long> mbar;
     SPtr<unsigned int> tmem_slot;
+    uint32_t stage_ofs, stage_bytes;   // the staged per-model tables: one contiguous, 16-byte aligned region (c_parents ... hct)
     int tc_ok;                // the model qualifies (f32, workspace in shared memory, n2 <= kTcM)
     int tc;                   // set by the launcher: tensor cores in use
 };
@@ -405,6 +408,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(mbar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+// bulk asynchronous copy global -> shared memory (the TMA engine on a contiguous run; 16-byte aligned, size a multiple of
+// 16), completing on an mbarrier by byte count
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -438,7 +450,10 @@ M2_HD Dims make_dims(const Model<real> &m) {
     d.nJ = m.nJ; d.M = m.M; d.S = 3 * m.M; d.PF = 3 * m.nJ; d.PR = m.p_red; d.nd = m.nd;
     d.NX = 3 + m.p_red + m.nd; d.NCt = (m.n_hand_full + 3) & ~3;   /* columns of the full-pose hand tile Jt */ d.n1 = m.n1; d.n2 = m.n2;
     d.npad = (m.n2 + 3) & ~3;
-    d.ld = d.npad;              // Cholesky factor: rows are 16-byte aligned (vector read-modify-write of 4x4 tiles)
+    // Cholesky factor: rows are 16-byte aligned (vector read-modify-write of 4x4 tiles) and the row length is 4 mod 8
+    // words, so that the panel's one-row-per-thread 16-byte accesses (eight consecutive rows per quarter warp) fall into
+    // eight different groups of four banks (at 112 words every second row started in the same bank: 16-way conflicts)
+    d.ld = ((m.n2 + 7) & ~7) + 4;   // (and >= the last 8-column block, which the panel reads whole)
     d.ldp = d.npad + 4;         // row length of the transposed panel (one extra row: the right-hand side)
     d.lda = d.npad | 1;         // A: odd leading dimension, so row-strided and transposed tile accesses spread over banks
     d.K = m.prior_k; d.D = m.prior_d; d.D4 = m.prior_d4; d.kw = m.kw;
@@ -512,22 +527,47 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.Pn.ofs = S.take<real>(size_t(kCholNB) * d.ldp);
     w.g.ofs = S.take<real>(d.npad); w.Ag.ofs = S.take<real>(d.npad); w.dgn.ofs = S.take<real>(d.npad);
     w.d.ofs = S.take<real>(d.npad); w.tmp.ofs = S.take<real>(d.npad); w.ds.ofs = S.take<real>(d.npad);
-    w.red.ofs = S.take<real>(8 * 33); w.sc.ofs = S.take<real>(16); w.hct.ofs = S.take<real>(hct_size + 4);
+    w.red.ofs = S.take<real>(8 * 33); w.sc.ofs = S.take<real>(16);
     w.colmap.ofs = S.take<int>(d.NX); w.colsrc.ofs = S.take<int>(d.n2); w.jlist.ofs = S.take<int>(d.nJ); w.isc.ofs = S.take<int>(8);
     w.prof.ofs = S.take<long long>(32);
-    w.mbar.ofs = S.take<unsigned long long>(1); w.tmem_slot.ofs = S.take<unsigned int>(2);
+    w.mbar.ofs = S.take<unsigned long long>(2); w.tmem_slot.ofs = S.take<unsigned int>(2);   // mbar[0]: tensor-core tiles, mbar[1]: table staging
     w.vis.ofs = S.take<uint8_t>(d.M);
     // small per-model tables are always staged in shared memory (a dependent global load costs ~600 cycles and the
-    // kinematic-tree walk chains three of them per level); the larger ones stay in global memory / L2
+    // kinematic-tree walk chains three of them per level); the larger ones stay in global memory / L2.  The tables that
+    // are plain copies of model arrays -- kinematic tree, skinning joints and weights, shaped template rows, marker
+    // coefficients, joint positions and directions, prior means, hand-PCA blocks, free-variable lists -- form ONE
+    // contiguous region: the host library keeps a byte-identical image of it (Model::stage_blob, stage_image below) and a chunk
+    // fetches it with a single bulk asynchronous copy (cp.async.bulk completing on an mbarrier) instead of thirteen copy loops.
+    S.off = (S.off + 15) & ~size_t(15);
+    w.stage_ofs = uint32_t(S.off);
     w.c_parents.ofs = S.take<int>(d.nJ); w.c_fk_order.ofs = S.take<int>(d.nJ);
     w.c_wj.ofs = S.take<int>(d.S * d.kw); w.c_free1.ofs = S.take<int>(d.n1); w.c_free2.ofs = S.take<int>(d.n2);
     w.c_pids.ofs = S.take<int>(d.D + 1);
     w.c_wv.ofs = S.take<real>(d.S * d.kw); w.c_v0.ofs = S.take<real>(3 * d.S); w.c_coefs.ofs = S.take<real>(3 * d.M);
     w.c_j0.ofs = S.take<real>(3 * d.nJ); w.c_hmean.ofs = S.take<real>(m.n_hand_full + 1);
-    w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ); w.c_amask.ofs = S.take<uint8_t>(size_t(d.S) * d.nJ);
-    w.c_chain.ofs = S.take<uint32_t>(size_t(d.nJ) * (kMaxDepth / 4));
     w.c_pmeans.ofs = S.take<real>(d.K * d.D + 1); w.c_pnlw.ofs = S.take<real>(d.K + 1);
     w.c_jd.ofs = S.take<real>(size_t(3) * d.nJ * d.nd + 1);
+    w.hct.ofs = S.take<real>(hct_size + 4);
+    S.off = (S.off + 15) & ~size_t(15);
+    w.stage_bytes = uint32_t(S.off) - w.stage_ofs;
+    // tables the chunk derives itself
+    w.c_tin.ofs = S.take<int>(d.nJ); w.c_tsz.ofs = S.take<int>(d.nJ); w.c_amask.ofs = S.take<uint8_t>(size_t(d.S) * d.nJ);
+    w.c_chain.ofs = S.take<uint32_t>(size_t(d.nJ) * (kMaxDepth / 4));
+}
+
+// The host-side image of the staged region: every table converted to the compute precision at the offset carve() gave it
+// (relative to Work::stage_ofs).  `put(byte offset, table id, element count)` is supplied by the caller and copies table
+// `id` (0-5: int tables, 6-14: real tables, in the order below) from wherever it keeps it.
+template <class real, bool BIG, class Put>
+inline void stage_image(const Work<real, BIG> &w, const Dims &d, int hct_size, int n_hand_full, Put put) {
+    const uint32_t b = w.stage_ofs;
+    put(w.c_parents.ofs - b, 0, size_t(d.nJ)); put(w.c_fk_order.ofs - b, 1, size_t(d.nJ));
+    put(w.c_wj.ofs - b, 2, size_t(d.S) * d.kw); put(w.c_free1.ofs - b, 3, size_t(d.n1)); put(w.c_free2.ofs - b, 4, size_t(d.n2));
+    put(w.c_pids.ofs - b, 5, size_t(d.D));
+    put(w.c_wv.ofs - b, 6, size_t(d.S) * d.kw); put(w.c_v0.ofs - b, 7, size_t(3) * d.S); put(w.c_coefs.ofs - b, 8, size_t(3) * d.M);
+    put(w.c_j0.ofs - b, 9, size_t(3) * d.nJ); put(w.c_hmean.ofs - b, 10, size_t(n_hand_full));
+    put(w.c_pmeans.ofs - b, 11, size_t(d.K) * d.D); put(w.c_pnlw.ofs - b, 12, size_t(d.K));
+    put(w.c_jd.ofs - b, 13, size_t(3) * d.nJ * d.nd); put(w.hct.ofs - b, 14, size_t(hct_size));
 }
 
 // configuration of one minimisation (one ch.minimize call of the reference)
@@ -1156,6 +1196,9 @@ struct Solver {
                         const int a = w.jlist[ji];
                         real blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                         if (a >= 1) {
+                            // (requesting the NEXT joint's vectors here, right after E has consumed the current ones, was
+                            // measured slower: the loop is bound by instruction issue -- about 500 warp instructions per
+                            // joint, a quarter of them FMAs -- not by the latency of these loads)
                             const real *P = Pslot + size_t(a - 1) * 9 * es;
                             Vec4<real> pv[9];
 #pragma unroll
@@ -1492,13 +1535,23 @@ struct Solver {
     // out = A v for the full symmetric A: one warp per row, lanes along the row
     M2_D void symv(const real *v, real *out, int n) {
 #if M2_GPU
+        // four rows per warp at a time: their shuffle reductions (five dependent steps each) run interleaved
         const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
-        for (int i = warp; i < n; i += nwarp) {
-            const real *Ar = w.A + i * d.lda;
-            real s = 0;
-            for (int j = lane; j < n; j += 32) s += Ar[j] * v[j];
-            s = warp_sum(s);
-            if (lane == 0) out[i] = s;
+        for (int i0 = warp; i0 < n; i0 += 4 * nwarp) {
+            real s[4] = {0, 0, 0, 0};
+            for (int j = lane; j < n; j += 32) {
+                const real vj = v[j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const int i = i0 + q * nwarp; if (i < n) s[q] += w.A[i * d.lda + j] * vj; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const int i = i0 + q * nwarp; if (i < n) out[i] = s[q]; }
+            }
         }
         __syncthreads();
 #else
@@ -1683,17 +1736,37 @@ struct Solver {
                 if (i <= n) {
                     real *row = w.Lm + i * ld + k0;
                     real av[NB];
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) av[cc] = cc < kb ? row[cc] : real(0);
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) {
-                        real sacc = 0;
-#pragma unroll
-                        for (int pp = 0; pp <= cc; ++pp) sacc += av[pp] * Li[cc * NB + pp];
-                        xr[cc] = cc < kb ? sacc : real(0);
+                    {   // (k0 is a multiple of 8 and ld of 4: two aligned 16-byte loads; columns >= kb are masked below)
+                        const Vec4<real> a0 = ld4(row), a1 = ld4(row + 4);
+                        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
                     }
 #pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) row[cc] = xr[cc];
+                    for (int cc = 0; cc < NB; ++cc) if (cc >= kb) av[cc] = real(0);
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) {
+                        const Vec4<real> l0 = ld4(Li + cc * NB);
+                        real sacc = av[0] * l0.x;
+                        if (cc >= 1) sacc += av[1] * l0.y;
+                        if (cc >= 2) sacc += av[2] * l0.z;
+                        if (cc >= 3) sacc += av[3] * l0.w;
+                        if (cc >= 4) {
+                            const Vec4<real> l1 = ld4(Li + cc * NB + 4);
+                            sacc += av[4] * l1.x;
+                            if (cc >= 5) sacc += av[5] * l1.y;
+                            if (cc >= 6) sacc += av[6] * l1.z;
+                            if (cc >= 7) sacc += av[7] * l1.w;
+                        }
+                        xr[cc] = cc < kb ? sacc : real(0);
+                    }
+                    if (kb == NB) {
+                        Vec4<real> o0, o1;
+                        o0.x = xr[0]; o0.y = xr[1]; o0.z = xr[2]; o0.w = xr[3]; o1.x = xr[4]; o1.y = xr[5]; o1.z = xr[6]; o1.w = xr[7];
+                        *reinterpret_cast<Vec4<real> *>(row) = o0;
+                        *reinterpret_cast<Vec4<real> *>(row + 4) = o1;
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < NB; ++cc) if (cc < kb) row[cc] = xr[cc];
+                    }
                 }
 #pragma unroll
                 for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.ldp + i] = xr[cc];
@@ -2141,19 +2214,26 @@ struct Solver {
             M2_SYNC();
         }
         CTA_FOR(i, d.NX) w.x[i] = 0;
-        CTA_FOR(i, m.hct_size) w.hct[i] = m.hct[i];
-        CTA_FOR(i, d.nJ) { w.c_parents[i] = m.parents[i]; w.c_fk_order[i] = m.fk_order[i]; }
-        CTA_FOR(i, d.S * d.kw) { w.c_wj[i] = m.w_joint[i]; w.c_wv[i] = m.w_val[i]; }
-        CTA_FOR(i, d.n1) w.c_free1[i] = m.free1[i];
-        CTA_FOR(i, d.D) w.c_pids[i] = m.prior_ids[i];
-        CTA_FOR(i, d.n2) w.c_free2[i] = m.free2[i];
-        CTA_FOR(i, 3 * d.S) w.c_v0[i] = m.v0[i];
-        CTA_FOR(i, 3 * d.M) w.c_coefs[i] = m.coefs[i];
-        CTA_FOR(i, 3 * d.nJ) w.c_j0[i] = m.j0[i];
-        CTA_FOR(i, m.n_hand_full) w.c_hmean[i] = m.hands_mean[i];
-        CTA_FOR(i, 3 * d.nJ * d.nd) w.c_jd[i] = m.jd[i];
-        CTA_FOR(i, d.K * d.D) w.c_pmeans[i] = m.prior_means[i];
-        CTA_FOR(i, d.K) w.c_pnlw[i] = m.prior_nlw[i];
+        // the per-model tables: one bulk asynchronous copy of the host-built image (see carve()), waited for below
+#if M2_GPU
+        {
+            const uint32_t bar = tc::smem_u32(static_cast<unsigned long long *>(w.mbar) + 1);
+            if (cta.tid == 0) tc::mbar_init(bar, 1);
+            __syncthreads();
+            if (cta.tid == 0) {
+                // (the region was last touched through the generic proxy, by the previous chunk of this block at most:
+                // order those accesses before the asynchronous writes)
+                tc::fence_async_smem();
+                tc::mbar_expect_tx(bar, w.stage_bytes);
+                tc::bulk_g2s(tc::smem_u32(m2_smem() + w.stage_ofs), m.stage_blob, w.stage_bytes, bar);
+            }
+            tc::mbar_wait(bar, 0);
+            __syncthreads();
+            if (cta.tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+        }
+#else
+        for (uint32_t i = 0; i < w.stage_bytes; ++i) (m2_smem() + w.stage_ofs)[i] = m.stage_blob[i];
+#endif
         CTA_FOR(i, 32) w.prof[i] = 0;
         M2_SYNC();
         if (cta.tid == 0) {                                    // pre-order numbering of the kinematic tree

@@ -13,7 +13,7 @@ import numpy as np
 
 from .pack import StageIIPack
 
-ABI_VERSION = 102          # MOSH2_VERSION of include/mosh2.h that the ctypes structs below encode
+ABI_VERSION = 103          # MOSH2_VERSION of include/mosh2.h that the ctypes structs below encode
 MOSH2_F32, MOSH2_F64 = 0, 1
 ST_SOLVED, ST_SKIPPED, ST_HAS_VELO, ST_HAS_EXTRAP, ST_GN_FALLBACK, ST_MAXITER, ST_SHORT_WARMUP = 1, 2, 4, 8, 16, 32, 64
 ERR_NAMES = ('data', 'poseB', 'velo', 'poseH', 'dmpl', 'extrap_dmpl', 'poseF', 'expr')   # column order of mosh2_result.errs
@@ -112,6 +112,7 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_job_create.argtypes = [vp, C.POINTER(Options), C.c_int32, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
     lib.mosh2_job_create_batch.argtypes = [vp, C.POINTER(Options), C.c_int32, _i32p, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
     lib.mosh2_job_upload.argtypes = [vp, _f64p, _u8p]
+    lib.mosh2_job_upload_markers.argtypes = [vp, _f64p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_int32, C.c_double, _f64p]
     lib.mosh2_job_upload_device_range.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp]
     lib.mosh2_job_upload_device.argtypes = [vp, vp, C.c_int32, vp, vp]
     lib.mosh2_job_row_width.argtypes = [vp]
@@ -141,7 +142,7 @@ EXPORTED_SYMBOLS = (
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
     'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
     'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks',
-    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance')
+    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance', 'mosh2_job_upload_markers')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -301,6 +302,19 @@ class Job:
         vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
         self._keep = (obs, vis8)
         self.model._check(self.lib.mosh2_job_upload(self.handle, _ptr(obs, _f64p), _ptr(vis8, _u8p)), 'mosh2_job_upload')
+
+    def upload_markers(self, raw: np.ndarray, col_of_marker, frame_start: int, frame_step: int, unit_per_metre: float, rot3x3=None):
+        """The mocap input adapter on the device (mosh2_job_upload_markers): ``raw`` = the capture file's marker table
+        [file frames, file columns, 3] float64 in file units; ``col_of_marker[i]`` = file column of latent marker i (-1: absent);
+        job frame f = file frame frame_start + f * frame_step."""
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        cols = np.ascontiguousarray(col_of_marker, dtype=np.int32)
+        assert raw.ndim == 3 and raw.shape[2] == 3 and cols.shape == (self.model.pk.n_markers,)
+        rot = None if rot3x3 is None else np.ascontiguousarray(rot3x3, dtype=np.float64).reshape(3, 3)
+        self._keep = (raw, cols, rot)
+        self.model._check(self.lib.mosh2_job_upload_markers(self.handle, _ptr(raw, _f64p), raw.shape[0], raw.shape[1], _ptr(cols, _i32p),
+                                                            int(frame_start), int(frame_step), float(unit_per_metre),
+                                                            _ptr(rot, _f64p) if rot is not None else None), 'mosh2_job_upload_markers')
 
     def upload_device(self, d_obs_ptr: int, obs_is_f64: bool, d_vis_ptr: int, producer_stream: int = 0):
         """Observations already on this job's GPU (raw device pointers, e.g. ``tensor.data_ptr()`` of an NCCL receive

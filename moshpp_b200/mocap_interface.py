@@ -46,13 +46,18 @@ def general_labels_map() -> Dict[str, str]:
     return _synonyms
 
 
-def rotate_points_xyz(points: np.ndarray, rxyz_deg: Sequence[float]) -> np.ndarray:
-    """F x N x 3 points rotated by Rz Ry Rx (degrees), as human_body_prior's helper of the same name."""
+def rotation_xyz(rxyz_deg: Sequence[float]) -> np.ndarray:
+    """Rz Ry Rx for angles in degrees (human_body_prior's ``rotate_points_xyz`` convention)."""
     ax, ay, az = np.radians(np.asarray(rxyz_deg, dtype=np.float64).ravel()[:3])
     rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
     ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
     rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
-    return np.einsum('cd,fnd->fnc', rz @ ry @ rx, points)
+    return rz @ ry @ rx
+
+
+def rotate_points_xyz(points: np.ndarray, rxyz_deg: Sequence[float]) -> np.ndarray:
+    """F x N x 3 points rotated by Rz Ry Rx (degrees), as human_body_prior's helper of the same name."""
+    return np.einsum('cd,fnd->fnc', rotation_xyz(rxyz_deg), points)
 
 
 # --------------------------------------------------------------------------------------
@@ -176,26 +181,61 @@ class MocapSession:
                                   exclude_markers=exclude_markers, ignore_stared_labels=ignore_stared_labels,
                                   remove_label_before_colon=remove_label_before_colon)
         subjects = {n: m[table.keep] for n, m in subject_masks(raw_labels).items()}
-        markers = raw[:, table.keep]
-        markers[~self.marker_availability_mask(markers)] = 0.0
-        if mocap_rotate is not None:
-            markers = rotate_points_xyz(markers, mocap_rotate).reshape(markers.shape)
         labels = table.labels
+        raw_cols = np.nonzero(table.keep)[0]                # file column of every kept column
         if only_subjects:
             missing = [s for s in only_subjects if s not in subjects]
             if missing:      # the reference logs an error and leaves the session unread (read_status False)
                 return
             cols = np.logical_or.reduce([subjects[s] for s in only_subjects])
             subjects = {s: subjects[s][cols] for s in only_subjects}
-            markers = markers[:, cols]
+            raw_cols = raw_cols[cols]
             labels = [l for l, c in zip(labels, cols) if c]
-        self.markers = markers / UNIT_PER_METRE[mocap_unit]
+        # Everything above works on labels only.  The marker array itself -- missing samples zeroed, rotated, in metres --
+        # is put together on first use of ``markers`` (the device path uploads the raw table and does this on the GPU,
+        # so the clean-up of the host copy can run behind the solve).
+        self.raw = raw
+        self.raw_columns = raw_cols
+        self.unit_per_metre = UNIT_PER_METRE[mocap_unit]
+        self.mocap_rotate = mocap_rotate
+        self._markers: Optional[np.ndarray] = None
         self.labels = labels
         self.subject_mask = subjects
         self.subject_names = list(only_subjects) if only_subjects else sorted(subjects)
         self.multi_subject = sum(1 for s in self.subject_names if s != 'null') > 1
         self.frame_rate = 120. if rate is None else rate
         self.read_status = True
+
+    @property
+    def markers(self) -> np.ndarray:
+        """F x L x 3, metres, missing samples zeroed (tools/mocap_interface.py:223-233)."""
+        if self._markers is None:
+            markers = self.raw[:, self.raw_columns]
+            markers[~self.marker_availability_mask(markers)] = 0.0
+            if self.mocap_rotate is not None:
+                markers = rotate_points_xyz(markers, self.mocap_rotate).reshape(markers.shape)
+            self._markers = markers / self.unit_per_metre
+        return self._markers
+
+    @markers.setter
+    def markers(self, value: np.ndarray):
+        self._markers = value
+
+    def raw_columns_for_labels(self, latent_labels: Sequence[str]):
+        """File column of every latent label (-1: the file has no such label), for the device-side adapter
+        (``Job.upload_markers``).  Returns None when a label owns several columns (the per-frame "last available one wins"
+        rule is then applied on the host, ``frames_for_labels``)."""
+        columns: Dict[str, List[int]] = {}
+        for c, l in enumerate(self.labels):
+            columns.setdefault(l, []).append(c)
+        out = np.full(len(latent_labels), -1, dtype=np.int32)
+        for m, l in enumerate(latent_labels):
+            cols = columns.get(l, ())
+            if len(cols) > 1:
+                return None
+            if cols:
+                out[m] = self.raw_columns[cols[0]]
+        return out
 
     @staticmethod
     def marker_availability_mask(markers: np.ndarray) -> np.ndarray:
@@ -238,11 +278,11 @@ class MocapSession:
         return [{l: self.markers[t, c] for c, l in enumerate(self.labels) if ok[t, c]} for t in range(len(self))]
 
     def __len__(self):
-        return self.markers.shape[0]
+        return (self.raw if self._markers is None else self._markers).shape[0]
 
     def __getitem__(self, given):
         return self.markers[given]
 
     def time_length(self):
         assert self.frame_rate is not None, ValueError(f'mocap frame_rate is unknown: {self.mocap_fname}')
-        return self.markers.shape[0] / self.frame_rate
+        return len(self) / self.frame_rate

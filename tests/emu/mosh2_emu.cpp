@@ -100,6 +100,20 @@ struct HostModel {
         }
         m.free1 = up<int>(d.free1, d.n_free1);
         m.free2 = up<int>(d.free2, d.n_free2);
+        {   // image of the staged shared-memory tables, as the CUDA library builds it (mosh2.cu DevModel::build)
+            const mosh2::Dims dd = mosh2::make_dims(m);
+            mosh2::Work<real, false> w{};
+            mosh2::Arena S{mosh2::kSmemHeader}, G{0};
+            mosh2::carve<real, false>(w, dd, m, S, G);
+            std::vector<unsigned char> img(w.stage_bytes, 0);
+            const int *isrc[6] = {m.parents, m.fk_order, m.w_joint, m.free1, m.free2, m.prior_ids};
+            const real *rsrc[9] = {m.w_val, m.v0, m.coefs, m.j0, m.hands_mean, m.prior_means, m.prior_nlw, m.jd, m.hct};
+            mosh2::stage_image(w, dd, m.hct_size, m.n_hand_full, [&](uint32_t ofs, int id, size_t n) {
+                if (id < 6) std::memcpy(img.data() + ofs, isrc[id], n * sizeof(int));
+                else std::memcpy(img.data() + ofs, rsrc[id - 6], n * sizeof(real));
+            });
+            m.stage_blob = up<unsigned char>(img.data(), img.size());
+        }
     }
 };
 

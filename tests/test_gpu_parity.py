@@ -232,3 +232,30 @@ def test_drop_in_callable_with_the_horse_model(cases):
     for k in ('data', 'poseB', 'poseB_jangles'):
         assert np.allclose(e[k], r[k], rtol=1e-7, atol=1e-10)
     assert np.abs(out['fullpose'][:, 84:]).max() == 0          # tail, mouth and ears stay at rest
+
+
+@pytest.mark.parametrize('name', ['C1', 'C2'])
+def test_device_input_adapter_equals_host_adapter(cases, name):
+    """mosh2_job_upload_markers: the raw marker table of the capture file (c3d in mm for C1, npz for C2; missing samples as
+    NaN or zeros; an unknown label; a frame range with a stride; a rotation) turned into observations + visibility on the
+    GPU gives bit for bit the result of the host adapter (MocapSession.frames_for_labels) in front of the same solve."""
+    import copy
+    from moshpp_b200.chmosh import mosh_stageii
+    case = cases(name)
+    cfg = copy.deepcopy(case['cfg'])
+    cfg.mocap.start_fidx, cfg.mocap.end_fidx, cfg.mocap.ds_rate = 1, -1, 2
+    cfg.mocap.rotate = [10.0, -20.0, 30.0] if name == 'C2' else None
+    args = (case['mocap_fname'], cfg, case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
+    a = mosh_stageii(*args, precision='f32', chunk_len=0, device_adapter=True)
+    b = mosh_stageii(*args, precision='f32', chunk_len=0, device_adapter=False)
+    assert a['stageii_debug_details']['b200']['device_adapter'] and not b['stageii_debug_details']['b200']['device_adapter']
+    da, db = a['stageii_debug_details'], b['stageii_debug_details']
+    assert da['labels_obs'] == db['labels_obs']
+    assert all(np.array_equal(x, y) for x, y in zip(da['markers_obs'], db['markers_obs']))       # (the host copy of both)
+    if cfg.mocap.rotate is None:
+        assert np.array_equal(a['fullpose'], b['fullpose']) and np.array_equal(a['trans'], b['trans'])
+        assert all(np.array_equal(x, y) for x, y in zip(da['markers_sim'], db['markers_sim']))
+    else:       # the rotation is a float64 3x3 product on either side, not necessarily rounded alike in the last bit
+        assert np.abs(a['fullpose'] - b['fullpose']).max() < 1e-4 and np.abs(a['trans'] - b['trans']).max() < 1e-5
+    assert np.array_equal(da['markers_orig'], db['markers_orig'])
+    assert sum(len(l) for l in da['labels_obs']) < len(da['labels_obs']) * len(case['latent_labels'])    # some samples are missing
