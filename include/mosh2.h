@@ -156,6 +156,21 @@ int mosh2_job_upload(mosh2_job *j, const double *obs, const uint8_t *vis);
  * observations (metres, compute precision) and visibility.  Async on the job's stream; replaces mosh2_job_upload. */
 int mosh2_job_upload_markers(mosh2_job *j, const double *markers, int32_t n_file_frames, int32_t n_cols, const int32_t *col_of_marker,
                              int32_t frame_start, int32_t frame_step, double unit_per_metre, const double *rot3x3);
+/* ---- Stage I building block (chmosh.py:83-455) ------------------------------------------------------------
+ * Linearise mode: the frames of the job are INDEPENDENT problems (the twelve frames of Stage I), each evaluated by one
+ * thread block at a state the caller gives -- x [F][3 + p_red + n_dmpl] = trans | reduced pose | linear coefficients.  The
+ * frame's own terms are data, the pose prior (+ joint-angle term) and, with step == 2, the finger term, under opt's
+ * wt_data / wt_poseB / wt_poseH taken as they are (Stage I's annealed weights; no visibility scaling).  step 1 / 2 picks the
+ * free-variable list free1 / free2 of the model description (n columns).  Outputs (host, float64, any pointer may be NULL):
+ *   errs [F][8] SSE per term, markers_sim [F][M][3], r [F][3M] weighted data residual (sim - obs) wt_data (0 where invisible),
+ *   vp [F][3M][3] posed attachment vertices; with build != 0 also A [F][n][n], g [F][n] (normal equations of the frame's own
+ *   terms, g = -J^T r) and J [F][3M][n] (the weighted data rows d r / d x_free).
+ * With the shape directions as the model's linear block these are all per-frame quantities the joint shape / latent-marker
+ * solve needs (moshpp_b200/stagei.py).  Float64 jobs of one-frame chunks only (chunk_len = 1).  Synchronous. */
+typedef struct mosh2_lin_out {
+    double *errs, *markers_sim, *r, *vp, *A, *g, *J;
+} mosh2_lin_out;
+int mosh2_job_linearize(mosh2_job *j, const mosh2_options *opt, int32_t step, int32_t build, const double *x, const mosh2_lin_out *out);
 /* The same from DEVICE memory (e.g. the receive buffer of an NCCL scatter): d_obs [F*M*3] float32 (obs_f64 = 0) or
  * float64 (obs_f64 = 1) on the job's device, d_vis [F*M]; converted to the job's precision on the device.  The
  * copy is ordered after the work already queued on `producer_stream` (a cudaStream_t, may be NULL = legacy stream). */

@@ -27,6 +27,13 @@ STAGEII_WEIGHTS = dict(stageii_wt_data=400, stageii_wt_velo=2.5, stageii_wt_dmpl
                        stageii_wt_poseB=1.6, stageii_wt_poseH=1.0, stageii_wt_poseF=1.0, stageii_wt_annealing=2.5)
 
 
+# Stage I (support_data/conf/moshpp_conf.yaml:99-117, the `smplh` weight block that every surface model type uses by default)
+STAGEI_WEIGHTS = dict(stagei_wt_poseH=3.0, stagei_wt_poseF=3., stagei_wt_expr=34., stagei_wt_pose=3., stagei_wt_poseB=3.,
+                      stagei_wt_init_finger_left=400.0, stagei_wt_init_finger_right=400.0, stagei_wt_init_finger=400.0,
+                      stagei_wt_betas=10., stagei_wt_init=300, stagei_wt_data=75., stagei_wt_surf=10000.,
+                      stagei_wt_annealing=[1., .5, .25, .125])
+
+
 def default_cfg(**over) -> AttrDict:
     """The Stage-II-relevant defaults of support_data/conf/moshpp_conf.yaml (lines 13-31,34-50,95-125)."""
     cfg = AttrDict.wrap({
@@ -38,7 +45,8 @@ def default_cfg(**over) -> AttrDict:
         'moshpp': {'pose_body_prior_fname': None, 'pose_hand_prior_fname': None, 'optimize_fingers': False,
                    'optimize_face': False, 'optimize_toes': False, 'optimize_betas': True,
                    'optimize_dynamics': False, 'verbosity': 1},
-        'opt_settings': {'weights_type': 'smplh', 'weights': dict(STAGEII_WEIGHTS), 'maxiter': 100},
+        'opt_settings': {'weights_type': 'smplh', 'weights': dict(STAGEII_WEIGHTS, **STAGEI_WEIGHTS), 'maxiter': 100,
+                         'stagei_lr': 1e-3, 'extra_initial_rigid_adjustment': False},
     })
     for k, v in over.items():
         node = cfg

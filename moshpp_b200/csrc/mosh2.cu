@@ -427,6 +427,9 @@ struct mosh2_job {
     // pinned staging
     void *h_obs = nullptr, *h_out = nullptr;
     uint8_t *h_vis = nullptr;
+    void *d_lin = nullptr;                       // linearise mode: states in, normal equations / Jacobian rows / residuals out
+    size_t lin_bytes = 0;
+    int lin_mode = 0, lin_step = 1;
     void *h_raw = nullptr, *d_raw = nullptr;     // raw marker table of mosh2_job_upload_markers (pinned staging, device copy)
     int *d_cols = nullptr;
     size_t raw_bytes = 0;
@@ -464,6 +467,18 @@ int launch(mosh2_job *j, const mosh2::Model<real> &m) {
     job.markers_sim = out + j->o_mk; job.errs = out + j->o_errs;
     job.status = j->d_status; job.counters = j->d_counters; job.totals = j->d_totals; job.prof = j->d_prof;
     job.gws = static_cast<char *>(j->d_gws); job.gws_stride = j->gws_stride;
+    job.lin_mode = j->lin_mode; job.lin_step = j->lin_step;
+    if (j->lin_mode) {      // layout of d_lin (reals): x [F][NX] | A [F][n][n] | g [F][n] | J [F][3M][n] | r [F][3M] | vp [F][9M]
+        const size_t F = j->n_frames, M = j->model->n_markers, NX = 3 + j->model->p_red + j->model->n_dmpl;
+        const size_t n = j->lin_step == 2 ? m.n2 : m.n1;
+        real *p = static_cast<real *>(j->d_lin);
+        job.lin_x = p; p += F * NX;
+        job.lin_A = p; p += F * n * n;
+        job.lin_g = p; p += F * n;
+        job.lin_J = p; p += F * 3 * M * n;
+        job.lin_r = p; p += F * 3 * M;
+        job.lin_vp = p;
+    }
     job.opt = j->opt;
     int threads = threads_for<real>();
     if (const char *e = getenv("MOSH2_DEV_THREADS")) {      // development aid: any multiple of 32 from 128 up to the launch bound
@@ -720,6 +735,52 @@ int mosh2_job_upload_markers(mosh2_job *j, const double *markers, int32_t n_file
     return 0;
 }
 
+int mosh2_job_linearize(mosh2_job *j, const mosh2_options *opt, int32_t step, int32_t build, const double *x, const mosh2_lin_out *out) {
+    if (!j || !x || !out || (step != 1 && step != 2)) return fail(MOSH2_E_INVALID, "bad argument");
+    if (j->precision != MOSH2_F64) return fail(MOSH2_E_INVALID, "mosh2_job_linearize needs a float64 job");
+    if (j->n_chunks < j->n_frames) return fail(MOSH2_E_INVALID, "mosh2_job_linearize needs a job of one-frame chunks (chunk_len = 1)");
+    CU(cudaSetDevice(j->model->device));
+    const mosh2::Model<double> &m = j->model->f64.m;
+    const size_t F = j->n_frames, M = j->model->n_markers, NX = 3 + j->model->p_red + j->model->n_dmpl;
+    const size_t n = step == 2 ? m.n2 : m.n1, n2 = m.n2 > m.n1 ? m.n2 : m.n1;
+    const size_t words = F * (NX + n2 * n2 + n2 + 3 * M * n2 + 3 * M + 9 * M);
+    if (words * sizeof(double) > j->lin_bytes) {
+        g_blocks.put(j->model->device, j->d_lin);
+        j->d_lin = nullptr; j->lin_bytes = 0;
+        CU(g_blocks.get(j->model->device, words * sizeof(double), &j->d_lin));
+        j->lin_bytes = words * sizeof(double);
+    }
+    if (opt) {      // the weights of this evaluation (Stage I anneals them between minimisations)
+        mosh2::Options &o = j->opt;
+        o.wt_data = opt->wt_data; o.wt_poseB = opt->wt_poseB; o.wt_poseH = opt->wt_poseH; o.optimize_fingers = opt->optimize_fingers;
+    }
+    CU(cudaMemcpyAsync(j->d_lin, x, F * NX * sizeof(double), cudaMemcpyHostToDevice, j->stream));
+    CU(cudaMemsetAsync(j->d_out, 0, j->n_out * j->esz, j->stream));
+    j->lin_mode = build ? 2 : 1;
+    j->lin_step = step;
+    j->subset = false;
+    j->launch_blocks = int(F);
+    const int rc = launch<double>(j, m);
+    j->lin_mode = 0;
+    j->launch_blocks = j->n_chunks;
+    if (rc) return rc;
+    const double *p = static_cast<const double *>(j->d_lin) + F * NX;
+    const double *dA = p; p += F * n * n;
+    const double *dg = p; p += F * n;
+    const double *dJ = p; p += F * 3 * M * n;
+    const double *dr = p; p += F * 3 * M;
+    const double *dvp = p;
+    const double *dout = static_cast<const double *>(j->d_out);
+    auto back = [&](double *dst, const double *src, size_t cnt) { return dst ? cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, j->stream) : cudaSuccess; };
+    if (build) { CU(back(out->A, dA, F * n * n)); CU(back(out->g, dg, F * n)); CU(back(out->J, dJ, F * 3 * M * n)); }
+    CU(back(out->r, dr, F * 3 * M));
+    CU(back(out->vp, dvp, F * 9 * M));
+    CU(back(out->errs, dout + j->o_errs, F * mosh2::N_ERR));
+    CU(back(out->markers_sim, dout + j->o_mk, F * 3 * M));
+    CU(cudaStreamSynchronize(j->stream));
+    return 0;
+}
+
 int mosh2_job_launch(mosh2_job *j) {
     if (!j) return fail(MOSH2_E_INVALID, "null job");
     CU(cudaSetDevice(j->model->device));
@@ -920,6 +981,7 @@ void mosh2_job_destroy(mosh2_job *j) {
                     static_cast<void *>(j->d_counters), static_cast<void *>(j->d_totals), static_cast<void *>(j->d_prof), j->d_gws})
         g_blocks.put(dv, p);
     g_blocks.put(dv, j->d_raw);
+    g_blocks.put(dv, j->d_lin);
     g_blocks.put(dv, j->d_cols);
     for (void *p : {j->h_obs, j->h_out, static_cast<void *>(j->h_vis), static_cast<void *>(j->h_status), static_cast<void *>(j->h_counters), j->h_raw})
         g_blocks.put(-1, p);

@@ -154,6 +154,14 @@ struct Job {
     long long *prof;        // [32] phase clock sums (MOSH2_PROFILE builds only, else unused)
     char *gws;              // optional per-CTA global workspace (f64 / large models)
     size_t gws_stride;
+    // Linearise mode (Stage I, mosh2_job_linearize): every frame is an independent problem evaluated at a GIVEN state; one
+    // thread block per frame evaluates the residual there and, with lin_mode == 2, builds and exports the linearisation.
+    int lin_mode;           // 0: the Stage-II frame loop; 1: residual only; 2: residual + normal equations + Jacobian rows
+    int lin_step;           // free-variable list: 1 = free1, 2 = free2 (+ the finger term)
+    const real *lin_x;      // [F][NX] states
+    real *lin_A, *lin_g;    // [F][n][n], [F][n]: normal equations of the frame's own terms (data, pose prior, fingers)
+    real *lin_J, *lin_r;    // [F][3M][n], [F][3M]: weighted data rows d r / d x_free and r = (sim - obs) wd (zero where invisible)
+    real *lin_vp;           // [F][3M][3]: posed attachment vertices (slot = 3 marker + t)
     Options opt;
 };
 
@@ -604,6 +612,7 @@ struct Solver {
     real resume_diff = 0;     // ... and how far the frame just solved is from the row it replaces
     unsigned int tc_tmem = 0, tc_phase = 0;   // tensor-memory base address, parity of the MMA completion barrier
     int tc_kt = 0;            // rows per Jacobian tile (K extent of one tile's MMAs)
+    int lin_f = -1;           // linearise mode: the frame this block works on (else -1)
 
     M2_D Solver(const Model<real> &m_, const Job<real> &j_, const Work<real, BIG> &w_, const Dims &d_, Cta c_)
         : m(m_), job(j_), w(w_), cta(c_), d(d_) {}
@@ -1368,6 +1377,10 @@ struct Solver {
             }
 #endif
             M2_TACC(8);
+            if (lin_f >= 0 && job.lin_J && !w.tc) {       // linearise mode: the finished rows of the tile go out as they are
+                real *Jo = job.lin_J + (size_t(lin_f) * 3 * d.M + 3 * t0) * n;
+                CTA_FOR(idx, trows * n) { const int row = idx / n, cc = idx - row * n; Jo[idx] = w.Jf[row * d.npad + cc]; }
+            }
             // T3: A += Jf^T Jf, g -= Jf^T r
 #if M2_GPU
             if (w.tc) {
@@ -1894,6 +1907,7 @@ struct Solver {
         enum { OP_PROCRUSTES, OP_BEGIN, OP_TRIAL, OP_OUTPUT };
         int op = first ? OP_PROCRUSTES : OP_BEGIN;
         int stage = first ? 0 : (light ? 4 : 3);   // 0..2 first-frame annealing (chmosh.py:637-653), 3 Step 1 (665-671), 4 Step 2 (676-705)
+        if (lin_f >= 0) stage = job.lin_step == 2 ? 4 : 3;      // linearise mode: the stage names the free-variable list
         const int maxit = light ? 1 : o.maxiter;
         StepCfg<real> c;
         c.free = w.c_free1; c.n = m.n1; c.velo = has_velo; c.poseH = false; c.dm_terms = false; c.extrap = false; c.face = false;
@@ -1927,6 +1941,12 @@ struct Solver {
                 eval(op == OP_TRIAL ? w.xt : w.x, c, reuse);
                 if (!reuse) fwd_has_prior = c.wp > real(0);
                 fwd_at_x = op != OP_TRIAL;                     // (a trial point becomes the state only if it is accepted)
+            }
+            if (lin_f >= 0) {                                  // linearise mode: what the evaluation left goes out
+                CTA_FOR(i, 3 * d.M) { job.markers_sim[size_t(f) * 3 * d.M + i] = w.mk[i]; if (job.lin_r) job.lin_r[size_t(f) * 3 * d.M + i] = w.rm[i]; }
+                CTA_FOR(i, N_ERR) job.errs[size_t(f) * N_ERR + i] = w.sc[1 + i];
+                if (job.lin_vp) CTA_FOR(i, 3 * d.S) job.lin_vp[size_t(f) * 3 * d.S + i] = w.vp[i];
+                if (job.lin_mode < 2) break;
             }
             if (op == OP_PROCRUSTES) {                         // chmosh.py:634
                 procrustes();
@@ -1964,6 +1984,11 @@ struct Solver {
             }
             // ---------------- the one linearisation site
             if (do_build && !done) build(w.x, c);
+            if (lin_f >= 0) {                                  // linearise mode: the normal equations go out, nothing is solved
+                CTA_FOR(idx, n * n) { const int i = idx / n, j = idx - i * n; job.lin_A[size_t(f) * n * n + idx] = w.A[i * d.lda + j]; }
+                CTA_FOR(i, n) job.lin_g[size_t(f) * n + i] = w.g[i];
+                break;
+            }
             if (op == OP_BEGIN) {
                 // chumpy stops on ||g||_inf < e_1 = 1e-15, i.e. only for a numerically zero gradient
                 real sq[1] = {0};
@@ -2161,58 +2186,8 @@ struct Solver {
     }
 
     // ---- the chunk loop
-    M2_D void run_chunk(int chunk) {
-        const Options &o = job.opt;
-        // chunk table (host-built, mosh2_host::chunk_table): the chunk emits frames [f_emit, f_end) of the sequence that
-        // starts at frame s0 of the job's frame axis (a job may hold several sequences of one subject back to back)
-        const int *rec = job.chunk_tab + kChunkRec * chunk;
-        const int f_emit = rec[0], f_end = rec[1], s0 = rec[2], warmup = rec[3], warm_full = rec[4];
-        int f_begin = f_emit, f_full = f_emit;
-        bool short_warmup = false;
-        if (cta.tid == 0 && job.warm_f) job.warm_f[chunk] = -1;
-        if (f_emit > s0 && warmup > 0) {   // (warmup < 0: resume, see below)
-            // The warm-up is counted in SOLVED frames (frames with at least one visible marker; the others are skipped,
-            // chmosh.py:586-588): walk back from the first emitted frame until `warmup` of them are found, so that a
-            // marker drop-out in front of a chunk does not shorten the history the chunk converges on.  The last
-            // `warm_full` solved warm-up frames run the full schedule.  A chunk that reaches the first frame of its
-            // sequence is the reference's own recursion from its own start: exact, never "short".
-            uint8_t *flag = reinterpret_cast<uint8_t *>(static_cast<real *>(w.red));      // >= 8*33*4 bytes of scratch
-            const int per = cta.nthr < 512 ? cta.nthr : 512;
-            const int max_back = 8 * warmup + 64;             // give up behind very long gaps
-            if (cta.tid == 0) { w.isc[4] = 0; w.isc[5] = f_emit; w.isc[6] = f_emit; w.isc[7] = 0; }
-            M2_SYNC();
-            for (int base = f_emit - 1; base >= s0; base -= per) {
-                if (cta.tid < per) {
-                    const int f = base - cta.tid;
-                    uint8_t any = 0;
-                    if (f >= s0) for (int i = 0; i < d.M; ++i) any |= job.vis[size_t(f) * d.M + i];
-                    flag[cta.tid] = any;
-                }
-                M2_SYNC();
-                if (cta.tid == 0) {
-                    int cnt = w.isc[4], fb = w.isc[5], ff = w.isc[6], stop = 0;
-                    for (int t = 0; t < per && !stop; ++t) {
-                        const int f = base - t;
-                        if (f < s0 || cnt >= warmup) { stop = 1; break; }
-                        if (f_emit - f > max_back) { stop = 2; break; }
-                        if (flag[t]) { ++cnt; fb = f; if (cnt <= warm_full) ff = f; }
-                    }
-                    if (cnt >= warmup) stop = 1;
-                    w.isc[4] = cnt; w.isc[5] = fb; w.isc[6] = ff; w.isc[7] = stop;
-                }
-                M2_SYNC();
-                if (w.isc[7]) break;
-            }
-            f_begin = w.isc[5]; f_full = w.isc[6];
-            // fewer solved warm-up frames than asked for, without having reached the start of the sequence
-            short_warmup = w.isc[4] < warmup && w.isc[7] == 2;
-            // The walk-back ran into the first frame of the sequence: the chunk starts where the reference starts.  If the
-            // frames in front of it cost no more fully solved than a regular warm-up does (light frames count a quarter),
-            // solve them all fully -- the chunk is then the reference's own recursion from its own start, bit for bit the
-            // rows the chunks in front of it emit, instead of a light-frame approximation of the very first frames.
-            if (w.isc[4] < warmup && w.isc[7] != 2 && w.isc[4] <= warm_full + (warmup - warm_full) / 4) f_full = f_begin;
-            M2_SYNC();
-        }
+    // ---- per-block set-up: zero state, the per-model tables, the kinematic tree numbering and subtree masks
+    M2_D void prologue() {
         CTA_FOR(i, d.NX) w.x[i] = 0;
         // the per-model tables: one bulk asynchronous copy of the host-built image (see carve()), waited for below
 #if M2_GPU
@@ -2274,6 +2249,68 @@ struct Solver {
             w.c_amask[idx] = uint8_t(mask);
         }
         M2_SYNC();
+    }
+
+    M2_D void run_chunk(int chunk) {
+        const Options &o = job.opt;
+        // Linearise mode (Stage I, Job::lin_mode): the block's "chunk" is the single frame `chunk`, taken at the state the
+        // caller gives and left after its first evaluation / linearisation.  The frame's own terms are the Stage-II ones
+        // without the temporal coupling -- data, pose prior (+ joint angles), with lin_step == 2 the finger term -- under
+        // the weights of the options as they are (no per-frame visibility scaling: chmosh.py:327,350).  It runs through the
+        // same frame loop and the same solve_frame call as a chunk (one call site each: instruction cache).
+        const bool lin = job.lin_mode != 0;
+        // chunk table (host-built, mosh2_host::chunk_table): the chunk emits frames [f_emit, f_end) of the sequence that
+        // starts at frame s0 of the job's frame axis (a job may hold several sequences of one subject back to back)
+        const int *rec = job.chunk_tab + kChunkRec * chunk;
+        const int f_emit = lin ? chunk : rec[0], f_end = lin ? chunk + 1 : rec[1], s0 = lin ? chunk : rec[2];
+        const int warmup = lin ? 0 : rec[3], warm_full = lin ? 0 : rec[4];
+        int f_begin = f_emit, f_full = f_emit;
+        bool short_warmup = false;
+        if (cta.tid == 0 && job.warm_f) job.warm_f[chunk] = -1;
+        if (f_emit > s0 && warmup > 0) {   // (warmup < 0: resume, see below)
+            // The warm-up is counted in SOLVED frames (frames with at least one visible marker; the others are skipped,
+            // chmosh.py:586-588): walk back from the first emitted frame until `warmup` of them are found, so that a
+            // marker drop-out in front of a chunk does not shorten the history the chunk converges on.  The last
+            // `warm_full` solved warm-up frames run the full schedule.  A chunk that reaches the first frame of its
+            // sequence is the reference's own recursion from its own start: exact, never "short".
+            uint8_t *flag = reinterpret_cast<uint8_t *>(static_cast<real *>(w.red));      // >= 8*33*4 bytes of scratch
+            const int per = cta.nthr < 512 ? cta.nthr : 512;
+            const int max_back = 8 * warmup + 64;             // give up behind very long gaps
+            if (cta.tid == 0) { w.isc[4] = 0; w.isc[5] = f_emit; w.isc[6] = f_emit; w.isc[7] = 0; }
+            M2_SYNC();
+            for (int base = f_emit - 1; base >= s0; base -= per) {
+                if (cta.tid < per) {
+                    const int f = base - cta.tid;
+                    uint8_t any = 0;
+                    if (f >= s0) for (int i = 0; i < d.M; ++i) any |= job.vis[size_t(f) * d.M + i];
+                    flag[cta.tid] = any;
+                }
+                M2_SYNC();
+                if (cta.tid == 0) {
+                    int cnt = w.isc[4], fb = w.isc[5], ff = w.isc[6], stop = 0;
+                    for (int t = 0; t < per && !stop; ++t) {
+                        const int f = base - t;
+                        if (f < s0 || cnt >= warmup) { stop = 1; break; }
+                        if (f_emit - f > max_back) { stop = 2; break; }
+                        if (flag[t]) { ++cnt; fb = f; if (cnt <= warm_full) ff = f; }
+                    }
+                    if (cnt >= warmup) stop = 1;
+                    w.isc[4] = cnt; w.isc[5] = fb; w.isc[6] = ff; w.isc[7] = stop;
+                }
+                M2_SYNC();
+                if (w.isc[7]) break;
+            }
+            f_begin = w.isc[5]; f_full = w.isc[6];
+            // fewer solved warm-up frames than asked for, without having reached the start of the sequence
+            short_warmup = w.isc[4] < warmup && w.isc[7] == 2;
+            // The walk-back ran into the first frame of the sequence: the chunk starts where the reference starts.  If the
+            // frames in front of it cost no more fully solved than a regular warm-up does (light frames count a quarter),
+            // solve them all fully -- the chunk is then the reference's own recursion from its own start, bit for bit the
+            // rows the chunks in front of it emit, instead of a light-frame approximation of the very first frames.
+            if (w.isc[4] < warmup && w.isc[7] != 2 && w.isc[4] <= warm_full + (warmup - warm_full) / 4) f_full = f_begin;
+            M2_SYNC();
+        }
+        prologue();
         M2_T0();
         bool first = true, have_prev = false, have_dm_prev = false;
         fwd_at_x = false;
@@ -2352,7 +2389,18 @@ struct Solver {
             }
             has_extrap = dyn && have_dm_prev;
             if (short_warmup && f >= f_emit) frame_flags |= ST_SHORT_WARMUP;
-            solve_frame(f, f >= f_emit, first, fingers, dyn, face, /*light=*/!first && f < f_full);
+            if (lin) {
+                lin_f = f;
+                CTA_FOR(i, d.NX) w.x[i] = job.lin_x[size_t(f) * d.NX + i];
+                wd = real(o.wt_data);
+                wp_frame = has_prior ? real(o.wt_poseB) : real(0);
+                wH = real(o.wt_poseH);
+                has_velo = false; has_extrap = false;
+                first = false;
+                M2_SYNC();
+            }
+            solve_frame(f, !lin && f >= f_emit, first, fingers, dyn, face, /*light=*/!first && f < f_full);
+            if (lin && cta.tid == 0) job.status[f] = ST_SOLVED;
             if (resuming) {
                 // merged with the old trajectory (two frames in a row within round-off of the rows they replace: the state
                 // the recursion carries, pose_t and pose_{t-1}, is the old one): the rest of the chunk stands as it is

@@ -71,6 +71,10 @@ class MeshDistanceOut(C.Structure):
     _fields_ = [('value', _f64p), ('tri', _i32p), ('part', _i32p), ('d_sample', _f64p), ('d_tri', _f64p)]
 
 
+class LinOut(C.Structure):
+    _fields_ = [('errs', _f64p), ('markers_sim', _f64p), ('r', _f64p), ('vp', _f64p), ('A', _f64p), ('g', _f64p), ('J', _f64p)]
+
+
 class Mosh2Error(RuntimeError):
     pass
 
@@ -112,6 +116,7 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_job_create.argtypes = [vp, C.POINTER(Options), C.c_int32, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
     lib.mosh2_job_create_batch.argtypes = [vp, C.POINTER(Options), C.c_int32, _i32p, C.POINTER(Schedule), C.c_int32, C.POINTER(vp)]
     lib.mosh2_job_upload.argtypes = [vp, _f64p, _u8p]
+    lib.mosh2_job_linearize.argtypes = [vp, C.POINTER(Options), C.c_int32, C.c_int32, _f64p, C.POINTER(LinOut)]
     lib.mosh2_job_upload_markers.argtypes = [vp, _f64p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_int32, C.c_double, _f64p]
     lib.mosh2_job_upload_device_range.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp]
     lib.mosh2_job_upload_device.argtypes = [vp, vp, C.c_int32, vp, vp]
@@ -142,7 +147,7 @@ EXPORTED_SYMBOLS = (
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
     'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
     'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks',
-    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance', 'mosh2_job_upload_markers')
+    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance', 'mosh2_job_upload_markers', 'mosh2_job_linearize')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -315,6 +320,22 @@ class Job:
         self.model._check(self.lib.mosh2_job_upload_markers(self.handle, _ptr(raw, _f64p), raw.shape[0], raw.shape[1], _ptr(cols, _i32p),
                                                             int(frame_start), int(frame_step), float(unit_per_metre),
                                                             _ptr(rot, _f64p) if rot is not None else None), 'mosh2_job_upload_markers')
+
+    def linearize(self, x: np.ndarray, options: Options, step: int, build: bool) -> Dict[str, np.ndarray]:
+        """mosh2_job_linearize: every frame of the job evaluated (and, with ``build``, linearised) at its row of ``x``
+        [F, 3 + p_red + n_dmpl]; see include/mosh2.h.  Needs a float64 job of one-frame chunks and uploaded observations."""
+        pk = self.model.pk
+        F, M = self.n_frames, pk.n_markers
+        n = len(pk.free_step2) if step == 2 else len(pk.free_step1)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (F, pk.nx)
+        out = dict(errs=np.zeros((F, len(ERR_NAMES))), markers_sim=np.zeros((F, M, 3)), r=np.zeros((F, 3 * M)), vp=np.zeros((F, 3 * M, 3)))
+        if build:
+            out.update(A=np.zeros((F, n, n)), g=np.zeros((F, n)), J=np.zeros((F, 3 * M, n)))
+        c = LinOut(*[_ptr(out[k], _f64p) if k in out else None for k in ('errs', 'markers_sim', 'r', 'vp', 'A', 'g', 'J')])
+        self.model._check(self.lib.mosh2_job_linearize(self.handle, C.byref(options), int(step), int(bool(build)), _ptr(x, _f64p),
+                                                       C.byref(c)), 'mosh2_job_linearize')
+        return out
 
     def upload_device(self, d_obs_ptr: int, obs_is_f64: bool, d_vis_ptr: int, producer_stream: int = 0):
         """Observations already on this job's GPU (raw device pointers, e.g. ``tensor.data_ptr()`` of an NCCL receive

@@ -245,7 +245,43 @@ def make_body_model(model_type: str, n_verts: Optional[int] = None, n_betas: int
 
     kintree = np.vstack([np.array(par, dtype=np.int64), np.arange(nj, dtype=np.int64)])
     kintree = kintree.astype(np.uint32)            # root parent becomes 4294967295 as in the public files
-    faces = np.stack([np.arange(V - 2), np.arange(1, V - 1), np.arange(2, V)], axis=1).astype(np.uint32)
+    # faces (used by Stage I's surface term only): a fan of triangles around every vertex -- its nearest neighbours ordered by
+    # angle in the tangent plane -- turned so that the normals point away from the nearest bone.  The fans overlap (this is
+    # not a manifold; the reference's body models are watertight meshes), but they follow the sampled surface closely, so
+    # distances to the mesh and their sign behave like on a real body.
+    from sklearn.neighbors import NearestNeighbors
+    kn = min(7, V)
+    _, nbr = NearestNeighbors(n_neighbors=kn).fit(verts).kneighbors(verts)
+    best = np.full(V, np.inf)
+    proj = np.zeros_like(verts)
+    for (_, a, b, _) in segs:
+        dseg, pseg = _seg_dist(verts, a, b)
+        upd = dseg < best
+        best[upd] = dseg[upd]
+        proj[upd] = pseg[upd]
+    outward = verts - proj
+    outward /= np.linalg.norm(outward, axis=1, keepdims=True) + 1e-12
+    ref = np.where(np.abs(outward[:, :1]) < 0.9, np.array([[1.0, 0, 0]]), np.array([[0, 1.0, 0]]))
+    t1 = np.cross(outward, ref)
+    t1 /= np.linalg.norm(t1, axis=1, keepdims=True)
+    t2 = np.cross(outward, t1)
+    rel = verts[nbr[:, 1:]] - verts[:, None, :]
+    ang = np.arctan2((rel * t2[:, None, :]).sum(-1), (rel * t1[:, None, :]).sum(-1))
+    order = np.argsort(ang, axis=1)
+    ring = np.take_along_axis(nbr[:, 1:], order, axis=1)
+    ang = np.take_along_axis(ang, order, axis=1)
+    nxt = np.roll(ring, -1, axis=1)
+    gap = np.mod(np.roll(ang, -1, axis=1) - ang, 2 * np.pi)
+    keep = gap < 2.2                                   # no triangle across an open side of the fan
+    centre = np.repeat(np.arange(V)[:, None], kn - 1, axis=1)
+    faces = np.stack([centre[keep], ring[keep], nxt[keep]], axis=1)
+    # a triangle found from several of its corners is kept once (duplicates with opposite orientation would make the SIGN of
+    # the distance a coin toss); its orientation follows the mean outward direction of its three corners
+    _, first = np.unique(np.sort(faces, axis=1), axis=0, return_index=True)
+    faces = faces[np.sort(first)]
+    flip = (np.cross(verts[faces[:, 1]] - verts[faces[:, 0]], verts[faces[:, 2]] - verts[faces[:, 0]]) * outward[faces].sum(1)).sum(1) < 0
+    faces[flip] = faces[flip][:, [0, 2, 1]]
+    faces = faces.astype(np.uint32)
     dd = {
         'v_template': verts, 'shapedirs': shapedirs, 'posedirs': posedirs, 'weights': W,
         'J_regressor': sp.csc_matrix(jr), 'kintree_table': kintree, 'f': faces,

@@ -95,3 +95,48 @@ def gpu_solve(case, chunk_len=0, warmup=0, precision='f32', obs_vis=None, warmup
                            precision={'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[precision])
     finally:
         model.close()
+
+
+class EmuStageIBackend:
+    """TEST-ONLY back end of moshpp_b200.stagei: the per-frame linearisation through the single-thread host build of the
+    device source (mosh2_emu_linearize), the point-to-mesh distances through the oracle (the CUDA kernel has no host build)."""
+
+    def __init__(self):
+        from moshpp_b200 import build, lib
+        self.lib = lib
+        self.handle = C.CDLL(build.build_emu())
+
+    def linearize(self, pk, options, obs, vis, x, step, build):
+        lib = self.lib
+        F, M = obs.shape[0], pk.n_markers
+        n = len(pk.free_step2) if step == 2 else len(pk.free_step1)
+        h = lib.DescHolder(pk)
+        o = np.ascontiguousarray(obs, dtype=np.float64)
+        v8 = np.ascontiguousarray(vis, dtype=np.uint8)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = dict(errs=np.zeros((F, len(lib.ERR_NAMES))), markers_sim=np.zeros((F, M, 3)), r=np.zeros((F, 3 * M)), vp=np.zeros((F, 3 * M, 3)))
+        if build:
+            out.update(A=np.zeros((F, n, n)), g=np.zeros((F, n)), J=np.zeros((F, 3 * M, n)))
+        c = lib.LinOut(*[lib._ptr(out[k], lib._f64p) if k in out else None for k in ('errs', 'markers_sim', 'r', 'vp', 'A', 'g', 'J')])
+        rc = self.handle.mosh2_emu_linearize(C.byref(h.desc), C.byref(options), F, lib._ptr(o, lib._f64p), lib._ptr(v8, lib._u8p),
+                                             int(step), int(bool(build)), lib._ptr(x, lib._f64p), C.byref(c))
+        assert rc == 0
+        return out
+
+    def squared_distance(self, samples, verts, faces):
+        from oracle import mesh_distance as omd
+        r, ds, dt, tri, part = omd.somedistance(samples, verts, faces, kind=omd.KIND_SQUARED)
+        return r, tri, part, ds, dt
+
+
+def stagei_case(cases, name='C2', n_pick=4, **kw):
+    """A Stage-I problem from a synthetic Stage-II case: ``n_pick`` frames of its mocap as label dictionaries."""
+    import copy
+    from moshpp_b200.mocap_interface import MocapSession
+    case = cases(name, **kw)
+    cfg = copy.deepcopy(case['cfg'])
+    cfg.moshpp.optimize_betas = True
+    mocap = MocapSession(case['mocap_fname'], cfg.mocap.unit)
+    frames = mocap.markers_asdict()
+    pick = np.linspace(0, len(frames) - 1, n_pick).astype(int)
+    return case, cfg, [frames[i] for i in pick]

@@ -205,7 +205,58 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     return 0;
 }
 
+// linearise mode (mosh2_job_linearize): every frame evaluated / linearised at the caller's state, float64
+int run_lin(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, const double *obs, const uint8_t *vis,
+            int step, int build, const double *x, const mosh2_lin_out *out) {
+    typedef double real;
+    HostModel<real> hm;
+    hm.build(*desc);
+    const size_t F = n_frames, M = desc->n_markers, PF = size_t(3) * desc->n_joints, PR = desc->p_red, nd = desc->n_dmpl;
+    const size_t NX = 3 + PR + nd, n = step == 2 ? desc->n_free2 : desc->n_free1;
+    std::vector<real> fullpose(F * PF), pose(F * PR), trans(F * 3), dmpls(F * nd + 1), mk(F * M * 3), errs(F * mosh2::N_ERR);
+    std::vector<real> A(F * n * n), g(F * n), J(F * 3 * M * n), r(F * 3 * M), vp(F * 9 * M);
+    mosh2::Job<real> job{};
+    job.n_frames = n_frames; job.n_chunks = n_frames;
+    job.obs = obs; job.vis = vis;
+    job.fullpose = fullpose.data(); job.pose = pose.data(); job.trans = trans.data();
+    job.dmpls = nd ? dmpls.data() : nullptr; job.markers_sim = mk.data(); job.errs = errs.data();
+    std::vector<int> status(F, 0), counters(F * 4, 0);
+    job.status = status.data(); job.counters = counters.data();
+    job.lin_mode = build ? 2 : 1; job.lin_step = step; job.lin_x = x;
+    job.lin_A = A.data(); job.lin_g = g.data(); job.lin_J = J.data(); job.lin_r = r.data(); job.lin_vp = vp.data();
+    mosh2::Options &q = job.opt;
+    q.wt_data = opt->wt_data; q.wt_poseB = opt->wt_poseB; q.wt_poseH = opt->wt_poseH; q.wt_velo = opt->wt_velo;
+    q.wt_dmpl = opt->wt_dmpl; q.wt_annealing = opt->wt_annealing; q.wt_extrap = opt->wt_extrap_dmpl;
+    q.num_train_markers = opt->num_train_markers; q.delta_0 = opt->delta_0; q.e3_first = opt->e3_first; q.e3 = opt->e3;
+    q.maxiter = opt->maxiter; q.optimize_fingers = opt->optimize_fingers; q.optimize_dynamics = opt->optimize_dynamics;
+    q.wt_poseF = opt->wt_poseF; q.wt_expr = opt->wt_expr; q.optimize_face = opt->optimize_face;
+    hm.m.tile_markers = 20;
+    hm.m.dev_no_tc = 1;
+    const mosh2::Dims d = mosh2::make_dims(hm.m);
+    mosh2::Work<real, false> w{};
+    mosh2::Arena S0{mosh2::kSmemHeader}, G0{0};
+    mosh2::carve<real, false>(w, d, hm.m, S0, G0);
+    std::vector<char> smem_raw(S0.off + 128);
+    char *smem_base = smem_raw.data() + ((32 - (reinterpret_cast<uintptr_t>(smem_raw.data()) & 31)) & 31);
+    mosh2::m2_smem_ref() = reinterpret_cast<unsigned char *>(smem_base);
+    for (int f = 0; f < n_frames; ++f) {
+        std::memset(smem_base, 0, S0.off + 64);
+        mosh2::Cta cta{0, 1};
+        mosh2::Solver<real, false> s(hm.m, job, w, d, cta);
+        s.run_chunk(f);
+    }
+    auto back = [](double *dst, const std::vector<real> &src) { if (dst) std::memcpy(dst, src.data(), src.size() * sizeof(double)); };
+    back(out->errs, errs); back(out->markers_sim, mk); back(out->r, r); back(out->vp, vp);
+    if (build) { back(out->A, A); back(out->g, g); back(out->J, J); }
+    return 0;
+}
+
 }  // namespace
+
+extern "C" int mosh2_emu_linearize(const mosh2_model_desc *desc, const mosh2_options *opt, int32_t n_frames, const double *obs,
+                                   const uint8_t *vis, int32_t step, int32_t build, const double *x, const mosh2_lin_out *out) {
+    return run_lin(desc, opt, n_frames, obs, vis, step, build, x, out);
+}
 
 extern "C" int mosh2_emu_solve(const mosh2_model_desc *desc, const mosh2_options *opt, int32_t n_frames,
                                const double *obs, const uint8_t *vis, const mosh2_schedule *sched,
