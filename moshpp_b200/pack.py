@@ -383,7 +383,8 @@ def pose_partitions(model_type: str, p_red: int, optimize_fingers: bool, optimiz
 def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarray, *,
                num_betas: int, prior: Optional[BodyPrior], dmpl_dirs: Optional[np.ndarray] = None,
                num_dmpls: int = 0, optimize_fingers: bool = False, optimize_toes: bool = False,
-               optimize_face: bool = False, expr_start: int = 0, num_expressions: int = 0) -> StageIIPack:
+               optimize_face: bool = False, expr_start: int = 0, num_expressions: int = 0,
+               can_verts: Optional[np.ndarray] = None, jd_lin: Optional[np.ndarray] = None) -> StageIIPack:
     """``optimize_face`` (SMPL-X, chmosh.py:560-566,685-689): the ``num_expressions`` shape components from
     ``expr_start`` become per-frame linear coefficients after the DMPL ones, and the jaw joins the free pose."""
     nj = model.n_joints
@@ -391,7 +392,8 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
     nb = min(num_betas, model.shapedirs.shape[-1], betas.shape[0])
     v_shaped = model.v_template + model.shapedirs[:, :, :nb].dot(betas[:nb])   # chmosh.py:499-500
     j0 = model.J_regressor.dot(v_shaped)                                       # smpl_fast_derivatives.py:186-191
-    can_verts = canonical_verts(model, v_shaped, j0)                           # can_model.r
+    if can_verts is None:          # (Stage I hands the canonical mesh in: it keeps it as an affine function of the shape)
+        can_verts = canonical_verts(model, v_shaped, j0)                       # can_model.r
     closest, coefs = attach_markers(can_verts, markers_latent)                 # chmosh.py:502
     M = closest.shape[0]
     slot_vid = closest.reshape(-1).astype(np.int64)                            # slot = 3*m + t
@@ -400,7 +402,7 @@ def build_pack(model: SurfaceModel, betas: np.ndarray, markers_latent: np.ndarra
     if nd:
         dm = np.asarray(dmpl_dirs, dtype=np.float64)[:, :, :nd]
         sd = dm[slot_vid]
-        jd = np.einsum('jv,vcd->jcd', model.J_regressor, dm)
+        jd = np.einsum('jv,vcd->jcd', model.J_regressor, dm) if jd_lin is None else np.asarray(jd_lin, dtype=np.float64)   # (constant per model)
     else:
         sd = np.zeros((3 * M, 3, 0))
         jd = np.zeros((nj, 3, 0))

@@ -97,9 +97,7 @@ def marker_points(tri_verts, k):
 def vertex_normals(v, f):
     """Normalised sum of the area-scaled triangle normals around every vertex (scan2mesh/ch_vert_normals.py:86-139)."""
     tn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
-    vn = np.zeros_like(v)
-    for c in range(3):
-        np.add.at(vn, f[:, c], tn)
+    vn = np.stack([np.bincount(f.reshape(-1), weights=np.repeat(tn[:, c], 3), minlength=len(v)) for c in range(3)], axis=1)
     ss = (vn ** 2).sum(1)
     ss[ss == 0] = 1e-10
     return vn / np.sqrt(ss)[:, None]
@@ -131,6 +129,31 @@ def rigid_fit(sim, obs):
     else:
         rv = th / (2.0 * np.sin(th)) * w
     return rv, T
+
+
+def _solve_arrow(A, g, ns, n_p, F):
+    """A d = g for the block-arrow normal equations [[S, B^T], [B, blockdiag(D_f)]]: shared unknowns first (ns), then F
+    private blocks of n_p -- by the Schur complement of the private blocks (each picked frame couples to the others only
+    through the shape and the latent markers).  Falls back to chumpy's dense solve / lstsq when a block is singular
+    (SURVEY.md A.6)."""
+    try:
+        S = A[:ns, :ns].copy()
+        gs = g[:ns].copy()
+        X = []
+        for f in range(F):
+            sl = slice(ns + f * n_p, ns + (f + 1) * n_p)
+            B = A[sl, :ns]
+            Xf = np.linalg.solve(A[sl, sl], np.concatenate([B, g[sl, None]], axis=1))
+            S -= B.T.dot(Xf[:, :ns])
+            gs -= B.T.dot(Xf[:, ns])
+            X.append(Xf)
+        ds = np.linalg.solve(S, gs)
+        return np.concatenate([ds] + [Xf[:, ns] - Xf[:, :ns].dot(ds) for Xf in X])
+    except np.linalg.LinAlgError:
+        try:
+            return np.linalg.solve(A, g)
+        except np.linalg.LinAlgError:
+            return np.linalg.lstsq(A, g, rcond=None)[0]
 
 
 class CanonicalBody:
@@ -219,6 +242,7 @@ class StageI:
         if betas is not None:
             self.betas[:self.nb] = np.asarray(betas)[:self.nb]                                   # chmosh.py:169-172
         self.can = CanonicalBody(model, self.betas, self.nb)
+        self.jd_lin = np.einsum('jv,vcd->jcd', model.J_regressor, model.shapedirs[:, :, :self.nb])    # joint directions of the shape block
         self.pose = np.zeros((F, model.p_red))
         self.trans = np.zeros((F, 3))
 
@@ -240,11 +264,12 @@ class StageI:
         self.stats = dict(evaluations=0, linearisations=0, iterations=0, minimisations=0)
 
     # ---- device pack of the current (betas, latent markers): the Stage-II constants with the shape directions as linear block
-    def pack_for(self, detailed: bool):
+    def pack_for(self, detailed: bool, can_v=None):
         sm, mp = self.cfg.surface_model, self.cfg.moshpp
         pk = _pack.build_pack(self.model, self.betas, self.ml, num_betas=self.nb, prior=self.prior,
                               dmpl_dirs=self.model.shapedirs[:, :, :self.nb], num_dmpls=self.nb,
-                              optimize_fingers=self.fingers, optimize_toes=bool(_get(mp, 'optimize_toes', False)))
+                              optimize_fingers=self.fingers, optimize_toes=bool(_get(mp, 'optimize_toes', False)),
+                              can_verts=can_v, jd_lin=self.jd_lin)
         lin = [3 + pk.p_red + i for i in range(self.nb)] if self.free_betas else []
         s1 = [int(i) for i in pk.free_step1 if i < 3 + pk.p_red]
         s2 = [int(i) for i in pk.free_step2 if i < 3 + pk.p_red]
@@ -270,7 +295,7 @@ class StageI:
         self.stats['evaluations'] += 1
         self.stats['linearisations'] += int(want_jac)
         can_v = self.can(self.betas[:self.nb])
-        pk = self.pack_for(detailed)
+        pk = self.pack_for(detailed, can_v)
         step = 2 if detailed else 1
         free = pk.free_step2 if detailed else pk.free_step1
         n_f = len(free)
@@ -427,10 +452,7 @@ class StageI:
                     d_dl = (delta / np.linalg.norm(d_sd)) * d_sd
                 else:
                     if d_gn is None:
-                        try:
-                            d_gn = np.linalg.solve(A, g)
-                        except np.linalg.LinAlgError:
-                            d_gn = np.linalg.lstsq(A, g, rcond=None)[0]
+                        d_gn = _solve_arrow(A, g, nb + 3 * self.M, n_p, self.F)
                     if np.linalg.norm(d_gn) <= delta:
                         d_dl = d_gn.copy()
                     else:

@@ -171,7 +171,8 @@ def test_f32_global_workspace_layout_matches_shared_memory_layout(cases, name, m
     assert np.array_equal(a.status, b.status)
     assert np.abs(b.pose[fid] - out['_pose_reduced'])[:, :bd].max() < 1e-3
     assert np.abs(b.trans[fid] - out['trans']).max() < 1e-4
-    assert np.abs(a.pose - b.pose)[:, :bd].max() < 1e-3 and np.abs(a.trans - b.trans).max() < 1e-4
+    # (each layout is inside the f32 tolerance of the oracle; against each other that allows twice the tolerance)
+    assert np.abs(a.pose - b.pose)[:, :bd].max() < 2e-3 and np.abs(a.trans - b.trans).max() < 2e-4
 
 
 def test_library_is_the_cuda_build():
