@@ -2,8 +2,8 @@
 
 Reference: src/moshpp/chmosh.py:83-455.  Same inputs (``stagei_frames``: one ``{label: xyz}`` dictionary
 per picked frame, ``cfg``, ``betas_fname``, ``v_template_fname``) and the same return dictionary (chmosh.py:436-455).  The
-reference loads the marker layout itself (``marker_layout_load(cfg.dirs.marker_layout.fname, ...)``, chmosh.py:121-125); the
-layout tooling is outside this build, so the loaded layout is passed in as ``marker_meta``.
+marker layout comes from ``cfg.dirs.marker_layout.fname`` (``load_marker_layout`` reads the reference's json, chmosh.py:121-125)
+or is passed in loaded (``marker_meta``); creating layouts is outside this build.
 
 What runs where
   device   per picked frame (one thread block each, ``mosh2_job_linearize``): SMPL forward, simulated markers, the residuals of
@@ -35,6 +35,56 @@ from .chmosh import _get, _read_vertices
 
 logger = logging.getLogger('moshpp_b200')
 NUM_TRAIN_MARKERS = 46      # chmosh.py:100
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# marker layout file (the json the reference's Stage I reads, marker_layout/edit_tools.py:83-183)
+# ---------------------------------------------------------------------------------------------------------------------
+def load_marker_layout(marker_layout_fname: str, labels_map='general', exclude_marker_types=None, exclude_markers=None,
+                       only_markers=None) -> dict:
+    """``marker_layout_load`` (marker_layout/edit_tools.py:83-183): marker types sorted by name, labels sorted within a type
+    (after the synonym map), ``marker_vids`` / ``marker_type`` / ``marker_type_mask`` / ``m2b_distance`` /
+    ``surface_model_type``.  As in the reference, ``exclude_markers`` is only logged there (:150-151, no ``continue``) and has
+    no effect; colours are a plain red-to-blue ramp (the reference uses the ``colour`` package; viewers only)."""
+    import json
+    from collections import OrderedDict
+    from .mocap_interface import general_labels_map
+    assert str(marker_layout_fname).endswith('.json')
+    with open(marker_layout_fname) as f:
+        d = json.load(f)
+    if isinstance(labels_map, str):
+        labels_map = general_labels_map()
+    only_markers = only_markers or []
+    exclude_marker_types = exclude_marker_types or []
+    marker_vids, marker_types, m2b = OrderedDict(), OrderedDict(), OrderedDict()
+    for ms in sorted(d['markersets'], key=lambda a: a['type']):
+        t = ms['type']
+        if t in exclude_marker_types:
+            continue
+        if t in m2b:
+            raise ValueError(f'Marker type appears in multiple occasions: {t}!')
+        m2b[t] = ms.get('distance_from_skin', 0.0095)
+        cur = ms['indices']
+        if labels_map:
+            cur = {labels_map.get(k, k): cur[k] for k in cur}
+        for label in sorted(cur):
+            if only_markers and label not in only_markers:
+                continue
+            if label in marker_vids:
+                raise ValueError(f'Label ({label}) is present in multiple occasions.')
+            marker_vids[label] = int(cur[label])
+            marker_types.setdefault(t, []).append(label)
+    mask = OrderedDict((k, np.array([l in marker_types[k] for l in marker_vids.keys()])) for k in marker_types)
+    mtype = OrderedDict()
+    for i, l in enumerate(marker_vids):
+        for k, m in mask.items():
+            if m[i]:
+                mtype[l] = k
+    n = max(1, len(marker_vids) - 1)
+    colors = OrderedDict((l, [1.0 - i / n, 0.0, i / n]) for i, l in enumerate(marker_vids))
+    colors['nan'] = [0.83, 1, 0]
+    return {'marker_vids': marker_vids, 'marker_colors': colors, 'marker_type': mtype, 'marker_type_mask': mask, 'm2b_distance': m2b,
+            'surface_model_type': d.get('surface_model_type', 'smplx'), 'marker_layout_fname': marker_layout_fname}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -515,10 +565,12 @@ class StageI:
 
 def mosh_stagei(stagei_frames: List[Dict[str, np.ndarray]], cfg, betas_fname=None, v_template_fname=None, *, marker_meta=None,
                 device: int = 0, backend=None) -> dict:
-    """Stage I of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:83-85); ``marker_meta`` = the loaded
-    marker layout (what ``marker_layout_load`` returns, chmosh.py:121-125)."""
-    if marker_meta is None:
-        raise ValueError('marker_meta (the loaded marker layout, chmosh.py:121-125) is required: the layout tooling is outside this build')
+    """Stage I of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:83-85).  The marker layout is read
+    from ``cfg.dirs.marker_layout.fname`` like the reference does (chmosh.py:120-125), or handed over loaded as ``marker_meta``."""
+    if marker_meta is None:                                                                      # chmosh.py:120-125
+        mc = cfg.mocap
+        marker_meta = load_marker_layout(cfg.dirs.marker_layout.fname, exclude_markers=_get(mc, 'exclude_markers'),
+                                         exclude_marker_types=_get(mc, 'exclude_marker_types'), only_markers=_get(mc, 'only_markers'))
     if marker_meta.get('surface_model_type', cfg.surface_model.type) != cfg.surface_model.type:
         raise ValueError(f"marker layout surface_model_type doesnt match that of curent mosh session surface_model.type: "
                          f"{marker_meta['surface_model_type']} == {cfg.surface_model.type}")

@@ -656,3 +656,16 @@ def make_case(out_dir: str, config: str = 'C2', *, frames: Optional[int] = None,
     return dict(cfg=cfg, mocap_fname=mocap_fname, markers_latent=markers_latent, latent_labels=labels,
                 betas=betas, marker_meta=marker_meta, pack=pk, gt_pose=pose, gt_trans=trans, gt_dmpl=dm,
                 gt_markers=mk, obs=obs, vis=vis, model=model, config=c)
+
+
+def write_marker_layout(fname: str, marker_meta: Dict) -> str:
+    """The marker layout json the reference's Stage I reads (marker_layout/edit_tools.py:115-160) from a ``marker_meta``."""
+    import json
+    sets = []
+    for t, mask in marker_meta['marker_type_mask'].items():
+        labels = [l for l, m in zip(marker_meta['marker_vids'].keys(), np.asarray(mask, dtype=bool)) if m]
+        sets.append({'type': t, 'distance_from_skin': float(marker_meta['m2b_distance'][t]),
+                     'indices': {l: int(marker_meta['marker_vids'][l]) for l in labels}})
+    with open(fname, 'w') as f:
+        json.dump({'surface_model_type': marker_meta['surface_model_type'], 'markersets': sets}, f)
+    return fname

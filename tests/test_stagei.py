@@ -89,3 +89,17 @@ def test_stagei_on_the_gpu_equals_oracle(cases):
     dt = time.perf_counter() - t0
     print(f'stage I on the GPU: {dt:.2f} s, {out["stagei_debug_details"]["b200"]}')
     _compare(out, ref, 1e-6)
+
+
+def test_marker_layout_file_round_trip(cases, tmp_path):
+    """The reference's call site passes no layout (mosh_head.py:242-244): Stage I reads cfg.dirs.marker_layout.fname."""
+    from moshpp_b200 import synth
+    from moshpp_b200.cfg import AttrDict
+    case = cases('C2')
+    fn = synth.write_marker_layout(str(tmp_path / 'layout.json'), case['marker_meta'])
+    meta = product.load_marker_layout(fn, labels_map=None)
+    ref = case['marker_meta']
+    assert list(meta['marker_vids'].items()) == [(k, int(v)) for k, v in ref['marker_vids'].items()]
+    assert dict(meta['marker_type']) == dict(ref['marker_type']) and meta['surface_model_type'] == ref['surface_model_type']
+    for k in ref['marker_type_mask']:
+        assert np.array_equal(meta['marker_type_mask'][k], ref['marker_type_mask'][k]) and meta['m2b_distance'][k] == ref['m2b_distance'][k]
