@@ -143,7 +143,8 @@ struct Job {
     const int *chunk_tab;   // [n_chunks][kChunkRec]: first emitted frame, end of the emitted range, first frame of the chunk's
                             // sequence, warm-up (solved frames), how many of them (the last ones) run the full per-frame schedule
     const int *chunk_ids;   // launch of a subset of the chunks: blockIdx.x -> chunk, or null (all chunks)
-    double merge_tol;       // resume mode: a re-solved frame within this of the row it replaces counts as merged (rad; 0.1 m)
+    double merge_tol;       // resume mode: a re-solved frame within this of the row it replaces counts as merged (rad on root + body pose;
+                            // x 10 on the other pose coefficients, x 0.1 m on the translation)
     real *warm_x;           // [n_chunks][NX] state after the chunk's last warm-up frame (boundary check against the emitted
     int *warm_f;            // [n_chunks]     result of that frame, which an earlier chunk produced), and that frame's index or -1
     const real *obs;        // F*M*3
@@ -2087,7 +2088,14 @@ struct Solver {
             // trajectories have merged: the remaining rows of the chunk are then still valid)
             real dm[1] = {0};
             if (job.status[f] & ST_SOLVED) {
-                CTA_FOR(i, d.PR) { const real e = r_abs(w.x[3 + i] - job.pose[size_t(f) * d.PR + i]); if (e > dm[0]) dm[0] = e; }
+                // root + body pose at full weight, the remaining pose coefficients (finger PCA, jaw) at a tenth: the ratio of
+                // their per-frame tolerances and of the boundary tolerances (chmosh.BOUNDARY_TOL)
+                const int nbody = m.body_dof < 66 ? m.body_dof : 66;
+                CTA_FOR(i, d.PR) {
+                    real e = r_abs(w.x[3 + i] - job.pose[size_t(f) * d.PR + i]);
+                    if (i >= nbody) e *= real(0.1);
+                    if (e > dm[0]) dm[0] = e;
+                }
                 CTA_FOR(i, 3) { const real e = real(10) * r_abs(w.x[i] - job.trans[size_t(f) * 3 + i]); if (e > dm[0]) dm[0] = e; }
             } else dm[0] = real(1);
             // (max via the sum reduction of a one-hot power is overkill: reduce the maximum over threads with shuffles)

@@ -274,6 +274,8 @@ class StageI:
         if bool(_get(mp, 'optimize_face', False)):
             raise NotImplementedError('optimize_face in Stage I (chmosh.py:283-295) is outside this build; run it with the face '
                                       'markers excluded and optimize_face off, as the reference itself advises (chmosh.py:103-118)')
+        if _get(mp, 'head_marker_corr_fname', None) is not None:
+            raise NotImplementedError('moshpp.head_marker_corr_fname (chmosh.py:250-264,364-372) is outside this build')
         self.model = model = _pack.load_surface_model(sm.fname, pose_hand_prior_fname=_get(mp, 'pose_hand_prior_fname'),
                                                       use_hands_mean=bool(sm.use_hands_mean), dof_per_hand=int(sm.dof_per_hand),
                                                       v_template=v_template, surface_model_type=sm.type)
