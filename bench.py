@@ -264,7 +264,11 @@ def time_job(model, pk, opts, obs, vis, args, chunk_len, flush, steps, warmup):
     prec = {'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[args.precision]
     tol = chmosh.BOUNDARY_TOL['fast']
     F = obs.shape[0]
-    job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full, precision=prec)
+    extra = chmosh.first_chunk_extra(args.chunk_warmup, args.warmup_full)
+    if chunk_len is None:            # the product's own plan (chmosh.mosh_stageii)
+        chunk_len = chmosh.plan_chunk_len([F], chmosh.NUM_SMS_B200, args.chunk_warmup, args.warmup_full, first_extra=extra)
+    job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=args.chunk_warmup, warmup_full=args.warmup_full, precision=prec,
+                    first_extra=extra)
     job.upload(obs, vis)
     job.sync()
     for _ in range(warmup):
@@ -289,7 +293,7 @@ def time_job(model, pk, opts, obs, vis, args, chunk_len, flush, steps, warmup):
             e2e.append(time.perf_counter() - t1)
     solved = int(((res.status & lib.ST_SOLVED) != 0).sum())
     out = dict(ms=float(np.mean(ms)), first_launch_ms=float(np.mean(first_ms)), e2e_job_ms=float(np.mean(e2e)) * 1e3, totals=totals,
-               chunks=job.num_chunks, solved=solved, wall=wall, flags=int(np.bitwise_or.reduce(res.status)), launches=launches,
+               chunks=job.num_chunks, chunk_len=chunk_len, first_extra=extra, solved=solved, wall=wall, flags=int(np.bitwise_or.reduce(res.status)), launches=launches,
                boundary=rep)
     job.close()
     return out
@@ -338,9 +342,9 @@ def run_single(args):
     pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
     obs, vis = dense(case)
     F = obs.shape[0]
-    chunk_len = args.chunk_len if args.chunk_len is not None else chmosh.auto_chunk_len(F)
     model = lib.Model(pk, device=dev)
-    ns = time_job(model, pk, opts, obs, vis, args, chunk_len, flush, args.steps, args.warmup)
+    ns = time_job(model, pk, opts, obs, vis, args, args.chunk_len, flush, args.steps, args.warmup)
+    chunk_len = ns['chunk_len']
     e2e_ms, out, e2e_each, e2e_cold = time_plugin(case, args, args.steps, 2, chunk_len=args.chunk_len)
     b = out['stageii_debug_details']['b200']
     h2d = b.get('h2d_bytes', obs.size * esz + vis.size)      # (device input adapter: the raw marker table of the file)
@@ -351,7 +355,7 @@ def run_single(args):
         'ms_per_step': ns['ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision,
         'data': 'synthetic (seeded procedural SMPL-H model, markers, motion)',
         'config': {'workload': NS_DESC, 'frames': F, 'markers': pk.n_markers, 'free_vars': ab['n'], 'residual_rows': ab['R'],
-                   'chunk_len': chunk_len, 'chunk_warmup': args.chunk_warmup, 'warmup_full': args.warmup_full,
+                   'chunk_len': chunk_len, 'first_chunk_extra': ns['first_extra'], 'chunk_warmup': args.chunk_warmup, 'warmup_full': args.warmup_full,
                    'chunks': ns['chunks'], 'l2': 'flushed between timed steps (256 MiB write)', 'frames_solved': ns['solved'],
                    'frame_iterations_per_step': ns['totals']['builds'],
                    'useful_frame_iterations': ns['totals']['emitted_builds'],
@@ -386,7 +390,7 @@ def run_single(args):
         pk2, opts2, _ = chmosh.prepare_stageii(c2['cfg'], c2['markers_latent'], c2['latent_labels'], c2['betas'], c2['marker_meta'])
         o2, v2 = dense(c2)
         m2 = lib.Model(pk2, device=dev)
-        r2 = time_job(m2, pk2, opts2, o2, v2, args, chmosh.auto_chunk_len(o2.shape[0]), flush, ksteps, 3)
+        r2 = time_job(m2, pk2, opts2, o2, v2, args, None, flush, ksteps, 3)
         m2.close()
         e2, _, _, _ = time_plugin(c2, args, ksteps, 2)
         line['secondary'] = {

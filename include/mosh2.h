@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOSH2_VERSION 103
+#define MOSH2_VERSION 104
 
 enum {
     MOSH2_OK = 0,
@@ -131,9 +131,13 @@ void mosh2_model_destroy(mosh2_model *m);
  * sequence into chunks solved concurrently; every chunk starts early enough to solve chunk_warmup frames (frames with
  * at least one visible marker) before its first emitted frame, from the reference's own cold start.  The last
  * warmup_full of those run the full per-frame schedule, the earlier ones a single linearisation of the Step-2 problem
- * (warmup_full < 0 or >= chunk_warmup: all of them run the full schedule). */
+ * (warmup_full < 0 or >= chunk_warmup: all of them run the full schedule).  first_extra > 0: the first chunk of every
+ * sequence -- which has no warm-up to solve -- emits chunk_len + first_extra frames, so that with first_extra = the cost
+ * of a warm-up all chunks of a sequence finish together and no chunk starts closer to the sequence start than a warm-up.
+ * A chunk whose walk-back does reach the first frame of its sequence solves all those frames with the full schedule: it
+ * is then the reference's own recursion from its own start, and its rows equal the sequential pass exactly. */
 typedef struct mosh2_schedule {
-    int32_t chunk_len, chunk_warmup, warmup_full, reserved;
+    int32_t chunk_len, chunk_warmup, warmup_full, first_extra;
 } mosh2_schedule;
 
 /* A job = device buffers for one sequence of n_frames frames. */
@@ -209,6 +213,8 @@ int mosh2_job_kernel_ms(mosh2_job *j, float *ms);
  * launched on their own streams at the same time: the span of the whole group is the maximum over all pairs), ms */
 int mosh2_job_span_ms(mosh2_job *first, mosh2_job *last, float *ms);
 int mosh2_job_num_chunks(mosh2_job *j);
+/* out [n_chunks * 2]: first emitted frame and end of the emitted range of every chunk (job frame axis) */
+int mosh2_job_chunk_ranges(mosh2_job *j, int32_t *out);
 /* work done by the last launch: out8 = {dog-leg iterations, residual evaluations, Jacobian / normal-equation builds,
  * minimisations} over ALL processed frames (warm-up included), then the same four over the EMITTED frames only */
 int mosh2_job_totals(mosh2_job *j, int32_t *out8);

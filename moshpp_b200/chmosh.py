@@ -80,12 +80,30 @@ def _read_vertices(fname: str) -> np.ndarray:
     raise NotImplementedError(f'cannot read v_template from {fname}')
 
 
+def first_chunk_extra(warmup: int = DEFAULT_WARMUP, warmup_full: int = DEFAULT_WARMUP_FULL) -> int:
+    """mosh2_schedule.first_extra of the planned schedules: what a warm-up costs in fully solved frames (light frames count
+    a quarter).  The first chunk of a sequence has no warm-up; emitting that many frames more it finishes with the others."""
+    wf = warmup if (warmup_full < 0 or warmup_full > warmup) else warmup_full
+    return int(wf + (warmup - wf) // 4) if warmup > 0 else 0
+
+
+def count_chunks(n_frames: int, chunk_len: int, first_extra: int = 0) -> int:
+    """Chunks mosh2_host::chunk_table cuts a sequence of ``n_frames`` into."""
+    if chunk_len <= 0 or chunk_len >= n_frames:
+        return 1
+    if first_extra > 0:
+        rest = n_frames - chunk_len - first_extra
+        return 1 + (-(-rest // chunk_len) if rest > 0 else 0)
+    return -(-n_frames // chunk_len)
+
+
 def plan_chunk_len(frame_counts, sm_budget: int = NUM_SMS_B200, warmup: int = DEFAULT_WARMUP,
-                   warmup_full: int = DEFAULT_WARMUP_FULL, min_len: int = 4) -> int:
+                   warmup_full: int = DEFAULT_WARMUP_FULL, min_len: int = 4, first_extra: int = 0) -> int:
     """Chunk length for a set of sequences that are solved together on one GPU (one thread block per chunk, one block
     per SM at a time).  The chunks run in waves of ``sm_budget``; a wave lasts as long as its longest chunk, i.e. about
     chunk_len + warm-up frame solves.  Returns the length that minimises waves x (chunk_len + warm-up cost), where the
-    light warm-up frames cost about a quarter of a full one and the cold start about five."""
+    light warm-up frames cost about a quarter of a full one and the cold start about five.  ``first_extra``: frames the
+    first chunk of every sequence emits on top (``first_chunk_extra``)."""
     counts = [int(f) for f in frame_counts if f > 0]
     if not counts:
         return min_len
@@ -95,7 +113,7 @@ def plan_chunk_len(frame_counts, sm_budget: int = NUM_SMS_B200, warmup: int = DE
         lo, hi = min_len, max(max(counts), min_len)
         while lo < hi:                                   # smallest L whose chunks fit `waves` waves
             mid = (lo + hi) // 2
-            if sum(-(-f // mid) for f in counts) <= waves * sm_budget:
+            if sum(count_chunks(f, mid, first_extra) for f in counts) <= waves * sm_budget:
                 hi = mid
             else:
                 lo = mid + 1
@@ -393,9 +411,9 @@ def solve_verified(job, obs, vis, *, tol, max_rounds: int = 12, while_running=No
     res = job.download()
     if len(bad):
         report['unverified_chunks'] = int(len(bad))
-        L = job.schedule.chunk_len
-        for c in bad:          # (single-sequence jobs: chunk c emits frames [c L, (c+1) L))
-            sl = slice(int(c) * L, (int(c) + 1) * L)
+        ranges = job.chunk_ranges()
+        for c in bad:
+            sl = slice(int(ranges[c, 0]), int(ranges[c, 1]))
             res.status[sl] |= np.where((res.status[sl] & _lib.ST_SOLVED) != 0, _lib.ST_SHORT_WARMUP, 0).astype(res.status.dtype)
         logger.warning('%d chunks did not pass the boundary check after %d repair rounds (max delta %s); their frames carry '
                        'MOSH2_ST_SHORT_WARMUP', len(bad), report['rounds'], report['boundary_delta_max'])
@@ -405,7 +423,7 @@ def solve_verified(job, obs, vis, *, tol, max_rounds: int = 12, while_running=No
 def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_labels: list, betas: np.ndarray,
                  marker_meta: dict, v_template_fname=None, *, device: int = 0, mode: str = 'fast',
                  chunk_len: Optional[int] = None, chunk_warmup: Optional[int] = None, warmup_full: Optional[int] = None,
-                 precision: Optional[str] = None, verify: bool = True, boundary_tol=None,
+                 first_extra: Optional[int] = None, precision: Optional[str] = None, verify: bool = True, boundary_tol=None,
                  sm_budget: int = NUM_SMS_B200, labels_map='general', subject_cache: bool = True,
                  device_adapter: bool = True) -> dict:
     """Stage II of MoSh++ on one B200.  Positional arguments as in the reference (chmosh.py:458-459).
@@ -414,7 +432,8 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
     BASELINE.md section 4's tolerances of the reference's sequential float64 result except on the few frames where that
     result is itself ill-conditioned; 'exact' = the parity mode: float64, long fully solved
     warm-up, tight boundary check.  ``chunk_len`` (None = planned, 0 = the reference's single sequential pass in one
-    thread block), ``chunk_warmup`` / ``warmup_full`` (mosh2_schedule, include/mosh2.h), ``precision`` 'f32' | 'f64',
+    thread block), ``chunk_warmup`` / ``warmup_full`` / ``first_extra`` (mosh2_schedule, include/mosh2.h; first_extra None =
+    the cost of a warm-up, so that the first chunk finishes with the others), ``precision`` 'f32' | 'f64',
     ``verify`` / ``boundary_tol`` override the mode's presets.  ``labels_map``: 'general' (default) = the synonym table
     the reference always applies (chmosh.py:466), a dict, or None for raw labels.  ``subject_cache``: keep the packed
     per-subject constants and their device copy for the next sequences of the same subject (keyed by the content of every
@@ -468,8 +487,11 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         F = len(selected_frames)
     if F == 0:
         raise ValueError('no frames selected')
+    if first_extra is None:
+        first_extra = first_chunk_extra(chunk_warmup, warmup_full)
     if chunk_len is None:
-        chunk_len = plan_chunk_len([F], sm_budget, chunk_warmup, warmup_full if warmup_full >= 0 else chunk_warmup)
+        chunk_len = plan_chunk_len([F], sm_budget, chunk_warmup, warmup_full if warmup_full >= 0 else chunk_warmup,
+                                   first_extra=first_extra)
     if chunk_len >= F:
         chunk_len = 0
     prec = {'f32': _lib.MOSH2_F32, 'f64': _lib.MOSH2_F64}[precision]
@@ -480,7 +502,8 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         model = _lib.Model(pk, device=device)
     mark('model_create_ms')
     try:
-        job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec)
+        job = model.job(F, opts, chunk_len=chunk_len, chunk_warmup=chunk_warmup, warmup_full=warmup_full, precision=prec,
+                        first_extra=first_extra)
         mark('job_create_ms')
         try:
             # the result-independent half of the output (per-frame observation / label lists, the copy of the original
@@ -524,7 +547,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
         'mocap_time_length': mocap.time_length(),
         'b200': {
             'kernel_ms': kernel_ms, 'wall_s': time.time() - t0, 'chunks': n_chunks, 'chunk_len': chunk_len,
-            'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'precision': precision, 'mode': mode,
+            'chunk_warmup': chunk_warmup, 'warmup_full': warmup_full, 'first_extra': first_extra, 'precision': precision, 'mode': mode,
             'boundary_check': report, 'totals': totals, 'host_ms': lap, 'subject_cache_hit': cache_hit,
             'device_adapter': raw_cols is not None,
             'h2d_bytes': int(((F - 1) * selected_frames.step + 1) * mocap.raw.shape[1] * 24 + 4 * len(latent_labels)) if raw_cols is not None

@@ -615,7 +615,8 @@ int mosh2_job_create_batch(mosh2_model *m, const mosh2_options *opt, int32_t n_s
     j->chunk_len = chunk_len > 0 ? chunk_len : 0;
     j->warmup = chunk_warmup > 0 ? chunk_warmup : 0;
     j->warm_full = (!sched || sched->warmup_full < 0 || sched->warmup_full > j->warmup) ? j->warmup : sched->warmup_full;
-    j->tab = mosh2_host::chunk_table(frame_counts, n_seq, j->chunk_len, j->warmup, j->warm_full);
+    const int first_extra = (sched && sched->first_extra > 0 && j->chunk_len > 0 && j->warmup > 0) ? sched->first_extra : 0;
+    j->tab = mosh2_host::chunk_table(frame_counts, n_seq, j->chunk_len, j->warmup, j->warm_full, first_extra);
     j->tab0 = j->tab;
     const std::vector<int> &tab = j->tab;
     j->n_chunks = int(tab.size() / mosh2::kChunkRec);
@@ -879,6 +880,15 @@ int mosh2_job_span_ms(mosh2_job *first, mosh2_job *last, float *ms) {
 }
 
 int mosh2_job_num_chunks(mosh2_job *j) { return j ? j->n_chunks : 0; }
+
+int mosh2_job_chunk_ranges(mosh2_job *j, int32_t *out) {
+    if (!j || !out) return fail(MOSH2_E_INVALID, "null argument");
+    for (int c = 0; c < j->n_chunks; ++c) {
+        out[2 * c] = j->tab0[size_t(c) * mosh2::kChunkRec];
+        out[2 * c + 1] = j->tab0[size_t(c) * mosh2::kChunkRec + 1];
+    }
+    return 0;
+}
 
 // development builds (-DMOSH2_PROFILE) only: 32 phase clock sums of the last launch; not part of mosh2.h
 int mosh2_dev_phase_clocks(mosh2_job *j, long long *out32) {

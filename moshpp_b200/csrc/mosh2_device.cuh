@@ -2311,11 +2311,12 @@ struct Solver {
             f_begin = w.isc[5]; f_full = w.isc[6];
             // fewer solved warm-up frames than asked for, without having reached the start of the sequence
             short_warmup = w.isc[4] < warmup && w.isc[7] == 2;
-            // The walk-back ran into the first frame of the sequence: the chunk starts where the reference starts.  If the
-            // frames in front of it cost no more fully solved than a regular warm-up does (light frames count a quarter),
-            // solve them all fully -- the chunk is then the reference's own recursion from its own start, bit for bit the
-            // rows the chunks in front of it emit, instead of a light-frame approximation of the very first frames.
-            if (w.isc[4] < warmup && w.isc[7] != 2 && w.isc[4] <= warm_full + (warmup - warm_full) / 4) f_full = f_begin;
+            // The walk-back ran into the first frame of the sequence: the chunk starts where the reference starts.  It solves
+            // the frames in front of it with the full schedule -- it is then the reference's own recursion from its own
+            // start, bit for bit the rows the chunks in front of it emit, instead of a shortened warm-up whose first frames
+            // are a light-frame approximation.  (At most warmup - 1 fully solved frames; with mosh2_schedule::first_extra
+            // at the cost of a warm-up only the second chunk of a short-chunk schedule gets here.)
+            if (w.isc[4] < warmup && w.isc[7] != 2) f_full = f_begin;
             M2_SYNC();
         }
         prologue();

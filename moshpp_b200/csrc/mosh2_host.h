@@ -49,16 +49,22 @@ inline int hand_blocks(const double *C, int n_red, int n_full, mosh2::HandBlock 
 // Chunk table of a job that holds n_seq sequences back to back on its frame axis: kChunkRec ints per chunk -- first
 // emitted frame, end of the emitted range, first frame of the chunk's sequence, warm-up length (solved frames), number of
 // fully solved warm-up frames.  chunk_len <= 0: one chunk per sequence (the reference's sequential pass).  Chunks never
-// straddle a sequence boundary.
-inline std::vector<int> chunk_table(const int *frame_counts, int n_seq, int chunk_len, int warmup, int warm_full) {
+// straddle a sequence boundary.  first_extra > 0: the FIRST chunk of every sequence emits chunk_len + first_extra frames --
+// it has no warm-up to solve, so with first_extra = the cost of a warm-up every chunk of the sequence finishes at the same
+// time, and no later chunk starts so close to the sequence start that its walk-back is cut short.
+inline std::vector<int> chunk_table(const int *frame_counts, int n_seq, int chunk_len, int warmup, int warm_full, int first_extra = 0) {
     std::vector<int> tab;
     int s0 = 0;
     for (int q = 0; q < n_seq; ++q) {
         const int F = frame_counts[q];
         const int L = (chunk_len > 0 && chunk_len < F) ? chunk_len : F;
-        for (int f = 0; f < F; f += L) {
-            const int rec[mosh2::kChunkRec] = {s0 + f, s0 + (f + L < F ? f + L : F), s0, warmup, warm_full};
+        const int E = (first_extra > 0 && L < F) ? first_extra : 0;
+        for (int f = 0; f < F;) {
+            long long e = (long long)f + L + (f == 0 ? E : 0);
+            if (e > F) e = F;
+            const int rec[mosh2::kChunkRec] = {s0 + f, s0 + int(e), s0, warmup, warm_full};
             tab.insert(tab.end(), rec, rec + mosh2::kChunkRec);
+            f = int(e);
         }
         s0 += F;
     }

@@ -13,7 +13,7 @@ import numpy as np
 
 from .pack import StageIIPack
 
-ABI_VERSION = 103          # MOSH2_VERSION of include/mosh2.h that the ctypes structs below encode
+ABI_VERSION = 104          # MOSH2_VERSION of include/mosh2.h that the ctypes structs below encode
 MOSH2_F32, MOSH2_F64 = 0, 1
 ST_SOLVED, ST_SKIPPED, ST_HAS_VELO, ST_HAS_EXTRAP, ST_GN_FALLBACK, ST_MAXITER, ST_SHORT_WARMUP = 1, 2, 4, 8, 16, 32, 64
 ERR_NAMES = ('data', 'poseB', 'velo', 'poseH', 'dmpl', 'extrap_dmpl', 'poseF', 'expr')   # column order of mosh2_result.errs
@@ -52,12 +52,13 @@ class Options(C.Structure):
 
 class Schedule(C.Structure):
     """mosh2_schedule: chunk_len <= 0 = the reference's sequential pass; warmup_full < 0 = every warm-up frame runs
-    the full per-frame schedule."""
-    _fields_ = [('chunk_len', C.c_int32), ('chunk_warmup', C.c_int32), ('warmup_full', C.c_int32), ('reserved', C.c_int32)]
+    the full per-frame schedule; first_extra = frames the first chunk of every sequence emits on top of chunk_len (it has
+    no warm-up to solve)."""
+    _fields_ = [('chunk_len', C.c_int32), ('chunk_warmup', C.c_int32), ('warmup_full', C.c_int32), ('first_extra', C.c_int32)]
 
 
-def make_schedule(chunk_len: int = 0, chunk_warmup: int = 0, warmup_full: int = -1, reserved: int = 0) -> Schedule:
-    return Schedule(int(chunk_len), int(chunk_warmup), int(warmup_full), int(reserved))
+def make_schedule(chunk_len: int = 0, chunk_warmup: int = 0, warmup_full: int = -1, first_extra: int = 0) -> Schedule:
+    return Schedule(int(chunk_len), int(chunk_warmup), int(warmup_full), int(first_extra))
 
 
 class Result(C.Structure):
@@ -130,6 +131,7 @@ def load_library(path: Optional[str] = None):
     lib.mosh2_job_sync.argtypes = [vp]
     lib.mosh2_job_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.mosh2_job_num_chunks.argtypes = [vp]
+    lib.mosh2_job_chunk_ranges.argtypes = [vp, _i32p]
     lib.mosh2_job_span_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     lib.mosh2_job_totals.argtypes = [vp, _i32p]
     lib.mosh2_job_destroy.argtypes = [vp]
@@ -147,7 +149,8 @@ EXPORTED_SYMBOLS = (
     'mosh2_job_sync', 'mosh2_job_kernel_ms', 'mosh2_job_num_chunks', 'mosh2_job_totals', 'mosh2_job_destroy',
     'mosh2_solve', 'mosh2_job_upload_device', 'mosh2_job_row_width', 'mosh2_job_download_device', 'mosh2_job_span_ms',
     'mosh2_job_create_batch', 'mosh2_job_upload_device_range', 'mosh2_job_warm_states', 'mosh2_job_relaunch_chunks',
-    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance', 'mosh2_job_upload_markers', 'mosh2_job_linearize')
+    'mosh2_job_boundary_deltas', 'mosh2_release_cached_memory', 'mosh2_mesh_distance', 'mosh2_job_upload_markers', 'mosh2_job_linearize',
+    'mosh2_job_chunk_ranges')
 
 
 def _ptr(a: np.ndarray, typ):
@@ -253,24 +256,24 @@ class Model:
             raise Mosh2Error(f'{what} failed ({rc}): {self.lib.mosh2_last_error().decode()}')
 
     def solve(self, obs: np.ndarray, vis: np.ndarray, options: Options, *, chunk_len: int = 0,
-              chunk_warmup: int = 0, warmup_full: int = -1, precision: int = MOSH2_F32) -> ResultArrays:
+              chunk_warmup: int = 0, warmup_full: int = -1, precision: int = MOSH2_F32, first_extra: int = 0) -> ResultArrays:
         """One blocking call: H2D, kernel, D2H (mosh2_solve)."""
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
         F = obs.shape[0]
         assert obs.shape == (F, self.pk.n_markers, 3) and vis8.shape == (F, self.pk.n_markers)
         res = ResultArrays(F, pack_dims(self.pk))
-        sched = make_schedule(chunk_len, chunk_warmup, warmup_full)
+        sched = make_schedule(chunk_len, chunk_warmup, warmup_full, first_extra)
         rc = self.lib.mosh2_solve(self.handle, C.byref(options), F, _ptr(obs, _f64p), _ptr(vis8, _u8p),
                                   C.byref(sched), precision, C.byref(res.c))
         self._check(rc, 'mosh2_solve')
         return res
 
     def job(self, n_frames: int, options: Options, *, chunk_len: int = 0, chunk_warmup: int = 0,
-            warmup_full: int = -1, precision: int = MOSH2_F32) -> 'Job':
+            warmup_full: int = -1, precision: int = MOSH2_F32, first_extra: int = 0) -> 'Job':
         """``n_frames``: frames of one sequence, or a list of frame counts = several sequences of this subject solved by
         one launch (mosh2_job_create_batch); the job's frame axis then holds them back to back."""
-        return Job(self, n_frames, options, make_schedule(chunk_len, chunk_warmup, warmup_full), precision)
+        return Job(self, n_frames, options, make_schedule(chunk_len, chunk_warmup, warmup_full, first_extra), precision)
 
     def close(self):
         if self.handle:
@@ -416,6 +419,12 @@ class Job:
     @property
     def num_chunks(self) -> int:
         return int(self.lib.mosh2_job_num_chunks(self.handle))
+
+    def chunk_ranges(self) -> np.ndarray:
+        """[n_chunks, 2]: first emitted frame and end of the emitted range of every chunk (job frame axis)."""
+        out = np.zeros((self.num_chunks, 2), dtype=np.int32)
+        self.model._check(self.lib.mosh2_job_chunk_ranges(self.handle, _ptr(out, _i32p)), 'mosh2_job_chunk_ranges')
+        return out
 
     def close(self):
         if self.handle:

@@ -126,10 +126,11 @@ class GpuRankSolver:
     def __init__(self, packs: Dict[int, object], options, frame_counts: Dict[int, int], device: int, *,
                  chunk_warmup: int, warmup_full: int, sm_budget: int = 148, precision=None):
         from . import lib
-        from .chmosh import plan_chunk_len
+        from .chmosh import first_chunk_extra, plan_chunk_len
         self.device = device
         prec = lib.MOSH2_F32 if precision is None else precision
-        common = plan_chunk_len(list(frame_counts.values()), sm_budget, chunk_warmup, warmup_full)
+        extra = first_chunk_extra(chunk_warmup, warmup_full)
+        common = plan_chunk_len(list(frame_counts.values()), sm_budget, chunk_warmup, warmup_full, first_extra=extra)
         groups: Dict[int, List[int]] = {}
         for i in frame_counts:
             groups.setdefault(id(packs[i]), []).append(i)
@@ -138,7 +139,7 @@ class GpuRankSolver:
             model = lib.Model(packs[ids[0]], device=device)
             counts = [int(frame_counts[i]) for i in ids]
             job = model.job(counts, options, chunk_len=common if common < max(counts) else 0, chunk_warmup=chunk_warmup,
-                            warmup_full=warmup_full, precision=prec)
+                            warmup_full=warmup_full, precision=prec, first_extra=extra)
             self.models.append(model)
             self.jobs.append(job)
             for k, i in enumerate(ids):

@@ -460,8 +460,11 @@ def mosh_stageii(mocap_fname, cfg, markers_latent, latent_labels, betas, marker_
     else:
         L, W = chunk[:2]
         W_full = chunk[2] if len(chunk) > 2 and 0 <= chunk[2] <= W else W
+        E = chunk[3] if len(chunk) > 3 and L < len(frames) else 0      # mosh2_schedule.first_extra: the first chunk is longer
         per = []
-        for s in range(0, len(frames), L):
+        starts = [0] + list(range(L + E, len(frames), L)) if E > 0 else list(range(0, len(frames), L))
+        for ci, s in enumerate(starts):
+            s_end = starts[ci + 1] if ci + 1 < len(starts) else len(frames)
             # the warm-up is counted in solved frames (frames with a visible marker), walking back from the chunk
             lo, full_from, cnt = s, s, 0
             while lo > 0 and cnt < W:
@@ -472,10 +475,10 @@ def mosh_stageii(mocap_fname, cfg, markers_latent, latent_labels, betas, marker_
                         full_from = lo
             while lo < s and frames[lo] is None:
                 lo += 1
-            if cnt < W and cnt <= W_full + (W - W_full) // 4:
+            if cnt < W:
                 full_from = lo      # the walk-back reached the first frame: the chunk is the sequential recursion itself
             solver.reset()
-            res = solver.solve_range(frames[lo:s + L], emit_from=s - lo, light_until=full_from - lo)
+            res = solver.solve_range(frames[lo:s_end], emit_from=s - lo, light_until=full_from - lo)
             for r in res:
                 r['fidx'] += lo
             per += res

@@ -58,7 +58,7 @@ def emu():
     from moshpp_b200 import build, lib
     handle = C.CDLL(build.build_emu())
 
-    def solve(case, chunk_len=0, warmup=0, precision=None, obs_vis=None, warmup_full=-1):
+    def solve(case, chunk_len=0, warmup=0, precision=None, obs_vis=None, warmup_full=-1, first_extra=0):
         precision = lib.MOSH2_F64 if precision is None else precision
         pk, cfg = case['pack'], case['cfg']
         obs, vis = obs_vis if obs_vis is not None else dense_obs(case)
@@ -70,7 +70,7 @@ def emu():
         res = lib.ResultArrays(F, lib.pack_dims(pk))
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         vis8 = np.ascontiguousarray(vis, dtype=np.uint8)
-        sched = lib.make_schedule(chunk_len, warmup, warmup_full)
+        sched = lib.make_schedule(chunk_len, warmup, warmup_full, first_extra)
         rc = handle.mosh2_emu_solve(C.byref(h.desc), C.byref(opt), F, obs.ctypes.data_as(lib._f64p),
                                     vis8.ctypes.data_as(lib._u8p), C.byref(sched), precision, C.byref(res.c))
         assert rc == 0
@@ -84,7 +84,7 @@ def run_oracle(case, **kw):
                                 case['betas'], case['marker_meta'], **kw)
 
 
-def gpu_solve(case, chunk_len=0, warmup=0, precision='f32', obs_vis=None, warmup_full=-1):
+def gpu_solve(case, chunk_len=0, warmup=0, precision='f32', obs_vis=None, warmup_full=-1, first_extra=0):
     from moshpp_b200 import chmosh, lib
     pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'],
                                              case['betas'], case['marker_meta'])
@@ -92,7 +92,7 @@ def gpu_solve(case, chunk_len=0, warmup=0, precision='f32', obs_vis=None, warmup
     model = lib.Model(pk, device=0)
     try:
         return model.solve(obs, vis, opts, chunk_len=chunk_len, chunk_warmup=warmup, warmup_full=warmup_full,
-                           precision={'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[precision])
+                           precision={'f32': lib.MOSH2_F32, 'f64': lib.MOSH2_F64}[precision], first_extra=first_extra)
     finally:
         model.close()
 

@@ -132,7 +132,8 @@ int run(const mosh2_model_desc *desc, const mosh2_options *opt, int n_frames, co
     job.n_frames = n_frames;
     const int wu = warmup > 0 ? warmup : 0;
     const int wf = (!sched || sched->warmup_full < 0 || sched->warmup_full > wu) ? wu : sched->warmup_full;
-    std::vector<int> tab = mosh2_host::chunk_table(seq_counts, n_seq, chunk_len, wu, wf);
+    const int first_extra = (sched && sched->first_extra > 0 && chunk_len > 0 && wu > 0) ? sched->first_extra : 0;
+    std::vector<int> tab = mosh2_host::chunk_table(seq_counts, n_seq, chunk_len, wu, wf, first_extra);
     job.n_chunks = int(tab.size() / mosh2::kChunkRec);
     job.chunk_tab = tab.data();
     job.chunk_ids = nullptr; job.warm_x = nullptr; job.warm_f = nullptr; job.merge_tol = 0;

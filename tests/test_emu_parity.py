@@ -210,9 +210,9 @@ def test_rank_deficient_frames_are_flagged_and_recovered(cases, emu):
 
 
 def test_chunks_that_reach_the_sequence_start_are_exact(cases, emu):
-    """A chunk whose warm-up walk-back runs into the first frame of the sequence solves those frames fully (as long as that
-    costs no more than a regular warm-up): it is the reference's own recursion from its own start, so its rows equal the
-    single sequential pass bit for bit.  The first chunk with a complete warm-up window keeps its light frames."""
+    """A chunk whose warm-up walk-back runs into the first frame of the sequence solves those frames fully: it is the
+    reference's own recursion from its own start, so its rows equal the single sequential pass bit for bit.  The first
+    chunk with a complete warm-up window keeps its light frames."""
     case = cases('C2')
     seq = emu(case)
     res = emu(case, chunk_len=4, warmup=12, warmup_full=8)
@@ -220,3 +220,18 @@ def test_chunks_that_reach_the_sequence_start_are_exact(cases, emu):
     assert np.array_equal(res.errs[:12], seq.errs[:12])
     d = np.abs(res.pose[12:] - seq.pose[12:]).max()
     assert 0 < d < 1e-1
+
+
+def test_longer_first_chunk_schedule(cases, emu):
+    """mosh2_schedule.first_extra: the first chunk of a sequence (no warm-up to solve) emits chunk_len + first_extra frames.
+    Its rows are the sequential pass bit for bit; the later chunks follow the oracle's emulation of the same schedule."""
+    case = cases('C2')
+    seq = emu(case)
+    res = emu(case, chunk_len=3, warmup=5, warmup_full=3, first_extra=4)
+    assert np.array_equal(res.pose[:7], seq.pose[:7]) and np.array_equal(res.errs[:7], seq.errs[:7])
+    assert (res.status & lib.ST_SOLVED).all()
+    out = run_oracle(case, chunk=(3, 5, 3, 4))
+    assert np.abs(res.pose - out['_pose_reduced']).max() < 1e-9
+    assert np.abs(res.trans - out['trans']).max() < 1e-9
+    plain = emu(case, chunk_len=3, warmup=5, warmup_full=3)
+    assert np.abs(plain.pose[7:] - res.pose[7:]).max() > 1e-9            # other chunk boundaries, other warm-up windows

@@ -43,6 +43,28 @@ def test_auto_chunk_len():
     assert chmosh.auto_chunk_len(4000, sm_budget=37) == 109
 
 
+def test_planned_schedule_counts_chunks_like_the_chunk_table():
+    """chmosh.count_chunks mirrors mosh2_host::chunk_table (incl. the longer first chunk), and the plan of the north-star
+    sequence fills the SMs with one wave."""
+    def brute(F, L, E):
+        if L <= 0 or L >= F:
+            return 1
+        n, f = 0, 0
+        while f < F:
+            f += L + (E if f == 0 else 0)
+            n += 1
+        return n
+    for F in (1, 5, 57, 500, 4000):
+        for L in (0, 1, 4, 27, 56, 4000):
+            for E in (0, 3, 52):
+                assert chmosh.count_chunks(F, L, E) == brute(F, L, E), (F, L, E)
+    assert chmosh.first_chunk_extra(64, 48) == 52 and chmosh.first_chunk_extra(256, -1) == 256 and chmosh.first_chunk_extra(0, 0) == 0
+    L = chmosh.plan_chunk_len([4000], 148, 64, 48, first_extra=52)
+    assert L == 27 and chmosh.count_chunks(4000, L, 52) <= 148 < chmosh.count_chunks(4000, L - 1, 52)
+    L5 = chmosh.plan_chunk_len([4000] * 32, 148, 64, 48, first_extra=52)
+    assert sum(chmosh.count_chunks(4000, L5, 52) for _ in range(32)) <= 2 * 148
+
+
 def test_options_follow_the_config(cases):
     case = cases('C2')
     pk, opts, flags = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
