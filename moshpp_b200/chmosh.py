@@ -25,7 +25,6 @@ import hashlib
 import logging
 import math
 import os
-import pickle
 import time
 from collections import OrderedDict
 from typing import Optional
@@ -239,8 +238,7 @@ def prepare_stageii(cfg, markers_latent, latent_labels, betas, marker_meta, v_te
         if sm.type not in ('smpl', 'smplh'):
             logger.warning('DMPL with %s is rejected by the reference (chmosh.py:508-509); running the '
                            'extension defined in DESIGN.md', sm.type)
-        with open(sm.dmpl_fname, 'rb') as f:
-            dmpl_dirs = pickle.load(f, encoding='latin-1')['eigvec']
+        dmpl_dirs = np.asarray(_pack.load_reference_pickle(sm.dmpl_fname)['eigvec'])
     pk = _pack.build_pack(model, np.asarray(betas, dtype=np.float64), np.asarray(markers_latent, dtype=np.float64),
                           num_betas=int(sm.num_betas), prior=prior, dmpl_dirs=dmpl_dirs,
                           num_dmpls=int(sm.num_dmpls) if dyn else 0,

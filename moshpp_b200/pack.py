@@ -71,6 +71,59 @@ def _dense_regressor(jreg) -> np.ndarray:
     return np.asarray(jreg, dtype=np.float64)
 
 
+class _ChLeaf:
+    """What a ``chumpy.ch.Ch`` leaf of a public body-model pickle becomes when chumpy is not installed.  The released
+    SMPL / SMPL-H / MANO files store ``v_template``, ``shapedirs``, ``posedirs``, ``weights``, ``J`` as pickled chumpy
+    objects (the reference reads them through chumpy, smpl_fast_derivatives.py:48,149-166); a leaf's state is a dict whose
+    ``x`` entry is the array.  Nothing of chumpy is evaluated: anything that is not a plain leaf is refused."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {})
+
+    def __array__(self, dtype=None, copy=None):
+        if 'x' not in self.__dict__:
+            raise TypeError('pickled chumpy object without an array payload (not a leaf): install chumpy to read this file')
+        a = np.asarray(self.__dict__['x'])
+        return a.astype(dtype) if dtype is not None else a
+
+    @property
+    def r(self):
+        return self.__array__()
+
+
+class _ModelUnpickler(pickle.Unpickler):
+    """pickle.load for body-model / prior files written by the reference's environment, without that environment:
+    chumpy classes resolve to chumpy when it is importable and to ``_ChLeaf`` otherwise; scipy.sparse classes pickled under
+    their old private module paths (``scipy.sparse.csc.csc_matrix`` ...) resolve to the public ones."""
+
+    def find_class(self, module, name):
+        top = module.split('.')[0]
+        if top == 'chumpy':
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                return _ChLeaf
+        if module.startswith('scipy.sparse.'):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                import scipy.sparse
+                return getattr(scipy.sparse, name)
+        return super().find_class(module, name)
+
+
+def load_reference_pickle(fname: str):
+    """A pickle of the reference's world (python-2 ``latin-1`` strings, chumpy leaves, old scipy paths) as plain data:
+    every chumpy value of a top-level dict is replaced by its array."""
+    with open(fname, 'rb') as f:
+        dd = _ModelUnpickler(f, encoding='latin-1').load()
+    if isinstance(dd, dict):
+        for k, v in list(dd.items()):
+            if not isinstance(v, np.ndarray) and hasattr(v, 'r') and not hasattr(v, 'toarray'):
+                dd[k] = np.asarray(v.r)
+    return dd
+
+
 _MODEL_FILE_CACHE: 'OrderedDict[tuple, dict]' = OrderedDict()
 
 
@@ -82,8 +135,7 @@ def _read_model_pickle(fname: str) -> dict:
     key = (os.path.realpath(fname), st.st_mtime_ns, st.st_size)
     dd = _MODEL_FILE_CACHE.get(key)
     if dd is None:
-        with open(fname, 'rb') as f:
-            dd = pickle.load(f, encoding='latin-1')
+        dd = load_reference_pickle(fname)
         _MODEL_FILE_CACHE[key] = dd
         while len(_MODEL_FILE_CACHE) > 2:
             _MODEL_FILE_CACHE.popitem(last=False)
@@ -223,16 +275,14 @@ HORSE_JANGLES_SIGNS = np.ones(12)
 def create_horse_body_prior(pose_body_prior_fname: str) -> BodyPrior:
     """smal_horse_prior (prior/horse_body_prior.py:40-53, tail / mouth / ears disabled): r = (pose[3:84] - mean) . pic, i.e.
     one component with Q = pic pic^T and no weight constant."""
-    with open(pose_body_prior_fname, 'rb') as f:
-        res = pickle.load(f, encoding='latin-1')
+    res = load_reference_pickle(pose_body_prior_fname)
     P = np.asarray(res['pic'], dtype=np.float64)[:81, :81]
     mu = np.asarray(res['mean_pose'], dtype=np.float64)[:81]
     return BodyPrior(means=np.ascontiguousarray(mu[None]), Q=np.ascontiguousarray((P @ P.T)[None]), neglogw=np.zeros(1))
 
 
 def create_gmm_body_prior(pose_body_prior_fname: str, exclude_hands: bool = False) -> BodyPrior:
-    with open(pose_body_prior_fname, 'rb') as f:
-        gmm = pickle.load(f, encoding='latin-1')
+    gmm = load_reference_pickle(pose_body_prior_fname)
     npose = 63 if exclude_hands else 69
     covars = np.asarray(gmm['covars'], dtype=np.float64)[:, :npose, :npose]
     means = np.asarray(gmm['means'], dtype=np.float64)[:, :npose]

@@ -158,3 +158,52 @@ def test_duplicate_labels_take_the_last_available_sample(tmp_path):
     assert [float(f['A'][0]) for f in d] == [10.0, 2.0, 3.0]
     fr = frames_from_mocap(s.markers, s.labels, ['A', 'B', 'C'])      # the oracle's restatement of the same rule
     assert [float(f[1][0, 0]) for f in fr] == [10.0, 2.0, 3.0]
+
+
+def test_model_pickles_with_chumpy_leaves_load_without_chumpy(cases, tmp_path):
+    """The released SMPL-family files hold chumpy objects (``chumpy.ch.Ch`` leaves with the array under ``x``) and scipy
+    sparse matrices pickled under old module paths; the reference reads them through chumpy
+    (smpl_fast_derivatives.py:61,149-166).  The loader resolves them to plain arrays without chumpy being installed and
+    the resulting SurfaceModel equals the one read from a plain-array pickle."""
+    import pickle
+    import sys
+    import types
+    import scipy.sparse as sp
+    from moshpp_b200 import pack
+    case = cases('C2')
+    sm = case['cfg'].surface_model
+    with open(sm.fname, 'rb') as f:
+        dd = pickle.load(f)
+    assert 'chumpy' not in sys.modules
+    mod, sub = types.ModuleType('chumpy'), types.ModuleType('chumpy.ch')
+
+    class Ch:                                       # what pickle records: the class path and the instance dict
+        def __init__(self, x):
+            self.x = np.asarray(x)
+            self._dirty_vars = set()
+    Ch.__module__, Ch.__qualname__ = 'chumpy.ch', 'Ch'
+    sub.Ch = Ch
+    mod.ch = sub
+    sys.modules['chumpy'], sys.modules['chumpy.ch'] = mod, sub
+    try:
+        chd = dict(dd)
+        for k in ('v_template', 'shapedirs', 'posedirs', 'weights'):
+            chd[k] = Ch(dd[k])
+        chd['J_regressor'] = sp.csc_matrix(np.asarray(dd['J_regressor'].toarray() if hasattr(dd['J_regressor'], 'toarray') else dd['J_regressor']))
+        fname = str(tmp_path / 'model_ch.pkl')
+        with open(fname, 'wb') as f:
+            pickle.dump(chd, f, protocol=2)
+    finally:
+        del sys.modules['chumpy'], sys.modules['chumpy.ch']
+    try:
+        with open(fname, 'rb') as f:
+            pickle.load(f)
+        raise AssertionError('plain pickle.load was expected to need chumpy')
+    except ModuleNotFoundError:
+        pass
+    kw = dict(pose_hand_prior_fname=case['cfg'].moshpp.pose_hand_prior_fname, use_hands_mean=bool(sm.use_hands_mean),
+              dof_per_hand=int(sm.dof_per_hand), surface_model_type=sm.type)
+    a = pack.load_surface_model(sm.fname, **kw)
+    b = pack.load_surface_model(fname, **kw)
+    for k in ('v_template', 'shapedirs', 'posedirs', 'weights', 'J_regressor', 'parents', 'hand_comps', 'hands_mean'):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
