@@ -43,9 +43,11 @@
 #if defined(MOSH2_PROFILE) && M2_GPU
 #define M2_T0() long long t_prev_ = clock64()
 #define M2_TACC(slot) do { if (cta.tid == 0) { const long long t_now_ = clock64(); w.prof[(slot) + prof_base] += t_now_ - t_prev_; t_prev_ = t_now_; } } while (0)
+#define M2_TRESET() do { t_prev_ = clock64(); } while (0)
 #else
 #define M2_T0() ((void)0)
 #define M2_TACC(slot) ((void)0)
+#define M2_TRESET() ((void)0)
 #endif
 
 namespace mosh2 {
@@ -217,6 +219,22 @@ template <> M2_HD double pivot_eps<double>() { return 1e-13; }
 template <class real> M2_HD real accept_slack();
 template <> M2_HD float accept_slack<float>() { return 1e-5f; }
 template <> M2_HD double accept_slack<double>() { return 0.0; }
+
+#if defined(__CUDA_ARCH__)
+// t == 0 ? a : (t == 1 ? b : c) as two select instructions
+__device__ __forceinline__ float sel3(int t, float a, float b, float c) {
+    float r;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.eq.s32 p, %1, 0;\n\tsetp.eq.s32 q, %1, 1;\n\tselp.f32 %0, %3, %4, q;\n\tselp.f32 %0, %2, %0, p;\n\t}"
+        : "=&f"(r) : "r"(t), "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ double sel3(int t, double a, double b, double c) {
+    double r;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.eq.s32 p, %1, 0;\n\tsetp.eq.s32 q, %1, 1;\n\tselp.f64 %0, %3, %4, q;\n\tselp.f64 %0, %2, %0, p;\n\t}"
+        : "=&d"(r) : "r"(t), "d"(a), "d"(b), "d"(c));
+    return r;
+}
+#endif
 
 template <class real> struct alignas(16) Vec4 { real x, y, z, w; };
 template <class real> M2_HD Vec4<real> ld4(const real *p) { return *reinterpret_cast<const Vec4<real> *>(p); }
@@ -1237,6 +1255,22 @@ struct Solver {
                         const int mask = mrow[a];
                         if (mask) {                                  // rigid part: u_{a,k} x q
                             real q[3] = {0, 0, 0};
+#if 1
+                            if (d.kw == 4) {
+                                // four skinning joints per slot (every released model): weights and joint-relative positions
+                                // of the slot as four 16-byte vectors, the subtree mask applied to the weights -- no branches
+                                const Vec4<real> wv = ld4(w.c_wv + 4 * sl);
+                                const real *pp = w.pj + 12 * sl;
+                                const Vec4<real> a0 = ld4(pp), a1 = ld4(pp + 4), a2 = ld4(pp + 8);
+                                const real g0 = w.tg[3 * a], g1 = w.tg[3 * a + 1], g2 = w.tg[3 * a + 2];
+                                const real w0 = (mask & 1) ? wv.x : real(0), w1 = (mask & 2) ? wv.y : real(0);
+                                const real w2 = (mask & 4) ? wv.z : real(0), w3 = (mask & 8) ? wv.w : real(0);
+                                q[0] = w0 * (a0.x - g0); q[1] = w0 * (a0.y - g1); q[2] = w0 * (a0.z - g2);
+                                q[0] += w1 * (a0.w - g0); q[1] += w1 * (a1.x - g1); q[2] += w1 * (a1.y - g2);
+                                q[0] += w2 * (a1.z - g0); q[1] += w2 * (a1.w - g1); q[2] += w2 * (a2.x - g2);
+                                q[0] += w3 * (a2.y - g0); q[1] += w3 * (a2.z - g1); q[2] += w3 * (a2.w - g2);
+                            } else
+#endif
                             for (int i = 0; i < d.kw; ++i)
                                 if ((mask >> i) & 1) {
                                     const real wt = w.c_wv[sl * d.kw + i];
@@ -1258,9 +1292,17 @@ struct Solver {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
                             const real b0 = blk[3 * r], b1 = blk[3 * r + 1], b2 = blk[3 * r + 2];
+#if 1
+                            // (two selects each; written as nested conditionals the compiler turned them into three divergent
+                            // branches per row -- every warp holds all three values of t)
+                            const real own = sel3(t, b0, b1, b2);
+                            const real to1 = sel3(t, b1, b2, b0);
+                            const real to2 = sel3(t, b2, b0, b1);
+#else
                             const real own = t == 0 ? b0 : (t == 1 ? b1 : b2);
                             const real to1 = t == 0 ? b1 : (t == 1 ? b2 : b0);   // what the lane with t+1 wants: column t+1
                             const real to2 = t == 0 ? b2 : (t == 1 ? b0 : b1);   // column t+2
+#endif
                             col3[r] = own + __shfl_sync(0xffffffffu, to1, src1) + __shfl_sync(0xffffffffu, to2, src2);
                         }
                         if (valid) {
@@ -1586,52 +1628,78 @@ struct Solver {
 #if M2_GPU
         {
 
-            // warp 0: every lane factors the whole 8x8 block in registers (36 values, all loops unrolled: no
-            // shuffles, no local memory; the dependent chain is one FMA + one reciprocal square root per
-            // column); lane c then forward-substitutes column c of the inverse.
+            // warp 0: every lane factors the whole 8x8 block in registers (all loops unrolled: no shuffles, no local
+            // memory) and lane c forward-substitutes column c of the inverse.  One warp executes this alone, so what counts
+            // is the dependent chain and the instruction count: rows come in as 16-byte vectors, the elimination is written
+            // right-looking (every entry receives its updates in the order of the left-looking sums -- the same numbers --
+            // but each as soon as its inputs exist), and one lane stores the factor back as vectors.  (Scalar loads and
+            // per-element predicated stores were 60 % of the instructions: 2k cycles per block.)
             const int lane = cta.tid;
+            real *base = w.Lm + (k0 * ld + k0);
             real Lb[NB][NB], invd[NB], x[NB];
 #pragma unroll
-            for (int r = 0; r < NB; ++r)
-#pragma unroll
-                for (int cc = 0; cc <= r; ++cc)
-                    Lb[r][cc] = (r < kb) ? w.Lm[(k0 + r) * ld + k0 + cc] : ((cc == r) ? real(1) : real(0));
+            for (int r = 0; r < NB; ++r) {
+                Vec4<real> v0, v1;
+                v0.x = v0.y = v0.z = v0.w = real(0);
+                v1 = v0;
+                if (r < kb) {
+                    v0 = ld4(base + r * ld);
+                    if (r >= 4) v1 = ld4(base + r * ld + 4);
+                } else {                                   // identity padding of a short last block
+                    if (r == 0) v0.x = real(1);
+                    if (r == 1) v0.y = real(1);
+                    if (r == 2) v0.z = real(1);
+                    if (r == 3) v0.w = real(1);
+                    if (r == 4) v1.x = real(1);
+                    if (r == 5) v1.y = real(1);
+                    if (r == 6) v1.z = real(1);
+                    if (r == 7) v1.w = real(1);
+                }
+                Lb[r][0] = v0.x; Lb[r][1] = v0.y; Lb[r][2] = v0.z; Lb[r][3] = v0.w;
+                Lb[r][4] = v1.x; Lb[r][5] = v1.y; Lb[r][6] = v1.z; Lb[r][7] = v1.w;
+            }
             bool ok = true;
 #pragma unroll
             for (int cc = 0; cc < NB; ++cc) {
                 real piv = Lb[cc][cc];
-#pragma unroll
-                for (int pp = 0; pp < cc; ++pp) piv -= Lb[cc][pp] * Lb[cc][pp];
                 if (!(piv > pivot_eps<real>())) { ok = false; piv = real(1); }
                 const real iv = r_rsqrt(piv);
                 Lb[cc][cc] = piv * iv;
                 invd[cc] = iv;
 #pragma unroll
-                for (int r = cc + 1; r < NB; ++r) {
-                    real t = Lb[r][cc];
+                for (int r = cc + 1; r < NB; ++r) Lb[r][cc] *= iv;
 #pragma unroll
-                    for (int pp = 0; pp < cc; ++pp) t -= Lb[r][pp] * Lb[cc][pp];
-                    Lb[r][cc] = t * iv;
-                }
+                for (int r = cc + 1; r < NB; ++r)
+#pragma unroll
+                    for (int q = cc + 1; q <= r; ++q) Lb[r][q] -= Lb[r][cc] * Lb[q][cc];
             }
             const int c = lane & (NB - 1);
 #pragma unroll
-            for (int r = 0; r < NB; ++r) {                 // x[r] = Linv[r][c]
-                real sacc = (r == c) ? real(1) : real(0);
+            for (int r = 0; r < NB; ++r) x[r] = (r == c) ? real(1) : real(0);
 #pragma unroll
-                for (int pp = 0; pp < r; ++pp) sacc -= Lb[r][pp] * x[pp];
-                x[r] = sacc * invd[r];
+            for (int pp = 0; pp < NB; ++pp) {              // x = column c of the inverse
+                x[pp] *= invd[pp];
+#pragma unroll
+                for (int r = pp + 1; r < NB; ++r) x[r] -= Lb[r][pp] * x[pp];
             }
             if (lane < NB) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r) Li[r * NB + lane] = x[r];   // rows/columns >= kb hold identity padding
             }
-            __syncwarp();                               // every lane has read the block before any lane rewrites it
+            __syncwarp();                               // every lane has read the block before one lane rewrites it
+            if (lane == 0) {
 #pragma unroll
-            for (int r = 0; r < NB; ++r)
-#pragma unroll
-                for (int cc = 0; cc <= r; ++cc)
-                    if (r < kb && lane == ((r * (r + 1) / 2 + cc) & 31)) w.Lm[(k0 + r) * ld + k0 + cc] = Lb[r][cc];
+                for (int r = 0; r < NB; ++r)
+                    if (r < kb) {                           // (the block's upper triangle is never read: zeros)
+                        Vec4<real> v0, v1;
+                        v0.x = Lb[r][0]; v0.y = r >= 1 ? Lb[r][1] : real(0); v0.z = r >= 2 ? Lb[r][2] : real(0); v0.w = r >= 3 ? Lb[r][3] : real(0);
+                        *reinterpret_cast<Vec4<real> *>(base + r * ld) = v0;
+                        if (r >= 4) {
+                            v1.x = Lb[r][4]; v1.y = r >= 5 ? Lb[r][5] : real(0); v1.z = r >= 6 ? Lb[r][6] : real(0); v1.w = r >= 7 ? Lb[r][7] : real(0);
+                            *reinterpret_cast<Vec4<real> *>(base + r * ld + 4) = v1;
+                        }
+                    }
+            }
             if (!ok && lane == 0) w.isc[3] = 0;
                 }
 #else
@@ -1702,6 +1770,53 @@ struct Solver {
         }
     }
 
+    // ---- one row of the panel below the diagonal block at k0 (kb columns):  x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p]),
+    //      written in place and, transposed, into Pn[c][row] (rows beyond n: zeros), which the trailing update reads
+    M2_D void panel_row(int i, int k0, int kb, const real *Li, int n) {
+        const int ld = d.ld;
+        constexpr int NB = kCholNB;
+        real xr[NB];
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) xr[cc] = 0;
+        if (i <= n) {
+            real *row = w.Lm + i * ld + k0;
+            real av[NB];
+            {   // (k0 is a multiple of 8 and ld of 4: two aligned 16-byte loads; columns >= kb are masked below)
+                const Vec4<real> a0 = ld4(row), a1 = ld4(row + 4);
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+            }
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) if (cc >= kb) av[cc] = real(0);
+#pragma unroll
+            for (int cc = 0; cc < NB; ++cc) {
+                const Vec4<real> l0 = ld4(Li + cc * NB);
+                real sacc = av[0] * l0.x;
+                if (cc >= 1) sacc += av[1] * l0.y;
+                if (cc >= 2) sacc += av[2] * l0.z;
+                if (cc >= 3) sacc += av[3] * l0.w;
+                if (cc >= 4) {
+                    const Vec4<real> l1 = ld4(Li + cc * NB + 4);
+                    sacc += av[4] * l1.x;
+                    if (cc >= 5) sacc += av[5] * l1.y;
+                    if (cc >= 6) sacc += av[6] * l1.z;
+                    if (cc >= 7) sacc += av[7] * l1.w;
+                }
+                xr[cc] = cc < kb ? sacc : real(0);
+            }
+            if (kb == NB) {
+                Vec4<real> o0, o1;
+                o0.x = xr[0]; o0.y = xr[1]; o0.z = xr[2]; o0.w = xr[3]; o1.x = xr[4]; o1.y = xr[5]; o1.z = xr[6]; o1.w = xr[7];
+                *reinterpret_cast<Vec4<real> *>(row) = o0;
+                *reinterpret_cast<Vec4<real> *>(row + 4) = o1;
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) if (cc < kb) row[cc] = xr[cc];
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.ldp + i] = xr[cc];
+    }
+
     // Gauss-Newton step dgn = A^-1 g by a Jacobi-scaled, blocked right-looking Cholesky in w.Lm (lower
     // triangle incl. diagonal).  One lane factors each 8x8 diagonal block and also inverts it; the panel and
     // both triangular solves then use the explicit block inverses (plain dot products, no divides and no
@@ -1730,90 +1845,85 @@ struct Solver {
         CTA_FOR(j, n) w.Lm[n * ld + j] = w.g[j] * w.ds[j];
         M2_SYNC();
         M2_TACC(11);
-        // Right-looking with a one-block look-ahead: while the other warps apply the trailing update of block k0,
-        // warp 0 updates the next diagonal block first (tiles 0..2 of the update) and factors it, so the serial
-        // 8x8 factorisation is off the critical path and a block costs two barriers instead of three.
-        if (cta.tid < 32) chol_diag(0, n);
-        M2_SYNC();
-        M2_TACC(12);
+#if M2_GPU
+        // Pipelined variant: warp 0 runs the serial chain of a block -- the eight panel rows that make up the next diagonal
+        // block, the update of that block, its factorisation and inversion -- while the other warps solve the rest of the
+        // panel and apply the trailing update; they only wait (named barrier 1) for warp 0's eight panel rows.  One full
+        // barrier per block, and a single call site of the diagonal-block factorisation (the pseudo-block k0 = -NB
+        // factors the first one).  (The launcher never starts fewer than 128 threads.)
+        {
+            const int nthr = cta.nthr;
+#pragma unroll 1
+            for (int k0 = -NB; k0 < n; k0 += NB) {
+                const int kb = k0 < 0 ? 0 : ((n - k0 < NB) ? n - k0 : NB);
+                const int r0 = k0 < 0 ? 0 : k0 + kb;
+                const real *Li = w.Linv + (k0 < 0 ? 0 : k0 / NB) * NB * NB;
+                const bool trail = k0 >= 0 && r0 < n;
+                if (cta.tid < 32) {
+                    if (k0 >= 0) {
+                        const int i = r0 + cta.tid;
+                        M2_TACC(14);
+                        if (cta.tid < NB && i < d.ldp) panel_row(i, k0, kb, Li, n);
+                        if (trail) {
+                            __threadfence_block();
+                            __syncwarp();
+                            asm volatile("bar.arrive 1, %0;" :: "r"(nthr) : "memory");
+                            // the next diagonal block (and the right-hand-side row where it falls into these eight rows):
+                            // lane -> row p, columns q0, q0 + 1 of the 8x8 square (its upper triangle is never read)
+                            {
+                                const int pr = cta.tid >> 2, q0 = (cta.tid & 3) * 2;
+                                const int ii = r0 + pr, jj = r0 + q0;
+                                if (ii <= n && jj < n) {
+                                    real acc0 = 0, acc1 = 0;
+#pragma unroll
+                                    for (int cc = 0; cc < NB; ++cc) {
+                                        const real pi = w.Pn[cc * d.ldp + ii];
+                                        acc0 += pi * w.Pn[cc * d.ldp + jj];
+                                        acc1 += pi * w.Pn[cc * d.ldp + jj + 1];
+                                    }
+                                    w.Lm[ii * ld + jj] -= acc0;
+                                    w.Lm[ii * ld + jj + 1] -= acc1;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    M2_TACC(12);
+                    if (r0 < n) chol_diag(r0, n);
+                    M2_TACC(13);
+                } else {
+                    if (k0 >= 0) {
+                        const int t = cta.tid - 32, nt_ = nthr - 32;
+                        for (int i = r0 + NB + t; i < d.ldp; i += nt_) panel_row(i, k0, kb, Li, n);
+                        if (trail) {
+                            asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
+                            const int R = n + 1 - r0, ntl = (R + kBS - 1) / kBS, ntri = ntl * (ntl + 1) / 2;
+                            for (int it = 3 + t; it < ntri; it += nt_) chol_tile(it, r0, n);
+                        }
+                    }
+                }
+                M2_SYNC();
+                if (w.isc[3] == 0) return false;
+            }
+            M2_TACC(14);
+        }
+#else
+        // host build: the same blocked right-looking factorisation, one block after the other
+        chol_diag(0, n);
         if (w.isc[3] == 0) return false;
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = (n - k0 < NB) ? n - k0 : NB;
-            real *Li = w.Linv + (k0 / NB) * NB * NB;
-            // panel rows below the block: x = a Linv^T  (x_c = sum_{p<=c} a_p Linv[c][p]); the solved panel is
-            // also kept transposed (Pn[c][row]) so that the trailing update reads consecutive vectors
-            CTA_FOR(ii, d.ldp - k0 - kb) {
-                const int i = k0 + kb + ii;
-                real xr[NB];
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) xr[cc] = 0;
-                if (i <= n) {
-                    real *row = w.Lm + i * ld + k0;
-                    real av[NB];
-                    {   // (k0 is a multiple of 8 and ld of 4: two aligned 16-byte loads; columns >= kb are masked below)
-                        const Vec4<real> a0 = ld4(row), a1 = ld4(row + 4);
-                        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) if (cc >= kb) av[cc] = real(0);
-#pragma unroll
-                    for (int cc = 0; cc < NB; ++cc) {
-                        const Vec4<real> l0 = ld4(Li + cc * NB);
-                        real sacc = av[0] * l0.x;
-                        if (cc >= 1) sacc += av[1] * l0.y;
-                        if (cc >= 2) sacc += av[2] * l0.z;
-                        if (cc >= 3) sacc += av[3] * l0.w;
-                        if (cc >= 4) {
-                            const Vec4<real> l1 = ld4(Li + cc * NB + 4);
-                            sacc += av[4] * l1.x;
-                            if (cc >= 5) sacc += av[5] * l1.y;
-                            if (cc >= 6) sacc += av[6] * l1.z;
-                            if (cc >= 7) sacc += av[7] * l1.w;
-                        }
-                        xr[cc] = cc < kb ? sacc : real(0);
-                    }
-                    if (kb == NB) {
-                        Vec4<real> o0, o1;
-                        o0.x = xr[0]; o0.y = xr[1]; o0.z = xr[2]; o0.w = xr[3]; o1.x = xr[4]; o1.y = xr[5]; o1.z = xr[6]; o1.w = xr[7];
-                        *reinterpret_cast<Vec4<real> *>(row) = o0;
-                        *reinterpret_cast<Vec4<real> *>(row + 4) = o1;
-                    } else {
-#pragma unroll
-                        for (int cc = 0; cc < NB; ++cc) if (cc < kb) row[cc] = xr[cc];
-                    }
-                }
-#pragma unroll
-                for (int cc = 0; cc < NB; ++cc) w.Pn[cc * d.ldp + i] = xr[cc];
-            }
-            M2_SYNC();
-            M2_TACC(13);
-            // trailing update with 4x4 register tiles, tiles with tj <= ti
+            const real *Li = w.Linv + (k0 / NB) * NB * NB;
+            for (int i = k0 + kb; i < d.ldp; ++i) panel_row(i, k0, kb, Li, n);
             const int r0 = k0 + kb, R = r0 < n ? n + 1 - r0 : 0;   // rows r0..n (row n = right-hand side), columns r0..n-1
             if (R > 0) {
                 const int nt = (R + kBS - 1) / kBS, ntri = nt * (nt + 1) / 2;
-#if M2_GPU
-                if (cta.nthr >= 64) {
-                    if (cta.tid < 32) {
-                        if (cta.tid < 3 && cta.tid < ntri) chol_tile(cta.tid, r0, n);   // the next diagonal block
-                        __syncwarp();
-                        chol_diag(r0, n);
-                    } else {
-                        for (int it = 3 + cta.tid - 32; it < ntri; it += cta.nthr - 32) chol_tile(it, r0, n);
-                    }
-                } else {
-                    CTA_FOR(it, ntri) chol_tile(it, r0, n);
-                    __syncthreads();
-                    if (cta.tid < 32) chol_diag(r0, n);
-                }
-#else
                 for (int it = 0; it < ntri; ++it) chol_tile(it, r0, n);
                 chol_diag(r0, n);
-#endif
-                M2_SYNC();
-                M2_TACC(14);
                 if (w.isc[3] == 0) return false;
             }
         }
+#endif
         // backward solve L^T y = z by the first warp (the forward solve happened inside the factorisation), column
         // oriented: once the block y_k = Linv_k^T z_k is known, every lane subtracts its contribution from the entries
         // z_i, i < k0, it owns -- that reads rows of L (consecutive words) and needs no reduction across lanes, where
@@ -1918,8 +2028,10 @@ struct Solver {
         real sse0 = 0, delta = 0, alpha = 0, nsd = 0, ngn2 = 0, gn_sd = 0, nstep = 0, npn = 0, gd = 0, dAd = 0;
         bool done = false, in_iter = false, have_gn = false, gn_ok = true;
         int iter = 0;
+        M2_T0();
         while (true) {
             if (need_setup) {
+                M2_TACC(25);
                 // configuration of this stage
                 c.free = w.c_free1; c.n = m.n1; c.poseH = false; c.dm_terms = false; c.extrap = false; c.face = false;
                 if (stage < 3) {
@@ -1932,6 +2044,7 @@ struct Solver {
                 }
                 stage_setup(c);
                 need_setup = false;
+                M2_TACC(20);
             }
             const int n = c.n;
             // ---------------- the one evaluation site
@@ -1939,7 +2052,9 @@ struct Solver {
                 // A stage that starts where the last accepted trial step ended (Step 2 after Step 1, Step 1 of the next
                 // frame, the output evaluation) finds the forward pass of that state still in shared memory.
                 const bool reuse = op != OP_TRIAL && fwd_at_x && (fwd_has_prior || !(c.wp > real(0)));
+                M2_TACC(25);
                 eval(op == OP_TRIAL ? w.xt : w.x, c, reuse);
+                M2_TRESET();
                 if (!reuse) fwd_has_prior = c.wp > real(0);
                 fwd_at_x = op != OP_TRIAL;                     // (a trial point becomes the state only if it is accepted)
             }
@@ -1984,7 +2099,9 @@ struct Solver {
                 }
             }
             // ---------------- the one linearisation site
+            M2_TACC(21);
             if (do_build && !done) build(w.x, c);
+            M2_TRESET();
             if (lin_f >= 0) {                                  // linearise mode: the normal equations go out, nothing is solved
                 CTA_FOR(idx, n * n) { const int i = idx / n, j = idx - i * n; job.lin_A[size_t(f) * n * n + idx] = w.A[i * d.lda + j]; }
                 CTA_FOR(i, n) job.lin_g[size_t(f) * n + i] = w.g[i];
@@ -2016,7 +2133,9 @@ struct Solver {
                 if (nsd >= delta) { kind = 0; scale_sd = delta / nsd * alpha; }
                 else {
                     if (!have_gn) {
+                        M2_TACC(22);
                         gn_ok = gauss_newton(n);               // the one factorisation site
+                        M2_TRESET();
                         have_gn = true;
                         if (gn_ok) {
                             real q[2] = {0, 0};
@@ -2062,6 +2181,7 @@ struct Solver {
                     CTA_FOR(i, n) w.xt[c.free[i]] += w.d[i];
                     M2_SYNC();
                     op = OP_TRIAL;
+                    M2_TACC(23);
                     continue;
                 }
             }
@@ -2118,6 +2238,7 @@ struct Solver {
             }
             M2_SYNC();
         }
+        M2_TACC(24);
     }
 
     // ---- Procrustes initialisation of root orientation and translation (rigid_transformations.py:39-83)

@@ -14,8 +14,8 @@ from moshpp_b200 import chmosh, lib, synth  # noqa: E402
 from moshpp_b200.mocap_interface import MocapSession  # noqa: E402
 
 NAMES = ['ev.fullpose', 'ev.rodrigues', 'ev.fk||blend', 'ev.skin+prior', 'ev.markers', 'ev.reduce', 'bd.pre', 'bd.T1',
-         'bd.T2', 'bd.T3', 'bd.closed', 'gn.init', 'gn.diag', 'gn.panel', 'gn.trailing', 'gn.solves', 'minimize(all)',
-         'chunk(all)', 'ev.fk alone', 'ev.prior alone', 'warm.fullpose', 'warm.rodrigues', 'warm.fk||blend', 'warm.skin+prior', 'warm.markers', 'warm.reduce']
+         'bd.T2', 'bd.T3', 'bd.closed', 'gn.init', 'gn.w0 panel+update', 'gn.w0 diag block', 'gn.w0 barrier wait', 'gn.solves', 'minimize(all)',
+         'chunk(all)', 'ev.fk alone', 'ev.prior alone', 'sf.stage_setup', 'sf.accept logic', 'sf.symv+reduce (pre GN)', 'sf.step+symv (post GN)', 'sf.output', 'sf.other']
 
 
 def main():
