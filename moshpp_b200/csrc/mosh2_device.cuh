@@ -269,8 +269,9 @@ M2_HD void cross3(const real *a, const real *b, real *o) {
 }
 
 // R = exp([w]x) and dR[k] = dR/dw_k (cv2.Rodrigues convention), cancellation-free near 0.
+// `only_k` >= 0: this caller writes only dR[only_k] (and R when only_k == 0) -- three threads share a joint.
 template <class real>
-M2_NOINLINE void rodrigues(const real *w, real *R, real *dR) {
+M2_NOINLINE void rodrigues(const real *w, real *R, real *dR, int only_k = -1) {
     const real x = w[0], y = w[1], z = w[2];
     const real t2 = x * x + y * y + z * z;
     real a, b, c1, c2;
@@ -291,15 +292,14 @@ M2_NOINLINE void rodrigues(const real *w, real *R, real *dR) {
     // K = [w]x, K2 = K K = w w^T - t2 I
     const real K[9] = {0, -z, y, z, 0, -x, -y, x, 0};
     const real K2[9] = {x * x - t2, x * y, x * z, x * y, y * y - t2, y * z, x * z, y * z, z * z - t2};
+    if (only_k <= 0) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = a * K[i] + b * K2[i];
-    R[0] += real(1);
-    R[4] += real(1);
-    R[8] += real(1);
+        for (int i = 0; i < 9; ++i) R[i] = a * K[i] + b * K2[i] + ((i == 0 || i == 4 || i == 8) ? real(1) : real(0));
+    }
     if (!dR) return;
     // dR/dw_k = c1 w_k K + a E_k + c2 w_k K2 + b (E_k K + K E_k),   E_k K + K E_k = e_k w^T + w e_k^T - 2 w_k I
 #pragma unroll 1
-    for (int k = 0; k < 3; ++k) {
+    for (int k = (only_k < 0 ? 0 : only_k); k < (only_k < 0 ? 3 : only_k + 1); ++k) {
         const real wk = w[k];
         real *D = dR + 9 * k;
 #pragma unroll
@@ -324,6 +324,9 @@ M2_NOINLINE void rodrigues(const real *w, real *R, real *dR) {
 template <class real, int NV>
 M2_D void cta_reduce(const Cta &c, real *vals, real *scratch /* >= 8*33 reals */) {
 #if M2_GPU
+    // warp sums by shuffles, one partial per warp through shared memory, then EVERY warp adds the partials with a second
+    // shuffle tree (lane = warp of the partial): no serial loop over the warps and no broadcast round (the serial
+    // version cost ~800 cycles a call, five calls per dog-leg iteration)
     const int lane = c.tid & 31, warp = c.tid >> 5, nwarp = (c.nthr + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -333,15 +336,14 @@ M2_D void cta_reduce(const Cta &c, real *vals, real *scratch /* >= 8*33 reals */
         if (lane == 0) scratch[i * 33 + warp] = v;
     }
     __syncthreads();
-    if (c.tid < NV) {
-        real s = 0;
-        for (int w = 0; w < nwarp; ++w) s += scratch[c.tid * 33 + w];
-        scratch[c.tid * 33 + 32] = s;
-    }
-    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) vals[i] = scratch[i * 33 + 32];
-    __syncthreads();
+    for (int i = 0; i < NV; ++i) {
+        real v = lane < nwarp ? scratch[i * 33 + lane] : real(0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        vals[i] = v;
+    }
+    __syncthreads();                 // (the partials may be overwritten by the next call)
 #else
     (void)c; (void)vals; (void)scratch;
 #endif
@@ -370,6 +372,7 @@ struct Work {
     BPtr<real, BIG> Jt, Jf, A, Lm;
     SPtr<real> red, sc, hct;
     SPtr<int> colmap, colsrc, jlist, isc;
+    SPtr<int> st_colmap, st_colsrc, st_jlist, st_meta;   // the two stage configurations (Step-1 / Step-2 variable lists), built once per chunk
     // small per-model tables staged in shared memory (a dependent global load costs several hundred cycles and the
     // kinematic-tree walk alone chains three of them per level)
     SPtr<int> c_parents, c_fk_order, c_wj, c_free1, c_free2, c_pids;
@@ -556,6 +559,7 @@ M2_HD void carve(Work<real, BIG> &w, const Dims &d, const Model<real> &m, Arena 
     w.d.ofs = S.take<real>(d.npad); w.tmp.ofs = S.take<real>(d.npad); w.ds.ofs = S.take<real>(d.npad);
     w.red.ofs = S.take<real>(8 * 33); w.sc.ofs = S.take<real>(16);
     w.colmap.ofs = S.take<int>(d.NX); w.colsrc.ofs = S.take<int>(d.n2); w.jlist.ofs = S.take<int>(d.nJ); w.isc.ofs = S.take<int>(8);
+    w.st_colmap.ofs = S.take<int>(2 * d.NX); w.st_colsrc.ofs = S.take<int>(2 * d.n2); w.st_jlist.ofs = S.take<int>(2 * d.nJ); w.st_meta.ofs = S.take<int>(4);
     w.prof.ofs = S.take<long long>(32);
     w.mbar.ofs = S.take<unsigned long long>(2); w.tmem_slot.ofs = S.take<unsigned int>(2);   // mbar[0]: tensor-core tiles, mbar[1]: table staging
     w.vis.ofs = S.take<uint8_t>(d.M);
@@ -778,7 +782,11 @@ struct Solver {
         CTA_FOR(i, d.D) w.pxg[i] = th[w.c_pids[i]];          // the pose coefficients the prior sees, in its own order
         M2_SYNC();
         M2_TACC(0);
+#if M2_GPU
+        CTA_FOR(jk, 3 * d.nJ) { const int j = jk / 3; rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + kDR * j, jk - 3 * j); }
+#else
         CTA_FOR(j, d.nJ) rodrigues(w.fullpose + 3 * j, w.Rl + 9 * j, w.dRl + kDR * j);
+#endif
         M2_SYNC();
         M2_TACC(1);
 #if M2_GPU
@@ -1479,6 +1487,28 @@ struct Solver {
                         }
                 }
             }
+#if M2_GPU
+            if (w.tc) {
+                // g -= J^T r straight from the operand tiles: a marker's three rows are one 16-byte vector of the hi and of
+                // the lo operand (scalar loads with their index arithmetic kept the four warps of the columns busy for 3k
+                // cycles per tile, longer than the tile's MMAs).  Same products in the same order as the scalar loop: the
+                // ill-conditioned hand-only fits take another dog-leg path on ANY other rounding of g -- measured with
+                // three partial sums per column, in float32 and in float64.
+                CTA_FOR(cc, n) {
+                    const int xb = (cc >> 3) * (tc_kt >> 2) * 32 + (cc & 7) * 4;
+                    const float *xh = w.Xhi + xb, *xl = w.Xlo + xb;
+                    real sacc = 0;
+                    for (int ml = 0; ml < tm; ++ml) {
+                        const float4 a = *reinterpret_cast<const float4 *>(xh + 32 * ml), b = *reinterpret_cast<const float4 *>(xl + 32 * ml);
+                        const real *rp = w.rm + 3 * (t0 + ml);
+                        sacc += real(a.x + b.x) * rp[0];
+                        sacc += real(a.y + b.y) * rp[1];
+                        sacc += real(a.z + b.z) * rp[2];
+                    }
+                    w.g[cc] -= sacc;
+                }
+            } else
+#endif
             CTA_FOR(cc, n) {
                 real s = 0;
                 for (int ml = 0; ml < tm; ++ml)
@@ -1499,13 +1529,17 @@ struct Solver {
             // accumulator (tensor memory, row i = lane i) -> A, mirrored from the upper triangle so that A is exactly
             // symmetric; warps 0..3 own the four lane quarters
             tc::fence_after();
-            if (cta.tid < 128) {
-                const int i = cta.tid, nc = (n + 15) & ~15;
-                for (int c0 = 0; c0 < nc; c0 += 16) {
+            {
+                // a warp reads the lane quarter (warp mod 4) of tensor memory; the groups of four warps share the columns
+                const int warp = cta.tid >> 5, lane = cta.tid & 31, ngrp = cta.nthr >> 7, grp = warp >> 2;
+                const int i = 32 * (warp & 3) + lane, nc = (n + 15) & ~15;
+                const uint32_t tbase = tc_tmem + (uint32_t(32 * (warp & 3)) << 16);
+                if (grp < ngrp)
+                for (int c0 = 16 * grp; c0 < nc; c0 += 16 * ngrp) {
                     float v[16], v1[16], v2[16];
-                    tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + c0, v);
-                    tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + 128 + c0, v1);
-                    tc::tmem_ld16(tc_tmem + (uint32_t(cta.tid & ~31) << 16) + 256 + c0, v2);
+                    tc::tmem_ld16(tbase + c0, v);
+                    tc::tmem_ld16(tbase + 128 + c0, v1);
+                    tc::tmem_ld16(tbase + 256 + c0, v2);
 #pragma unroll
                     for (int q = 0; q < 16; ++q) v[q] = (v[q] + v1[q]) + v2[q];
                     if (i < n) {
@@ -1526,24 +1560,39 @@ struct Solver {
             const int D = d.D, ks = w.isc[0];
             const real w2 = c.wp * c.wp;
             const real *Q = m.prior_Q4 + size_t(ks) * D * d.D4;
-            // blocks of eight entries per thread with a fixed trip count: the (L2) loads of a block issue back to back
+            // item = (row i, four columns): one 16-byte (L2) load, three items in flight per thread, the column map looked up
+            // once per row and once per column of the vector
+            const int nq = d.D4 >> 2;
 #pragma unroll 1
-            for (int base = cta.tid; base < D * D; base += 8 * cta.nthr) {
-                real qv[8];
-                int dst[8];
+            for (int base = cta.tid; base < D * nq; base += 3 * cta.nthr) {
+                Vec4<real> qv[3];
+                int ci[3], l0[3];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 3; ++u) {
                     const int idx = base + u * cta.nthr;
-                    dst[u] = -1;
-                    qv[u] = 0;
-                    if (idx < D * D) {
-                        const int i = idx / D, l = idx - i * D;
-                        const int ci = w.colmap[3 + w.c_pids[i]], cl = w.colmap[3 + w.c_pids[l]];
-                        if (ci >= 0 && cl >= 0) { dst[u] = ci * ld + cl; qv[u] = Q[i * d.D4 + l]; }
+                    ci[u] = -1;
+                    l0[u] = 0;
+                    qv[u].x = qv[u].y = qv[u].z = qv[u].w = real(0);
+                    if (idx < D * nq) {
+                        const int i = idx / nq;
+                        l0[u] = 4 * (idx - i * nq);
+                        ci[u] = w.colmap[3 + w.c_pids[i]];
+                        if (ci[u] >= 0) qv[u] = ld4(Q + i * d.D4 + l0[u]);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) if (dst[u] >= 0) w.A[dst[u]] += w2 * qv[u];
+                for (int u = 0; u < 3; ++u)
+                    if (ci[u] >= 0) {
+                        const real q4[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int l = l0[u] + e;
+                            if (l < D) {
+                                const int cl = w.colmap[3 + w.c_pids[l]];
+                                if (cl >= 0) w.A[ci[u] * ld + cl] += w2 * q4[e];
+                            }
+                        }
+                    }
             }
             CTA_FOR(i, D) {
                 const int ci = w.colmap[3 + w.c_pids[i]];
@@ -1591,22 +1640,25 @@ struct Solver {
     // out = A v for the full symmetric A: one warp per row, lanes along the row
     M2_D void symv(const real *v, real *out, int n) {
 #if M2_GPU
-        // four rows per warp at a time: their shuffle reductions (five dependent steps each) run interleaved
-        const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
-        for (int i0 = warp; i0 < n; i0 += 4 * nwarp) {
-            real s[4] = {0, 0, 0, 0};
-            for (int j = lane; j < n; j += 32) {
-                const real vj = v[j];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { const int i = i0 + q * nwarp; if (i < n) s[q] += w.A[i * d.lda + j] * vj; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { const int i = i0 + q * nwarp; if (i < n) out[i] = s[q]; }
+        // three adjacent lanes per row, each a third of the columns (A has an odd leading dimension: the rows of a warp
+        // start in different banks), two shuffles to add the thirds.  (One warp per row with a five-step shuffle tree, four
+        // rows in flight, needed three passes over the warps and ~1.5k cycles.)
+        {
+            const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
+            const int part = lane % 3, rl = lane / 3;                      // 10 rows per warp (lanes 30, 31 idle)
+            const int third = (n + 2) / 3, j0 = part * third, j1 = (j0 + third < n) ? j0 + third : n;
+            const int src0 = lane - part;
+            for (int i0 = warp * 10; i0 < n; i0 += nwarp * 10) {
+                const int i = i0 + rl;
+                const bool on = lane < 30 && i < n;
+                const real *Ar = w.A + (on ? i : 0) * d.lda;
+                real s0 = 0, s1 = 0;
+                int j = j0;
+                for (; j + 1 < j1; j += 2) { s0 += Ar[j] * v[j]; s1 += Ar[j + 1] * v[j + 1]; }
+                if (j < j1) s0 += Ar[j] * v[j];
+                real sacc = on ? s0 + s1 : real(0);
+                const real a1 = __shfl_sync(0xffffffffu, sacc, (src0 + 1) & 31), a2 = __shfl_sync(0xffffffffu, sacc, (src0 + 2) & 31);
+                if (on && part == 0) out[i] = (sacc + a1) + a2;
             }
         }
         __syncthreads();
@@ -1661,8 +1713,8 @@ struct Solver {
             bool ok = true;
 #pragma unroll
             for (int cc = 0; cc < NB; ++cc) {
-                real piv = Lb[cc][cc];
-                if (!(piv > pivot_eps<real>())) { ok = false; piv = real(1); }
+                const real piv = Lb[cc][cc];
+                if (!(piv > pivot_eps<real>())) ok = false;    // (the factor is discarded then: no substitute pivot on the chain)
                 const real iv = r_rsqrt(piv);
                 Lb[cc][cc] = piv * iv;
                 invd[cc] = iv;
@@ -1893,12 +1945,20 @@ struct Solver {
                     M2_TACC(13);
                 } else {
                     if (k0 >= 0) {
+#if defined(MOSH2_GN_QUIET)
+                        // (experiment: the warps that share warp 0's scheduler stay out of the way)
+                        const int wq = cta.tid >> 5, nwq = nthr >> 5;
+                        const bool worker = (wq & 3) != 0;
+                        const int t = (wq - 1 - (wq >> 2)) * 32 + (cta.tid & 31), nt_ = (nwq - ((nwq + 3) >> 2)) * 32;
+#else
+                        const bool worker = true;
                         const int t = cta.tid - 32, nt_ = nthr - 32;
-                        for (int i = r0 + NB + t; i < d.ldp; i += nt_) panel_row(i, k0, kb, Li, n);
+#endif
+                        if (worker) for (int i = r0 + NB + t; i < d.ldp; i += nt_) panel_row(i, k0, kb, Li, n);
                         if (trail) {
                             asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
                             const int R = n + 1 - r0, ntl = (R + kBS - 1) / kBS, ntri = ntl * (ntl + 1) / 2;
-                            for (int it = 3 + t; it < ntri; it += nt_) chol_tile(it, r0, n);
+                            if (worker) for (int it = 3 + t; it < ntri; it += nt_) chol_tile(it, r0, n);
                         }
                     }
                 }
@@ -1928,6 +1988,64 @@ struct Solver {
         // oriented: once the block y_k = Linv_k^T z_k is known, every lane subtracts its contribution from the entries
         // z_i, i < k0, it owns -- that reads rows of L (consecutive words) and needs no reduction across lanes, where
         // the row-oriented form read columns (16-way bank conflicts at ld = 112) and eight warp reductions per block.
+#if M2_GPU
+        // Four warps (named barrier 2): every warp forms y_k = Linv_k^T z_k itself, the 128 threads share the rows i < k0 of
+        // the update z_i -= L[k, i] y_k -- one round per block instead of four by a single warp (560 -> cycles per block
+        // are the dependent shared-memory round trips, not the arithmetic).
+        if (cta.tid < 128) {
+            const int tid = cta.tid;
+            for (int i = tid; i < n; i += 128) w.tmp[i] = w.Lm[n * ld + i];     // z = L^-1 (ds*g), see above
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll 1
+            for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
+                const int kb = (n - k0 < NB) ? n - k0 : NB;
+                const real *Li = w.Linv + (k0 / NB) * NB * NB;
+                real zv[NB], y[NB], Lr[NB][NB];
+                {
+                    const Vec4<real> z0 = ld4(w.tmp + k0), z1 = ld4(w.tmp + k0 + 4);
+                    zv[0] = z0.x; zv[1] = z0.y; zv[2] = z0.z; zv[3] = z0.w; zv[4] = z1.x; zv[5] = z1.y; zv[6] = z1.z; zv[7] = z1.w;
+                }
+#pragma unroll
+                for (int cc = 1; cc < NB; ++cc) if (cc >= kb) zv[cc] = real(0);
+#pragma unroll
+                for (int pp = 0; pp < NB; ++pp) {
+                    const Vec4<real> l0 = ld4(Li + pp * NB);
+                    Lr[pp][0] = l0.x; Lr[pp][1] = l0.y; Lr[pp][2] = l0.z; Lr[pp][3] = l0.w;
+                    if (pp >= 4) {
+                        const Vec4<real> l1 = ld4(Li + pp * NB + 4);
+                        Lr[pp][4] = l1.x; Lr[pp][5] = l1.y; Lr[pp][6] = l1.z; Lr[pp][7] = l1.w;
+                    }
+                }
+#pragma unroll
+                for (int cc = 0; cc < NB; ++cc) {          // y = Linv^T z (every thread, redundantly)
+                    real sacc = 0;
+#pragma unroll
+                    for (int pp = cc; pp < NB; ++pp) sacc += Lr[pp][cc] * zv[pp];
+                    y[cc] = sacc;
+                }
+                for (int i = tid; i < k0; i += 128) {
+                    real zi = w.tmp[i];
+#pragma unroll
+                    for (int cc = 0; cc < NB; ++cc) if (cc < kb) zi -= w.Lm[(k0 + cc) * ld + i] * y[cc];
+                    w.tmp[i] = zi;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");   // (every thread has read z_k before thread 0 replaces it by y_k)
+                if (tid == 0) {
+                    if (kb == NB) {
+                        Vec4<real> o0, o1;
+                        o0.x = y[0]; o0.y = y[1]; o0.z = y[2]; o0.w = y[3]; o1.x = y[4]; o1.y = y[5]; o1.z = y[6]; o1.w = y[7];
+                        *reinterpret_cast<Vec4<real> *>(w.tmp + k0) = o0;
+                        *reinterpret_cast<Vec4<real> *>(w.tmp + k0 + 4) = o1;
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < NB; ++cc) if (cc < kb) w.tmp[k0 + cc] = y[cc];
+                    }
+                }
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            for (int i = tid; i < n; i += 128) w.dgn[i] = w.tmp[i] * w.ds[i];
+        }
+#else
         const int wl = cta.nthr < 32 ? cta.nthr : 32;
         if (cta.tid < wl) {
             const int lane = cta.tid;
@@ -1961,20 +2079,22 @@ struct Solver {
             }
             for (int i = lane; i < n; i += wl) w.dgn[i] = w.tmp[i] * w.ds[i];
         }
+#endif
         M2_SYNC();
         M2_TACC(15);
         return true;
     }
 
-    // ---- per-stage set-up of one ch.minimize call: column maps and the joints whose columns are needed
-    M2_D void stage_setup(const StepCfg<real> &c) {
-        ++n_min;
-        const int n = c.n;
+    // ---- column maps and needed joints of one free-variable list (Step 1: which = 0, Step 2: which = 1), built once per
+    //      chunk (prologue) into the stage cache
+    M2_D void stage_tables(int which) {
+        const int *free = which ? static_cast<const int *>(w.c_free2) : static_cast<const int *>(w.c_free1);
+        const int n = which ? m.n2 : m.n1;
         CTA_FOR(i, d.NX) w.colmap[i] = -1;
         CTA_FOR(i, d.nJ) w.jlist[i] = 0;
         M2_SYNC();
         CTA_FOR(i, n) {
-            const int fv = c.free[i];
+            const int fv = free[i];
             w.colmap[fv] = i;
             int src;
             if (fv < 3) src = -1 - fv;
@@ -1997,12 +2117,27 @@ struct Solver {
             }
             int cnt = 0;
             for (int j = 0; j < d.nJ; ++j) if (w.jlist[j]) w.jlist[cnt++] = j;
-            w.isc[1] = cnt;
-            w.isc[2] = hf;
+            w.st_meta[2 * which] = cnt;
+            w.st_meta[2 * which + 1] = hf;
         }
         M2_SYNC();
-        njl = w.isc[1];
-        hand_free = w.isc[2] != 0;
+        CTA_FOR(i, d.NX) w.st_colmap[which * d.NX + i] = w.colmap[i];
+        CTA_FOR(i, n) w.st_colsrc[which * d.n2 + i] = w.colsrc[i];
+        CTA_FOR(i, d.nJ) w.st_jlist[which * d.nJ + i] = w.jlist[i];
+        M2_SYNC();
+    }
+
+    // ---- per-stage set-up of one ch.minimize call: the column maps and the joints whose columns are needed come from the
+    //      stage cache (the thread-0 loops that build them cost 7k cycles per call, twice per frame)
+    M2_D void stage_setup(const StepCfg<real> &c) {
+        ++n_min;
+        const int which = c.free == static_cast<const int *>(w.c_free2) ? 1 : 0;
+        CTA_FOR(i, d.NX) w.colmap[i] = w.st_colmap[which * d.NX + i];
+        CTA_FOR(i, c.n) w.colsrc[i] = w.st_colsrc[which * d.n2 + i];
+        CTA_FOR(i, d.nJ) w.jlist[i] = w.st_jlist[which * d.nJ + i];
+        njl = w.st_meta[2 * which];
+        hand_free = w.st_meta[2 * which + 1] != 0;
+        M2_SYNC();
     }
 
     // ---- one frame: [Procrustes] + the ch.minimize calls of the reference + the output evaluation, written as
@@ -2378,6 +2513,8 @@ struct Solver {
             w.c_amask[idx] = uint8_t(mask);
         }
         M2_SYNC();
+        stage_tables(0);
+        stage_tables(1);
     }
 
     M2_D void run_chunk(int chunk) {
