@@ -260,11 +260,17 @@ def observation_lists(obs: np.ndarray, vis: np.ndarray, latent_labels) -> dict:
     frames with at least one visible marker (the frames the reference solves, chmosh.py:586-588).  Computed on the host
     while the device solves (``mosh_stageii``); ``assemble_stageii_data`` builds it itself when it is not handed over."""
     fid = np.nonzero(vis.any(1))[0]
-    vf = vis[fid]
+    vf = vis if len(fid) == len(vis) else vis[fid]
     cnt = vf.sum(1)
     ends = np.cumsum(cnt)
     starts = ends - cnt
-    obs_cat = obs[fid][vf]
+    # positions of the visible markers of the solved frames in the flattened (frame, marker) grid: one take() per array
+    # (a fancy-index copy followed by a boolean gather costs ten times as much)
+    M = vis.shape[1]
+    flat_idx = np.flatnonzero(vf)
+    if len(fid) != len(vis):
+        flat_idx = flat_idx + (fid[flat_idx // M] - flat_idx // M) * M
+    obs_cat = np.take(obs.reshape(-1, 3), flat_idx, axis=0)
     labels = np.asarray(latent_labels, dtype=object)
     # the label lists are built once per visibility pattern (drop-outs come in runs) and copied
     by_pattern: dict = {}
@@ -275,7 +281,7 @@ def observation_lists(obs: np.ndarray, vis: np.ndarray, latent_labels) -> dict:
         if names is None:
             names = by_pattern[key] = labels[row].tolist()
         labels_obs.append(list(names))
-    return {'fid': fid, 'vf': vf, 'starts': starts, 'ends': ends, 'labels_obs': labels_obs,
+    return {'fid': fid, 'vf': vf, 'starts': starts, 'ends': ends, 'flat_idx': flat_idx, 'labels_obs': labels_obs,
             'markers_obs': [obs_cat[a:b] for a, b in zip(starts, ends)]}
 
 
@@ -303,9 +309,10 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         errs['extrap_dmpl'] = res.errs[fid, 5][(st & _lib.ST_HAS_EXTRAP) != 0]
     errs['velo'] = res.errs[fid, 2][(st & _lib.ST_HAS_VELO) != 0]
     errs = {k: np.array(v) for k, v in errs.items() if k in ('data', 'poseB', 'poseB_jangles', 'poseH', 'dmpl', 'poseF', 'expr') or len(v)}
+    every = len(fid) == len(res.status)          # (the result arrays belong to this call: no second copy)
     data = {
-        'fullpose': res.fullpose[fid].copy(),
-        'trans': res.trans[fid].copy(),
+        'fullpose': res.fullpose if every else res.fullpose[fid],
+        'trans': res.trans if every else res.trans[fid],
     }
     if dyn:
         data['dmpls'] = res.dmpls[fid, :pk.n_dmpl - pk.n_expr].copy()
@@ -317,7 +324,7 @@ def assemble_stageii_data(res: '_lib.ResultArrays', obs: np.ndarray, vis: np.nda
         expr[:, :pk.n_expr] = res.dmpls[fid, pk.n_dmpl - pk.n_expr:pk.n_dmpl]
         data['expression'] = expr
     # per-frame lists over the visible markers (chmosh.py:716-718): one gather, cut into per-frame views
-    sim_cat = res.markers_sim[fid][lists['vf']]
+    sim_cat = np.take(res.markers_sim.reshape(-1, 3), lists['flat_idx'], axis=0)
     data['stageii_debug_details'] = {
         'stageii_errs': errs,
         'markers_sim': [sim_cat[a:b] for a, b in zip(lists['starts'], lists['ends'])],
@@ -551,7 +558,7 @@ def mosh_stageii(mocap_fname: str, cfg, markers_latent: np.ndarray, latent_label
             'h2d_bytes': int(((F - 1) * selected_frames.step + 1) * mocap.raw.shape[1] * 24 + 4 * len(latent_labels)) if raw_cols is not None
             else int(obs.size * (4 if precision == 'f32' else 8) + vis.size),
             'status': res.status.copy(),
-            'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0].copy(),
+            'counters': res.counters.copy(), 'pose_reduced': res.pose[(res.status & _lib.ST_SOLVED) != 0],
             'frame_ids': np.nonzero((res.status & _lib.ST_SOLVED) != 0)[0],
         },
     })

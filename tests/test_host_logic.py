@@ -26,6 +26,12 @@ def test_result_assembly_matches_reference_layout(cases, emu):
     assert len(dbg['markers_sim']) == len(dbg['markers_obs']) == len(dbg['labels_obs']) == n
     for mk, ob, lb in zip(dbg['markers_sim'], dbg['markers_obs'], dbg['labels_obs']):
         assert mk.shape == ob.shape == (len(lb), 3)
+    solved = np.nonzero(vis.any(1))[0]
+    for k, f in enumerate(solved):                   # the lists are cut out of the right frames, in label order
+        assert np.array_equal(dbg['markers_sim'][k], res.markers_sim[f][vis[f]])
+        assert np.array_equal(dbg['markers_obs'][k], obs[f][vis[f]])
+        assert dbg['labels_obs'][k] == [l for l, v in zip(case['latent_labels'], vis[f]) if v]
+    assert np.array_equal(data['fullpose'], res.fullpose[solved]) and np.array_equal(data['trans'], res.trans[solved])
     e = dbg['stageii_errs']
     assert list(e.keys()) == ['data', 'poseB', 'poseH', 'dmpl', 'extrap_dmpl', 'velo']
     assert len(e['data']) == n and len(e['extrap_dmpl']) == n - 1 and len(e['velo']) == n - 2
