@@ -1,5 +1,5 @@
 """Development tool: phase clock breakdown of the Stage-II kernel (needs moshpp_b200/libmosh2_prof.so built with
--DMOSH2_PROFILE).  Usage: python tools/gpu_phases.py C2 [frames] [L:W]"""
+-DMOSH2_PROFILE).  Usage: python tools/gpu_phases.py C2 [frames] [L:W] [f32|f64]"""
 import ctypes as C
 import json
 import os
@@ -22,6 +22,7 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else 'C2'
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     L, W = (int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else '0:0').split(':'))
+    prec = lib.MOSH2_F64 if (len(sys.argv) > 4 and sys.argv[4] == 'f64') else lib.MOSH2_F32
     d = tempfile.mkdtemp(prefix='mosh_phase_')
     case = synth.make_case(d, name, frames=frames)
     pk, opts, _ = chmosh.prepare_stageii(case['cfg'], case['markers_latent'], case['latent_labels'], case['betas'], case['marker_meta'])
@@ -29,7 +30,7 @@ def main():
     obs, vis = mocap.frames_for_labels(case['latent_labels'], range(len(mocap)))
     path = os.path.join(ROOT, 'moshpp_b200', os.environ.get('MOSH2_PROF_LIB', 'libmosh2_prof.so'))
     model = lib.Model(pk, device=0, library_path=path)
-    job = model.job(obs.shape[0], opts, chunk_len=L, chunk_warmup=W, precision=lib.MOSH2_F32)
+    job = model.job(obs.shape[0], opts, chunk_len=L, chunk_warmup=W, precision=prec)
     job.upload(obs, vis)
     job.launch(); job.sync()
     job.launch(); job.sync()
