@@ -220,7 +220,7 @@ template <class real> M2_HD real accept_slack();
 template <> M2_HD float accept_slack<float>() { return 1e-5f; }
 template <> M2_HD double accept_slack<double>() { return 0.0; }
 
-#if defined(__CUDA_ARCH__)
+#if M2_GPU
 // t == 0 ? a : (t == 1 ? b : c) as two select instructions
 __device__ __forceinline__ float sel3(int t, float a, float b, float c) {
     float r;
@@ -233,6 +233,14 @@ __device__ __forceinline__ double sel3(int t, double a, double b, double c) {
     asm("{\n\t.reg .pred p, q;\n\tsetp.eq.s32 p, %1, 0;\n\tsetp.eq.s32 q, %1, 1;\n\tselp.f64 %0, %3, %4, q;\n\tselp.f64 %0, %2, %0, p;\n\t}"
         : "=&d"(r) : "r"(t), "d"(a), "d"(b), "d"(c));
     return r;
+}
+#endif
+
+#if M2_GPU
+// D = A B + D, one warp: A 8x4 (row), B 4x8 (col), D 8x8, float64 (lane: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// d0, d1 = D[lane/4][2 (lane%4) + 0, 1])
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 #endif
 
@@ -1394,12 +1402,24 @@ struct Solver {
                     const real *J0 = w.Jt + 3 * ml * d.NCt + hb.q0, *J1 = J0 + d.NCt, *J2 = J1 + d.NCt;
                     const real *ct = w.hct + hb.ct_off + 4 * rg;
                     real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int q = 0; q < nq; ++q) {
-                        const real j0 = J0[q], j1 = J1[q], j2 = J2[q];
-                        const Vec4<real> cv = ld4(ct + q * hb.rw4);
-                        acc[0] += j0 * cv.x; acc[1] += j0 * cv.y; acc[2] += j0 * cv.z; acc[3] += j0 * cv.w;
-                        acc[4] += j1 * cv.x; acc[5] += j1 * cv.y; acc[6] += j1 * cv.z; acc[7] += j1 * cv.w;
-                        acc[8] += j2 * cv.x; acc[9] += j2 * cv.y; acc[10] += j2 * cv.z; acc[11] += j2 * cv.w;
+                    // (global-workspace layout: the full-pose tile lives in L2 -- five columns in flight; same order of the sums)
+                    constexpr int U = BIG ? 5 : 1;
+                    for (int q = 0; q < nq; q += U) {
+                        real j0[U], j1[U], j2[U];
+                        Vec4<real> cv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int qq = q + u < nq ? q + u : nq - 1;
+                            j0[u] = J0[qq]; j1[u] = J1[qq]; j2[u] = J2[qq];
+                            cv[u] = ld4(ct + qq * hb.rw4);
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (q + u < nq) {
+                                acc[0] += j0[u] * cv[u].x; acc[1] += j0[u] * cv[u].y; acc[2] += j0[u] * cv[u].z; acc[3] += j0[u] * cv[u].w;
+                                acc[4] += j1[u] * cv[u].x; acc[5] += j1[u] * cv[u].y; acc[6] += j1[u] * cv[u].z; acc[7] += j1[u] * cv[u].w;
+                                acc[8] += j2[u] * cv[u].x; acc[9] += j2[u] * cv[u].y; acc[10] += j2[u] * cv[u].z; acc[11] += j2[u] * cv[u].w;
+                            }
                     }
                     const real sc = w.vis[t0 + ml] ? wd : real(0);
 #pragma unroll
@@ -1457,6 +1477,48 @@ struct Solver {
                 }
             } else
 #endif
+#if M2_GPU
+            if constexpr (sizeof(real) == 8) {
+                // float64: J^T J on the tensor cores as well -- mma.sync m8n8k4 (DMMA), a warp per 16x16 block of the upper
+                // triangle, K = the tile's rows in steps of four.  The FP64 pipe of the CUDA cores issues one warp
+                // instruction per ~25 cycles and SM sub-partition here: the register-tile product below took half of the
+                // float64 kernel's time (measured; 8x8 register tiles, i.e. half the operand bytes, took twice as long).
+                const int lane = cta.tid & 31, warp = cta.tid >> 5, nwarp = cta.nthr >> 5;
+                const int g = lane >> 2, tq = lane & 3;
+                const int nb16 = (n + 15) >> 4, ntile = nb16 * (nb16 + 1) / 2;
+                for (int tile = warp; tile < ntile; tile += nwarp) {
+                    int ti = 0, rem = tile;
+                    while (rem >= nb16 - ti) { rem -= nb16 - ti; ++ti; }
+                    const int tj = ti + rem, i0 = 16 * ti, j0 = 16 * tj;
+                    double c[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+                    // operand columns of this lane (beyond the padded row length: nothing to read)
+                    const int ca0 = i0 + g, ca1 = i0 + 8 + g, cb0 = j0 + g, cb1 = j0 + 8 + g;
+                    for (int k0 = 0; k0 < trows; k0 += 4) {
+                        const int k = k0 + tq;
+                        const bool kin = k < trows;
+                        const real *Jr = w.Jf + (kin ? k : 0) * d.npad;
+                        const double a0 = (kin && ca0 < d.npad) ? double(Jr[ca0]) : 0.0, a1 = (kin && ca1 < d.npad) ? double(Jr[ca1]) : 0.0;
+                        const double b0 = (kin && cb0 < d.npad) ? double(Jr[cb0]) : 0.0, b1 = (kin && cb1 < d.npad) ? double(Jr[cb1]) : 0.0;
+                        dmma_m8n8k4(c[0][0][0], c[0][0][1], a0, b0);
+                        dmma_m8n8k4(c[0][1][0], c[0][1][1], a0, b1);
+                        dmma_m8n8k4(c[1][0][0], c[1][0][1], a1, b0);
+                        dmma_m8n8k4(c[1][1][0], c[1][1][1], a1, b1);
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int i = i0 + 8 * mi + g, j = j0 + 8 * ni + 2 * tq + e;
+                                if (j < n && i <= j) {
+                                    w.A[i * ld + j] += real(c[mi][ni][e]);
+                                    if (i < j) w.A[j * ld + i] += real(c[mi][ni][e]);
+                                }
+                            }
+                }
+            } else
+#endif
             {
                 const int nb = (n + kBS - 1) / kBS, nblk = nb * (nb + 1) / 2;
                 CTA_FOR(b, nblk) {
@@ -1466,14 +1528,26 @@ struct Solver {
                     real acc[kBS * kBS];
 #pragma unroll
                     for (int q = 0; q < kBS * kBS; ++q) acc[q] = 0;
-                    for (int row = 0; row < trows; ++row) {
-                        const real *Jr = w.Jf + row * d.npad;
-                        const Vec4<real> av = ld4(Jr + bi * kBS), bv = ld4(Jr + bj * kBS);
-                        const real ai[4] = {av.x, av.y, av.z, av.w}, bjv[4] = {bv.x, bv.y, bv.z, bv.w};
+                    // four rows in flight: in the float64 / oversized layout the tile lives in the global workspace (L2), and a
+                    // loop that waits for every row's two loads before its sixteen FMAs ran at a fourteenth of the FP64 rate
+                    // (half of the float64 kernel's time).  Same products in the same order.
+                    for (int row = 0; row < trows; row += 4) {
+                        Vec4<real> av[4], bv[4];
 #pragma unroll
-                        for (int p = 0; p < kBS; ++p)
+                        for (int u = 0; u < 4; ++u) {
+                            const real *Jr = w.Jf + (row + u < trows ? row + u : trows - 1) * d.npad;
+                            av[u] = ld4(Jr + bi * kBS);
+                            bv[u] = ld4(Jr + bj * kBS);
+                        }
 #pragma unroll
-                            for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bjv[q];
+                        for (int u = 0; u < 4; ++u)
+                            if (row + u < trows) {
+                                const real ai[4] = {av[u].x, av[u].y, av[u].z, av[u].w}, bjv[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+#pragma unroll
+                                for (int p = 0; p < kBS; ++p)
+#pragma unroll
+                                    for (int q = 0; q < kBS; ++q) acc[p * kBS + q] += ai[p] * bjv[q];
+                            }
                     }
 #pragma unroll
                     for (int p = 0; p < kBS; ++p)
@@ -1509,10 +1583,15 @@ struct Solver {
                 }
             } else
 #endif
-            CTA_FOR(cc, n) {
+            CTA_FOR(cc, n) {                                 // (six rows in flight, for the same reason; same order of the sum)
                 real s = 0;
-                for (int ml = 0; ml < tm; ++ml)
-                    for (int r = 0; r < 3; ++r) s += jf_load(ml, r, cc) * w.rm[3 * (t0 + ml) + r];
+                for (int row = 0; row < trows; row += 6) {
+                    real jv[6];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) jv[u] = w.Jf[(row + u < trows ? row + u : trows - 1) * d.npad + cc];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) if (row + u < trows) s += jv[u] * w.rm[3 * t0 + row + u];
+                }
                 w.g[cc] -= s;
             }
 #if M2_GPU
@@ -1945,20 +2024,12 @@ struct Solver {
                     M2_TACC(13);
                 } else {
                     if (k0 >= 0) {
-#if defined(MOSH2_GN_QUIET)
-                        // (experiment: the warps that share warp 0's scheduler stay out of the way)
-                        const int wq = cta.tid >> 5, nwq = nthr >> 5;
-                        const bool worker = (wq & 3) != 0;
-                        const int t = (wq - 1 - (wq >> 2)) * 32 + (cta.tid & 31), nt_ = (nwq - ((nwq + 3) >> 2)) * 32;
-#else
-                        const bool worker = true;
                         const int t = cta.tid - 32, nt_ = nthr - 32;
-#endif
-                        if (worker) for (int i = r0 + NB + t; i < d.ldp; i += nt_) panel_row(i, k0, kb, Li, n);
+                        for (int i = r0 + NB + t; i < d.ldp; i += nt_) panel_row(i, k0, kb, Li, n);
                         if (trail) {
                             asm volatile("bar.sync 1, %0;" :: "r"(nthr) : "memory");
                             const int R = n + 1 - r0, ntl = (R + kBS - 1) / kBS, ntri = ntl * (ntl + 1) / 2;
-                            if (worker) for (int it = 3 + t; it < ntri; it += nt_) chol_tile(it, r0, n);
+                            for (int it = 3 + t; it < ntri; it += nt_) chol_tile(it, r0, n);
                         }
                     }
                 }
