@@ -1504,6 +1504,19 @@ struct Solver {
                         dmma_m8n8k4(c[1][0][0], c[1][0][1], a1, b0);
                         dmma_m8n8k4(c[1][1][0], c[1][1][1], a1, b1);
                     }
+                    // A += block, mirrored.  The old values are fetched together (in the global-workspace layout A lives in L2,
+                    // and sixteen read-modify-writes one after the other cost a launch's worth of latency per tile: that, not the
+                    // product, was the phase); the mirror entry receives the same sum -- it has received the same terms.
+                    real old[2][2][2];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int i = i0 + 8 * mi + g, j = j0 + 8 * ni + 2 * tq + e;
+                                old[mi][ni][e] = (j < n && i <= j) ? w.A[i * ld + j] : real(0);
+                            }
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -1512,8 +1525,9 @@ struct Solver {
                             for (int e = 0; e < 2; ++e) {
                                 const int i = i0 + 8 * mi + g, j = j0 + 8 * ni + 2 * tq + e;
                                 if (j < n && i <= j) {
-                                    w.A[i * ld + j] += real(c[mi][ni][e]);
-                                    if (i < j) w.A[j * ld + i] += real(c[mi][ni][e]);
+                                    const real v = old[mi][ni][e] + real(c[mi][ni][e]);
+                                    w.A[i * ld + j] = v;
+                                    if (i < j) w.A[j * ld + i] = v;
                                 }
                             }
                 }
