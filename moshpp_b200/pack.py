@@ -231,8 +231,15 @@ def attach_markers(can_verts: np.ndarray, markers_latent: np.ndarray):
     can_verts = np.asarray(can_verts, dtype=np.float64)
     markers_latent = np.asarray(markers_latent, dtype=np.float64)
     cand = can_verts[:SMPLX_FIRST_EYEBALL_VID] if len(can_verts) == SMPLX_NUM_VERTS else can_verts
-    # brute-force L2 8-NN, distance-sorted like sklearn's kd_tree query
-    d2 = ((markers_latent[:, None, :] - cand[None, :, :]) ** 2).sum(-1)
+    # brute-force L2 8-NN, distance-sorted like sklearn's kd_tree query.  Axis by axis: the same squares added in the same
+    # order as ((m - v) ** 2).sum(-1), without the M x V x 3 temporary (four times faster; Stage I attaches per evaluation)
+    ct = np.ascontiguousarray(cand.T)
+    d = markers_latent[:, 0, None] - ct[0][None, :]
+    d2 = d * d
+    d = markers_latent[:, 1, None] - ct[1][None, :]
+    d2 += d * d
+    d = markers_latent[:, 2, None] - ct[2][None, :]
+    d2 += d * d
     k = min(8, cand.shape[0])
     part = np.argpartition(d2, k - 1, axis=1)[:, :k]
     order = np.argsort(np.take_along_axis(d2, part, axis=1), axis=1, kind='stable')
