@@ -74,8 +74,33 @@ def main():
                         last_frame=np.array(r.last_frame), labels=np.array([s.strip() for s in r.point_labels]))
     with open(fn, 'rb') as h:
         blob = np.frombuffer(h.read(), dtype=np.uint8)
-    np.savez_compressed(os.path.join(HERE, 'ref_c3d.npz'), file_bytes=blob, data=data, in_labels=np.array(labels), **meta)
-    print('ref_c3d.npz:', {k: (v.tolist() if v.size < 8 else v.shape) for k, v in meta.items()})
+    # the same content in the DEC and the SGI/MIPS processor formats: header and parameters as the reference's parser
+    # reads them (tools/c3d.py:35-100,368-424), and the reference's own DEC -> IEEE conversion of random DEC numbers
+    extra = {}
+    for proc in ('dec', 'mips'):
+        fnp = os.path.join(d, f'written_{proc}.c3d')
+        c3d_io.write_c3d(fnp, data, labels, frame_rate=120.0, processor=proc)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            with open(fnp, 'rb') as h:
+                r = ref_c3d.Reader(h)
+                extra[f'{proc}_point_rate'] = np.array(r.point_rate)
+                extra[f'{proc}_point_scale'] = np.array(r.point_scale)
+                extra[f'{proc}_point_used'] = np.array(r.point_used)
+                extra[f'{proc}_first_frame'] = np.array(r.first_frame)
+                extra[f'{proc}_last_frame'] = np.array(r.last_frame)
+                extra[f'{proc}_labels'] = np.array([s.strip() for s in r.point_labels])
+        with open(fnp, 'rb') as h:
+            extra[f'{proc}_file_bytes'] = np.frombuffer(h.read(), dtype=np.uint8)
+    vals = np.concatenate([rng.normal(0, 800, 400), rng.normal(0, 1e-3, 50), [0.0, 1.0, -1.0, 0.5, 1234.5]]).astype(np.float32)
+    dec_bytes = np.frombuffer(c3d_io.ieee_to_dec(vals), dtype=np.uint8)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        extra['dec_bytes'] = dec_bytes
+        extra['dec_as_ieee_by_reference'] = np.array(ref_c3d.DEC_to_IEEE_BYTES(dec_bytes.tobytes()), dtype=np.float32)
+        extra['dec_scalar_by_reference'] = np.array([ref_c3d.DEC_to_IEEE(int(u)) for u in dec_bytes.view('<u4')[:64]], dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, 'ref_c3d.npz'), file_bytes=blob, data=data, in_labels=np.array(labels), **meta, **extra)
+    print('ref_c3d.npz:', {k: (v.tolist() if v.size < 8 else v.shape) for k, v in {**meta, **extra}.items()})
 
 
 def prior_and_marker_vectors():

@@ -5,6 +5,7 @@ of the Stage-II path cannot be imported (chumpy / psbody / ezc3d absent) and sta
 import os
 
 import numpy as np
+import pytest
 
 from moshpp_b200 import c3d_io
 from oracle import rigid
@@ -41,6 +42,37 @@ def test_c3d_writer_output_is_what_the_reference_parser_read(tmp_path):
     pts, lab, rate = c3d_io.read_c3d(fn)
     assert lab == labels and rate == 120.0
     assert np.allclose(pts, g['data'], rtol=0, atol=1e-3, equal_nan=True)                   # float32 millimetres
+
+
+@pytest.mark.parametrize('proc', ['dec', 'mips'])
+def test_c3d_dec_and_mips_files_as_the_reference_parser_reads_them(tmp_path, proc):
+    """The same content in the DEC (VAX F-floating numbers) and SGI/MIPS (big-endian) processor formats: the file our writer
+    produces is the one the reference's parser (tools/c3d.py:35-100,368-424, unmodified) read rate, scale, counts and labels
+    from, and our reader returns the data."""
+    g = np.load(os.path.join(GOLD, 'ref_c3d.npz'))
+    fn = str(tmp_path / f'{proc}.c3d')
+    labels = [str(s) for s in g['in_labels']]
+    c3d_io.write_c3d(fn, g['data'], labels, frame_rate=120.0, processor=proc)
+    with open(fn, 'rb') as h:
+        assert np.array_equal(np.frombuffer(h.read(), dtype=np.uint8), g[f'{proc}_file_bytes'])
+    assert float(g[f'{proc}_point_rate']) == 120.0 and float(g[f'{proc}_point_scale']) == -1.0
+    assert int(g[f'{proc}_point_used']) == len(labels)
+    assert int(g[f'{proc}_last_frame']) - int(g[f'{proc}_first_frame']) + 1 == g['data'].shape[0]
+    assert [str(s) for s in g[f'{proc}_labels']] == labels
+    pts, lab, rate = c3d_io.read_c3d(fn)
+    assert lab == labels and rate == 120.0
+    assert np.allclose(pts, g['data'], rtol=0, atol=1e-3, equal_nan=True)
+
+
+def test_dec_float_conversion_equals_the_reference():
+    """VAX F-floating -> IEEE: the reference's own converters (tools/c3d.py:115-190, array and scalar form) on 455 numbers."""
+    g = np.load(os.path.join(GOLD, 'ref_c3d.npz'))
+    mine = c3d_io.dec_to_ieee(g['dec_bytes'].tobytes())
+    ref = g['dec_as_ieee_by_reference']
+    normal = np.abs(ref) > 1e-30                       # (the reference's exponent decrement is undefined on zero)
+    assert normal.sum() >= 450 and np.array_equal(mine[normal], ref[normal])
+    assert np.array_equal(mine[:64][normal[:64]], g['dec_scalar_by_reference'][normal[:64]])
+    assert np.array_equal(c3d_io.dec_to_ieee(c3d_io.ieee_to_dec(ref[normal])), ref[normal])
 
 
 # --------------------------------------------------------------------------------------------------------------------
