@@ -51,9 +51,15 @@ def merge_stageii(stageii_data: dict, stagei_data: dict, cfg, elapsed_time: floa
     return stageii_data
 
 
+STAGEI_NPZ_KEYS = ('gender', 'surface_model_type', 'markers_latent', 'latent_labels', 'markers_latent_vids', 'betas', 'v_template')
+
+
 def load_as_amass_npz(stageii_pkl_data_or_fname: Union[dict, str], stageii_npz_fname: Optional[str] = None,
-                      include_markers: bool = False) -> dict:
-    """AMASS npz dictionary of a merged Stage-II result (mosh_head.py:444-541).  The reference slices ``dmpls``
+                      stagei_npz_fname: Optional[str] = None, include_markers: bool = False,
+                      include_extra_details: bool = False) -> dict:
+    """AMASS npz dictionary of a merged Stage-II result, same arguments as the reference (mosh_head.py:444-541): with
+    ``stageii_npz_fname`` the sequence file is written and next to it (or at ``stagei_npz_fname``) the per-subject
+    ``<gender>_stagei.npz`` with the Stage-I keys, each only if it does not exist yet.  The reference slices ``dmpls``
     along frames by mistake (``[:num_dmpls]``, mosh_head.py:499); here the coefficient
     axis is sliced, which is what AMASS files contain."""
     if isinstance(stageii_pkl_data_or_fname, dict):
@@ -75,6 +81,10 @@ def load_as_amass_npz(stageii_pkl_data_or_fname: Union[dict, str], stageii_npz_f
         'trans': d['trans'],
         'poses': d['fullpose'],
     }
+    if include_extra_details:
+        out['surface_model_fname'] = sm.get('fname')
+    if 'v_template' in d.get('stagei_debug_details', {}):
+        out['v_template'] = d['stagei_debug_details']['v_template']
     if mp.get('optimize_betas', True):
         out['betas'] = np.asarray(d['betas'])[:sm['num_betas']]
         out['num_betas'] = sm['num_betas']
@@ -93,7 +103,13 @@ def load_as_amass_npz(stageii_pkl_data_or_fname: Union[dict, str], stageii_npz_f
         out['markers_sim'] = np.array(dbg['markers_sim'], dtype=object)
         out['marker_meta'] = d.get('marker_meta')
         out['num_markers'] = np.asarray(dbg['markers_orig']).shape[1]
-    if stageii_npz_fname and not os.path.exists(stageii_npz_fname):
-        os.makedirs(os.path.dirname(os.path.abspath(stageii_npz_fname)), exist_ok=True)
-        np.savez(stageii_npz_fname, **{k: v for k, v in out.items() if v is not None})
+    if stageii_npz_fname:
+        if not os.path.exists(stageii_npz_fname):
+            os.makedirs(os.path.dirname(os.path.abspath(stageii_npz_fname)), exist_ok=True)
+            np.savez(stageii_npz_fname, **{k: v for k, v in out.items() if v is not None})
+        if stagei_npz_fname is None:
+            stagei_npz_fname = os.path.join(os.path.dirname(os.path.abspath(stageii_npz_fname)), f"{out['gender']}_stagei.npz")
+        if not os.path.exists(stagei_npz_fname):
+            os.makedirs(os.path.dirname(os.path.abspath(stagei_npz_fname)), exist_ok=True)
+            np.savez(stagei_npz_fname, **{k: v for k, v in out.items() if k in STAGEI_NPZ_KEYS and v is not None})
     return out

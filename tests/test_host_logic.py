@@ -115,6 +115,16 @@ def test_amass_writer_round_trip(cases, emu, tmp_path):
     assert npz['dmpls'].shape == (n, 8) and npz['betas'].shape == (16,) and npz['surface_model_type'] == 'smplx'
     back = np.load(str(tmp_path / 'x_stageii.npz'), allow_pickle=True)
     assert np.array_equal(back['trans'], merged['trans']) and back['num_markers'] == 67
+    # the per-subject file next to it (mosh_head.py:521-537): the Stage-I keys only, written once
+    s1 = np.load(str(tmp_path / f"{npz['gender']}_stagei.npz"), allow_pickle=True)
+    assert set(s1.files) == {'gender', 'surface_model_type', 'markers_latent', 'latent_labels', 'markers_latent_vids', 'betas'}
+    assert np.array_equal(s1['markers_latent'], case['markers_latent']) and s1['betas'].shape == (16,)
+    merged['stagei_debug_details'] = {'v_template': np.zeros((5, 3))}
+    more = amass_io.load_as_amass_npz(merged, str(tmp_path / 'y_stageii.npz'), str(tmp_path / 'sub' / 'subject_stagei.npz'),
+                                      include_extra_details=True)
+    assert more['surface_model_fname'] == case['cfg'].surface_model.fname and more['v_template'].shape == (5, 3)
+    assert 'v_template' in np.load(str(tmp_path / 'sub' / 'subject_stagei.npz'), allow_pickle=True).files
+    assert 'markers' not in more
     parts = amass_io.turn_fullpose_into_parts(np.zeros((2, 48)), 'mano')
     assert parts['pose_hand'].shape == (2, 45) and 'pose_body' not in parts
 
